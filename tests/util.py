@@ -1,0 +1,40 @@
+"""Shared assertion helpers and the tolerances BASELINE.json:north_star states."""
+import numpy as np
+
+RTOL_STAT = 1e-10      # Score, variance-derived statistics: relative
+RTOL_P = 1e-8          # p-values: relative (log10 p to 6 digits below 1e-300)
+
+
+def rel_err(x, ref, floor=0.0):
+    """max |x-ref| / max(|ref|, floor); NaN patterns must match exactly."""
+    x, ref = np.asarray(x, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    assert x.shape == ref.shape, (x.shape, ref.shape)
+    assert np.array_equal(np.isnan(x), np.isnan(ref)), "NaN pattern differs"
+    ok = ~np.isnan(ref)
+    if not ok.any():
+        return 0.0
+    den = np.maximum(np.abs(ref[ok]), floor)
+    num = np.abs(x[ok] - ref[ok])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r = np.where(num == 0, 0.0, num / den)
+    return float(np.max(r))
+
+
+def assert_stats_close(got: dict, ref: dict, score_floor: float = 0.0, keys=None):
+    """Score/Score_se/Est/Est_se within 1e-10 relative, p-values within 1e-8 relative.
+
+    `score_floor`: absolute scale below which a Score is considered cancelled to rounding
+    (|U| far below sqrt(sum (r_j g_j)^2) — the reference's own BLAS order would move it too)."""
+    for k in (keys or ref.keys()):
+        if k == "pvalue_log":
+            # p = exp(-pvalue_log): relative error of p is the ABSOLUTE error of pvalue_log
+            a, b = np.asarray(got[k]), np.asarray(ref[k])
+            assert np.array_equal(np.isnan(a), np.isnan(b))
+            ok = ~np.isnan(b)
+            err = np.abs(a[ok] - b[ok])
+            lim = np.maximum(RTOL_P, 1e-6 * np.log(10) * 0 + RTOL_P * np.abs(b[ok]))
+            assert np.all(err <= lim), f"pvalue_log: max abs err {err.max():.3e}"
+        else:
+            floor = score_floor if k in ("Score", "Est") else 0.0
+            e = rel_err(got[k], ref[k], floor)
+            assert e <= RTOL_STAT, f"{k}: rel err {e:.3e} > {RTOL_STAT}"
