@@ -1,0 +1,194 @@
+/*
+ * staar_b200.h — C ABI of the B200-native score-test hot path.
+ *
+ * Drop-in boundary for the 13 native functions of xihaoli/STAARpipeline
+ * (reference tree: /root/reference, v0.9.8).  Each "frozen-signature" entry
+ * point below takes exactly the operands the corresponding Rcpp export
+ * receives, as plain host pointers + sizes, and fills caller-allocated output
+ * arrays; the reference-side binding (the Rcpp shim that replaces
+ * src/*.cpp behind the unchanged RcppExports.cpp) is in
+ * staarpipeline_b200/rshim/ and described in INTEGRATION.md.
+ *
+ * Conventions
+ *  - dense matrices: column-major FP64 (Armadillo layout), leading dim = rows;
+ *  - sparse matrices: CSC, FP64 values, uint64 row indices / column pointers
+ *    (ARMA_64BIT_WORD=1, reference src/Makevars:2);
+ *  - every function returns 0 on success, non-zero on error;
+ *    staar_last_error() returns the message (the shim turns it into
+ *    Rcpp::stop, mirroring BEGIN_RCPP/END_RCPP, src/RcppExports.cpp:20,30);
+ *  - calls are synchronous for the caller; one staar_ctx per host thread;
+ *  - there is NO CPU fallback: without a CUDA device every compute entry
+ *    point fails with STAAR_ERR_CUDA.
+ */
+#ifndef STAAR_B200_H
+#define STAAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STAAR_OK 0
+#define STAAR_ERR_ARG 1      /* bad argument / dimension mismatch (Armadillo would throw)   */
+#define STAAR_ERR_CUDA 2     /* CUDA runtime failure, or no device                          */
+#define STAAR_ERR_SINGULAR 3 /* inv() of a singular matrix (reachable in _cond, cond.cpp:49) */
+#define STAAR_ERR_STATE 4    /* required null-model operands not set                        */
+
+typedef struct staar_ctx staar_ctx;
+
+/* ---- context ---------------------------------------------------------- */
+int staar_abi_version(void);
+const char *staar_last_error(void);
+/* device: CUDA ordinal (one context = one GPU = one rank) */
+int staar_ctx_create(int device, staar_ctx **out);
+void staar_ctx_destroy(staar_ctx *ctx);
+/* stream the context launches on (cudaStream_t as void*), for CUDA-event timing by the caller */
+void *staar_ctx_stream(staar_ctx *ctx);
+int staar_ctx_synchronize(staar_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+uint64_t staar_ctx_launch_count(staar_ctx *ctx);
+
+/* ======================================================================= */
+/* A. Frozen-signature entry points (host buffers in, host buffers out).    */
+/*    One per Rcpp export; citations are the reference definitions.         */
+/* ======================================================================= */
+
+/* matrix_flip_mean(arma::mat G) -> List{Geno, AF, MAF}       src/matrix_flip_mean.cpp:8-74
+ * matrix_flip_minor(arma::mat G)                              src/matrix_flip_minor.cpp:8-99
+ * G: n x p, NaN or any value <= -1 is missing.  Geno_out (n x p) may alias G or be NULL
+ * (AF/MAF only). */
+int staar_matrix_flip_mean(staar_ctx *ctx, const double *G, int64_t n, int64_t p,
+                           double *Geno_out, double *AF, double *MAF);
+int staar_matrix_flip_minor(staar_ctx *ctx, const double *G, int64_t n, int64_t p,
+                            double *Geno_out, double *AF, double *MAF);
+
+/* Individual_Score_Test(G, Sigma_i, Sigma_iX, cov, residuals)  src/Individual_Score_Test.cpp:9-67
+ * outputs: 5 arrays of length p. */
+int staar_individual_score_test(staar_ctx *ctx, const double *G, int64_t n, int64_t p,
+                                const double *Si_values, const uint64_t *Si_row_idx, const uint64_t *Si_col_ptr,
+                                const double *Sigma_iX, int64_t q, const double *cov, const double *residuals,
+                                double *Score, double *Score_se, double *pvalue_log, double *Est, double *Est_se);
+
+/* Individual_Score_Test_sp(sp_mat G, ...)                      src/Individual_Score_Test_sp.cpp:9-67 */
+int staar_individual_score_test_sp(staar_ctx *ctx, const double *G_values, const uint64_t *G_row_idx,
+                                   const uint64_t *G_col_ptr, int64_t n, int64_t p,
+                                   const double *Si_values, const uint64_t *Si_row_idx, const uint64_t *Si_col_ptr,
+                                   const double *Sigma_iX, int64_t q, const double *cov, const double *residuals,
+                                   double *Score, double *Score_se, double *pvalue_log, double *Est, double *Est_se);
+
+/* Individual_Score_Test_denseGRM(G, P, residuals)              src/Individual_Score_Test_denseGRM.cpp:9-61 */
+int staar_individual_score_test_denseGRM(staar_ctx *ctx, const double *G, int64_t n, int64_t p,
+                                         const double *P, const double *residuals,
+                                         double *Score, double *Score_se, double *pvalue_log, double *Est, double *Est_se);
+/* Individual_Score_Test_sp_denseGRM(sp_mat G, P, residuals)    src/Individual_Score_Test_sp_denseGRM.cpp:9-61 */
+int staar_individual_score_test_sp_denseGRM(staar_ctx *ctx, const double *G_values, const uint64_t *G_row_idx,
+                                            const uint64_t *G_col_ptr, int64_t n, int64_t p,
+                                            const double *P, const double *residuals,
+                                            double *Score, double *Score_se, double *pvalue_log, double *Est, double *Est_se);
+
+/* Individual_Score_Test_multi(G, Sigma_i, Sigma_iX, cov, residuals, n_pheno)
+ *                                                              src/Individual_Score_Test_multi.cpp:9-68
+ * G is n x p with p = n_pheno*pp (the R caller passes I_k (x) G0 with n = k*n0).
+ * outputs: Score (length p), pvalue_log (length p/n_pheno). */
+int staar_individual_score_test_multi(staar_ctx *ctx, const double *G, int64_t n, int64_t p,
+                                      const double *Si_values, const uint64_t *Si_row_idx, const uint64_t *Si_col_ptr,
+                                      const double *Sigma_iX, int64_t q, const double *cov, const double *residuals,
+                                      int n_pheno, double *Score, double *pvalue_log);
+/* Individual_Score_Test_sp_multi(sp_mat G, ...)                src/Individual_Score_Test_sp_multi.cpp:9-68 */
+int staar_individual_score_test_sp_multi(staar_ctx *ctx, const double *G_values, const uint64_t *G_row_idx,
+                                         const uint64_t *G_col_ptr, int64_t n, int64_t p,
+                                         const double *Si_values, const uint64_t *Si_row_idx, const uint64_t *Si_col_ptr,
+                                         const double *Sigma_iX, int64_t q, const double *cov, const double *residuals,
+                                         int n_pheno, double *Score, double *pvalue_log);
+/* Individual_Score_Test_denseGRM_multi(G, P, residuals, n_pheno)   src/Individual_Score_Test_denseGRM_multi.cpp:9-62 */
+int staar_individual_score_test_denseGRM_multi(staar_ctx *ctx, const double *G, int64_t n, int64_t p,
+                                               const double *P, const double *residuals, int n_pheno,
+                                               double *Score, double *pvalue_log);
+/* Individual_Score_Test_sp_denseGRM_multi(sp_mat G, P, residuals, n_pheno)
+ *                                                              src/Individual_Score_Test_sp_denseGRM_multi.cpp:9-62 */
+int staar_individual_score_test_sp_denseGRM_multi(staar_ctx *ctx, const double *G_values, const uint64_t *G_row_idx,
+                                                  const uint64_t *G_col_ptr, int64_t n, int64_t p,
+                                                  const double *P, const double *residuals, int n_pheno,
+                                                  double *Score, double *pvalue_log);
+
+/* Individual_Score_Test_cond(G, Sigma_i, Sigma_iX, cov, X_adj, residuals)
+ *                                                              src/Individual_Score_Test_cond.cpp:10-75
+ * X_adj: n x m.  Returns STAAR_ERR_SINGULAR where arma::inv(X_adj'X_adj) would throw. */
+int staar_individual_score_test_cond(staar_ctx *ctx, const double *G, int64_t n, int64_t p,
+                                     const double *Si_values, const uint64_t *Si_row_idx, const uint64_t *Si_col_ptr,
+                                     const double *Sigma_iX, int64_t q, const double *cov,
+                                     const double *X_adj, int64_t m, const double *residuals,
+                                     double *Score, double *Score_se, double *pvalue_log, double *Est, double *Est_se);
+/* Individual_Score_Test_cond_multi(..., n_pheno)               src/Individual_Score_Test_cond_multi.cpp:10-74 */
+int staar_individual_score_test_cond_multi(staar_ctx *ctx, const double *G, int64_t n, int64_t p,
+                                           const double *Si_values, const uint64_t *Si_row_idx, const uint64_t *Si_col_ptr,
+                                           const double *Sigma_iX, int64_t q, const double *cov,
+                                           const double *X_adj, int64_t m, const double *residuals, int n_pheno,
+                                           double *Score, double *pvalue_log);
+
+/* Individual_Score_Test_SPA(G, XW, XXWX_inv, residuals, muhat, tol, max_iter) -> p-values (NOT log)
+ *                                                              src/Individual_Score_Test_SPA.cpp:38-533
+ * XW: q x n, XXWX_inv: n x q.  trace (optional, may be NULL): 4 int64 per variant
+ * {passes over n, NR iterations, 0, branch bits} — see oracle/staar_oracle.h. */
+int staar_individual_score_test_SPA(staar_ctx *ctx, const double *G, int64_t n, int64_t p,
+                                    const double *XW, const double *XXWX_inv, int64_t q,
+                                    const double *residuals, const double *muhat, double tol, int max_iter,
+                                    double *pvalue, int64_t *trace);
+
+/* ======================================================================= */
+/* B. Resident fast path: packed dosage columns + null model kept in HBM.   */
+/*    (What bench.py's `value` measures; the Rcpp shim reaches it through   */
+/*    the operand cache inside the A-entry points.)                         */
+/* ======================================================================= */
+
+/* Packed dosage block: variant-major, 2 bits per genotype, sample j of a variant in byte j/4,
+ * bits 2*(j%4)..+1; codes 0/1/2 = dosage, 3 = missing.  stride_bytes >= ceil(n/4), multiple of 16;
+ * bits beyond sample n-1 must be 0. */
+size_t staar_packed_stride(int64_t n);
+
+/* host FP64 dosage (n x p, NaN / <= -1 missing) -> packed host buffer (p x stride).  Returns
+ * STAAR_ERR_ARG if a non-missing value is not exactly 0, 1 or 2 (such matrices take the FP64 path). */
+int staar_pack_dosage_host(const double *G, int64_t n, int64_t p, uint8_t *packed, size_t stride_bytes, int threads);
+
+/* Null model, uploaded once (host pointers) ... */
+int staar_nullmodel_set_sparse(staar_ctx *ctx, int64_t n, int64_t q,
+                               const double *Si_values, const uint64_t *Si_row_idx, const uint64_t *Si_col_ptr,
+                               const double *Sigma_iX, const double *cov, const double *residuals);
+/* ... or adopted from device memory the caller owns (e.g. torch tensors filled by an NCCL broadcast):
+ * CSR of Sigma_i with int32 columns / int64 row pointers, all pointers device. */
+int staar_nullmodel_set_sparse_device(staar_ctx *ctx, int64_t n, int64_t q,
+                                      const int64_t *d_row_ptr, const int32_t *d_col, const double *d_val,
+                                      const double *d_Sigma_iX, const double *d_cov, const double *d_residuals);
+
+#define STAAR_IMPUTE_MEAN 0
+#define STAAR_IMPUTE_MINOR 1
+
+/* K1 alone: AF / MAF / flip flag / missing count per variant from packed columns (device pointers).
+ * Bit-exact with matrix_flip_mean / matrix_flip_minor on the same dosages. */
+int staar_packed_flip_stats_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride_bytes, int64_t n, int64_t p,
+                                   int impute, double *d_AF, double *d_MAF, int32_t *d_flip, int32_t *d_nmiss);
+
+/* The fused per-variant path on resident packed columns: flip/impute + Individual_Score_Test.
+ * All pointers are DEVICE pointers; outputs are 7 arrays of length p. Requires staar_nullmodel_set_sparse*. */
+int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride_bytes, int64_t n, int64_t p,
+                              int impute, double *d_AF, double *d_MAF, double *d_Score, double *d_Score_se,
+                              double *d_pvalue_log, double *d_Est, double *d_Est_se);
+
+/* Same, host buffers (packed host columns in, 7 host arrays out); H2D/D2H inside. */
+int staar_packed_score_host(staar_ctx *ctx, const uint8_t *packed, size_t stride_bytes, int64_t n, int64_t p,
+                            int impute, double *AF, double *MAF, double *Score, double *Score_se,
+                            double *pvalue_log, double *Est, double *Est_se);
+
+/* Synthetic packed dosage columns generated on the device (bench / parity subsets); per-variant
+ * thresholds as in staarpipeline_b200/synth.py (device pointers, uint64 / uint8). */
+int staar_synth_packed_device(staar_ctx *ctx, uint8_t *d_packed, size_t stride_bytes, int64_t n,
+                              int64_t first_variant, int64_t p, uint64_t seed,
+                              const uint64_t *d_thr_hom, const uint64_t *d_thr_het, const uint64_t *d_thr_miss,
+                              const uint8_t *d_store_alt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STAAR_B200_H */

@@ -1,0 +1,321 @@
+"""Host-side mirror of the reference's native interface, on top of the C ABI (include/staar_b200.h).
+
+Function names, argument order/meaning, return conventions and error behaviour follow the reference's exported
+R functions (/root/reference/R/RcppExports.R:4-54 -> src/RcppExports.cpp:17-291): each score test returns the
+named list ``{Score, Score_se, pvalue_log, Est, Est_se}`` (``pvalue_log`` is -ln p), the multi-trait tests
+``{Score, pvalue_log}``, the flips ``{Geno, AF, MAF}``, SPA a bare vector of p-values; a condition under which
+Armadillo would throw (dimension mismatch, singular ``inv``) raises ``StaarError`` (the Rcpp shim turns the same
+status into ``Rcpp::stop``).  Inputs are numpy arrays / scipy.sparse matrices, the Python stand-ins for
+``arma::mat`` / ``arma::sp_mat`` (R itself is absent from this image; the real binding is in rshim/).
+
+Everything computes on the GPU through ``libstaar_b200.so``; there is NO CPU fallback — importing works anywhere
+(so the symbol-table tests run on CPU), but creating a :class:`Context` without the library or a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import scipy.sparse as sp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstaar_b200.so")
+_dp = C.POINTER(C.c_double)
+_u64p = C.POINTER(C.c_uint64)
+_u8p = C.POINTER(C.c_uint8)
+
+IMPUTE_MEAN, IMPUTE_MINOR = 0, 1
+
+
+class StaarError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[staar_b200 status {code}] {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the CUDA library; fails loudly when it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise StaarError(2, f"{LIB_PATH} is missing: build it with `python -m staarpipeline_b200.build` "
+                                "(this package has no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.staar_last_error.restype = C.c_char_p
+        _lib.staar_packed_stride.restype = C.c_size_t
+        _lib.staar_packed_stride.argtypes = [C.c_int64]
+        _lib.staar_ctx_stream.restype = C.c_void_p
+        _lib.staar_ctx_launch_count.restype = C.c_uint64
+    return _lib
+
+
+def _f(a) -> np.ndarray:
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(_dp)
+
+
+class _Csc:
+    """arma::sp_mat stand-in: CSC with uint64 indices (ARMA_64BIT_WORD, reference src/Makevars:2)."""
+
+    def __init__(self, m):
+        m = sp.csc_matrix(m, dtype=np.float64)
+        m.sort_indices()
+        self.shape = m.shape
+        self.values = np.ascontiguousarray(m.data, dtype=np.float64)
+        self.row_idx = np.ascontiguousarray(m.indices, dtype=np.uint64)
+        self.col_ptr = np.ascontiguousarray(m.indptr, dtype=np.uint64)
+
+    def args(self):
+        return (_p(self.values), self.row_idx.ctypes.data_as(_u64p), self.col_ptr.ctypes.data_as(_u64p))
+
+
+class Context:
+    """One context = one GPU = one rank."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.staar_ctx_create(C.c_int(device), C.byref(self._h))
+        if rc != 0:
+            raise StaarError(rc, self._lib.staar_last_error().decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.staar_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _call(self, name: str, *args):
+        rc = getattr(self._lib, name)(self._h, *args)
+        if rc != 0:
+            raise StaarError(rc, self._lib.staar_last_error().decode())
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.staar_ctx_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.staar_ctx_launch_count(self._h))
+
+    def synchronize(self):
+        self._call("staar_ctx_synchronize")
+
+    # ------------------------------------------------------------------ flips
+    def _flip(self, fn: str, G, want_geno=True):
+        G = _f(G)
+        if G.ndim != 2:
+            raise StaarError(1, "G must be a matrix")
+        n, p = G.shape
+        AF, MAF = np.zeros(p), np.zeros(p)
+        Geno = np.empty((n, p), order="F") if want_geno else None
+        self._call(fn, _p(G), C.c_int64(n), C.c_int64(p), _p(Geno) if want_geno else None, _p(AF), _p(MAF))
+        return {"Geno": Geno, "AF": AF, "MAF": MAF}
+
+    def matrix_flip_mean(self, G, want_geno=True):
+        return self._flip("staar_matrix_flip_mean", G, want_geno)
+
+    def matrix_flip_minor(self, G, want_geno=True):
+        return self._flip("staar_matrix_flip_minor", G, want_geno)
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _sigma_args(n, Sigma_i, Sigma_iX, cov, residuals):
+        S = _Csc(Sigma_i)
+        if S.shape != (n, n):
+            raise StaarError(1, f"Sigma_i is {S.shape}, expected ({n}, {n})")
+        SX = _f(Sigma_iX)
+        if SX.ndim != 2 or SX.shape[0] != n:
+            raise StaarError(1, "matrix multiplication: incompatible matrix dimensions (Sigma_iX)")
+        q = SX.shape[1]
+        cv = _f(cov)
+        if cv.shape != (q, q):
+            raise StaarError(1, "matrix multiplication: incompatible matrix dimensions (cov)")
+        r = _f(residuals).ravel()
+        if r.size != n:
+            raise StaarError(1, "matrix multiplication: incompatible matrix dimensions (residuals)")
+        keep = (S, SX, cv, r)
+        return keep, (*S.args(), _p(SX), C.c_int64(q), _p(cv), _p(r))
+
+    @staticmethod
+    def _out5(p):
+        o = [np.zeros(p) for _ in range(5)]
+        return o, [_p(a) for a in o]
+
+    @staticmethod
+    def _pack5(o):
+        return dict(zip(("Score", "Score_se", "pvalue_log", "Est", "Est_se"), o))
+
+    # ------------------------------------------------------------------ single trait
+    def Individual_Score_Test(self, G, Sigma_i, Sigma_iX, cov, residuals):
+        G = _f(G); n, p = G.shape
+        keep, sargs = self._sigma_args(n, Sigma_i, Sigma_iX, cov, residuals)
+        o, po = self._out5(p)
+        self._call("staar_individual_score_test", _p(G), C.c_int64(n), C.c_int64(p), *sargs, *po)
+        return self._pack5(o)
+
+    def Individual_Score_Test_sp(self, G, Sigma_i, Sigma_iX, cov, residuals):
+        Gs = _Csc(G); n, p = Gs.shape
+        keep, sargs = self._sigma_args(n, Sigma_i, Sigma_iX, cov, residuals)
+        o, po = self._out5(p)
+        self._call("staar_individual_score_test_sp", *Gs.args(), C.c_int64(n), C.c_int64(p), *sargs, *po)
+        return self._pack5(o)
+
+    @staticmethod
+    def _dense_args(n, P, residuals):
+        Pm = _f(P)
+        if Pm.shape != (n, n):
+            raise StaarError(1, "matrix multiplication: incompatible matrix dimensions (P)")
+        r = _f(residuals).ravel()
+        if r.size != n:
+            raise StaarError(1, "matrix multiplication: incompatible matrix dimensions (residuals)")
+        return (Pm, r), (_p(Pm), _p(r))
+
+    def Individual_Score_Test_denseGRM(self, G, P, residuals):
+        G = _f(G); n, p = G.shape
+        keep, dargs = self._dense_args(n, P, residuals)
+        o, po = self._out5(p)
+        self._call("staar_individual_score_test_denseGRM", _p(G), C.c_int64(n), C.c_int64(p), *dargs, *po)
+        return self._pack5(o)
+
+    def Individual_Score_Test_sp_denseGRM(self, G, P, residuals):
+        Gs = _Csc(G); n, p = Gs.shape
+        keep, dargs = self._dense_args(n, P, residuals)
+        o, po = self._out5(p)
+        self._call("staar_individual_score_test_sp_denseGRM", *Gs.args(), C.c_int64(n), C.c_int64(p), *dargs, *po)
+        return self._pack5(o)
+
+    # ------------------------------------------------------------------ multi trait
+    def Individual_Score_Test_multi(self, G, Sigma_i, Sigma_iX, cov, residuals, n_pheno=1):
+        G = _f(G); n, p = G.shape
+        keep, sargs = self._sigma_args(n, Sigma_i, Sigma_iX, cov, residuals)
+        Score, pl = np.zeros(p), np.zeros(p // max(n_pheno, 1))
+        self._call("staar_individual_score_test_multi", _p(G), C.c_int64(n), C.c_int64(p), *sargs, C.c_int(n_pheno),
+                   _p(Score), _p(pl))
+        return {"Score": Score, "pvalue_log": pl}
+
+    def Individual_Score_Test_sp_multi(self, G, Sigma_i, Sigma_iX, cov, residuals, n_pheno=1):
+        Gs = _Csc(G); n, p = Gs.shape
+        keep, sargs = self._sigma_args(n, Sigma_i, Sigma_iX, cov, residuals)
+        Score, pl = np.zeros(p), np.zeros(p // max(n_pheno, 1))
+        self._call("staar_individual_score_test_sp_multi", *Gs.args(), C.c_int64(n), C.c_int64(p), *sargs,
+                   C.c_int(n_pheno), _p(Score), _p(pl))
+        return {"Score": Score, "pvalue_log": pl}
+
+    def Individual_Score_Test_denseGRM_multi(self, G, P, residuals, n_pheno=1):
+        G = _f(G); n, p = G.shape
+        keep, dargs = self._dense_args(n, P, residuals)
+        Score, pl = np.zeros(p), np.zeros(p // max(n_pheno, 1))
+        self._call("staar_individual_score_test_denseGRM_multi", _p(G), C.c_int64(n), C.c_int64(p), *dargs,
+                   C.c_int(n_pheno), _p(Score), _p(pl))
+        return {"Score": Score, "pvalue_log": pl}
+
+    def Individual_Score_Test_sp_denseGRM_multi(self, G, P, residuals, n_pheno=1):
+        Gs = _Csc(G); n, p = Gs.shape
+        keep, dargs = self._dense_args(n, P, residuals)
+        Score, pl = np.zeros(p), np.zeros(p // max(n_pheno, 1))
+        self._call("staar_individual_score_test_sp_denseGRM_multi", *Gs.args(), C.c_int64(n), C.c_int64(p), *dargs,
+                   C.c_int(n_pheno), _p(Score), _p(pl))
+        return {"Score": Score, "pvalue_log": pl}
+
+    # ------------------------------------------------------------------ conditional
+    def Individual_Score_Test_cond(self, G, Sigma_i, Sigma_iX, cov, X_adj, residuals):
+        G = _f(G); n, p = G.shape
+        keep, sargs = self._sigma_args(n, Sigma_i, Sigma_iX, cov, residuals)
+        A = _f(X_adj)
+        if A.ndim != 2 or A.shape[0] != n:
+            raise StaarError(1, "matrix multiplication: incompatible matrix dimensions (X_adj)")
+        o, po = self._out5(p)
+        self._call("staar_individual_score_test_cond", _p(G), C.c_int64(n), C.c_int64(p), *sargs[:-1], _p(A),
+                   C.c_int64(A.shape[1]), sargs[-1], *po)
+        return self._pack5(o)
+
+    def Individual_Score_Test_cond_multi(self, G, Sigma_i, Sigma_iX, cov, X_adj, residuals, n_pheno=1):
+        G = _f(G); n, p = G.shape
+        keep, sargs = self._sigma_args(n, Sigma_i, Sigma_iX, cov, residuals)
+        A = _f(X_adj)
+        if A.ndim != 2 or A.shape[0] != n:
+            raise StaarError(1, "matrix multiplication: incompatible matrix dimensions (X_adj)")
+        Score, pl = np.zeros(p), np.zeros(p // max(n_pheno, 1))
+        self._call("staar_individual_score_test_cond_multi", _p(G), C.c_int64(n), C.c_int64(p), *sargs[:-1], _p(A),
+                   C.c_int64(A.shape[1]), sargs[-1], C.c_int(n_pheno), _p(Score), _p(pl))
+        return {"Score": Score, "pvalue_log": pl}
+
+    # ------------------------------------------------------------------ SPA
+    def Individual_Score_Test_SPA(self, G, XW, XXWX_inv, residuals, muhat, tol, max_iter, return_trace=False):
+        G = _f(G); n, p = G.shape
+        XWm, XXi = _f(XW), _f(XXWX_inv)
+        q = XWm.shape[0]
+        if XWm.shape != (q, n) or XXi.shape != (n, q):
+            raise StaarError(1, "matrix multiplication: incompatible matrix dimensions (XW / XXWX_inv)")
+        r, mu = _f(residuals).ravel(), _f(muhat).ravel()
+        pv = np.zeros(p)
+        trace = np.zeros((p, 4), dtype=np.int64) if return_trace else None
+        self._call("staar_individual_score_test_SPA", _p(G), C.c_int64(n), C.c_int64(p), _p(XWm), _p(XXi), C.c_int64(q),
+                   _p(r), _p(mu), C.c_double(tol), C.c_int(max_iter), _p(pv),
+                   trace.ctypes.data_as(C.POINTER(C.c_int64)) if return_trace else None)
+        return (pv, trace) if return_trace else pv
+
+    # ------------------------------------------------------------------ packed fast path
+    def set_nullmodel_sparse(self, Sigma_i, Sigma_iX, cov, residuals):
+        n = sp.csc_matrix(Sigma_i).shape[0]
+        keep, sargs = self._sigma_args(n, Sigma_i, Sigma_iX, cov, residuals)
+        S, SX, cv, r = keep
+        self._call("staar_nullmodel_set_sparse", C.c_int64(n), C.c_int64(SX.shape[1]), *S.args(), _p(SX), _p(cv), _p(r))
+        self._n = n
+
+    def packed_score_host(self, packed: np.ndarray, n: int, impute: int = IMPUTE_MEAN):
+        """packed: (p, stride) uint8 host array of 2-bit dosage columns -> dict of 7 arrays (host)."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        p, stride = packed.shape
+        o = [np.zeros(p) for _ in range(7)]
+        self._call("staar_packed_score_host", packed.ctypes.data_as(_u8p), C.c_size_t(stride), C.c_int64(n),
+                   C.c_int64(p), C.c_int(impute), *[_p(a) for a in o])
+        return dict(zip(("AF", "MAF", "Score", "Score_se", "pvalue_log", "Est", "Est_se"), o))
+
+    def packed_score_device(self, d_packed: int, stride: int, n: int, p: int, impute: int, d_out7):
+        """device pointers (ints): packed columns and 7 output arrays; asynchronous on the context stream."""
+        self._call("staar_packed_score_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n), C.c_int64(p),
+                   C.c_int(impute), *[C.c_void_p(x) for x in d_out7])
+
+    def packed_flip_stats_device(self, d_packed: int, stride: int, n: int, p: int, impute: int, d_AF: int, d_MAF: int,
+                                 d_flip: int, d_nmiss: int):
+        self._call("staar_packed_flip_stats_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n),
+                   C.c_int64(p), C.c_int(impute), C.c_void_p(d_AF), C.c_void_p(d_MAF), C.c_void_p(d_flip),
+                   C.c_void_p(d_nmiss))
+
+    def synth_packed_device(self, d_packed: int, stride: int, n: int, first_variant: int, p: int, seed: int,
+                            d_thr_hom: int, d_thr_het: int, d_thr_miss: int, d_store_alt: int):
+        self._call("staar_synth_packed_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n),
+                   C.c_int64(first_variant), C.c_int64(p), C.c_uint64(seed), C.c_void_p(d_thr_hom),
+                   C.c_void_p(d_thr_het), C.c_void_p(d_thr_miss), C.c_void_p(d_store_alt))
+
+
+def packed_stride(n: int) -> int:
+    return int(load_library().staar_packed_stride(C.c_int64(n)))
+
+
+def pack_dosage_host(G, threads: int = 0) -> np.ndarray:
+    """FP64 `$dosage` matrix (n x p, NaN / <= -1 missing) -> (p, stride) uint8 packed columns (host, threaded)."""
+    lib = load_library()
+    G = _f(G); n, p = G.shape
+    stride = packed_stride(n)
+    out = np.zeros((p, stride), dtype=np.uint8)
+    rc = lib.staar_pack_dosage_host(_p(G), C.c_int64(n), C.c_int64(p), out.ctypes.data_as(_u8p), C.c_size_t(stride),
+                                    C.c_int(threads))
+    if rc != 0:
+        raise StaarError(rc, lib.staar_last_error().decode())
+    return out

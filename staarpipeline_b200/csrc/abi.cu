@@ -1,0 +1,598 @@
+// abi.cu — the extern "C" entry points declared in include/staar_b200.h.
+//
+// Host-side orchestration only: operand residency (content-hashed null-model cache), H2D/D2H of the per-call
+// genotype block and results, and the kernel sequence of each reference function.  No arithmetic of the score
+// tests happens on the host except the m x m (X_adj'X_adj)^-1 algebra of the conditional test, which the
+// reference recomputes per call on n x m operands (src/Individual_Score_Test_cond.cpp:48-49) and which here
+// acts on m x m matrices already reduced on the device.
+#include "common.cuh"
+#include <algorithm>
+#include <cstring>
+#include <thread>
+
+namespace staar {
+uint64_t hash_bytes(const void *data, size_t bytes, uint64_t seed);
+uint64_t hash_sampled(const double *data, size_t count, uint64_t seed);
+int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *Sv, const uint64_t *Sr,
+                            const uint64_t *Sc, const double *SX, const double *cov, const double *res, uint64_t fp,
+                            uint64_t res_fp, bool want_sliced);
+int nullmodel_dense_upload(staar_ctx *ctx, int64_t n, const double *P, const double *res, uint64_t fp);
+
+namespace {
+
+struct Guard {   // every entry point runs on the context's device
+    explicit Guard(staar_ctx *c) { cudaSetDevice(c->device); }
+};
+
+#define CHECK_CTX(ctx)                                           \
+    if (!(ctx)) { staar::set_error("null context"); return STAAR_ERR_ARG; } \
+    staar::Guard guard__(ctx)
+
+int h2d(staar_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return STAAR_OK;
+    STAAR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return STAAR_OK;
+}
+int d2h(staar_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0 || !dst) return STAAR_OK;
+    STAAR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return STAAR_OK;
+}
+int sync(staar_ctx *ctx)
+{
+    STAAR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return STAAR_OK;
+}
+
+// ---- null-model residency -------------------------------------------------------------------------------
+int ensure_sparse(staar_ctx *ctx, int64_t n, int64_t q, const double *Sv, const uint64_t *Sr, const uint64_t *Sc,
+                  const double *SX, const double *cov, const double *res)
+{
+    if (!Sv || !Sr || !Sc || !SX || !cov || !res) { set_error("null-model operand pointer is NULL"); return STAAR_ERR_ARG; }
+    const uint64_t nnz = Sc[n];
+    uint64_t fp = hash_bytes(Sv, nnz * 8, 11) ^ hash_bytes(Sr, nnz * 8, 12) ^ hash_bytes(Sc, (n + 1) * 8, 13) ^
+                  hash_bytes(SX, (size_t)n * q * 8, 14) ^ hash_bytes(cov, (size_t)q * q * 8, 15) ^
+                  ((uint64_t)n * 0x9E3779B97F4A7C15ull) ^ (uint64_t)q;
+    const uint64_t rfp = hash_bytes(res, (size_t)n * 8, 16);
+    NullSparse &ns = ctx->ns;
+    if (ns.set && ns.fingerprint == fp && ns.n == n && ns.q == q) {
+        if (ns.res_fingerprint != rfp) {          // same Sigma_i / Sigma_iX / cov, new residual vector
+            STAAR_TRY(ctx->tmp.reserve(sizeof(double) * n));
+            STAAR_TRY(h2d(ctx, ctx->tmp.p, res, sizeof(double) * n));
+            STAAR_TRY(launch_set_Y_col0(ctx, n, ns.ldY, ctx->tmp.as<double>(), ns.Y));
+            ns.res_fingerprint = rfp;
+            ns.sliced = false;
+        }
+        return STAAR_OK;
+    }
+    return nullmodel_sparse_upload(ctx, n, q, Sv, Sr, Sc, SX, cov, res, fp, rfp, false);
+}
+
+int ensure_dense(staar_ctx *ctx, int64_t n, const double *P)
+{
+    if (!P) { set_error("P is NULL"); return STAAR_ERR_ARG; }
+    const uint64_t fp = hash_sampled(P, (size_t)n * n, 21) ^ (uint64_t)n;
+    if (ctx->nd.set && ctx->nd.fingerprint == fp && ctx->nd.n == n) return STAAR_OK;
+    return nullmodel_dense_upload(ctx, n, P, nullptr, fp);
+}
+
+// ---- genotype block on the device ---------------------------------------------------------------------------
+int upload_dense_G(staar_ctx *ctx, const double *G, int64_t n, int64_t p)
+{
+    STAAR_TRY(ctx->G.reserve(sizeof(double) * (size_t)n * std::max<int64_t>(p, 1)));
+    return h2d(ctx, ctx->G.p, G, sizeof(double) * (size_t)n * p);
+}
+
+int upload_csc_G(staar_ctx *ctx, const double *Gv, const uint64_t *Gr, const uint64_t *Gc, int64_t n, int64_t p)
+{
+    if (!Gv || !Gr || !Gc) { set_error("sparse G pointer is NULL"); return STAAR_ERR_ARG; }
+    const uint64_t nnz = Gc[p];
+    STAAR_TRY(ctx->G.reserve(sizeof(double) * (size_t)n * std::max<int64_t>(p, 1)));
+    const size_t bytes = nnz * 16 + (size_t)(p + 1) * 8;
+    STAAR_TRY(ctx->pk.reserve(bytes + 64));
+    double *dval = ctx->pk.as<double>();
+    int64_t *drow = reinterpret_cast<int64_t *>(dval + nnz);
+    int64_t *dcp = drow + nnz;
+    STAAR_TRY(h2d(ctx, dval, Gv, nnz * 8));
+    STAAR_TRY(h2d(ctx, drow, Gr, nnz * 8));            // uint64 indices < 2^63: same bits as int64
+    STAAR_TRY(h2d(ctx, dcp, Gc, (size_t)(p + 1) * 8));
+    return launch_csc_to_dense(ctx, dval, drow, dcp, n, p, ctx->G.as<double>());
+}
+
+// ---- host LU for the m x m algebra of the conditional test ----------------------------------------------
+int host_inv(std::vector<double> &A, int k, std::vector<double> &inv)
+{
+    std::vector<int> piv(k);
+    for (int c = 0; c < k; c++) {
+        int pr = c; double best = fabs(A[c + c * k]);
+        for (int r = c + 1; r < k; r++) if (fabs(A[r + c * k]) > best) { best = fabs(A[r + c * k]); pr = r; }
+        piv[c] = pr;
+        if (pr != c) for (int cc = 0; cc < k; cc++) std::swap(A[c + cc * k], A[pr + cc * k]);
+        const double d = A[c + c * k];
+        if (d == 0.0) return 1;
+        for (int r = c + 1; r < k; r++) {
+            const double f = A[r + c * k] / d; A[r + c * k] = f;
+            for (int cc = c + 1; cc < k; cc++) A[r + cc * k] -= f * A[c + cc * k];
+        }
+    }
+    inv.assign((size_t)k * k, 0.0);
+    for (int c = 0; c < k; c++) {
+        double *x = inv.data() + (size_t)c * k;
+        x[c] = 1.0;
+        for (int r = 0; r < k; r++) if (piv[r] != r) std::swap(x[r], x[piv[r]]);
+        for (int r = 0; r < k; r++) for (int cc = 0; cc < r; cc++) x[r] -= A[r + cc * k] * x[cc];
+        for (int r = k - 1; r >= 0; r--) {
+            for (int cc = r + 1; cc < k; cc++) x[r] -= A[r + cc * k] * x[cc];
+            x[r] /= A[r + r * k];
+        }
+    }
+    return 0;
+}
+
+struct CondOperands { int m = 0; double *dM = nullptr, *dMQM = nullptr; const double *dY = nullptr; int ldY = 0, colA0 = 0, colPA0 = 0; };
+
+// PX_adj, (X_adj'X_adj)^-1 and M (PX_adj'X_adj) M on the device / m x m host algebra; Ycond = [res|SX|A|PA]
+int prepare_cond(staar_ctx *ctx, const double *X_adj, int64_t m, const double *cov_host, CondOperands &co)
+{
+    NullSparse &ns = ctx->ns;
+    const int64_t n = ns.n, q = ns.q;
+    const int ldc = (int)((1 + q + 2 * m + 7) / 8 * 8), ld2 = (int)((1 + 2 * m + 7) / 8 * 8);
+    // aux layout: A (n*m) | PA (n*m) | Ycond (n*ldc) | Y2 (n*ld2) | T1 (q*m) | M (m*m) | MQM (m*m)
+    const size_t need = sizeof(double) * ((size_t)2 * n * m + (size_t)n * ldc + (size_t)n * ld2 + q * m + 2 * m * m);
+    STAAR_TRY(ctx->aux.reserve(need));
+    double *dA = ctx->aux.as<double>(), *dPA = dA + n * m, *dYc = dPA + n * m, *dY2 = dYc + (size_t)n * ldc;
+    double *dT1 = dY2 + (size_t)n * ld2, *dM = dT1 + q * m, *dMQM = dM + m * m;
+    STAAR_TRY(h2d(ctx, dA, X_adj, sizeof(double) * n * m));
+    // trans(Sigma_iX) * X_adj  (q x m): contraction of the m columns of A against Y = [res | SX]
+    STAAR_TRY(ctx->L.reserve(sizeof(double) * (size_t)m * std::max(ns.ldY, ld2)));
+    STAAR_TRY(launch_contract_dense(ctx, dA, n, m, ns.Y, ns.ldY, (int)(1 + q), ctx->L.as<double>(), ns.ldY));
+    std::vector<double> LA((size_t)m * ns.ldY);
+    STAAR_TRY(d2h(ctx, LA.data(), ctx->L.p, sizeof(double) * LA.size()));
+    STAAR_TRY(sync(ctx));
+    std::vector<double> T1((size_t)q * m);
+    for (int64_t c = 0; c < m; c++)
+        for (int64_t a = 0; a < q; a++) {
+            double s = 0;
+            for (int64_t b = 0; b < q; b++) s += cov_host[a + b * q] * LA[(size_t)c * ns.ldY + 1 + b];
+            T1[a + c * q] = s;
+        }
+    STAAR_TRY(h2d(ctx, dT1, T1.data(), sizeof(double) * q * m));
+    STAAR_TRY(launch_px_adj(ctx, n, ns.row_ptr, ns.col, ns.val, dA, (int)m, ns.SX, (int)q, dT1, dPA));   // :48
+    // X_adj'X_adj and PX_adj'X_adj via one more contraction against [A | PA]
+    STAAR_TRY(launch_build_Y(ctx, n, ld2, nullptr, nullptr, 0, dA, dPA, (int)m, dY2));
+    STAAR_TRY(launch_contract_dense(ctx, dA, n, m, dY2, ld2, (int)(1 + 2 * m), ctx->L.as<double>(), ld2));
+    std::vector<double> L2((size_t)m * ld2);
+    STAAR_TRY(d2h(ctx, L2.data(), ctx->L.p, sizeof(double) * L2.size()));
+    STAAR_TRY(sync(ctx));
+    std::vector<double> AtA((size_t)m * m), PAtA((size_t)m * m), M, tmp((size_t)m * m), MQM((size_t)m * m);
+    for (int64_t a = 0; a < m; a++)
+        for (int64_t b = 0; b < m; b++) {
+            AtA[a + b * m] = L2[(size_t)a * ld2 + 1 + b];          // sum_j A[j,a] A[j,b]
+            PAtA[a + b * m] = L2[(size_t)b * ld2 + 1 + m + a];     // sum_j PA[j,a] A[j,b]
+        }
+    if (host_inv(AtA, (int)m, M) != 0) {
+        set_error("inv(): matrix is singular (trans(X_adj)*X_adj)");
+        return STAAR_ERR_SINGULAR;
+    }
+    for (int64_t a = 0; a < m; a++)
+        for (int64_t b = 0; b < m; b++) {
+            double s = 0;
+            for (int64_t c = 0; c < m; c++) s += M[a + c * m] * PAtA[c + b * m];
+            tmp[a + b * m] = s;
+        }
+    for (int64_t a = 0; a < m; a++)
+        for (int64_t b = 0; b < m; b++) {
+            double s = 0;
+            for (int64_t c = 0; c < m; c++) s += tmp[a + c * m] * M[c + b * m];
+            MQM[a + b * m] = s;
+        }
+    STAAR_TRY(h2d(ctx, dM, M.data(), sizeof(double) * m * m));
+    STAAR_TRY(h2d(ctx, dMQM, MQM.data(), sizeof(double) * m * m));
+    // Ycond: column 0 is the refit residual vector of THIS call (already in ns.Y column 0 via ensure_sparse)
+    STAAR_TRY(ctx->tmp.reserve(sizeof(double) * n));
+    STAAR_CUDA(cudaMemcpy2DAsync(ctx->tmp.p, sizeof(double), ns.Y, sizeof(double) * ns.ldY, sizeof(double), n,
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+    STAAR_TRY(launch_build_Y(ctx, n, ldc, ctx->tmp.as<double>(), ns.SX, (int)q, dA, dPA, (int)m, dYc));
+    STAAR_TRY(sync(ctx));       // host vectors above go out of scope
+    co.m = (int)m; co.dM = dM; co.dMQM = dMQM; co.dY = dYc; co.ldY = ldc; co.colA0 = (int)(1 + q); co.colPA0 = (int)(1 + q + m);
+    return STAAR_OK;
+}
+
+// ---- the sparse-Sigma family on a device-resident dense G ----------------------------------------------
+// k == 0: single trait (5 outputs of length p); k >= 1: block test (Score length p, pvalue_log length p/k).
+int run_sparse_family(staar_ctx *ctx, int64_t n, int64_t p, int k, const CondOperands *co,
+                      double *Score, double *Score_se, double *pl, double *Est, double *Est_se)
+{
+    NullSparse &ns = ctx->ns;
+    const int kk = k > 0 ? k : 1;
+    if (k > 0 && p % k != 0) { set_error("number of columns of G (%lld) is not a multiple of n_pheno (%d)", (long long)p, k); return STAAR_ERR_ARG; }
+    const int64_t pp = p / kk, npairs = pp * kk * kk;
+    const double *dY = co ? co->dY : ns.Y;
+    const int ldY = co ? co->ldY : ns.ldY;
+    const int ncols = (int)(1 + ns.q + (co ? 2 * co->m : 0));
+    const double *dG = ctx->G.as<double>();
+    STAAR_TRY(ctx->L.reserve(sizeof(double) * (size_t)std::max<int64_t>(p, 1) * ldY));
+    STAAR_TRY(launch_contract_dense(ctx, dG, n, p, dY, ldY, ncols, ctx->L.as<double>(), ldY));
+    STAAR_TRY(ctx->tmp.reserve(sizeof(int32_t) * 2 * (size_t)npairs + sizeof(double) * (size_t)npairs + 64));
+    double *dquad = ctx->tmp.as<double>();
+    int32_t *dcolA = reinterpret_cast<int32_t *>(dquad + npairs), *dcolB = dcolA + npairs;
+    STAAR_TRY(launch_fill_pairs(ctx, pp, kk, dcolA, dcolB));
+    STAAR_TRY(launch_quad_pairs_csr(ctx, dG, n, ns.row_ptr, ns.col, ns.val, dcolA, dcolB, npairs, dquad));
+    STAAR_TRY(ctx->out.reserve(sizeof(double) * 5 * (size_t)std::max<int64_t>(p, 1)));
+    double *o = ctx->out.as<double>();
+    STAAR_TRY(launch_epilogue_general(ctx, p, k, ctx->L.as<double>(), ldY, (int)ns.q, ns.cov, dquad, co ? co->m : 0,
+                                      co ? co->dM : nullptr, co ? co->dMQM : nullptr, co ? co->colA0 : 0,
+                                      co ? co->colPA0 : 0, o, o + p, o + 2 * p, o + 3 * p, o + 4 * p));
+    STAAR_TRY(d2h(ctx, Score, o, sizeof(double) * p));
+    if (k == 0) {
+        STAAR_TRY(d2h(ctx, Score_se, o + p, sizeof(double) * p));
+        STAAR_TRY(d2h(ctx, pl, o + 2 * p, sizeof(double) * p));
+        STAAR_TRY(d2h(ctx, Est, o + 3 * p, sizeof(double) * p));
+        STAAR_TRY(d2h(ctx, Est_se, o + 4 * p, sizeof(double) * p));
+    } else {
+        STAAR_TRY(d2h(ctx, pl, o + 2 * p, sizeof(double) * pp));
+    }
+    return sync(ctx);
+}
+
+// ---- the dense-P family ----------------------------------------------------------------------------------
+int run_dense_family(staar_ctx *ctx, int64_t n, int64_t p, int k, const double *residuals,
+                     double *Score, double *Score_se, double *pl, double *Est, double *Est_se)
+{
+    const int kk = k > 0 ? k : 1;
+    if (k > 0 && p % k != 0) { set_error("number of columns of G (%lld) is not a multiple of n_pheno (%d)", (long long)p, k); return STAAR_ERR_ARG; }
+    const int64_t pp = p / kk, npairs = pp * kk * kk;
+    const double *dG = ctx->G.as<double>();
+    // Uscore = trans(residuals)*G: contraction against the single column [res]
+    const int ldY = 8;
+    STAAR_TRY(ctx->aux.reserve(sizeof(double) * ((size_t)n * ldY + (size_t)n)));
+    double *dYr = ctx->aux.as<double>(), *dres = dYr + (size_t)n * ldY;
+    STAAR_TRY(h2d(ctx, dres, residuals, sizeof(double) * n));
+    STAAR_TRY(launch_build_Y(ctx, n, ldY, dres, nullptr, 0, nullptr, nullptr, 0, dYr));
+    STAAR_TRY(ctx->L.reserve(sizeof(double) * (size_t)std::max<int64_t>(p, 1) * ldY));
+    STAAR_TRY(launch_contract_dense(ctx, dG, n, p, dYr, ldY, 1, ctx->L.as<double>(), ldY));
+    // W = P*G, Cov entries = g_a' W[:,b]   (Individual_Score_Test_denseGRM.cpp:37)
+    STAAR_TRY(ctx->tmp2.reserve(sizeof(double) * (size_t)n * std::max<int64_t>(p, 1)));
+    // note: launch_contract_dense may have used tmp2 for split-K partials; they are consumed by now (stream order)
+    STAAR_TRY(launch_dense_P_times_G(ctx, ctx->nd.P, dG, n, p, ctx->tmp2.as<double>()));
+    STAAR_TRY(ctx->tmp.reserve(sizeof(int32_t) * 2 * (size_t)npairs + sizeof(double) * (size_t)npairs + 64));
+    double *dquad = ctx->tmp.as<double>();
+    int32_t *dcolA = reinterpret_cast<int32_t *>(dquad + npairs), *dcolB = dcolA + npairs;
+    STAAR_TRY(launch_fill_pairs(ctx, pp, kk, dcolA, dcolB));
+    STAAR_TRY(launch_dot_pairs(ctx, dG, ctx->tmp2.as<double>(), n, dcolA, dcolB, npairs, dquad));
+    STAAR_TRY(ctx->out.reserve(sizeof(double) * 5 * (size_t)std::max<int64_t>(p, 1)));
+    double *o = ctx->out.as<double>();
+    STAAR_TRY(launch_epilogue_general(ctx, p, k, ctx->L.as<double>(), ldY, 0, nullptr, dquad, 0, nullptr, nullptr, 0, 0,
+                                      o, o + p, o + 2 * p, o + 3 * p, o + 4 * p));
+    STAAR_TRY(d2h(ctx, Score, o, sizeof(double) * p));
+    if (k == 0) {
+        STAAR_TRY(d2h(ctx, Score_se, o + p, sizeof(double) * p));
+        STAAR_TRY(d2h(ctx, pl, o + 2 * p, sizeof(double) * p));
+        STAAR_TRY(d2h(ctx, Est, o + 3 * p, sizeof(double) * p));
+        STAAR_TRY(d2h(ctx, Est_se, o + 4 * p, sizeof(double) * p));
+    } else {
+        STAAR_TRY(d2h(ctx, pl, o + 2 * p, sizeof(double) * pp));
+    }
+    return sync(ctx);
+}
+
+int check_dims(int64_t n, int64_t p)
+{
+    if (n <= 0 || p < 0) { set_error("bad dimensions n=%lld p=%lld", (long long)n, (long long)p); return STAAR_ERR_ARG; }
+    return STAAR_OK;
+}
+
+int flip_entry(staar_ctx *ctx, const double *G, int64_t n, int64_t p, bool minor, double *Geno_out, double *AF, double *MAF)
+{
+    STAAR_TRY(check_dims(n, p));
+    if (!G || !AF || !MAF) { set_error("matrix_flip: NULL pointer"); return STAAR_ERR_ARG; }
+    STAAR_TRY(upload_dense_G(ctx, G, n, p));
+    STAAR_TRY(ctx->out.reserve(sizeof(double) * 2 * (size_t)std::max<int64_t>(p, 1)));
+    double *o = ctx->out.as<double>();
+    STAAR_TRY(launch_flip_dense(ctx, ctx->G.as<double>(), n, p, minor, Geno_out != nullptr, o, o + p));
+    STAAR_TRY(d2h(ctx, AF, o, sizeof(double) * p));
+    STAAR_TRY(d2h(ctx, MAF, o + p, sizeof(double) * p));
+    STAAR_TRY(d2h(ctx, Geno_out, ctx->G.p, sizeof(double) * (size_t)n * p));
+    return sync(ctx);
+}
+
+}  // namespace
+}  // namespace staar
+
+using namespace staar;
+
+extern "C" {
+
+int staar_matrix_flip_mean(staar_ctx *ctx, const double *G, int64_t n, int64_t p, double *Geno_out, double *AF, double *MAF)
+{
+    CHECK_CTX(ctx);
+    return flip_entry(ctx, G, n, p, false, Geno_out, AF, MAF);
+}
+int staar_matrix_flip_minor(staar_ctx *ctx, const double *G, int64_t n, int64_t p, double *Geno_out, double *AF, double *MAF)
+{
+    CHECK_CTX(ctx);
+    return flip_entry(ctx, G, n, p, true, Geno_out, AF, MAF);
+}
+
+int staar_individual_score_test(staar_ctx *ctx, const double *G, int64_t n, int64_t p, const double *Sv,
+                                const uint64_t *Sr, const uint64_t *Sc, const double *SX, int64_t q, const double *cov,
+                                const double *res, double *Score, double *Score_se, double *pl, double *Est, double *Est_se)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    STAAR_TRY(ensure_sparse(ctx, n, q, Sv, Sr, Sc, SX, cov, res));
+    STAAR_TRY(upload_dense_G(ctx, G, n, p));
+    return run_sparse_family(ctx, n, p, 0, nullptr, Score, Score_se, pl, Est, Est_se);
+}
+
+int staar_individual_score_test_sp(staar_ctx *ctx, const double *Gv, const uint64_t *Gr, const uint64_t *Gc, int64_t n,
+                                   int64_t p, const double *Sv, const uint64_t *Sr, const uint64_t *Sc, const double *SX,
+                                   int64_t q, const double *cov, const double *res, double *Score, double *Score_se,
+                                   double *pl, double *Est, double *Est_se)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    STAAR_TRY(ensure_sparse(ctx, n, q, Sv, Sr, Sc, SX, cov, res));
+    STAAR_TRY(upload_csc_G(ctx, Gv, Gr, Gc, n, p));
+    return run_sparse_family(ctx, n, p, 0, nullptr, Score, Score_se, pl, Est, Est_se);
+}
+
+int staar_individual_score_test_denseGRM(staar_ctx *ctx, const double *G, int64_t n, int64_t p, const double *P,
+                                         const double *res, double *Score, double *Score_se, double *pl, double *Est,
+                                         double *Est_se)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    STAAR_TRY(ensure_dense(ctx, n, P));
+    STAAR_TRY(upload_dense_G(ctx, G, n, p));
+    return run_dense_family(ctx, n, p, 0, res, Score, Score_se, pl, Est, Est_se);
+}
+
+int staar_individual_score_test_sp_denseGRM(staar_ctx *ctx, const double *Gv, const uint64_t *Gr, const uint64_t *Gc,
+                                            int64_t n, int64_t p, const double *P, const double *res, double *Score,
+                                            double *Score_se, double *pl, double *Est, double *Est_se)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    STAAR_TRY(ensure_dense(ctx, n, P));
+    STAAR_TRY(upload_csc_G(ctx, Gv, Gr, Gc, n, p));
+    return run_dense_family(ctx, n, p, 0, res, Score, Score_se, pl, Est, Est_se);
+}
+
+int staar_individual_score_test_multi(staar_ctx *ctx, const double *G, int64_t n, int64_t p, const double *Sv,
+                                      const uint64_t *Sr, const uint64_t *Sc, const double *SX, int64_t q,
+                                      const double *cov, const double *res, int n_pheno, double *Score, double *pl)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    if (n_pheno < 1) { set_error("n_pheno must be >= 1"); return STAAR_ERR_ARG; }
+    STAAR_TRY(ensure_sparse(ctx, n, q, Sv, Sr, Sc, SX, cov, res));
+    STAAR_TRY(upload_dense_G(ctx, G, n, p));
+    return run_sparse_family(ctx, n, p, n_pheno, nullptr, Score, nullptr, pl, nullptr, nullptr);
+}
+
+int staar_individual_score_test_sp_multi(staar_ctx *ctx, const double *Gv, const uint64_t *Gr, const uint64_t *Gc,
+                                         int64_t n, int64_t p, const double *Sv, const uint64_t *Sr, const uint64_t *Sc,
+                                         const double *SX, int64_t q, const double *cov, const double *res, int n_pheno,
+                                         double *Score, double *pl)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    if (n_pheno < 1) { set_error("n_pheno must be >= 1"); return STAAR_ERR_ARG; }
+    STAAR_TRY(ensure_sparse(ctx, n, q, Sv, Sr, Sc, SX, cov, res));
+    STAAR_TRY(upload_csc_G(ctx, Gv, Gr, Gc, n, p));
+    return run_sparse_family(ctx, n, p, n_pheno, nullptr, Score, nullptr, pl, nullptr, nullptr);
+}
+
+int staar_individual_score_test_denseGRM_multi(staar_ctx *ctx, const double *G, int64_t n, int64_t p, const double *P,
+                                               const double *res, int n_pheno, double *Score, double *pl)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    if (n_pheno < 1) { set_error("n_pheno must be >= 1"); return STAAR_ERR_ARG; }
+    STAAR_TRY(ensure_dense(ctx, n, P));
+    STAAR_TRY(upload_dense_G(ctx, G, n, p));
+    return run_dense_family(ctx, n, p, n_pheno, res, Score, nullptr, pl, nullptr, nullptr);
+}
+
+int staar_individual_score_test_sp_denseGRM_multi(staar_ctx *ctx, const double *Gv, const uint64_t *Gr,
+                                                  const uint64_t *Gc, int64_t n, int64_t p, const double *P,
+                                                  const double *res, int n_pheno, double *Score, double *pl)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    if (n_pheno < 1) { set_error("n_pheno must be >= 1"); return STAAR_ERR_ARG; }
+    STAAR_TRY(ensure_dense(ctx, n, P));
+    STAAR_TRY(upload_csc_G(ctx, Gv, Gr, Gc, n, p));
+    return run_dense_family(ctx, n, p, n_pheno, res, Score, nullptr, pl, nullptr, nullptr);
+}
+
+int staar_individual_score_test_cond(staar_ctx *ctx, const double *G, int64_t n, int64_t p, const double *Sv,
+                                     const uint64_t *Sr, const uint64_t *Sc, const double *SX, int64_t q,
+                                     const double *cov, const double *X_adj, int64_t m, const double *res,
+                                     double *Score, double *Score_se, double *pl, double *Est, double *Est_se)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    if (!X_adj || m < 1) { set_error("X_adj must have at least one column"); return STAAR_ERR_ARG; }
+    STAAR_TRY(ensure_sparse(ctx, n, q, Sv, Sr, Sc, SX, cov, res));
+    CondOperands co;
+    STAAR_TRY(prepare_cond(ctx, X_adj, m, cov, co));
+    STAAR_TRY(upload_dense_G(ctx, G, n, p));
+    return run_sparse_family(ctx, n, p, 0, &co, Score, Score_se, pl, Est, Est_se);
+}
+
+int staar_individual_score_test_cond_multi(staar_ctx *ctx, const double *G, int64_t n, int64_t p, const double *Sv,
+                                           const uint64_t *Sr, const uint64_t *Sc, const double *SX, int64_t q,
+                                           const double *cov, const double *X_adj, int64_t m, const double *res,
+                                           int n_pheno, double *Score, double *pl)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    if (!X_adj || m < 1) { set_error("X_adj must have at least one column"); return STAAR_ERR_ARG; }
+    if (n_pheno < 1) { set_error("n_pheno must be >= 1"); return STAAR_ERR_ARG; }
+    STAAR_TRY(ensure_sparse(ctx, n, q, Sv, Sr, Sc, SX, cov, res));
+    CondOperands co;
+    STAAR_TRY(prepare_cond(ctx, X_adj, m, cov, co));
+    STAAR_TRY(upload_dense_G(ctx, G, n, p));
+    return run_sparse_family(ctx, n, p, n_pheno, &co, Score, nullptr, pl, nullptr, nullptr);
+}
+
+int staar_individual_score_test_SPA(staar_ctx *ctx, const double *G, int64_t n, int64_t p, const double *XW,
+                                    const double *XXWX_inv, int64_t q, const double *res, const double *muhat,
+                                    double tol, int max_iter, double *pvalue, int64_t *trace)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    if (!G || !XW || !XXWX_inv || !res || !muhat || !pvalue) { set_error("SPA: NULL pointer"); return STAAR_ERR_ARG; }
+    STAAR_TRY(upload_dense_G(ctx, G, n, p));
+    const int slots = spa_scratch_slots(ctx, std::max<int64_t>(p, 1));
+    // aux: XW (q*n) | XXWX_inv (n*q) | res (n) | mu (n) | gt scratch (slots*n)
+    STAAR_TRY(ctx->aux.reserve(sizeof(double) * ((size_t)2 * n * q + 2 * (size_t)n + (size_t)slots * n)));
+    double *dXW = ctx->aux.as<double>(), *dXX = dXW + n * q, *dres = dXX + n * q, *dmu = dres + n, *dgt = dmu + n;
+    STAAR_TRY(h2d(ctx, dXW, XW, sizeof(double) * n * q));
+    STAAR_TRY(h2d(ctx, dXX, XXWX_inv, sizeof(double) * n * q));
+    STAAR_TRY(h2d(ctx, dres, res, sizeof(double) * n));
+    STAAR_TRY(h2d(ctx, dmu, muhat, sizeof(double) * n));
+    STAAR_TRY(ctx->out.reserve(sizeof(double) * (size_t)std::max<int64_t>(p, 1) + sizeof(long long) * 4 * (size_t)std::max<int64_t>(p, 1)));
+    double *dpv = ctx->out.as<double>();
+    long long *dtr = reinterpret_cast<long long *>(dpv + std::max<int64_t>(p, 1));
+    STAAR_TRY(launch_spa(ctx, ctx->G.as<double>(), n, p, dXW, dXX, (int)q, dres, dmu, tol, max_iter, dgt, dpv,
+                         trace ? dtr : nullptr));
+    STAAR_TRY(d2h(ctx, pvalue, dpv, sizeof(double) * p));
+    if (trace) STAAR_TRY(d2h(ctx, trace, dtr, sizeof(long long) * 4 * p));
+    return sync(ctx);
+}
+
+// ============================================================================================ packed fast path
+size_t staar_packed_stride(int64_t n) { return (size_t)(((n + 3) / 4 + 15) / 16 * 16); }
+
+int staar_pack_dosage_host(const double *G, int64_t n, int64_t p, uint8_t *packed, size_t stride, int threads)
+{
+    if (!G || !packed || stride < (size_t)((n + 3) / 4) || stride % 16 != 0) { set_error("pack_dosage: bad arguments"); return STAAR_ERR_ARG; }
+    if (threads < 1) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    threads = (int)std::min<int64_t>(threads, std::max<int64_t>(p, 1));
+    std::vector<int> bad(threads, 0);
+    auto work = [&](int tid) {
+        for (int64_t i = tid; i < p; i += threads) {
+            const double *g = G + i * n;
+            uint8_t *dst = packed + (size_t)i * stride;
+            memset(dst, 0, stride);
+            for (int64_t j = 0; j < n; j++) {
+                const double v = g[j];
+                uint32_t code;
+                if (!(v > -1.0)) code = 3;
+                else if (v == 0.0) code = 0;
+                else if (v == 1.0) code = 1;
+                else if (v == 2.0) code = 2;
+                else { bad[tid] = 1; code = 0; }
+                dst[j >> 2] |= (uint8_t)(code << (2 * (j & 3)));
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int b : bad) if (b) { set_error("pack_dosage: a non-missing genotype is not 0, 1 or 2"); return STAAR_ERR_ARG; }
+    return STAAR_OK;
+}
+
+int staar_nullmodel_set_sparse(staar_ctx *ctx, int64_t n, int64_t q, const double *Sv, const uint64_t *Sr,
+                               const uint64_t *Sc, const double *SX, const double *cov, const double *res)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(ensure_sparse(ctx, n, q, Sv, Sr, Sc, SX, cov, res));
+    if (!ctx->ns.sliced) STAAR_TRY(build_sliced_operand(ctx, nullptr));
+    return STAAR_OK;
+}
+
+int staar_nullmodel_set_sparse_device(staar_ctx *ctx, int64_t n, int64_t q, const int64_t *d_row_ptr,
+                                      const int32_t *d_col, const double *d_val, const double *d_SX,
+                                      const double *d_cov, const double *d_res)
+{
+    CHECK_CTX(ctx);
+    // Operands arrive in device memory the caller owns (filled by an NCCL broadcast).  The set-up work (diagonal,
+    // kinship flags, row-major Y, INT8 slicing) is a once-per-run host pass, so stage them through the host path.
+    if (n <= 0 || q < 0) { set_error("bad dimensions"); return STAAR_ERR_ARG; }
+    std::vector<int64_t> rp(n + 1);
+    STAAR_CUDA(cudaMemcpy(rp.data(), d_row_ptr, sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost));
+    const int64_t nnz = rp[n];
+    std::vector<int32_t> col(nnz); std::vector<double> val(nnz), SX((size_t)n * q), cov((size_t)q * q), res(n);
+    STAAR_CUDA(cudaMemcpy(col.data(), d_col, sizeof(int32_t) * nnz, cudaMemcpyDeviceToHost));
+    STAAR_CUDA(cudaMemcpy(val.data(), d_val, sizeof(double) * nnz, cudaMemcpyDeviceToHost));
+    STAAR_CUDA(cudaMemcpy(SX.data(), d_SX, sizeof(double) * n * q, cudaMemcpyDeviceToHost));
+    STAAR_CUDA(cudaMemcpy(cov.data(), d_cov, sizeof(double) * q * q, cudaMemcpyDeviceToHost));
+    STAAR_CUDA(cudaMemcpy(res.data(), d_res, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    // CSR of a symmetric matrix is its CSC
+    std::vector<uint64_t> Sr(nnz), Sc(n + 1);
+    for (int64_t e = 0; e < nnz; e++) Sr[e] = (uint64_t)col[e];
+    for (int64_t r = 0; r <= n; r++) Sc[r] = (uint64_t)rp[r];
+    return staar_nullmodel_set_sparse(ctx, n, q, val.data(), Sr.data(), Sc.data(), SX.data(), cov.data(), res.data());
+}
+
+int staar_packed_flip_stats_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p,
+                                   int impute, double *d_AF, double *d_MAF, int32_t *d_flip, int32_t *d_nmiss)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    if (stride % 16 != 0 || stride < (size_t)((n + 3) / 4)) { set_error("packed stride must be a multiple of 16 and >= ceil(n/4)"); return STAAR_ERR_ARG; }
+    STAAR_TRY(launch_flip_stats_packed(ctx, d_packed, stride, n, p, impute, d_AF, d_MAF, d_flip, d_nmiss));
+    return sync(ctx);
+}
+
+int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
+                              double *d_AF, double *d_MAF, double *d_Score, double *d_Score_se, double *d_pl,
+                              double *d_Est, double *d_Est_se)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    NullSparse &ns = ctx->ns;
+    if (!ns.set) { set_error("packed score: call staar_nullmodel_set_sparse first"); return STAAR_ERR_STATE; }
+    if (ns.n != n) { set_error("packed score: n = %lld does not match the null model (n = %lld)", (long long)n, (long long)ns.n); return STAAR_ERR_ARG; }
+    if (stride % 16 != 0 || stride < (size_t)((n + 3) / 4)) { set_error("packed stride must be a multiple of 16 and >= ceil(n/4)"); return STAAR_ERR_ARG; }
+    if (!ns.sliced) STAAR_TRY(build_sliced_operand(ctx, nullptr));
+    if (!ns.sliced) { set_error("packed score supports at most %d fixed-effect columns (q = %lld)", kColsPerSlice - 1, (long long)ns.q); return STAAR_ERR_ARG; }
+    if (p == 0) return STAAR_OK;
+    // scratch: flip (p i32) | mu (p) | quad (p) | Sm (16p) | hi (16p i64) | lo (16p i64)
+    const size_t pi = (size_t)((p + 1) / 2 * 2);
+    STAAR_TRY(ctx->tmp.reserve(sizeof(int32_t) * pi + sizeof(double) * (2 * (size_t)p + 16 * (size_t)p) + sizeof(long long) * 32 * (size_t)p));
+    int32_t *dflip = ctx->tmp.as<int32_t>();
+    double *dmu = reinterpret_cast<double *>(dflip + pi), *dquad = dmu + p, *dSm = dquad + p;
+    long long *dhi = reinterpret_cast<long long *>(dSm + 16 * p), *dlo = dhi + 16 * p;
+    STAAR_TRY(launch_scan_packed(ctx, d_packed, stride, n, p, impute, d_AF, d_MAF, dflip, dmu, dquad, dSm));
+    STAAR_TRY(launch_contract_packed(ctx, d_packed, stride, n, p, dflip, dhi, dlo));
+    STAAR_TRY(launch_finalize_packed(ctx, p, dmu, dquad, dSm, dhi, dlo, d_Score, d_Score_se, d_pl, d_Est, d_Est_se));
+    return STAAR_OK;      // asynchronous on ctx->stream: the caller times with events / staar_ctx_synchronize
+}
+
+int staar_packed_score_host(staar_ctx *ctx, const uint8_t *packed, size_t stride, int64_t n, int64_t p, int impute,
+                            double *AF, double *MAF, double *Score, double *Score_se, double *pl, double *Est,
+                            double *Est_se)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    STAAR_TRY(ctx->pk.reserve(stride * (size_t)std::max<int64_t>(p, 1)));
+    STAAR_TRY(h2d(ctx, ctx->pk.p, packed, stride * (size_t)p));
+    STAAR_TRY(ctx->out.reserve(sizeof(double) * 7 * (size_t)std::max<int64_t>(p, 1)));
+    double *o = ctx->out.as<double>();
+    STAAR_TRY(staar_packed_score_device(ctx, ctx->pk.as<uint8_t>(), stride, n, p, impute, o, o + p, o + 2 * p, o + 3 * p,
+                                        o + 4 * p, o + 5 * p, o + 6 * p));
+    double *dst[7] = {AF, MAF, Score, Score_se, pl, Est, Est_se};
+    for (int a = 0; a < 7; a++) STAAR_TRY(d2h(ctx, dst[a], o + (size_t)a * p, sizeof(double) * p));
+    return sync(ctx);
+}
+
+int staar_synth_packed_device(staar_ctx *ctx, uint8_t *d_packed, size_t stride, int64_t n, int64_t first_variant,
+                              int64_t p, uint64_t seed, const uint64_t *d_thr_hom, const uint64_t *d_thr_het,
+                              const uint64_t *d_thr_miss, const uint8_t *d_store_alt)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(launch_synth_packed(ctx, d_packed, stride, n, first_variant, p, seed, d_thr_hom, d_thr_het, d_thr_miss,
+                                  d_store_alt));
+    return sync(ctx);
+}
+
+}  // extern "C"

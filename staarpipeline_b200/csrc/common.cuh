@@ -1,0 +1,236 @@
+// common.cuh — shared declarations for the sm_100a score-test kernels and the C ABI behind them.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cmath>
+#include <vector>
+#include <string>
+#include "../../include/staar_b200.h"
+
+namespace staar {
+
+// ------------------------------------------------------------------ errors
+void set_error(const char *fmt, ...);
+#define STAAR_CUDA(x)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (x);                                                                 \
+        if (e__ != cudaSuccess) {                                                              \
+            staar::set_error("%s:%d: %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e__)); \
+            return STAAR_ERR_CUDA;                                                             \
+        }                                                                                      \
+    } while (0)
+#define STAAR_TRY(x)                   \
+    do {                               \
+        int rc__ = (x);                \
+        if (rc__ != STAAR_OK) return rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------ device buffers
+// Grow-only device scratch owned by the context: chunk calls reuse it instead of cudaMalloc per call.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+// Sliced (exact INT8) operand of the packed contraction: see contract_packed.cu.
+constexpr int kSlices = 7;          // 7 balanced base-256 digits = 54-bit fixed point per column
+constexpr int kColsPerSlice = 16;   // 1 + q <= 16 columns per slice group (r | Sigma_iX), padded
+constexpr int kNT = kSlices * kColsPerSlice / 8;   // n-tiles of 8 columns (14)
+constexpr int kChunkSamples = 256;  // samples per k-chunk (8 IMMA k32 steps)
+constexpr int kChunkBytesB = 8 * kNT * 32 * 8;      // bytes of fragment-major B per k-chunk (28672)
+
+struct NullSparse {
+    bool set = false, owned = true;
+    int64_t n = 0, q = 0;
+    // CSR of Sigma_i (symmetric), full rows including the diagonal
+    int64_t nnz = 0, nnz_offdiag = 0;
+    int64_t *row_ptr = nullptr;   // n+1
+    int32_t *col = nullptr;       // nnz
+    double *val = nullptr;        // nnz
+    double *diag = nullptr;       // n   (Sigma_i[j,j])
+    uint32_t *has_off = nullptr;  // bit j: row j has off-diagonal entries
+    double *SX = nullptr;         // Sigma_iX, n x q column-major (kept for the conditional test)
+    // Y = [residuals | Sigma_iX], row-major n x ldY (ldY = 16-padded 1+q), FP64
+    int ldY = 0;
+    double *Y = nullptr;
+    double *cov = nullptr;        // q x q column-major
+    // exact INT8 slices of Y in IMMA-fragment-major order, and their exact column sums
+    bool sliced = false;
+    int64_t n_chunks = 0;
+    int8_t *Yfrag = nullptr;      // n_chunks * kChunkBytesB
+    double *col_scale = nullptr;  // kColsPerSlice: 2^(e_c - 54)
+    uint64_t fingerprint = 0;     // content hash of (Sigma_i, Sigma_iX, cov): cache key of the frozen-signature entry points
+    uint64_t res_fingerprint = 0; // content hash of the residual vector currently in column 0 of Y
+    void release();
+};
+
+struct NullDense {
+    bool set = false;
+    int64_t n = 0;
+    double *P = nullptr;          // n x n column-major
+    double *residuals = nullptr;
+    uint64_t fingerprint = 0;
+    void release();
+};
+
+}  // namespace staar
+
+struct staar_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    staar::NullSparse ns;
+    staar::NullDense nd;
+    // scratch
+    staar::DevBuf G, L, aux, out, tmp, tmp2, pk;
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+};
+
+namespace staar {
+
+int pinned_reserve(staar_ctx *ctx, size_t bytes);
+
+// ------------------------------------------------------------------ kernel launch wrappers (one per .cu)
+// flip.cu — K1
+int launch_flip_dense(staar_ctx *ctx, double *dG, int64_t n, int64_t p, bool minor, bool write_geno,
+                      double *dAF, double *dMAF);
+int launch_flip_stats_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p,
+                             int impute, double *dAF, double *dMAF, int32_t *dflip, int32_t *dnmiss);
+// contract_dense.cu — K2 (FP64 G): L[i, c] = sum_j G[j,i] * Y[j,c]   (L: p x ldL row-major)
+int launch_contract_dense(staar_ctx *ctx, const double *dG, int64_t n, int64_t p, const double *dY, int ldY, int ncols,
+                          double *dL, int ldL);
+// quadform.cu — K3/K4
+// out[pair] = g_a' * S * g_b for column pairs of a dense FP64 G and a CSR S (full rows)
+int launch_quad_pairs_csr(staar_ctx *ctx, const double *dG, int64_t n, const int64_t *row_ptr, const int32_t *col,
+                          const double *val, const int32_t *d_colA, const int32_t *d_colB, int64_t npairs, double *d_out);
+// W = P * G (n x p), then out[pair] = g_a' * W[:, b]
+int launch_dense_P_times_G(staar_ctx *ctx, const double *dP, const double *dG, int64_t n, int64_t p, double *dW);
+int launch_dot_pairs(staar_ctx *ctx, const double *dG, const double *dW, int64_t n, const int32_t *d_colA,
+                     const int32_t *d_colB, int64_t npairs, double *d_out);
+// epilogue.cu — K5/K7.  k == 0: single-trait outputs; k >= 1: k-trait block test (pl has p_total/k entries).
+// m > 0 adds the conditional terms (columns colA0.. = X_adj'G, colPA0.. = PX_adj'G of L).
+int launch_epilogue_general(staar_ctx *ctx, int64_t p_total, int k, const double *dL, int ldL, int q,
+                            const double *d_cov, const double *d_quad, int m, const double *dM, const double *dMQM,
+                            int colA0, int colPA0, double *dScore, double *dScore_se, double *dpl, double *dEst,
+                            double *dEst_se);
+// spa.cu — K6
+int launch_spa(staar_ctx *ctx, const double *dG, int64_t n, int64_t p, const double *dXW, const double *dXXWX_inv,
+               int q, const double *d_res, const double *d_mu, double tol, int max_iter, double *d_gt,
+               double *d_pvalue, long long *d_trace);
+// packed path — scan_packed.cu / contract_packed.cu / finalize
+int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
+                       double *dAF, double *dMAF, int32_t *dflip, double *d_mu, double *d_quad, double *d_Sm);
+int launch_contract_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p,
+                           const int32_t *d_flip, long long *d_hi, long long *d_lo);
+int launch_finalize_packed(staar_ctx *ctx, int64_t p, const double *d_mu, const double *d_quad,
+                           const double *d_Sm, const long long *d_hi, const long long *d_lo,
+                           double *dScore, double *dScore_se, double *dpl, double *dEst, double *dEst_se);
+int build_sliced_operand(staar_ctx *ctx, const double *hY /* n x ldY row-major host */);
+// synth.cu
+int launch_synth_packed(staar_ctx *ctx, uint8_t *d_packed, size_t stride, int64_t n, int64_t first_variant, int64_t p,
+                        uint64_t seed, const uint64_t *thr_hom, const uint64_t *thr_het, const uint64_t *thr_miss,
+                        const uint8_t *store_alt);
+// misc.cu
+int launch_csc_to_dense(staar_ctx *ctx, const double *d_val, const int64_t *d_row, const int64_t *d_colptr,
+                        int64_t n, int64_t p, double *dG);
+int launch_build_Y(staar_ctx *ctx, int64_t n, int ldY, const double *d_res, const double *d_SX, int q, const double *dA,
+                   const double *dPA, int m, double *dY);
+int launch_set_Y_col0(staar_ctx *ctx, int64_t n, int ldY, const double *d_res, double *dY);
+int launch_px_adj(staar_ctx *ctx, int64_t n, const int64_t *row_ptr, const int32_t *col, const double *val,
+                  const double *dA, int m, const double *dSX, int q, const double *dT1, double *dOut);
+int launch_fill_pairs(staar_ctx *ctx, int64_t pp, int k, int32_t *d_colA, int32_t *d_colB);
+int spa_scratch_slots(staar_ctx *ctx, int64_t p);
+
+// ------------------------------------------------------------------ device math shared by kernels
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum with a fixed tree (deterministic: no atomics).  `red` = shared double[32].
+__device__ __forceinline__ double block_sum(double v, double *red)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = (lane < nw) ? red[lane] : 0.0;
+    t = warp_sum(t);
+    return t;   // every thread holds the total
+}
+
+// log Q(a, y): regularised upper incomplete gamma in the log domain.  Same algorithm as the oracle's
+// stand-in for R::pchisq(x, df, lower=false, log=true)  (reference src/Individual_Score_Test.cpp:57).
+__device__ inline double log_gamma_q(double a, double y)
+{
+    if (isnan(a) || isnan(y)) return nan("");
+    if (y <= 0.0) return 0.0;
+    if (isinf(y)) return -INFINITY;
+    if (y < a + 1.0) {
+        double ap = a, term = 1.0 / a, sum = term;
+        for (int i = 0; i < 100000; i++) {
+            ap += 1.0;
+            term *= y / ap;
+            sum += term;
+            if (fabs(term) < fabs(sum) * 1e-17) break;
+        }
+        double logP = a * log(y) - y - lgamma(a) + log(sum);
+        return log1p(-exp(logP));
+    }
+    const double tiny = 1e-300;
+    double b = y + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+    for (int i = 1; i < 100000; i++) {
+        double an = -(double)i * ((double)i - a);
+        b += 2.0;
+        d = an * d + b; if (fabs(d) < tiny) d = tiny;
+        c = b + an / c; if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    return a * log(y) - y - lgamma(a) + log(h);
+}
+
+// R::pnorm(x, 0, 1, lower, false) with nmath's exact-0/1 cut-offs (reference _SPA.cpp:151,282)
+__device__ inline double pnorm_std(double x, bool lower)
+{
+    if (isnan(x)) return nan("");
+    if (lower) {
+        if (x <= -37.5193) return 0.0;
+        if (x >= 8.2924) return 1.0;
+        return 0.5 * erfc(-x * 0.70710678118654752440);
+    }
+    if (x >= 37.5193) return 0.0;
+    if (x <= -8.2924) return 1.0;
+    return 0.5 * erfc(x * 0.70710678118654752440);
+}
+
+// The per-variant branch every single-trait test ends with (reference Individual_Score_Test.cpp:45-64)
+__device__ inline void single_trait_stats(double U, double C, double &se, double &pl, double &est, double &est_se)
+{
+    if (C == 0.0) {
+        se = 0.0; pl = 0.0; est = 0.0; est_se = 0.0;
+    } else {
+        double stat = (U * U) / C;
+        pl = -log_gamma_q(0.5, 0.5 * stat);
+        se = sqrt(C);
+        est = U / C;
+        est_se = 1.0 / se;
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace staar

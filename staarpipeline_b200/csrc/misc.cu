@@ -1,0 +1,129 @@
+// misc.cu — small layout kernels around the hot path (operand assembly, sparse-genotype scatter,
+// Sigma_i * X_adj for the conditional test).  All HBM-bound streaming work.
+#include "common.cuh"
+
+namespace staar {
+
+namespace {
+
+// scatter a CSC genotype matrix (what as(Geno,"dgCMatrix") hands to the _sp entry points,
+// R/Individual_Analysis.R:343) into a zeroed dense n x p column-major matrix
+__global__ void csc_scatter_kernel(const double *__restrict__ val, const int64_t *__restrict__ row,
+                                   const int64_t *__restrict__ colptr, int64_t n, int64_t p, double *__restrict__ G)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp; c < p; c += nwarps) {
+        const int64_t e1 = colptr[c + 1];
+        for (int64_t e = colptr[c] + lane; e < e1; e += 32) G[c * n + row[e]] = val[e];
+    }
+}
+
+// Y (row-major n x ldY) <- columns gathered from up to four column-major blocks:
+//   col 0 = residuals, cols 1..q = Sigma_iX, then X_adj (m cols) and PX_adj (m cols) for the conditional test.
+__global__ void build_Y_kernel(int64_t n, int ldY, const double *__restrict__ res, const double *__restrict__ SX, int q,
+                               const double *__restrict__ A, const double *__restrict__ PA, int m, double *__restrict__ Y)
+{
+    const int64_t total = n * (int64_t)ldY;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = idx / ldY;
+        const int c = (int)(idx - j * ldY);
+        double v = 0.0;
+        if (c == 0) v = res ? res[j] : 0.0;
+        else if (c <= q) v = SX[j + (int64_t)(c - 1) * n];
+        else if (c <= q + m) v = A[j + (int64_t)(c - 1 - q) * n];
+        else if (c <= q + 2 * m) v = PA[j + (int64_t)(c - 1 - q - m) * n];
+        Y[idx] = v;
+    }
+}
+
+// only column 0 (residuals) of an existing Y
+__global__ void set_Y_col0_kernel(int64_t n, int ldY, const double *__restrict__ res, double *__restrict__ Y)
+{
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+        Y[j * ldY] = res[j];
+}
+
+// out (n x m col-major) = S (CSR) * A (n x m col-major) - SX (n x q) * T1 (q x m)   [PX_adj, cond.cpp:48]
+__global__ void px_adj_kernel(int64_t n, const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                              const double *__restrict__ val, const double *__restrict__ A, int m,
+                              const double *__restrict__ SX, int q, const double *__restrict__ T1,
+                              double *__restrict__ out)
+{
+    const int64_t total = n * (int64_t)m;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = idx / n, j = idx - c * n;
+        double s = 0.0;
+        for (int64_t e = row_ptr[j]; e < row_ptr[j + 1]; e++) s += val[e] * A[col[e] + c * n];
+        double t = 0.0;
+        for (int a = 0; a < q; a++) t += SX[j + (int64_t)a * n] * T1[a + c * q];
+        out[idx] = s - t;
+    }
+}
+
+__global__ void fill_pairs_kernel(int64_t pp, int k, int32_t *__restrict__ colA, int32_t *__restrict__ colB)
+{
+    const int64_t total = pp * k * k;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = idx / (k * k);
+        const int r = (int)(idx - i * k * k), a = r / k, b = r - a * k;
+        colA[idx] = (int32_t)(a * pp + i);      // id_single(k) = k*pp + i  (Individual_Score_Test_multi.cpp:47-50)
+        colB[idx] = (int32_t)(b * pp + i);
+    }
+}
+
+inline int grid_for(staar_ctx *ctx, int64_t work, int threads)
+{
+    return (int)std::max<int64_t>(1, std::min<int64_t>((work + threads - 1) / threads, (int64_t)ctx->sm_count * 16));
+}
+
+}  // namespace
+
+int launch_csc_to_dense(staar_ctx *ctx, const double *d_val, const int64_t *d_row, const int64_t *d_colptr, int64_t n,
+                        int64_t p, double *dG)
+{
+    STAAR_CUDA(cudaMemsetAsync(dG, 0, sizeof(double) * (size_t)n * p, ctx->stream));
+    if (p == 0) return STAAR_OK;
+    csc_scatter_kernel<<<grid_for(ctx, p * 32, 256), 256, 0, ctx->stream>>>(d_val, d_row, d_colptr, n, p, dG);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+int launch_build_Y(staar_ctx *ctx, int64_t n, int ldY, const double *d_res, const double *d_SX, int q, const double *dA,
+                   const double *dPA, int m, double *dY)
+{
+    build_Y_kernel<<<grid_for(ctx, n * ldY, 256), 256, 0, ctx->stream>>>(n, ldY, d_res, d_SX, q, dA, dPA, m, dY);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+int launch_set_Y_col0(staar_ctx *ctx, int64_t n, int ldY, const double *d_res, double *dY)
+{
+    set_Y_col0_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(n, ldY, d_res, dY);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+int launch_px_adj(staar_ctx *ctx, int64_t n, const int64_t *row_ptr, const int32_t *col, const double *val,
+                  const double *dA, int m, const double *dSX, int q, const double *dT1, double *dOut)
+{
+    px_adj_kernel<<<grid_for(ctx, n * m, 256), 256, 0, ctx->stream>>>(n, row_ptr, col, val, dA, m, dSX, q, dT1, dOut);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+int launch_fill_pairs(staar_ctx *ctx, int64_t pp, int k, int32_t *d_colA, int32_t *d_colB)
+{
+    if (pp == 0) return STAAR_OK;
+    fill_pairs_kernel<<<grid_for(ctx, pp * k * k, 256), 256, 0, ctx->stream>>>(pp, k, d_colA, d_colB);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+}  // namespace staar

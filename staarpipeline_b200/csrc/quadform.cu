@@ -1,0 +1,185 @@
+// quadform.cu — K3/K4: the quadratic forms g_a' * S * g_b behind diag(Cov) and the k x k trait blocks.
+//
+//  * quad_pairs_csr  : S = Sigma_i sparse (CSR, symmetric, full rows) — the (trans(G)*Sigma_i)*G factor of
+//                      src/Individual_Score_Test.cpp:43, _sp.cpp:43, _multi.cpp:40, _cond.cpp:49, but only the
+//                      entries the reference actually reads: the diagonal, or Cov(id_single,id_single)
+//                      (src/Individual_Score_Test_multi.cpp:47-52).
+//  * dense_P_times_G : W = P*G for the dense-GRM family (src/Individual_Score_Test_denseGRM.cpp:37) as an
+//                      FP64 tensor-core GEMM (mma.sync m8n8k4 DMMA, 128x64 CTA tile, next tiles
+//                      prefetched into registers under the MMAs); dot_pairs then takes g_a' * W[:,b].
+// FP64 throughout (1e-10 parity); deterministic tree reductions, no atomics.
+#include "common.cuh"
+
+namespace staar {
+
+namespace {
+
+__global__ void __launch_bounds__(256) quad_pairs_csr_kernel(const double *__restrict__ G, int64_t n,
+                                                             const int64_t *__restrict__ row_ptr,
+                                                             const int32_t *__restrict__ col,
+                                                             const double *__restrict__ val,
+                                                             const int32_t *__restrict__ colA,
+                                                             const int32_t *__restrict__ colB, int64_t npairs,
+                                                             double *__restrict__ out)
+{
+    __shared__ double red[32];
+    for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+        const double *ga = G + (int64_t)colA[pr] * n;
+        const double *gb = G + (int64_t)colB[pr] * n;
+        double acc = 0.0;
+        for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+            const double a = ga[j];
+            if (a != 0.0) {
+                double s = 0.0;
+                const int64_t e1 = row_ptr[j + 1];
+                for (int64_t e = row_ptr[j]; e < e1; e++) s += val[e] * gb[col[e]];
+                acc += a * s;
+            }
+        }
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) out[pr] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) dot_pairs_kernel(const double *__restrict__ G, const double *__restrict__ W,
+                                                        int64_t n, const int32_t *__restrict__ colA,
+                                                        const int32_t *__restrict__ colB, int64_t npairs,
+                                                        double *__restrict__ out)
+{
+    __shared__ double red[32];
+    for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+        const double *ga = G + (int64_t)colA[pr] * n;
+        const double *wb = W + (int64_t)colB[pr] * n;
+        double acc = 0.0;
+        for (int64_t j = threadIdx.x; j < n; j += blockDim.x) acc += ga[j] * wb[j];
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) out[pr] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- W = P * G  (FP64 DMMA GEMM)
+constexpr int BM = 128, BN = 64, BK = 16;
+constexpr int RSA = BM + 4;      // sP[k][i], stride = 4 mod 16 doubles -> conflict-free A fragments
+constexpr int RSB = BK + 4;      // sG[v][k], stride = 4 mod 16 doubles -> conflict-free B fragments
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// P: n x n column-major; G: n x p column-major; W: n x p column-major.  256 threads = 8 warps (4 x 2),
+// warp tile 32 x 32.
+__global__ void __launch_bounds__(256) dgemm_PG_kernel(const double *__restrict__ P, const double *__restrict__ G,
+                                                       int64_t n, int64_t p, double *__restrict__ W)
+{
+    __shared__ double sP[BK * RSA];
+    __shared__ double sG[BN * RSB];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int a = lane & 3, b = lane >> 2;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int64_t i0 = (int64_t)blockIdx.x * BM, v0 = (int64_t)blockIdx.y * BN;
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+    double rp[8], rg[4];
+    auto load_tiles = [&](int64_t k0) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {           // P tile: 16 k-columns x 128 rows
+            const int idx = tid + u * 256, kk = idx >> 7, ii = idx & 127;
+            const int64_t i = i0 + ii, k = k0 + kk;
+            rp[u] = (i < n && k < n) ? P[i + k * n] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {           // G tile: 64 variants x 16 samples
+            const int idx = tid + u * 256, vv = idx >> 4, kk = idx & 15;
+            const int64_t v = v0 + vv, k = k0 + kk;
+            rg[u] = (v < p && k < n) ? G[k + v * n] : 0.0;
+        }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int idx = tid + u * 256, kk = idx >> 7, ii = idx & 127;
+            sP[kk * RSA + ii] = rp[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int idx = tid + u * 256, vv = idx >> 4, kk = idx & 15;
+            sG[vv * RSB + kk] = rg[u];
+        }
+    };
+
+    const int64_t nk = (n + BK - 1) / BK;
+    load_tiles(0);
+    for (int64_t kt = 0; kt < nk; kt++) {
+        store_tiles();
+        __syncthreads();
+        if (kt + 1 < nk) load_tiles((kt + 1) * BK);   // global loads in flight under the DMMAs
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ks++) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) af[mt] = sP[(ks * 4 + a) * RSA + wm * 32 + mt * 8 + b];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) bf[nt] = sG[(wn * 32 + nt * 8 + b) * RSB + ks * 4 + a];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            const int64_t i = i0 + wm * 32 + mt * 8 + b;
+            const int64_t v = v0 + wn * 32 + nt * 8 + 2 * a;
+            if (i < n) {
+                if (v < p) W[i + v * n] = acc[mt][nt][0];
+                if (v + 1 < p) W[i + (v + 1) * n] = acc[mt][nt][1];
+            }
+        }
+}
+
+}  // namespace
+
+int launch_quad_pairs_csr(staar_ctx *ctx, const double *dG, int64_t n, const int64_t *row_ptr, const int32_t *col,
+                          const double *val, const int32_t *d_colA, const int32_t *d_colB, int64_t npairs,
+                          double *d_out)
+{
+    if (npairs == 0) return STAAR_OK;
+    int grid = (int)std::min<int64_t>(npairs, (int64_t)ctx->sm_count * 16);
+    quad_pairs_csr_kernel<<<grid, 256, 0, ctx->stream>>>(dG, n, row_ptr, col, val, d_colA, d_colB, npairs, d_out);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+int launch_dot_pairs(staar_ctx *ctx, const double *dG, const double *dW, int64_t n, const int32_t *d_colA,
+                     const int32_t *d_colB, int64_t npairs, double *d_out)
+{
+    if (npairs == 0) return STAAR_OK;
+    int grid = (int)std::min<int64_t>(npairs, (int64_t)ctx->sm_count * 16);
+    dot_pairs_kernel<<<grid, 256, 0, ctx->stream>>>(dG, dW, n, d_colA, d_colB, npairs, d_out);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+int launch_dense_P_times_G(staar_ctx *ctx, const double *dP, const double *dG, int64_t n, int64_t p, double *dW)
+{
+    if (p == 0 || n == 0) return STAAR_OK;
+    dim3 grid((unsigned)((n + BM - 1) / BM), (unsigned)((p + BN - 1) / BN));
+    dgemm_PG_kernel<<<grid, 256, 0, ctx->stream>>>(dP, dG, n, p, dW);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+}  // namespace staar

@@ -33,3 +33,12 @@ def reference(oracle):
     if not have_reference():
         pytest.skip("oracle/_ref/libstaar_ref.so not built (needs /root/reference)")
     return Oracle("reference")
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx():
+    """The CUDA path under test, reached through the C ABI.  No fallback: a missing library or device FAILS."""
+    from staarpipeline_b200.api import Context
+    ctx = Context(0)
+    yield ctx
+    ctx.close()

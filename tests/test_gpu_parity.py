@@ -1,0 +1,178 @@
+"""-m gpu: the CUDA path (through the C ABI, include/staar_b200.h) against the CPU oracle on the same seeded inputs
+and against the committed golden vectors (outputs of the reference build).  Tolerances are BASELINE.json's:
+Score / variance statistics 1e-10 relative, p-values 1e-8 relative; flips, AF, MAF bit-exact."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import cases
+from util import assert_stats_close, rel_err
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+make_golden = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(make_golden)
+GOLD = np.load(os.path.join(HERE, "golden", "reference_outputs.npz"))
+
+
+def score_floor(G, residuals):
+    """|U| below this is cancellation noise for ANY summation order: 1e-3 of the typical |U| = ||r o g||_2."""
+    G = G.toarray() if sp.issparse(G) else np.asarray(G)
+    r = np.asarray(residuals)[:, None] if G.shape[0] == np.size(residuals) else None
+    return 1e-3 * np.sqrt(((G * r) ** 2).sum(axis=0)).max() if r is not None else 0.0
+
+
+# ------------------------------------------------------------------ K1
+@pytest.mark.parametrize("fn", ["matrix_flip_mean", "matrix_flip_minor"])
+def test_flip_dense_bit_exact(gpu_ctx, oracle, fn):
+    G0 = cases.raw_dosage(777, 90)
+    got, want = getattr(gpu_ctx, fn)(G0), getattr(oracle, fn)(G0)
+    for k in ("Geno", "AF", "MAF"):
+        assert np.array_equal(got[k], want[k], equal_nan=True), (fn, k)
+
+
+def test_flip_dense_real_valued(gpu_ctx, oracle):
+    """AI-weighted (non-integer) genotypes: sums are order dependent, so 1e-10 rather than bit-exact."""
+    rng = np.random.default_rng(5)
+    G0 = cases.raw_dosage(500, 40) * rng.uniform(0.2, 1.7, size=48)[None, :]
+    got, want = gpu_ctx.matrix_flip_mean(G0), oracle.matrix_flip_mean(G0)
+    for k in ("Geno", "AF", "MAF"):
+        assert rel_err(got[k], want[k], 1e-300) < 1e-10
+
+
+def test_flip_edge_shapes(gpu_ctx, oracle):
+    for n, p in ((1, 1), (3, 1), (1, 5), (17, 2)):
+        G0 = cases.raw_dosage(n, p, adversarial=False)
+        got, want = gpu_ctx.matrix_flip_mean(G0), oracle.matrix_flip_mean(G0)
+        for k in ("Geno", "AF", "MAF"):
+            assert np.array_equal(got[k], want[k], equal_nan=True)
+
+
+# ------------------------------------------------------------------ golden vectors (reference build outputs)
+@pytest.mark.parametrize("name", sorted({k.split("/")[0] for k in GOLD.files}))
+def test_gpu_matches_golden(gpu_ctx, oracle, name):
+    fn, kw = make_golden.all_cases(oracle)[name]
+    assert make_golden.fingerprint(kw) == GOLD[f"{name}/__sha256__"].tobytes().decode()
+    res = getattr(gpu_ctx, fn)(**kw)
+    if not isinstance(res, dict):
+        res = {"pvalue": res}
+    want = {k: GOLD[f"{name}/{k}"] for k in res}
+    if name.startswith("flip"):
+        for k in want:
+            assert np.array_equal(res[k], want[k], equal_nan=True), k
+    elif name == "score_spa":
+        assert rel_err(res["pvalue"], want["pvalue"], 1e-300) < 1e-8
+    elif "multi" in name:
+        assert rel_err(res["Score"], want["Score"], score_floor(kw["G"], kw["residuals"])) < 1e-10
+        assert np.all(np.abs(res["pvalue_log"] - want["pvalue_log"]) <= 1e-8 * np.maximum(1.0, np.abs(want["pvalue_log"])))
+    else:
+        assert_stats_close(res, want, score_floor(kw["G"], kw["residuals"]))
+
+
+# ------------------------------------------------------------------ score tests vs oracle, more shapes
+@pytest.mark.parametrize("n,p,q", [(64, 5, 2), (1000, 130, 13), (2500, 33, 7)])
+def test_score_sparse_vs_oracle(gpu_ctx, oracle, n, p, q):
+    c, _ = cases.case_sparse(oracle, n=n, p=p, q=q, seed=n)
+    assert_stats_close(gpu_ctx.Individual_Score_Test(**c), oracle.Individual_Score_Test(**c), score_floor(c["G"], c["residuals"]))
+    cs = dict(c, G=sp.csc_matrix(c["G"]))
+    assert_stats_close(gpu_ctx.Individual_Score_Test_sp(**cs), oracle.Individual_Score_Test_sp(**cs), score_floor(c["G"], c["residuals"]))
+
+
+def test_score_nullmodel_cache_and_residual_swap(gpu_ctx, oracle):
+    """Same Sigma_i/Sigma_iX/cov with a new residual vector must not reuse the stale residuals."""
+    c, _ = cases.case_sparse(oracle, n=400, p=20, q=4, seed=2)
+    a = gpu_ctx.Individual_Score_Test(**c)
+    c2 = dict(c, residuals=c["residuals"][::-1].copy())
+    b = gpu_ctx.Individual_Score_Test(**c2)
+    assert_stats_close(b, oracle.Individual_Score_Test(**c2), score_floor(c2["G"], c2["residuals"]))
+    assert_stats_close(gpu_ctx.Individual_Score_Test(**c), a)
+
+
+def test_score_dense_grm_vs_oracle(gpu_ctx, oracle):
+    c, _ = cases.case_dense(oracle, n=700, p=77, q=6, seed=31)
+    assert_stats_close(gpu_ctx.Individual_Score_Test_denseGRM(**c), oracle.Individual_Score_Test_denseGRM(**c),
+                       score_floor(c["G"], c["residuals"]))
+
+
+def test_score_cond_singular_raises(gpu_ctx, oracle):
+    from staarpipeline_b200.api import StaarError
+    c, _ = cases.case_cond(oracle)
+    A = np.column_stack([c["X_adj"], np.zeros(c["X_adj"].shape[0])])      # zero column -> exactly singular
+    with pytest.raises(StaarError) as e:
+        gpu_ctx.Individual_Score_Test_cond(**dict(c, X_adj=A))
+    assert e.value.code == 3
+
+
+def test_dimension_mismatch_raises(gpu_ctx, oracle):
+    from staarpipeline_b200.api import StaarError
+    c, _ = cases.case_sparse(oracle, n=100, p=4, q=3)
+    with pytest.raises(StaarError):
+        gpu_ctx.Individual_Score_Test(**dict(c, residuals=c["residuals"][:-1]))
+
+
+def test_spa_trace_and_parity(gpu_ctx, oracle):
+    c, _ = cases.case_spa(oracle, n=6000, p=48, seed=41)
+    got, tr = gpu_ctx.Individual_Score_Test_SPA(**c, return_trace=True)
+    want, otr = oracle.Individual_Score_Test_SPA(**c, return_trace=True)
+    assert rel_err(got, want, 1e-300) < 1e-8
+    # same branches taken and same number of Newton iterations as the reference's control flow
+    assert np.array_equal(tr[:, 3], otr[:, 3])
+
+
+# ------------------------------------------------------------------ packed fast path
+def _packed_case(oracle, n, p, q, seed, related=True, impute="mean"):
+    from staarpipeline_b200 import synth
+    nm = synth.nullmodel_sparse_grm(n, seed=seed, q=q, shuffle=True) if related else synth.nullmodel_unrelated(n, seed=seed, q=q)
+    G0 = cases.raw_dosage(n, p, seed)
+    codes = np.where(np.isnan(G0) | (G0 <= -1), 3, G0).astype(np.uint8)
+    flipped = getattr(oracle, f"matrix_flip_{impute}")(G0)
+    want = oracle.Individual_Score_Test(flipped["Geno"], nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+    want.update(AF=flipped["AF"], MAF=flipped["MAF"])
+    return nm, G0, synth.pack_codes(np.asfortranarray(codes)), want, flipped["Geno"]
+
+
+@pytest.mark.parametrize("n,p,q,related,impute", [(1000, 70, 13, True, "mean"), (777, 40, 5, False, "mean"),
+                                                 (2049, 300, 13, True, "minor"), (255, 9, 1, True, "mean")])
+def test_packed_score_vs_oracle(gpu_ctx, oracle, n, p, q, related, impute):
+    from staarpipeline_b200.api import IMPUTE_MEAN, IMPUTE_MINOR
+    nm, G0, packed, want, Gf = _packed_case(oracle, n, p, q, seed=n + p, related=related, impute=impute)
+    gpu_ctx.set_nullmodel_sparse(nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+    got = gpu_ctx.packed_score_host(packed, n, IMPUTE_MEAN if impute == "mean" else IMPUTE_MINOR)
+    assert np.array_equal(got["AF"], want["AF"]) and np.array_equal(got["MAF"], want["MAF"])      # bit-exact
+    assert_stats_close({k: got[k] for k in ("Score", "Score_se", "pvalue_log", "Est", "Est_se")},
+                       {k: want[k] for k in ("Score", "Score_se", "pvalue_log", "Est", "Est_se")},
+                       score_floor(Gf, nm.residuals))
+    # exact-zero variance branch (monomorphic / all-missing columns) must be hit exactly as in the reference
+    zero = want["Score_se"] == 0
+    assert zero.any() and np.array_equal(got["Score_se"] == 0, zero)
+
+
+def test_host_packer_matches_numpy(oracle):
+    from staarpipeline_b200 import api, synth
+    G0 = cases.raw_dosage(333, 21)
+    codes = np.where(np.isnan(G0) | (G0 <= -1), 3, G0).astype(np.uint8)
+    assert np.array_equal(api.pack_dosage_host(G0, threads=3), synth.pack_codes(np.asfortranarray(codes)))
+    with pytest.raises(api.StaarError):
+        api.pack_dosage_host(G0 * 0.5)
+
+
+def test_device_generator_matches_host(gpu_ctx):
+    import torch
+    from staarpipeline_b200 import api, synth
+    n, p, first = 1234, 50, 1000
+    prm = synth.variant_params(n, first, p)
+    stride = api.packed_stride(n)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).to(dev)
+    th, te, tm, sa = t(prm.thr_hom), t(prm.thr_het), t(prm.thr_miss), t(prm.store_alt)
+    out = torch.zeros((p, stride), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    gpu_ctx.synth_packed_device(out.data_ptr(), stride, n, first, p, synth.BASE_SEED, th.data_ptr(), te.data_ptr(),
+                                tm.data_ptr(), sa.data_ptr())
+    want = synth.pack_codes(synth.dosage_codes(n, first, p, params=prm), stride)
+    assert np.array_equal(out.cpu().numpy(), want)
