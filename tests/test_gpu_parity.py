@@ -56,8 +56,8 @@ def test_flip_edge_shapes(gpu_ctx, oracle):
 # ------------------------------------------------------------------ golden vectors (reference build outputs)
 @pytest.mark.parametrize("name", sorted({k.split("/")[0] for k in GOLD.files}))
 def test_gpu_matches_golden(gpu_ctx, oracle, name):
-    fn, kw = make_golden.all_cases(oracle)[name]
-    assert make_golden.fingerprint(kw) == GOLD[f"{name}/__sha256__"].tobytes().decode()
+    fn, kw = make_golden.all_cases(oracle, GOLD)[name]
+    assert make_golden.fingerprint_G(kw) == GOLD[f"{name}/__sha256__"].tobytes().decode()
     res = getattr(gpu_ctx, fn)(**kw)
     if not isinstance(res, dict):
         res = {"pvalue": res}
