@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py — variants/sec of the per-variant score-test hot path (BASELINE.json metric).
+
+Workload (N = 1 and every N of the scaling run): BASELINE.json configs[1] — continuous trait, sparse GRM
+(related samples), n = 100,000 samples, 10 M variants on 8 GPUs — sharded by variants: every rank holds
+10 M / 8 = 1.25 M variants as 2-bit packed dosage columns resident in HBM (31 GB, >> L2), plus a replica of the
+null model broadcast once over NCCL.  One step = one pass of the fused path (flip/impute/AF -> G'[r | Sigma_iX] ->
+sparse quadratic form -> per-variant statistics) over the rank's whole shard.  `scaling` = weak.
+
+One JSON line on stdout (rank 0): value (device-resident), e2e (host FP64 dosage chunks through the C ABI, H2D/D2H
+inside the timed region), roofline (dominant kernel, live CUDA-event time), cpu_baseline (the reference's own
+sources, oracle/_ref, on a bounded sample on this box's host cores), clocks, gpu_launches.
+
+`--impl reference` times the reference's CPU implementation (oracle/_ref: /root/reference/src/*.cpp compiled
+against stand-in headers; falls back to the oracle port) on the R driver's call sequence for this workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SAMPLES = 100_000
+Q_COVARIATES = 13
+VARIANTS_PER_GPU = 1_250_000           # 10 M variants / 8 GPUs (BASELINE.json configs[1])
+CHUNK = 5_000                          # R driver's subset_variants_num (R/Individual_Analysis.R:45)
+METRIC = "variants/sec of score tests (n=100k samples)"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception as e:  # noqa: BLE001
+            log("clock sampler unavailable:", e)
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference CPU path
+def reference_chunk(ref, G, nm, mac_cutoff=20):
+    """The reference's native calls for one chunk, in the R driver's order (R/Individual_Analysis.R:189-443):
+    matrix_flip_mean -> common variants: Individual_Score_Test (dense G) -> rare: Individual_Score_Test_sp."""
+    import scipy.sparse as sp
+    n = G.shape[0]
+    t0 = time.perf_counter()
+    fl = ref.matrix_flip_mean(G)
+    t_native = time.perf_counter() - t0
+    maf = fl["MAF"]
+    common = maf >= 0.05
+    rare = (maf > (mac_cutoff - 0.5) / n / 2) & (maf < 0.05)
+    tested = int(common.sum() + rare.sum())
+    if common.any():
+        Gc = np.asfortranarray(fl["Geno"][:, common])
+        t0 = time.perf_counter()
+        ref.Individual_Score_Test(Gc, nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+        t_native += time.perf_counter() - t0
+    if rare.sum() >= 2:
+        Gr = sp.csc_matrix(fl["Geno"][:, rare])          # as(Geno_rare, "dgCMatrix"): R-side, not timed
+        t0 = time.perf_counter()
+        ref.Individual_Score_Test_sp(Gr, nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+        t_native += time.perf_counter() - t0
+    return t_native, tested
+
+
+def load_reference():
+    from oracle.pyoracle import Oracle, have_reference
+    if have_reference():
+        ref = Oracle("reference")
+        blas = ref.set_blas()
+        return ref, "reference", blas
+    return Oracle("port"), "port", False
+
+
+def host_chunk(n, p, first_variant, seed):
+    """FP64 `$dosage` block on the host from the same hash RNG as the device generator (NaN = missing)."""
+    from staarpipeline_b200 import synth
+    prm = synth.variant_params(n, first_variant, p, seed)
+    out = np.empty((n, p), order="F")
+    step = 256
+    for a in range(0, p, step):
+        b = min(p, a + step)
+        sub = synth.VariantParams(prm.thr_hom[a:b], prm.thr_het[a:b], prm.thr_miss[a:b], prm.store_alt[a:b], prm.alt_freq[a:b])
+        out[:, a:b] = synth.codes_to_dosage(synth.dosage_codes(n, first_variant + a, b - a, seed, params=sub))
+    return out
+
+
+def run_reference(args):
+    """--impl reference: rank 0 only; each step = one R-driver chunk on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from staarpipeline_b200 import synth
+    ref, kind, blas = load_reference()
+    cores = os.cpu_count() or 1
+    n, p = args.n, args.ref_chunk
+    nm = synth.nullmodel_sparse_grm(n, seed=synth.BASE_SEED, q=Q_COVARIATES, shuffle=True)
+    G = host_chunk(n, p, 0, synth.BASE_SEED)
+    times, tested = [], 0
+    for s in range(args.warmup + args.steps):
+        t, tested = reference_chunk(ref, G, nm)
+        if s >= args.warmup:
+            times.append(t)
+        log(f"[reference] step {s}: {t:.2f} s native for {p} variants ({tested} tested)")
+    total = float(np.sum(times))
+    value = p * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "variants/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, p),
+        "cpu_baseline": {"value": value, "unit": "variants/s", "cores": cores if blas else 1, "kind": kind,
+                         "sample": f"{args.steps} chunks of {p} variants x {n} samples; native calls of the R driver "
+                                   f"(matrix_flip_mean, Individual_Score_Test, Individual_Score_Test_sp); dense GEMM on "
+                                   f"{'OpenBLAS, ' + str(cores) + ' threads' if blas else 'in-order loops'}; "
+                                   "Armadillo/Rmath are stand-ins (oracle/ref_stub)"},
+        "e2e": {"value": value, "unit": "variants/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, variants_per_step):
+    return {"workload": "BASELINE configs[1]: Individual_Analysis continuous trait, sparse GRM (related samples), "
+                        f"n={args.n}, q={Q_COVARIATES}; per-GPU shard of the 10M-variant job",
+            "n_samples": args.n, "variants_per_gpu_per_step": variants_per_step, "genotype_bits": 2,
+            "impute": "mean", "parallelism": f"variant-sharded x{args.gpus}, null model replicated",
+            "l2": "inputs (31 GB/GPU) larger than L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from staarpipeline_b200 import api, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    n, V = args.n, args.variants_per_gpu
+    seed = synth.BASE_SEED
+
+    # ---- null model: built on rank 0, replicated by NCCL broadcast over NVLink once per run
+    t0 = time.perf_counter()
+    if rank == 0:
+        nm = synth.nullmodel_sparse_grm(n, seed=seed, q=Q_COVARIATES, shuffle=True)
+        S = nm.Sigma_i.tocsc(); S.sort_indices()
+        parts = [S.data.astype(np.float64), S.indices.astype(np.int64), S.indptr.astype(np.int64),
+                 np.ascontiguousarray(nm.Sigma_iX.T).ravel(), nm.cov.ravel(order="F").copy(), nm.residuals.copy()]
+        sizes = torch.tensor([x.size for x in parts], dtype=torch.int64, device=dev)
+    else:
+        parts, sizes = None, torch.zeros(6, dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(sizes, 0)
+        bufs = []
+        for i, sz in enumerate(sizes.tolist()):
+            dt = torch.int64 if i in (1, 2) else torch.float64
+            t = torch.from_numpy(parts[i]).to(dev) if rank == 0 else torch.empty(sz, dtype=dt, device=dev)
+            dist.broadcast(t, 0)
+            bufs.append(t.cpu().numpy())
+        parts = bufs
+    import scipy.sparse as sp
+    Sigma_i = sp.csc_matrix((parts[0], parts[1], parts[2]), shape=(n, n))
+    Sigma_iX = np.asfortranarray(parts[3].reshape(Q_COVARIATES, n).T)
+    cov = np.asfortranarray(parts[4].reshape(Q_COVARIATES, Q_COVARIATES, order="F"))
+    residuals = parts[5]
+    ctx = api.Context(local)
+    ctx.set_nullmodel_sparse(Sigma_i, Sigma_iX, cov, residuals)
+    log(f"[rank {rank}] null model ready in {time.perf_counter() - t0:.1f} s (nnz(Sigma_i) = {Sigma_i.nnz})")
+
+    # ---- this rank's shard of packed dosage columns, generated on the device
+    t0 = time.perf_counter()
+    stride = api.packed_stride(n)
+    first = rank * V
+    packed = torch.empty((V, stride), dtype=torch.uint8, device=dev)
+    gen = 125_000
+    for a in range(0, V, gen):
+        b = min(V, a + gen)
+        prm = synth.variant_params(n, first + a, b - a, seed)
+        th = torch.from_numpy(prm.thr_hom.view(np.int64)).to(dev)
+        te = torch.from_numpy(prm.thr_het.view(np.int64)).to(dev)
+        tm = torch.from_numpy(prm.thr_miss.view(np.int64)).to(dev)
+        sa = torch.from_numpy(prm.store_alt).to(dev)
+        torch.cuda.synchronize()
+        ctx.synth_packed_device(packed[a:b].data_ptr(), stride, n, first + a, b - a, seed, th.data_ptr(), te.data_ptr(),
+                                tm.data_ptr(), sa.data_ptr())
+    outs = torch.zeros((7, V), dtype=torch.float64, device=dev)
+    optrs = [outs[i].data_ptr() for i in range(7)]
+    torch.cuda.synchronize()
+    log(f"[rank {rank}] {V} packed variants x {n} samples resident ({V * stride / 1e9:.1f} GB) in {time.perf_counter() - t0:.1f} s")
+
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def step():
+        ctx.packed_score_device(packed.data_ptr(), stride, n, V, api.IMPUTE_MEAN, optrs)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(args.steps):
+        step()
+    e1.record(ext)
+    barrier()
+    launches = ctx.launch_count - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = float(ms.item())
+    value = world * V * args.steps / (ms_total / 1e3)
+
+    # ---- per-kernel device times (CUDA events on the launching stream) for the roofline figure
+    ctx.set_profiling(True)
+    stage = {"scan": [], "contract": [], "finalize": []}
+    for _ in range(3):
+        step()
+        for k, v in ctx.last_stage_ms().items():
+            stage[k].append(v)
+    ctx.set_profiling(False)
+    stage_ms = {k: float(np.mean(v)) for k, v in stage.items()}
+    dominant = max(stage_ms, key=stage_ms.get)
+    bytes_per_variant = n * 2 / 8 + 56                 # n*E/8 + 7 doubles out, E = 2 bits
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = V * bytes_per_variant / (stage_ms[dominant] / 1e3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dominant)
+    except Exception:  # noqa: BLE001
+        pass
+    roofline = {"bound": "hbm", "kernel": {"scan": "scan_packed_kernel", "contract": "contract_packed_kernel",
+                                           "finalize": "finalize_packed_kernel"}[dominant],
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "stage_ms": stage_ms, "step_frac": stage_ms[dominant] / sum(stage_ms.values()),
+                "whole_step": {"achieved": V * bytes_per_variant / (ms_total / args.steps / 1e3) / 1e9,
+                               "frac": V * bytes_per_variant / (ms_total / args.steps / 1e3) / 1e9 / hbm_peak}}
+    # secondary roof: the INT8 tensor pipe the contraction runs on (mma.sync s8, measured by tools/pipe_peaks.cu)
+    try:
+        pp = json.load(open(os.path.join(ROOT, "profiles", "r01_pipe_peaks.json")))
+        ops = 2.0 * V * n * 112                         # 7 digit slices x 16 columns per genotype
+        roofline["int8_mma"] = {"achieved_tops": ops / (stage_ms["contract"] / 1e3) / 1e12,
+                                "peak_tops": pp["int8_mma_m16n8k32_tops"],
+                                "frac": ops / (stage_ms["contract"] / 1e3) / 1e12 / pp["int8_mma_m16n8k32_tops"]}
+    except Exception:  # noqa: BLE001
+        pass
+
+    # ---- end to end: host FP64 dosage chunks (what the Rcpp boundary delivers) through the C-ABI chunk driver
+    e2e = None
+    if not args.no_e2e:
+        p = CHUNK
+        host = torch.from_numpy(host_chunk_from_device(packed[:p], n, dev).T).pin_memory()   # (p, n) C-order, pinned
+        G = host.numpy().T                                                                    # n x p, F-order view
+        out7 = [np.zeros(p) for _ in range(7)]
+        for _ in range(max(1, min(args.warmup, 2))):
+            ctx.individual_analysis_chunk(G, api.IMPUTE_MEAN, 0, out7)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.individual_analysis_chunk(G, api.IMPUTE_MEAN, 0, out7)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * p * args.steps / float(dt.item()), "unit": "variants/s",
+               "h2d_bytes_per_step": int(p * stride), "d2h_bytes_per_step": int(7 * p * 8),
+               "call": "staar_individual_analysis_chunk (host FP64 n x 5000 dosage block, pinned; host 2-bit packing, "
+                       "H2D, flip+score kernels, D2H of 7 result arrays inside the timed region)",
+               "ms_per_chunk": 1e3 * float(dt.item()) / args.steps, "host_bytes_read_per_step": int(p * n * 8)}
+        # parity of the device-resident step against the host-buffer path on the same variants (bit-identical)
+        same = all(np.array_equal(outs[i, :p].cpu().numpy(), out7[i], equal_nan=True) for i in range(7))
+        e2e["matches_resident_path"] = bool(same)
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref, kind, blas = load_reference()
+        pc = args.cpu_chunk
+        Gc = np.asfortranarray(host_chunk_from_device(packed[:pc], n, dev))
+        nm_like = argparse.Namespace(Sigma_i=Sigma_i, Sigma_iX=Sigma_iX, cov=cov, residuals=residuals)
+        t, tested = reference_chunk(ref, Gc, nm_like)
+        cpu = {"value": pc / t, "unit": "variants/s", "cores": (os.cpu_count() or 1) if blas else 1, "kind": kind,
+               "sample": f"one chunk of {pc} variants x {n} samples ({tested} pass the MAC filter): native calls of the R "
+                         f"driver (matrix_flip_mean, Individual_Score_Test, Individual_Score_Test_sp), {t:.1f} s; "
+                         "reference sources with stand-in Armadillo/Rmath (oracle/ref_stub), dense GEMM on "
+                         f"{'OpenBLAS all cores' if blas else 'in-order loops'}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "variants/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int8 x int8 -> int32 exact contraction of 54-bit sliced f64 operands; f64 statistics",
+                "data": "synthetic", "config": workload_config(args, V), "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def host_chunk_from_device(packed_rows, n, dev):
+    """unpack device-resident 2-bit columns into the FP64 `$dosage` matrix (n x p, F-order, NaN = missing)"""
+    import torch
+    p = packed_rows.shape[0]
+    sh = torch.tensor([0, 2, 4, 6], dtype=torch.uint8, device=dev)
+    codes = ((packed_rows.unsqueeze(-1) >> sh) & 3).reshape(p, -1)[:, :n]
+    G = codes.to(torch.float64)
+    G[codes == 3] = float("nan")
+    return G.cpu().numpy().T          # (n, p) view of a C-order (p, n) array == F-order n x p
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=N_SAMPLES)
+    ap.add_argument("--variants-per-gpu", type=int, default=VARIANTS_PER_GPU)
+    ap.add_argument("--cpu-chunk", type=int, default=2000, help="variants in the bounded cpu_baseline sample")
+    ap.add_argument("--ref-chunk", type=int, default=2000, help="variants per step of --impl reference")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

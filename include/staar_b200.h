@@ -176,10 +176,25 @@ int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t st
                               int impute, double *d_AF, double *d_MAF, double *d_Score, double *d_Score_se,
                               double *d_pvalue_log, double *d_Est, double *d_Est_se);
 
+/* Per-kernel device times of the LAST staar_packed_score_device call, measured with CUDA events on the context
+ * stream when profiling is on: ms[0] = scan (K1+K3), ms[1] = contraction (K2), ms[2] = finalize (K5).
+ * Used by bench.py for the live roofline figure; off by default (no events recorded). */
+int staar_ctx_set_profiling(staar_ctx *ctx, int on);
+int staar_ctx_last_stage_ms(staar_ctx *ctx, float ms[3]);
+
 /* Same, host buffers (packed host columns in, 7 host arrays out); H2D/D2H inside. */
 int staar_packed_score_host(staar_ctx *ctx, const uint8_t *packed, size_t stride_bytes, int64_t n, int64_t p,
                             int impute, double *AF, double *MAF, double *Score, double *Score_se,
                             double *pvalue_log, double *Est, double *Est_se);
+
+/* One chunk of the single-variant driver (R/Individual_Analysis.R:186-196, 264): an FP64 `$dosage` block in HOST
+ * memory (n x p, NaN / <= -1 missing) -> flip/impute + Individual_Score_Test statistics (7 host arrays of length p)
+ * in one call, without materialising Geno on the host.  0/1/2/NA blocks are packed to 2 bits by `threads` host
+ * threads (0 = all cores) so that 1/32 of the bytes cross PCIe; real-valued blocks take the FP64 kernels.
+ * Requires staar_nullmodel_set_sparse*. */
+int staar_individual_analysis_chunk(staar_ctx *ctx, const double *G, int64_t n, int64_t p, int impute, int threads,
+                                    double *AF, double *MAF, double *Score, double *Score_se, double *pvalue_log,
+                                    double *Est, double *Est_se);
 
 /* Synthetic packed dosage columns generated on the device (bench / parity subsets); per-variant
  * thresholds as in staarpipeline_b200/synth.py (device pointers, uint64 / uint8). */

@@ -114,6 +114,14 @@ class Context:
     def synchronize(self):
         self._call("staar_ctx_synchronize")
 
+    def set_profiling(self, on: bool):
+        self._call("staar_ctx_set_profiling", C.c_int(int(on)))
+
+    def last_stage_ms(self):
+        ms = (C.c_float * 3)()
+        self._call("staar_ctx_last_stage_ms", ms)
+        return {"scan": ms[0], "contract": ms[1], "finalize": ms[2]}
+
     # ------------------------------------------------------------------ flips
     def _flip(self, fn: str, G, want_geno=True):
         G = _f(G)
@@ -284,6 +292,15 @@ class Context:
         o = [np.zeros(p) for _ in range(7)]
         self._call("staar_packed_score_host", packed.ctypes.data_as(_u8p), C.c_size_t(stride), C.c_int64(n),
                    C.c_int64(p), C.c_int(impute), *[_p(a) for a in o])
+        return dict(zip(("AF", "MAF", "Score", "Score_se", "pvalue_log", "Est", "Est_se"), o))
+
+    def individual_analysis_chunk(self, G, impute: int = IMPUTE_MEAN, threads: int = 0, out=None):
+        """FP64 `$dosage` host block (n x p, F-order; a raw pointer to pinned memory also works via `out`-style reuse)
+        -> dict of the 7 per-variant arrays.  One call per chunk of the R driver (flip + score test)."""
+        G = _f(G); n, p = G.shape
+        o = out if out is not None else [np.zeros(p) for _ in range(7)]
+        self._call("staar_individual_analysis_chunk", _p(G), C.c_int64(n), C.c_int64(p), C.c_int(impute), C.c_int(threads),
+                   *[_p(a) for a in o])
         return dict(zip(("AF", "MAF", "Score", "Score_se", "pvalue_log", "Est", "Est_se"), o))
 
     def packed_score_device(self, d_packed: int, stride: int, n: int, p: int, impute: int, d_out7):

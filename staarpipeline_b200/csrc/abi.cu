@@ -479,17 +479,23 @@ int staar_pack_dosage_host(const double *G, int64_t n, int64_t p, uint8_t *packe
         for (int64_t i = tid; i < p; i += threads) {
             const double *g = G + i * n;
             uint8_t *dst = packed + (size_t)i * stride;
-            memset(dst, 0, stride);
-            for (int64_t j = 0; j < n; j++) {
-                const double v = g[j];
-                uint32_t code;
-                if (!(v > -1.0)) code = 3;
-                else if (v == 0.0) code = 0;
-                else if (v == 1.0) code = 1;
-                else if (v == 2.0) code = 2;
-                else { bad[tid] = 1; code = 0; }
-                dst[j >> 2] |= (uint8_t)(code << (2 * (j & 3)));
+            // branch-free: code = [v==1] + 2[v==2] + 3[!(v>-1)]; anything else (incl. 0 < v < 1) is flagged
+            auto enc = [](double v, unsigned &okacc) -> unsigned {
+                const unsigned is1 = v == 1.0, is2 = v == 2.0, is0 = v == 0.0, miss = !(v > -1.0);
+                okacc &= (is0 | is1 | is2 | miss);
+                return is1 + 2u * is2 + 3u * miss;
+            };
+            unsigned ok = 1;
+            const int64_t n4 = n / 4;
+            for (int64_t b = 0; b < n4; b++) {
+                const double *s = g + 4 * b;
+                dst[b] = (uint8_t)(enc(s[0], ok) | (enc(s[1], ok) << 2) | (enc(s[2], ok) << 4) | (enc(s[3], ok) << 6));
             }
+            unsigned last = 0;
+            for (int64_t j = 4 * n4; j < n; j++) last |= enc(g[j], ok) << (2 * (j & 3));
+            memset(dst + n4, 0, stride - n4);
+            if (n & 3) dst[n4] = (uint8_t)last;
+            if (!ok) bad[tid] = 1;
         }
     };
     std::vector<std::thread> th;
@@ -562,10 +568,32 @@ int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t st
     int32_t *dflip = ctx->tmp.as<int32_t>();
     double *dmu = reinterpret_cast<double *>(dflip + pi), *dquad = dmu + p, *dSm = dquad + p;
     long long *dhi = reinterpret_cast<long long *>(dSm + 16 * p), *dlo = dhi + 16 * p;
+    const bool prof = ctx->profiling;
+    if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     STAAR_TRY(launch_scan_packed(ctx, d_packed, stride, n, p, impute, d_AF, d_MAF, dflip, dmu, dquad, dSm));
+    if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     STAAR_TRY(launch_contract_packed(ctx, d_packed, stride, n, p, dflip, dhi, dlo));
+    if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
     STAAR_TRY(launch_finalize_packed(ctx, p, dmu, dquad, dSm, dhi, dlo, d_Score, d_Score_se, d_pl, d_Est, d_Est_se));
+    if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
     return STAAR_OK;      // asynchronous on ctx->stream: the caller times with events / staar_ctx_synchronize
+}
+
+int staar_ctx_set_profiling(staar_ctx *ctx, int on)
+{
+    CHECK_CTX(ctx);
+    if (on && !ctx->ev[0]) for (int i = 0; i < 4; i++) STAAR_CUDA(cudaEventCreate(&ctx->ev[i]));
+    ctx->profiling = on != 0;
+    return STAAR_OK;
+}
+
+int staar_ctx_last_stage_ms(staar_ctx *ctx, float ms[3])
+{
+    CHECK_CTX(ctx);
+    if (!ctx->ev[0]) { set_error("profiling was never enabled on this context"); return STAAR_ERR_STATE; }
+    STAAR_CUDA(cudaEventSynchronize(ctx->ev[3]));
+    for (int i = 0; i < 3; i++) STAAR_CUDA(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    return STAAR_OK;
 }
 
 int staar_packed_score_host(staar_ctx *ctx, const uint8_t *packed, size_t stride, int64_t n, int64_t p, int impute,
@@ -583,6 +611,38 @@ int staar_packed_score_host(staar_ctx *ctx, const uint8_t *packed, size_t stride
     double *dst[7] = {AF, MAF, Score, Score_se, pl, Est, Est_se};
     for (int a = 0; a < 7; a++) STAAR_TRY(d2h(ctx, dst[a], o + (size_t)a * p, sizeof(double) * p));
     return sync(ctx);
+}
+
+// One chunk of the single-variant driver (R/Individual_Analysis.R:186-196,264): FP64 `$dosage` block in host memory
+// -> flip/impute + Individual_Score_Test statistics, without materialising Geno on the host.  0/1/2/NA dosages are
+// packed to 2 bits on the host (threaded) so 1/32 of the bytes cross PCIe; anything else takes the FP64 kernels.
+int staar_individual_analysis_chunk(staar_ctx *ctx, const double *G, int64_t n, int64_t p, int impute, int threads,
+                                    double *AF, double *MAF, double *Score, double *Score_se, double *pl, double *Est,
+                                    double *Est_se)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    NullSparse &ns = ctx->ns;
+    if (!ns.set || ns.n != n) { set_error("individual_analysis_chunk: null model not set for n = %lld", (long long)n); return STAAR_ERR_STATE; }
+    if (p == 0) return STAAR_OK;
+    const size_t stride = staar_packed_stride(n);
+    bool packed_ok = false;
+    if (ns.q + 1 <= kColsPerSlice) {
+        STAAR_TRY(pinned_reserve(ctx, stride * (size_t)p));
+        packed_ok = staar_pack_dosage_host(G, n, p, static_cast<uint8_t *>(ctx->pinned), stride, threads) == STAAR_OK;
+    }
+    if (packed_ok)
+        return staar_packed_score_host(ctx, static_cast<const uint8_t *>(ctx->pinned), stride, n, p, impute, AF, MAF,
+                                       Score, Score_se, pl, Est, Est_se);
+    // real-valued genotypes: FP64 flip kernel in place on the device copy, then the FP64 score kernels
+    STAAR_TRY(upload_dense_G(ctx, G, n, p));
+    STAAR_TRY(ctx->out.reserve(sizeof(double) * 5 * (size_t)p));
+    double *o = ctx->out.as<double>();
+    STAAR_TRY(launch_flip_dense(ctx, ctx->G.as<double>(), n, p, impute == STAAR_IMPUTE_MINOR, true, o, o + p));
+    STAAR_TRY(d2h(ctx, AF, o, sizeof(double) * p));
+    STAAR_TRY(d2h(ctx, MAF, o + p, sizeof(double) * p));
+    STAAR_TRY(sync(ctx));
+    return run_sparse_family(ctx, n, p, 0, nullptr, Score, Score_se, pl, Est, Est_se);
 }
 
 int staar_synth_packed_device(staar_ctx *ctx, uint8_t *d_packed, size_t stride, int64_t n, int64_t first_variant,

@@ -91,6 +91,9 @@ struct staar_ctx {
     staar::DevBuf G, L, aux, out, tmp, tmp2, pk;
     void *pinned = nullptr;
     size_t pinned_cap = 0;
+    // optional per-kernel timing of the packed path (bench.py roofline)
+    bool profiling = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace staar {

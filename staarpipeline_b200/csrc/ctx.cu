@@ -218,6 +218,7 @@ void staar_ctx_destroy(staar_ctx *ctx)
     ctx->G.release(); ctx->L.release(); ctx->aux.release(); ctx->out.release(); ctx->tmp.release();
     ctx->tmp2.release(); ctx->pk.release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

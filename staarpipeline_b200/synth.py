@@ -55,15 +55,15 @@ def variant_params(n: int, first_variant: int, p: int, seed: int = BASE_SEED, ma
     """ALT-allele frequency f ~ 0.5*Beta(0.15,4) truncated to expected MAC >= mac_min; HWE genotypes;
     95% of variants stored as REF dosage (so they need the flip), 5% stored as ALT count;
     1% of variants carry 2% missing entries, the rest 0.1%."""
-    from scipy.stats import beta
     v = np.arange(first_variant, first_variant + p, dtype=np.uint64)
     zero = np.zeros(p, dtype=np.uint64)
     u_f = (hash_u32(seed, v, zero, 1).astype(np.float64) + 0.5) / 2.0 ** 32
     u_m = hash_u32(seed, v, zero, 2).astype(np.float64) / 2.0 ** 32
     u_s = hash_u32(seed, v, zero, 3).astype(np.float64) / 2.0 ** 32
     lo = min(0.5, (mac_min + 1.0) / (2.0 * n))
-    c_lo = beta.cdf(2.0 * lo, 0.15, 4.0)
-    f = 0.5 * beta.ppf(c_lo + u_f * (1.0 - c_lo), 0.15, 4.0)
+    grid_u, grid_f = _beta_table()
+    c_lo = float(np.interp(2.0 * lo, grid_f, grid_u))
+    f = 0.5 * np.interp(c_lo + u_f * (1.0 - c_lo), grid_u, grid_f)
     f = np.clip(f, lo, 0.5)
     two32 = 2.0 ** 32
     thr_hom = np.floor(f * f * two32).astype(np.uint64)
@@ -72,6 +72,19 @@ def variant_params(n: int, first_variant: int, p: int, seed: int = BASE_SEED, ma
     thr_miss = np.floor(miss_rate * two32).astype(np.uint64)
     store_alt = (u_s < 0.05).astype(np.uint8)
     return VariantParams(thr_hom, thr_het, thr_miss, store_alt, f)
+
+
+_BETA_TABLE = None
+
+
+def _beta_table():
+    """inverse CDF of Beta(0.15, 4) on a fixed grid (beta.ppf per variant is far too slow for 1e7 variants)"""
+    global _BETA_TABLE
+    if _BETA_TABLE is None:
+        from scipy.stats import beta
+        f = np.concatenate([[0.0], np.logspace(-9, 0, 4096)])
+        _BETA_TABLE = (beta.cdf(f, 0.15, 4.0), f)
+    return _BETA_TABLE
 
 
 def dosage_codes(n: int, first_variant: int, p: int, seed: int = BASE_SEED,
