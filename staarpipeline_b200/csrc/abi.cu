@@ -560,7 +560,7 @@ int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t st
     if (ns.n != n) { set_error("packed score: n = %lld does not match the null model (n = %lld)", (long long)n, (long long)ns.n); return STAAR_ERR_ARG; }
     if (stride % 16 != 0 || stride < (size_t)((n + 3) / 4)) { set_error("packed stride must be a multiple of 16 and >= ceil(n/4)"); return STAAR_ERR_ARG; }
     if (!ns.sliced) STAAR_TRY(build_sliced_operand(ctx, nullptr));
-    if (!ns.sliced) { set_error("packed score supports at most %d fixed-effect columns (q = %lld)", kColsPerSlice - 1, (long long)ns.q); return STAAR_ERR_ARG; }
+    if (!ns.sliced) { set_error("packed score supports at most %d fixed-effect columns (q = %lld)", kColsPerSlice - 2, (long long)ns.q); return STAAR_ERR_ARG; }
     if (p == 0) return STAAR_OK;
     // scratch: flip (p i32) | mu (p) | quad (p) | Sm (16p) | hi (16p i64) | lo (16p i64)
     const size_t pi = (size_t)((p + 1) / 2 * 2);
@@ -627,7 +627,7 @@ int staar_individual_analysis_chunk(staar_ctx *ctx, const double *G, int64_t n, 
     if (p == 0) return STAAR_OK;
     const size_t stride = staar_packed_stride(n);
     bool packed_ok = false;
-    if (ns.q + 1 <= kColsPerSlice) {
+    if (ns.q + 2 <= kColsPerSlice) {
         STAAR_TRY(pinned_reserve(ctx, stride * (size_t)p));
         packed_ok = staar_pack_dosage_host(G, n, p, static_cast<uint8_t *>(ctx->pinned), stride, threads) == STAAR_OK;
     }

@@ -53,9 +53,19 @@ struct NullSparse {
     int32_t *col = nullptr;       // nnz
     double *val = nullptr;        // nnz
     double *diag = nullptr;       // n   (Sigma_i[j,j])
-    uint32_t *has_off = nullptr;  // bit j: row j has off-diagonal entries
+    // per-sample record for the carrier scan: {Sigma_i[j,j], first off-diagonal entry, #off-diagonal entries}
+    struct alignas(16) SampleInfo { double diag; uint32_t off_start, off_count; };
+    struct alignas(16) OffEntry { double val; int32_t col; int32_t pad; };
+    SampleInfo *sinfo = nullptr;  // n
+    OffEntry *off_ent = nullptr;  // nnz_offdiag
+    // carrier scan of the packed path: 2-bit mask (11 = sample has kinship off-diagonals) in the genotype packing,
+    // and one 64-byte record per sample with up to 5 inline off-diagonal entries (count > 5: fall back to off_ent)
+    struct alignas(64) RelRecord { double val[5]; int32_t col[5]; int32_t count; };
+    uint8_t *relmask = nullptr;   // packed_stride(n) bytes
+    RelRecord *rel = nullptr;     // n (only when nnz_offdiag > 0)
     double *SX = nullptr;         // Sigma_iX, n x q column-major (kept for the conditional test)
-    // Y = [residuals | Sigma_iX], row-major n x ldY (ldY = 16-padded 1+q), FP64
+    // Y = [residuals | Sigma_iX | diag(Sigma_i)], row-major n x ldY (ldY = 8-padded 2+q), FP64.  The last column
+    // rides along in the packed contraction (sum_j g_j s_jj); the FP64 kernels use the first 1+q columns only.
     int ldY = 0;
     double *Y = nullptr;
     double *cov = nullptr;        // q x q column-major

@@ -156,13 +156,9 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
         for (int mt = 0; mt < kMT; mt++)
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                uint4 w = make_uint4(0, 0, 0, 0);
-                if (rok[mt][h] && off + 16 <= stride) {
-                    w = ldg_nc_u4(rowp[mt][h] + off);
-                    // g -> 2-g in the bit domain; codes flipped beyond sample n-1 meet all-zero digits
-                    if (rflip[mt][h]) { w.x = flip_word(w.x); w.y = flip_word(w.y); w.z = flip_word(w.z); w.w = flip_word(w.w); }
-                }
-                dst[mt][h] = w;
+                // raw codes only: touching the loaded value here would stall on the prefetch
+                if (rok[mt][h] && off + 16 <= stride) dst[mt][h] = ldg_nc_u4(rowp[mt][h] + off);
+                else dst[mt][h] = make_uint4(0, 0, 0, 0);
             }
     };
 
@@ -174,8 +170,20 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
 #pragma unroll
             for (int e = 0; e < 4; e++) acc[mt][j][e] = 0;
 
+    // g -> 2-g in the bit domain once a prefetched chunk becomes current; codes flipped beyond sample n-1 (and in
+    // the zero rows of out-of-range variants) meet all-zero digits
+    auto adopt = [&](uint4 (&cur)[kMT][2], const uint4 (&nxt)[kMT][2]) {
+#pragma unroll
+        for (int mt = 0; mt < kMT; mt++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint4 w = nxt[mt][h];
+                if (rflip[mt][h]) { w.x = flip_word(w.x); w.y = flip_word(w.y); w.z = flip_word(w.z); w.w = flip_word(w.w); }
+                cur[mt][h] = w;
+            }
+    };
     uint4 Acur[kMT][2], Anext[kMT][2];
-    if (nkc > 0) load_A(kc_begin, Acur);
+    if (nkc > 0) { load_A(kc_begin, Anext); adopt(Acur, Anext); }
 
     for (int64_t it = 0; it < nkc; it++) {
         const int stage = (int)(it % kStages);
@@ -212,8 +220,7 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
         // release the stage back to the producer
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
-#pragma unroll
-        for (int mt = 0; mt < kMT; mt++) { Acur[mt][0] = Anext[mt][0]; Acur[mt][1] = Anext[mt][1]; }
+        if (it + 1 < nkc) adopt(Acur, Anext);
     }
 
     // recombine the 7 digit sums per (variant, column) in 64-bit integers: X = hi * 256^3 + lo
@@ -288,7 +295,7 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
 {
     NullSparse &ns = ctx->ns;
     const int64_t n = ns.n;
-    const int ncol = (int)ns.q + 1, ldY = ns.ldY;
+    const int ncol = (int)ns.q + 2, ldY = ns.ldY;      // [r | Sigma_iX | diag(Sigma_i)]
     ns.sliced = false;
     cudaFree(ns.Yfrag); cudaFree(ns.col_scale);
     ns.Yfrag = nullptr; ns.col_scale = nullptr;

@@ -56,7 +56,7 @@ void NullSparse::release()
     if (owned) {
         cudaFree(row_ptr); cudaFree(col); cudaFree(val); cudaFree(SX); cudaFree(cov);
     }
-    cudaFree(diag); cudaFree(has_off); cudaFree(Y); cudaFree(Yfrag); cudaFree(col_scale);
+    cudaFree(diag); cudaFree(sinfo); cudaFree(off_ent); cudaFree(relmask); cudaFree(rel); cudaFree(Y); cudaFree(Yfrag); cudaFree(col_scale);
     *this = NullSparse();
 }
 void NullDense::release()
@@ -119,7 +119,6 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
     std::vector<double> val(nnz);
     std::vector<int64_t> pos(row_ptr.begin(), row_ptr.end() - 1);
     std::vector<double> diag(n, 0.0);
-    std::vector<uint32_t> has_off((n + 31) / 32, 0u);
     int64_t nnz_off = 0;
     for (int64_t c = 0; c < n; c++)
         for (uint64_t e = Sc[c]; e < Sc[c + 1]; e++) {
@@ -127,20 +126,52 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
             const int64_t d = pos[r]++;
             col[d] = (int32_t)c; val[d] = Sv[e];
             if (r == c) diag[r] += Sv[e];
-            else if (Sv[e] != 0.0) { has_off[r >> 5] |= 1u << (r & 31); nnz_off++; }
+            else if (Sv[e] != 0.0) nnz_off++;
         }
-    const int ldY = (int)(((1 + q) + 7) / 8 * 8);
+    std::vector<NullSparse::SampleInfo> sinfo(n);
+    std::vector<NullSparse::OffEntry> off_ent(std::max<int64_t>(nnz_off, 1));
+    {
+        int64_t o = 0;
+        for (int64_t r = 0; r < n; r++) {
+            sinfo[r].diag = diag[r]; sinfo[r].off_start = (uint32_t)o;
+            for (int64_t e = row_ptr[r]; e < row_ptr[r + 1]; e++)
+                if (col[e] != r && val[e] != 0.0) { off_ent[o].val = val[e]; off_ent[o].col = col[e]; off_ent[o].pad = 0; o++; }
+            sinfo[r].off_count = (uint32_t)(o - sinfo[r].off_start);
+        }
+    }
+    const int ldY = (int)(((2 + q) + 7) / 8 * 8);
     std::vector<double> Y((size_t)n * ldY, 0.0);
     for (int64_t j = 0; j < n; j++) {
         Y[(size_t)j * ldY] = res[j];
         for (int64_t c = 0; c < q; c++) Y[(size_t)j * ldY + 1 + c] = SX[j + c * n];
+        Y[(size_t)j * ldY + 1 + q] = diag[j];
     }
     ns.n = n; ns.q = q; ns.nnz = nnz; ns.nnz_offdiag = nnz_off; ns.ldY = ldY; ns.owned = true;
     STAAR_CUDA(cudaMalloc(&ns.row_ptr, sizeof(int64_t) * (n + 1)));
     STAAR_CUDA(cudaMalloc(&ns.col, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
     STAAR_CUDA(cudaMalloc(&ns.val, sizeof(double) * std::max<int64_t>(nnz, 1)));
     STAAR_CUDA(cudaMalloc(&ns.diag, sizeof(double) * n));
-    STAAR_CUDA(cudaMalloc(&ns.has_off, sizeof(uint32_t) * has_off.size()));
+    // relatives mask + inline records for the packed carrier scan
+    const size_t pstride = staar_packed_stride(n);
+    std::vector<uint8_t> relmask(pstride, 0);
+    std::vector<NullSparse::RelRecord> rel;
+    if (nnz_off > 0) {
+        rel.resize(n);
+        for (int64_t r = 0; r < n; r++) {
+            NullSparse::RelRecord &rr = rel[r];
+            memset(&rr, 0, sizeof rr);
+            rr.count = (int32_t)sinfo[r].off_count;
+            if (rr.count > 0) relmask[r >> 2] |= (uint8_t)(3u << (2 * (r & 3)));
+            if (rr.count <= 5)
+                for (int t = 0; t < rr.count; t++) { rr.val[t] = off_ent[sinfo[r].off_start + t].val; rr.col[t] = off_ent[sinfo[r].off_start + t].col; }
+        }
+        STAAR_CUDA(cudaMalloc(&ns.rel, sizeof(NullSparse::RelRecord) * n));
+        STAAR_CUDA(cudaMemcpyAsync(ns.rel, rel.data(), sizeof(NullSparse::RelRecord) * n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    STAAR_CUDA(cudaMalloc(&ns.relmask, pstride));
+    STAAR_CUDA(cudaMemcpyAsync(ns.relmask, relmask.data(), pstride, cudaMemcpyHostToDevice, ctx->stream));
+    STAAR_CUDA(cudaMalloc(&ns.sinfo, sizeof(NullSparse::SampleInfo) * n));
+    STAAR_CUDA(cudaMalloc(&ns.off_ent, sizeof(NullSparse::OffEntry) * off_ent.size()));
     STAAR_CUDA(cudaMalloc(&ns.SX, sizeof(double) * std::max<int64_t>(n * q, 1)));
     STAAR_CUDA(cudaMalloc(&ns.cov, sizeof(double) * std::max<int64_t>(q * q, 1)));
     STAAR_CUDA(cudaMalloc(&ns.Y, sizeof(double) * (size_t)n * ldY));
@@ -149,7 +180,8 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
     STAAR_CUDA(cudaMemcpyAsync(ns.col, col.data(), sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, st));
     STAAR_CUDA(cudaMemcpyAsync(ns.val, val.data(), sizeof(double) * nnz, cudaMemcpyHostToDevice, st));
     STAAR_CUDA(cudaMemcpyAsync(ns.diag, diag.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    STAAR_CUDA(cudaMemcpyAsync(ns.has_off, has_off.data(), sizeof(uint32_t) * has_off.size(), cudaMemcpyHostToDevice, st));
+    STAAR_CUDA(cudaMemcpyAsync(ns.sinfo, sinfo.data(), sizeof(NullSparse::SampleInfo) * n, cudaMemcpyHostToDevice, st));
+    STAAR_CUDA(cudaMemcpyAsync(ns.off_ent, off_ent.data(), sizeof(NullSparse::OffEntry) * off_ent.size(), cudaMemcpyHostToDevice, st));
     STAAR_CUDA(cudaMemcpyAsync(ns.SX, SX, sizeof(double) * n * q, cudaMemcpyHostToDevice, st));
     STAAR_CUDA(cudaMemcpyAsync(ns.cov, cov, sizeof(double) * q * q, cudaMemcpyHostToDevice, st));
     STAAR_CUDA(cudaMemcpyAsync(ns.Y, Y.data(), sizeof(double) * (size_t)n * ldY, cudaMemcpyHostToDevice, st));
