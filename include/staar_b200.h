@@ -182,6 +182,13 @@ int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t st
 int staar_ctx_set_profiling(staar_ctx *ctx, int on);
 int staar_ctx_last_stage_ms(staar_ctx *ctx, float ms[3]);
 
+/* Test hook: intermediates of the LAST staar_packed_score_device call, copied to host arrays (any may be NULL):
+ * hi/lo (p x 16 int64: exact integer contraction, X = hi*2^24 + lo in units of col_scale[c]; slot 15 = hom-minor
+ * sum against diag(Sigma_i)), Sm (p x 16 sums over missing samples), quad (kinship off-diagonal part), mu, flip,
+ * col_scale (16). */
+int staar_packed_debug_dump(staar_ctx *ctx, int64_t p, long long *hi, long long *lo, double *Sm, double *quad,
+                            double *mu, int32_t *flip, double *col_scale);
+
 /* Same, host buffers (packed host columns in, 7 host arrays out); H2D/D2H inside. */
 int staar_packed_score_host(staar_ctx *ctx, const uint8_t *packed, size_t stride_bytes, int64_t n, int64_t p,
                             int impute, double *AF, double *MAF, double *Score, double *Score_se,

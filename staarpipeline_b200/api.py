@@ -303,6 +303,16 @@ class Context:
                    *[_p(a) for a in o])
         return dict(zip(("AF", "MAF", "Score", "Score_se", "pvalue_log", "Est", "Est_se"), o))
 
+    def packed_debug_dump(self, p: int):
+        """intermediates of the last packed score call (test hook)"""
+        hi, lo = np.zeros((p, 16), dtype=np.int64), np.zeros((p, 16), dtype=np.int64)
+        Sm, quad, mu = np.zeros((p, 16)), np.zeros(p), np.zeros(p)
+        flip, scale = np.zeros(p, dtype=np.int32), np.zeros(16)
+        i64 = C.POINTER(C.c_longlong)
+        self._call("staar_packed_debug_dump", C.c_int64(p), hi.ctypes.data_as(i64), lo.ctypes.data_as(i64), _p(Sm),
+                   _p(quad), _p(mu), flip.ctypes.data_as(C.POINTER(C.c_int32)), _p(scale))
+        return dict(hi=hi, lo=lo, Sm=Sm, quad=quad, mu=mu, flip=flip, col_scale=scale)
+
     def packed_score_device(self, d_packed: int, stride: int, n: int, p: int, impute: int, d_out7):
         """device pointers (ints): packed columns and 7 output arrays; asynchronous on the context stream."""
         self._call("staar_packed_score_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n), C.c_int64(p),

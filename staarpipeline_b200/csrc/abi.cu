@@ -560,7 +560,7 @@ int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t st
     if (ns.n != n) { set_error("packed score: n = %lld does not match the null model (n = %lld)", (long long)n, (long long)ns.n); return STAAR_ERR_ARG; }
     if (stride % 16 != 0 || stride < (size_t)((n + 3) / 4)) { set_error("packed stride must be a multiple of 16 and >= ceil(n/4)"); return STAAR_ERR_ARG; }
     if (!ns.sliced) STAAR_TRY(build_sliced_operand(ctx, nullptr));
-    if (!ns.sliced) { set_error("packed score supports at most %d fixed-effect columns (q = %lld)", kColsPerSlice - 2, (long long)ns.q); return STAAR_ERR_ARG; }
+    if (!ns.sliced) { set_error("packed score supports at most %d fixed-effect columns (q = %lld)", kColsPerSlice - 3, (long long)ns.q); return STAAR_ERR_ARG; }
     if (p == 0) return STAAR_OK;
     // scratch: flip (p i32) | mu (p) | quad (p) | Sm (16p) | hi (16p i64) | lo (16p i64)
     const size_t pi = (size_t)((p + 1) / 2 * 2);
@@ -577,6 +577,28 @@ int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t st
     STAAR_TRY(launch_finalize_packed(ctx, p, dmu, dquad, dSm, dhi, dlo, d_Score, d_Score_se, d_pl, d_Est, d_Est_se));
     if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
     return STAAR_OK;      // asynchronous on ctx->stream: the caller times with events / staar_ctx_synchronize
+}
+
+// Test hook: the intermediate arrays of the LAST staar_packed_score_device call (any pointer may be NULL).
+// hi/lo: p x 16 exact integer contraction results (X = hi * 2^24 + lo in units of col_scale[c]; slot 15 = hom-minor
+// sum against diag(Sigma_i)); Sm: p x 16 column sums over missing samples; quad: kinship off-diagonal part.
+int staar_packed_debug_dump(staar_ctx *ctx, int64_t p, long long *hi, long long *lo, double *Sm, double *quad,
+                            double *mu, int32_t *flip, double *col_scale)
+{
+    CHECK_CTX(ctx);
+    const size_t pi = (size_t)((p + 1) / 2 * 2);
+    int32_t *dflip = ctx->tmp.as<int32_t>();
+    double *dmu = reinterpret_cast<double *>(dflip + pi), *dquad = dmu + p, *dSm = dquad + p;
+    long long *dhi = reinterpret_cast<long long *>(dSm + 16 * p), *dlo = dhi + 16 * p;
+    STAAR_TRY(sync(ctx));
+    STAAR_TRY(d2h(ctx, hi, dhi, sizeof(long long) * 16 * p));
+    STAAR_TRY(d2h(ctx, lo, dlo, sizeof(long long) * 16 * p));
+    STAAR_TRY(d2h(ctx, Sm, dSm, sizeof(double) * 16 * p));
+    STAAR_TRY(d2h(ctx, quad, dquad, sizeof(double) * p));
+    STAAR_TRY(d2h(ctx, mu, dmu, sizeof(double) * p));
+    STAAR_TRY(d2h(ctx, flip, dflip, sizeof(int32_t) * p));
+    STAAR_TRY(d2h(ctx, col_scale, ctx->ns.col_scale, sizeof(double) * kColsPerSlice));
+    return sync(ctx);
 }
 
 int staar_ctx_set_profiling(staar_ctx *ctx, int on)
@@ -627,7 +649,7 @@ int staar_individual_analysis_chunk(staar_ctx *ctx, const double *G, int64_t n, 
     if (p == 0) return STAAR_OK;
     const size_t stride = staar_packed_stride(n);
     bool packed_ok = false;
-    if (ns.q + 2 <= kColsPerSlice) {
+    if (ns.q + 2 <= kColsPerSlice - 1) {
         STAAR_TRY(pinned_reserve(ctx, stride * (size_t)p));
         packed_ok = staar_pack_dosage_host(G, n, p, static_cast<uint8_t *>(ctx->pinned), stride, threads) == STAAR_OK;
     }

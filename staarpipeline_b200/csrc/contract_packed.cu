@@ -14,7 +14,8 @@
 // only rounding left is the 2^-54 truncation of Y (relative to the column maximum) — far inside the 1e-10 budget.
 // The flip to the minor allele (decided by scan_packed.cu) is applied to the 2-bit codes in registers.
 //
-// Kernel: M = variants (2 m16 tiles per warp, 8 warps per CTA), N = 7 slices x 16 columns = 14 n8 tiles,
+// Kernel: M = variants (2 m16 tiles per warp, 8 warps per CTA), N = 7 slices x 16 columns = 14 n8 tiles (+1 tile:
+// the hom-minor indicator [g == 2] against the 7 digit slices of diag(Sigma_i), for sum_j s_jj g_j^2),
 // K = samples, mma.sync.m16n8k32.s8 (measured 1.14 POP/s on B200).  The digit operand is pre-arranged in
 // fragment-major order so a k-chunk (256 samples, 28 KiB) is ONE contiguous bulk copy: it is streamed from L2 into
 // a 4-stage shared-memory ring by cp.async.bulk (TMA 1-D) completing on mbarriers, and read back with conflict-free
@@ -162,13 +163,16 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
             }
     };
 
-    int acc[kMT][kNT][4];
+    int acc[kMT][kNT][4], acc2[kMT][4];      // acc2: [code == 2] x the 7 digit slices of diag(Sigma_i)
 #pragma unroll
-    for (int mt = 0; mt < kMT; mt++)
+    for (int mt = 0; mt < kMT; mt++) {
 #pragma unroll
         for (int j = 0; j < kNT; j++)
 #pragma unroll
             for (int e = 0; e < 4; e++) acc[mt][j][e] = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) acc2[mt][e] = 0;
+    }
 
     // g -> 2-g in the bit domain once a prefetched chunk becomes current; codes flipped beyond sample n-1 (and in
     // the zero rows of out-of-range variants) meet all-zero digits
@@ -206,7 +210,7 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
                 a[mt][2] = fields_to_s8(w0, f + 1);  // row g,   k = 16 + 4t + y
                 a[mt][3] = fields_to_s8(w1, f + 1);  // row g+8, k = 16 + 4t + y
             }
-            const uint4 *bs = reinterpret_cast<const uint4 *>(sb + (size_t)s * (kNT * 256));
+            const uint4 *bs = reinterpret_cast<const uint4 *>(sb + (size_t)s * kStepBytesB);
 #pragma unroll
             for (int jj = 0; jj < kNT / 2; jj++) {
                 const uint4 b = bs[jj * 32 + lane];   // n-tiles 2jj (b.x,b.y) and 2jj+1 (b.z,b.w)
@@ -216,6 +220,12 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
                     imma16832(acc[mt][2 * jj + 1], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b.z, b.w);
                 }
             }
+            // hom-minor indicator (g^2 - g = 2 [g == 2]) against the digit slices of diag(Sigma_i): one more n-tile
+            const uint2 b14 = reinterpret_cast<const uint2 *>(sb + (size_t)s * kStepBytesB + (kNT / 2) * 512)[lane];
+#pragma unroll
+            for (int mt = 0; mt < kMT; mt++)
+                imma16832(acc2[mt], (a[mt][0] >> 1) & 0x01010101u, (a[mt][1] >> 1) & 0x01010101u,
+                          (a[mt][2] >> 1) & 0x01010101u, (a[mt][3] >> 1) & 0x01010101u, b14.x, b14.y);
         }
         // release the stage back to the producer
         __syncwarp();
@@ -228,6 +238,25 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
     for (int mt = 0; mt < kMT; mt++)
 #pragma unroll
         for (int h = 0; h < 2; h++) {
+            // hom-minor tile: lane t holds digit slices 2t, 2t+1 of row (h ? g+8 : g); gather the quad's partials
+            {
+                const long long part = (long long)acc2[mt][h * 2] * 256 + (long long)acc2[mt][h * 2 + 1];
+                const int q0 = lane & ~3;
+                const long long p0 = __shfl_sync(0xffffffffu, part, q0), p1 = __shfl_sync(0xffffffffu, part, q0 + 1);
+                const long long p2 = __shfl_sync(0xffffffffu, part, q0 + 2);
+                const long long d6 = __shfl_sync(0xffffffffu, (long long)acc2[mt][h * 2], q0 + 3);
+                if (t == 0 && rok[mt][h]) {
+                    const int64_t v = v0 + mt * 16 + h * 8 + g;
+                    const long long hi2 = p0 * 65536 + p1, lo2 = p2 * 256 + d6;
+                    if (use_atomics) {
+                        atomicAdd(reinterpret_cast<unsigned long long *>(out_hi + v * 16 + 15), (unsigned long long)hi2);
+                        atomicAdd(reinterpret_cast<unsigned long long *>(out_lo + v * 16 + 15), (unsigned long long)lo2);
+                    } else {
+                        out_hi[v * 16 + 15] = hi2;
+                        out_lo[v * 16 + 15] = lo2;
+                    }
+                }
+            }
             if (!rok[mt][h]) continue;
             const int64_t v = v0 + mt * 16 + h * 8 + g;
 #pragma unroll
@@ -235,6 +264,7 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int c = cg * 8 + 2 * t + e;
+                    if (c == 15) continue;                 // slot 15 carries the hom-minor sum written above
                     long long hi = 0, lo = 0;
 #pragma unroll
                     for (int sl = 0; sl < 4; sl++) hi = hi * 256 + (long long)acc[mt][2 * sl + cg][h * 2 + e];
@@ -299,7 +329,7 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
     ns.sliced = false;
     cudaFree(ns.Yfrag); cudaFree(ns.col_scale);
     ns.Yfrag = nullptr; ns.col_scale = nullptr;
-    if (ncol > kColsPerSlice) return STAAR_OK;      // wider designs take the FP64 path
+    if (ncol > kColsPerSlice - 1) return STAAR_OK;  // wider designs take the FP64 path (slot 15 is reserved)
     std::vector<double> pulled;
     if (!hY) {                                      // current operand (incl. an updated residual column) from HBM
         pulled.resize((size_t)n * ldY);
@@ -338,7 +368,7 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
                 for (int sl = 0; sl < kSlices; sl++) {
                     const int j = 2 * sl + cg, jj = j / 2, within = j % 2;
                     for (int t = 0; t < 4; t++) {
-                        int8_t *dst = frag.data() + (size_t)kc * kChunkBytesB + (size_t)s * (kNT * 256) +
+                        int8_t *dst = frag.data() + (size_t)kc * kChunkBytesB + (size_t)s * kStepBytesB +
                                       ((size_t)jj * 32 + (4 * g + t)) * 16 + within * 8;
                         for (int half = 0; half < 2; half++)
                             for (int y = 0; y < 4; y++) {
@@ -347,6 +377,21 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
                             }
                     }
                 }
+        if (c == ncol - 1) {
+            // extra n-tile: column g (0..6) = digit slice g of diag(Sigma_i), column 7 = 0; same sample map
+            for (int64_t kc = 0; kc < n_chunks; kc++)
+                for (int s = 0; s < 8; s++)
+                    for (int sl = 0; sl < kSlices; sl++)
+                        for (int t = 0; t < 4; t++) {
+                            int8_t *dst = frag.data() + (size_t)kc * kChunkBytesB + (size_t)s * kStepBytesB +
+                                          (size_t)(kNT / 2) * 512 + (size_t)(4 * sl + t) * 8;
+                            for (int half = 0; half < 2; half++)
+                                for (int y = 0; y < 4; y++) {
+                                    const int64_t smp = kc * 256 + 64 * t + 16 * (s / 2) + 4 * y + 2 * (s % 2) + half;
+                                    dst[half * 4 + y] = smp < n ? digits[(size_t)smp * kSlices + sl] : (int8_t)0;
+                                }
+                        }
+        }
     }
     STAAR_CUDA(cudaMalloc(&ns.Yfrag, frag.size()));
     STAAR_CUDA(cudaMalloc(&ns.col_scale, sizeof(double) * kColsPerSlice));

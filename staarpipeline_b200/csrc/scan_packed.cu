@@ -33,7 +33,8 @@ struct ScanParams {
 };
 
 constexpr int kScanWarps = 8;
-constexpr int kListCap = 1024;          // genotypes scanned per warp iteration (32 lanes x 8 bytes x 4)
+constexpr int kCarrierCap = 1024 + 32;  // related carriers found in one iteration (<= 1024) + a carried remainder (< 32)
+constexpr int kPairCap = 32 * 5 + 32;   // pairs expanded from one round of 32 carriers (<= 160) + remainder (< 32)
 
 __device__ __forceinline__ double code_value(uint32_t code, double mu)
 {
@@ -50,22 +51,24 @@ __device__ __forceinline__ double lookup_value(const uint8_t *colp, int64_t k, b
 
 // One warp per variant, two sweeps over the 2-bit column.
 //  sweep 1: popcounts -> AF / MAF / flip / imputation value.
-//  sweep 2: only the genotypes the integer contraction cannot account for are visited:
-//            code 2 after the flip (hom-minor: g^2 = g + 2, contributes 2 s_jj to the quadratic form),
-//            code 3 (missing: column sums of Y for the imputation correction),
+//  sweep 2: only what the integer contraction cannot account for is visited:
+//            code 3 (missing): column sums of Y for the imputation correction;
 //            carriers whose sample has kinship off-diagonals (relmask): sum_k s_jk g_j g_k.
-//           They are compacted (bit tricks only) into a per-warp shared-memory list, then processed lane-parallel
-//           so the latency-bound gathers have 32 independent loads in flight per instruction.
-// The diagonal part sum_j s_jj g_j of g' Sigma_i g rides in the tensor-core contraction as an extra column of Y.
+//           Related carriers are compacted (bit tricks only) into a per-warp shared-memory list; full rounds of 32
+//           carriers fetch their row location and expand into a list of (carrier, relative) PAIRS; full rounds of
+//           32 pairs then do the latency-bound gathers (kinship entry -> relative's genotype byte) with every
+//           lane busy.  Remainders (< 32) are carried to the next iteration and flushed at the end of the column.
+// The diagonal of g' Sigma_i g rides in the tensor-core contraction (column q+1 of Y and the hom-minor tile).
 template <bool HAS_OFF>
 __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams P)
 {
-    __shared__ uint32_t s_list[kScanWarps][kListCap];
+    __shared__ uint32_t s_car[HAS_OFF ? kScanWarps : 1][kCarrierCap];
+    __shared__ uint32_t s_pair[HAS_OFF ? kScanWarps : 1][kPairCap];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int nvec8 = (int)(P.stride >> 3);
-    uint32_t *list = s_list[wib];
+    uint32_t *car = s_car[HAS_OFF ? wib : 0], *pair = s_pair[HAS_OFF ? wib : 0];
     const uint2 *rmask = reinterpret_cast<const uint2 *>(P.relmask);
     for (int64_t i = warp; i < P.p; i += nwarps) {
         const uint8_t *colp = P.packed + (size_t)i * P.stride;
@@ -74,6 +77,54 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams
         const bool flip = vf.flip != 0;
         const double mu = vf.mu;
         double quad = 0.0, sm = 0.0;           // sm: lane c (< ncol) accumulates sum over missing j of Y[j][c]
+        int ncar = 0, npair = 0;               // warp-uniform fill levels of the two lists
+
+        // 32 pairs: kinship entry -> relative's genotype -> accumulate
+        auto pair_round = [&](int first) {
+            const uint32_t pe = pair[first + lane];
+            const NullSparse::OffEntry oe = P.off_ent[pe >> 2];
+            quad += code_value(pe & 3u, mu) * oe.val * lookup_value(colp, oe.col, flip, mu);
+        };
+        // 32 carriers: row location -> append one pair entry per kinship off-diagonal
+        auto carrier_round = [&](int first, int count) {
+            uint32_t ce = 0u; uint32_t start = 0u; int cnt = 0;
+            if (lane < count) {
+                ce = car[first + lane];
+                const NullSparse::SampleInfo si = P.sinfo[ce >> 2];
+                start = si.off_start; cnt = (int)si.off_count;
+                if (cnt > 5) {                 // unusually large family: finish this carrier in place
+                    double s = 0.0;
+                    for (int t = 0; t < cnt; t++) {
+                        const NullSparse::OffEntry oe = P.off_ent[start + t];
+                        s += oe.val * lookup_value(colp, oe.col, flip, mu);
+                    }
+                    quad += code_value(ce & 3u, mu) * s;
+                    cnt = 0;
+                }
+            }
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            int pos = npair + incl - cnt;
+            for (int t = 0; t < cnt; t++) pair[pos + t] = ((start + t) << 2) | (ce & 3u);
+            npair += total;
+            __syncwarp();
+            int done = 0;
+            while (npair - done >= 32) { pair_round(done); done += 32; }
+            if (done) {                        // move the remainder (< 32 entries) to the front
+                const int rem = npair - done;
+                const uint32_t keep = lane < rem ? pair[done + lane] : 0u;
+                __syncwarp();
+                if (lane < rem) pair[lane] = keep;
+                npair = rem;
+                __syncwarp();
+            }
+        };
+
         const uint2 *vecs = reinterpret_cast<const uint2 *>(colp);
         for (int k0 = 0; k0 < nvec8; k0 += 32) {
             const int k = k0 + lane;
@@ -82,10 +133,11 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams
                 q2 = __ldg(vecs + k);
                 if (HAS_OFF) r2 = __ldg(rmask + k);
             }
-            uint32_t w[2] = {q2.x, q2.y}, sel[2];
+            uint32_t w[2] = {q2.x, q2.y}, sel[2], mis[2];
             const uint32_t rm[2] = {r2.x, r2.y};
             const int64_t base = (int64_t)k * 32;                   // first sample of this lane's 8 bytes
             int cnt = 0;
+            bool any_missing = false;
 #pragma unroll
             for (int wi = 0; wi < 2; wi++) {
                 if (flip) {
@@ -93,65 +145,73 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams
                     const int64_t valid = P.n - (base + wi * 16);  // padding codes would flip to 2
                     if (valid < 16) w[wi] &= (valid <= 0) ? 0u : ((1u << (2 * valid)) - 1u);
                 }
-                const uint32_t hi = (w[wi] >> 1) & 0x55555555u;                      // codes 2 and 3
-                const uint32_t nz = (w[wi] | (w[wi] >> 1)) & 0x55555555u;            // any carrier
-                sel[wi] = hi | (nz & rm[wi]);                                         // one bit per selected sample
+                const uint32_t lo = w[wi] & 0x55555555u, hi = (w[wi] >> 1) & 0x55555555u;
+                mis[wi] = lo & hi;                                                    // code 3
+                // related carriers; a missing sample counts only if its imputed value is non-zero
+                sel[wi] = HAS_OFF ? ((lo | hi) & rm[wi] & ~(mu == 0.0 ? mis[wi] : 0u)) : 0u;
                 cnt += __popc(sel[wi]);
+                any_missing |= mis[wi] != 0u;
             }
-            if (!__any_sync(0xffffffffu, cnt != 0)) continue;
-            int incl = cnt;
+            // ---- missing entries (rare): all lanes cooperate on the Y row (lane c adds column c)
+            if (__any_sync(0xffffffffu, any_missing)) {
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            int pos = incl - cnt;
-#pragma unroll
-            for (int wi = 0; wi < 2; wi++) {
-                uint32_t ss = sel[wi];
-                while (ss) {
-                    const int b = __ffs(ss) - 1;                     // even bit position = 2 * field
-                    ss &= ss - 1;
-                    const uint32_t code = (w[wi] >> b) & 3u;
-                    list[pos++] = ((uint32_t)(base + wi * 16 + (b >> 1)) << 2) | code;
-                }
-            }
-            __syncwarp();
-            for (int e0 = 0; e0 < total; e0 += 32) {
-                const int e = e0 + lane;
-                const bool live = e < total;
-                const uint32_t ent = live ? list[e] : 0u;
-                const uint32_t code = ent & 3u;
-                const int64_t j = ent >> 2;
-                if (live) {
-                    const double v = code_value(code, mu);
-                    if (code == 2u) quad += 2.0 * P.diag[j];                       // g^2 - g for g = 2
-                    if (HAS_OFF && v != 0.0) {
-                        const bool related = (__ldg(P.relmask + (j >> 2)) >> (2 * (j & 3))) & 1u;
-                        if (related) {
-                            const NullSparse::RelRecord rr = P.rel[j];
-                            double s = 0.0;
-                            if (rr.count <= 5) {
-#pragma unroll
-                                for (int t = 0; t < 5; t++)
-                                    if (t < rr.count) s += rr.val[t] * lookup_value(colp, rr.col[t], flip, mu);
-                            } else {
-                                const NullSparse::SampleInfo si = P.sinfo[j];
-                                const NullSparse::OffEntry *oe = P.off_ent + si.off_start;
-                                for (uint32_t t = 0; t < si.off_count; t++) s += oe[t].val * lookup_value(colp, oe[t].col, flip, mu);
-                            }
-                            quad += v * s;
+                for (int wi = 0; wi < 2; wi++) {
+                    uint32_t mine = mis[wi];
+                    uint32_t who = __ballot_sync(0xffffffffu, mine != 0u);
+                    while (who) {
+                        const int src = __ffs(who) - 1;
+                        who &= who - 1;
+                        uint32_t mw = __shfl_sync(0xffffffffu, mine, src);
+                        const int64_t b0 = __shfl_sync(0xffffffffu, base, src) + wi * 16;
+                        while (mw) {
+                            const int b = __ffs(mw) - 1;
+                            mw &= mw - 1;
+                            if (lane < P.ncol) sm += P.Y[(b0 + (b >> 1)) * P.ldY + lane];
                         }
                     }
                 }
-                // missing entries: all lanes cooperate on the Y row (lane c adds column c)
-                uint32_t mm = __ballot_sync(0xffffffffu, live && code == 3u);
-                while (mm) {
-                    const int src = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    const int64_t jm = __shfl_sync(0xffffffffu, ent, src) >> 2;
-                    if (lane < P.ncol) sm += P.Y[jm * P.ldY + lane];
+            }
+            if (!HAS_OFF) continue;
+            // ---- related carriers: append to the carrier list, then run full rounds
+            if (__any_sync(0xffffffffu, cnt != 0)) {
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                int pos = ncar + incl - cnt;
+#pragma unroll
+                for (int wi = 0; wi < 2; wi++) {
+                    uint32_t ss = sel[wi];
+                    while (ss) {
+                        const int b = __ffs(ss) - 1;                 // even bit position = 2 * field
+                        ss &= ss - 1;
+                        car[pos++] = ((uint32_t)(base + wi * 16 + (b >> 1)) << 2) | ((w[wi] >> b) & 3u);
+                    }
+                }
+                ncar += total;
+                __syncwarp();
+                int done = 0;
+                while (ncar - done >= 32) { carrier_round(done, 32); done += 32; }
+                if (done) {
+                    const int rem = ncar - done;
+                    const uint32_t keep = lane < rem ? car[done + lane] : 0u;
+                    __syncwarp();
+                    if (lane < rem) car[lane] = keep;
+                    ncar = rem;
+                    __syncwarp();
+                }
+            }
+        }
+        if (HAS_OFF) {                         // flush the remainders
+            if (ncar > 0) carrier_round(0, ncar);
+            if (npair > 0) {
+                const uint32_t pe = lane < npair ? pair[lane] : 0u;
+                if (lane < npair) {
+                    const NullSparse::OffEntry oe = P.off_ent[pe >> 2];
+                    quad += code_value(pe & 3u, mu) * oe.val * lookup_value(colp, oe.col, flip, mu);
                 }
             }
             __syncwarp();
@@ -190,11 +250,14 @@ __global__ void __launch_bounds__(128) finalize_packed_kernel(FinParams P)
             tct += xb * L[1 + b];
         }
         // g' Sigma_i g = sum_j s_jj g_j (column q+1 of the contraction, non-missing samples)
-        //                + [2 s_jj over hom-minor carriers + kinship off-diagonals]  (scan_packed_kernel)
+        //                + 2 s_jj over hom-minor carriers (g^2 - g = 2 [g == 2]; extra tile of the contraction)
+        //                + kinship off-diagonals over related carriers  (scan_packed_kernel)
         //                + mu^2 * sum_missing s_jj
         const long long shi = P.hi[i * 16 + P.q + 1], slo = P.lo[i * 16 + P.q + 1];
         const double dlin = ((double)shi * 16777216.0 + (double)slo) * P.scale[P.q + 1];
-        const double quad = dlin + P.quad[i] + mu * mu * P.Sm[i * kColsPerSlice + P.q + 1];
+        // slot 15: sum over hom-minor carriers of s_jj (exact integer, [g == 2] tile of the contraction)
+        const double s2 = ((double)P.hi[i * 16 + 15] * 16777216.0 + (double)P.lo[i * 16 + 15]) * P.scale[P.q + 1];
+        const double quad = dlin + 2.0 * s2 + P.quad[i] + mu * mu * P.Sm[i * kColsPerSlice + P.q + 1];
         const double C = quad - tct;
         P.Score[i] = U;
         single_trait_stats(U, C, P.Score_se[i], P.pl[i], P.Est[i], P.Est_se[i]);

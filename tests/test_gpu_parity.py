@@ -176,3 +176,29 @@ def test_device_generator_matches_host(gpu_ctx):
                                 tm.data_ptr(), sa.data_ptr())
     want = synth.pack_codes(synth.dosage_codes(n, first, p, params=prm), stride)
     assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_packed_contraction_is_exact_integer(gpu_ctx, oracle):
+    """K2 (packed): the INT8-sliced tensor-core contraction must equal, bit for bit, the integer sum
+    sum_j g_j * round(Y[j,c] * 2^(54-e_c)) — including the hom-minor slot and the split-K (atomic) path."""
+    import math
+    from staarpipeline_b200 import synth
+    from staarpipeline_b200.api import IMPUTE_MEAN
+    for n, p, q in ((700, 40, 5), (5000, 24, 13)):
+        nm, G0, packed, want, Gf = _packed_case(oracle, n, p, q, seed=3 * n, related=True)
+        gpu_ctx.set_nullmodel_sparse(nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+        gpu_ctx.packed_score_host(packed, n, IMPUTE_MEAN)
+        P = packed.shape[0]
+        d = gpu_ctx.packed_debug_dump(P)
+        Y = np.column_stack([nm.residuals, nm.Sigma_iX, nm.Sigma_i.diagonal()])
+        miss = np.isnan(G0) | (G0 <= -1)
+        Gint = np.where(miss, 0.0, Gf).astype(np.int64)                 # post-flip codes, missing -> 0
+        got = d["hi"].astype(object) * (1 << 24) + d["lo"].astype(object)
+        for c in range(q + 2):
+            e = math.frexp(np.abs(Y[:, c]).max())[1]
+            assert d["col_scale"][c] == math.ldexp(1.0, e - 54)
+            X = np.array([int(np.rint(math.ldexp(float(y), 54 - e))) for y in Y[:, c]], dtype=object)
+            assert list(got[:, c]) == list((Gint.astype(object) * X[:, None]).sum(axis=0)), f"column {c}"
+            if c == q + 1:                                              # hom-minor slot
+                assert list(got[:, 15]) == list(((Gint == 2).astype(object) * X[:, None]).sum(axis=0))
+        assert np.array_equal(d["flip"] != 0, oracle.matrix_flip_mean(G0)["AF"] > 0.5)
