@@ -60,11 +60,13 @@ struct NullSparse {
     struct alignas(16) OffEntry { double val; int32_t col; int32_t pad; };
     SampleInfo *sinfo = nullptr;  // n
     OffEntry *off_ent = nullptr;  // nnz_offdiag
-    // carrier scan of the packed path: 2-bit mask (11 = sample has kinship off-diagonals) in the genotype packing,
-    // and one 64-byte record per sample with up to 5 inline off-diagonal entries (count > 5: fall back to off_ent)
-    struct alignas(64) RelRecord { double val[5]; int32_t col[5]; int32_t count; };
+    // carrier scan of the packed path (upper triangle only: each related pair j < k is visited from j and doubled):
+    // 2-bit mask (11 = sample has kinship off-diagonals with a LARGER index) in the genotype packing, one 32-byte
+    // record per sample with its first two such entries inline, and the remaining ones in `up_ent`.
+    struct alignas(32) CarrierRec { double val[2]; int32_t col[2]; uint32_t start, count; };
     uint8_t *relmask = nullptr;   // packed_stride(n) bytes
-    RelRecord *rel = nullptr;     // n (only when nnz_offdiag > 0)
+    CarrierRec *rel = nullptr;    // n (only when nnz_offdiag > 0)
+    OffEntry *up_ent = nullptr;   // upper-triangle off-diagonal entries, rows concatenated
     double *SX = nullptr;         // Sigma_iX, n x q column-major (kept for the conditional test)
     // Y = [residuals | Sigma_iX | diag(Sigma_i)], row-major n x ldY (ldY = 8-padded 2+q), FP64.  The last column
     // rides along in the packed contraction (sum_j g_j s_jj); the FP64 kernels use the first 1+q columns only.

@@ -56,7 +56,7 @@ void NullSparse::release()
     if (owned) {
         cudaFree(row_ptr); cudaFree(col); cudaFree(val); cudaFree(SX); cudaFree(cov);
     }
-    cudaFree(diag); cudaFree(sinfo); cudaFree(off_ent); cudaFree(relmask); cudaFree(rel); cudaFree(Y); cudaFree(Yfrag); cudaFree(col_scale);
+    cudaFree(diag); cudaFree(sinfo); cudaFree(off_ent); cudaFree(relmask); cudaFree(rel); cudaFree(up_ent); cudaFree(Y); cudaFree(Yfrag); cudaFree(col_scale);
     *this = NullSparse();
 }
 void NullDense::release()
@@ -151,22 +151,32 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
     STAAR_CUDA(cudaMalloc(&ns.col, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
     STAAR_CUDA(cudaMalloc(&ns.val, sizeof(double) * std::max<int64_t>(nnz, 1)));
     STAAR_CUDA(cudaMalloc(&ns.diag, sizeof(double) * n));
-    // relatives mask + inline records for the packed carrier scan
+    // relatives mask + inline records for the packed carrier scan (upper triangle)
     const size_t pstride = staar_packed_stride(n);
     std::vector<uint8_t> relmask(pstride, 0);
-    std::vector<NullSparse::RelRecord> rel;
+    std::vector<NullSparse::CarrierRec> rel;
+    std::vector<NullSparse::OffEntry> up_ent;
     if (nnz_off > 0) {
         rel.resize(n);
         for (int64_t r = 0; r < n; r++) {
-            NullSparse::RelRecord &rr = rel[r];
+            NullSparse::CarrierRec &rr = rel[r];
             memset(&rr, 0, sizeof rr);
-            rr.count = (int32_t)sinfo[r].off_count;
+            rr.start = (uint32_t)up_ent.size();
+            for (uint32_t t = 0; t < sinfo[r].off_count; t++) {
+                const NullSparse::OffEntry &oe = off_ent[sinfo[r].off_start + t];
+                if (oe.col <= r) continue;
+                if (rr.count < 2) { rr.val[rr.count] = oe.val; rr.col[rr.count] = oe.col; }
+                up_ent.push_back(oe);
+                rr.count++;
+            }
             if (rr.count > 0) relmask[r >> 2] |= (uint8_t)(3u << (2 * (r & 3)));
-            if (rr.count <= 5)
-                for (int t = 0; t < rr.count; t++) { rr.val[t] = off_ent[sinfo[r].off_start + t].val; rr.col[t] = off_ent[sinfo[r].off_start + t].col; }
         }
-        STAAR_CUDA(cudaMalloc(&ns.rel, sizeof(NullSparse::RelRecord) * n));
-        STAAR_CUDA(cudaMemcpyAsync(ns.rel, rel.data(), sizeof(NullSparse::RelRecord) * n, cudaMemcpyHostToDevice, ctx->stream));
+        if (up_ent.empty()) up_ent.resize(1);
+        STAAR_CUDA(cudaMalloc(&ns.rel, sizeof(NullSparse::CarrierRec) * n));
+        STAAR_CUDA(cudaMemcpyAsync(ns.rel, rel.data(), sizeof(NullSparse::CarrierRec) * n, cudaMemcpyHostToDevice, ctx->stream));
+        STAAR_CUDA(cudaMalloc(&ns.up_ent, sizeof(NullSparse::OffEntry) * up_ent.size()));
+        STAAR_CUDA(cudaMemcpyAsync(ns.up_ent, up_ent.data(), sizeof(NullSparse::OffEntry) * up_ent.size(), cudaMemcpyHostToDevice, ctx->stream));
+        STAAR_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     STAAR_CUDA(cudaMalloc(&ns.relmask, pstride));
     STAAR_CUDA(cudaMemcpyAsync(ns.relmask, relmask.data(), pstride, cudaMemcpyHostToDevice, ctx->stream));

@@ -23,18 +23,15 @@ namespace {
 
 struct ScanParams {
     const uint8_t *packed; size_t stride; int64_t n, p; int impute;
-    const double *diag;                    // Sigma_i[j,j]
-    const uint8_t *relmask;                // 2-bit mask, 11 = sample has kinship off-diagonals
-    const NullSparse::RelRecord *rel;      // per-sample inline off-diagonal entries (64 B)
-    const NullSparse::SampleInfo *sinfo;   // CSR fallback for rows with more than 5 off-diagonals
-    const NullSparse::OffEntry *off_ent;
+    const uint8_t *relmask;                // 2-bit mask, 11 = sample has kinship off-diagonals with a larger index
+    const NullSparse::CarrierRec *rel;     // per-sample record: first two such entries inline (32 B)
+    const NullSparse::OffEntry *up_ent;    // all upper-triangle entries (rows with more than two)
     const double *Y; int ldY, ncol;
     double *AF, *MAF; int32_t *flip; double *mu, *quad, *Sm;
 };
 
 constexpr int kScanWarps = 8;
 constexpr int kCarrierCap = 1024 + 32;  // related carriers found in one iteration (<= 1024) + a carried remainder (< 32)
-constexpr int kPairCap = 32 * 5 + 32;   // pairs expanded from one round of 32 carriers (<= 160) + remainder (< 32)
 
 __device__ __forceinline__ double code_value(uint32_t code, double mu)
 {
@@ -45,7 +42,7 @@ __device__ __forceinline__ double code_value(uint32_t code, double mu)
 __device__ __forceinline__ double lookup_value(const uint8_t *colp, int64_t k, bool flip, double mu)
 {
     uint32_t code = (__ldg(colp + (k >> 2)) >> (2 * (k & 3))) & 3u;
-    if (flip && code != 3u && code != 1u) code ^= 2u;
+    if (flip && !(code & 1u)) code ^= 2u;
     return code_value(code, mu);
 }
 
@@ -53,22 +50,21 @@ __device__ __forceinline__ double lookup_value(const uint8_t *colp, int64_t k, b
 //  sweep 1: popcounts -> AF / MAF / flip / imputation value.
 //  sweep 2: only what the integer contraction cannot account for is visited:
 //            code 3 (missing): column sums of Y for the imputation correction;
-//            carriers whose sample has kinship off-diagonals (relmask): sum_k s_jk g_j g_k.
-//           Related carriers are compacted (bit tricks only) into a per-warp shared-memory list; full rounds of 32
-//           carriers fetch their row location and expand into a list of (carrier, relative) PAIRS; full rounds of
-//           32 pairs then do the latency-bound gathers (kinship entry -> relative's genotype byte) with every
-//           lane busy.  Remainders (< 32) are carried to the next iteration and flushed at the end of the column.
+//            carriers with a kinship off-diagonal towards a larger sample index (relmask):
+//            2 * g_j * sum_{k > j} s_jk g_k   (each related pair once, from its smaller index).
+//           Those carriers are compacted (bit tricks only) into a per-warp shared-memory list and handled in full
+//           rounds of 32, so the latency-bound gathers (32-byte record -> relatives' genotype bytes) always have
+//           every lane busy; the remainder (< 32) is carried over and flushed at the end of the column.
 // The diagonal of g' Sigma_i g rides in the tensor-core contraction (column q+1 of Y and the hom-minor tile).
 template <bool HAS_OFF>
 __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams P)
 {
     __shared__ uint32_t s_car[HAS_OFF ? kScanWarps : 1][kCarrierCap];
-    __shared__ uint32_t s_pair[HAS_OFF ? kScanWarps : 1][kPairCap];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int nvec8 = (int)(P.stride >> 3);
-    uint32_t *car = s_car[HAS_OFF ? wib : 0], *pair = s_pair[HAS_OFF ? wib : 0];
+    uint32_t *car = s_car[HAS_OFF ? wib : 0];
     const uint2 *rmask = reinterpret_cast<const uint2 *>(P.relmask);
     for (int64_t i = warp; i < P.p; i += nwarps) {
         const uint8_t *colp = P.packed + (size_t)i * P.stride;
@@ -77,51 +73,19 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams
         const bool flip = vf.flip != 0;
         const double mu = vf.mu;
         double quad = 0.0, sm = 0.0;           // sm: lane c (< ncol) accumulates sum over missing j of Y[j][c]
-        int ncar = 0, npair = 0;               // warp-uniform fill levels of the two lists
+        int ncar = 0;                          // warp-uniform fill level of the carrier list
 
-        // 32 pairs: kinship entry -> relative's genotype -> accumulate
-        auto pair_round = [&](int first) {
-            const uint32_t pe = pair[first + lane];
-            const NullSparse::OffEntry oe = P.off_ent[pe >> 2];
-            quad += code_value(pe & 3u, mu) * oe.val * lookup_value(colp, oe.col, flip, mu);
-        };
-        // 32 carriers: row location -> append one pair entry per kinship off-diagonal
         auto carrier_round = [&](int first, int count) {
-            uint32_t ce = 0u; uint32_t start = 0u; int cnt = 0;
             if (lane < count) {
-                ce = car[first + lane];
-                const NullSparse::SampleInfo si = P.sinfo[ce >> 2];
-                start = si.off_start; cnt = (int)si.off_count;
-                if (cnt > 5) {                 // unusually large family: finish this carrier in place
-                    double s = 0.0;
-                    for (int t = 0; t < cnt; t++) {
-                        const NullSparse::OffEntry oe = P.off_ent[start + t];
-                        s += oe.val * lookup_value(colp, oe.col, flip, mu);
-                    }
-                    quad += code_value(ce & 3u, mu) * s;
-                    cnt = 0;
+                const uint32_t ce = car[first + lane];
+                const NullSparse::CarrierRec rr = P.rel[ce >> 2];
+                double s = rr.val[0] * lookup_value(colp, rr.col[0], flip, mu);
+                if (rr.count > 1) s += rr.val[1] * lookup_value(colp, rr.col[1], flip, mu);
+                for (uint32_t t = 2; t < rr.count; t++) {
+                    const NullSparse::OffEntry oe = P.up_ent[rr.start + t];
+                    s += oe.val * lookup_value(colp, oe.col, flip, mu);
                 }
-            }
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            int pos = npair + incl - cnt;
-            for (int t = 0; t < cnt; t++) pair[pos + t] = ((start + t) << 2) | (ce & 3u);
-            npair += total;
-            __syncwarp();
-            int done = 0;
-            while (npair - done >= 32) { pair_round(done); done += 32; }
-            if (done) {                        // move the remainder (< 32 entries) to the front
-                const int rem = npair - done;
-                const uint32_t keep = lane < rem ? pair[done + lane] : 0u;
-                __syncwarp();
-                if (lane < rem) pair[lane] = keep;
-                npair = rem;
-                __syncwarp();
+                quad += 2.0 * code_value(ce & 3u, mu) * s;
             }
         };
 
@@ -172,7 +136,7 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams
                 }
             }
             if (!HAS_OFF) continue;
-            // ---- related carriers: append to the carrier list, then run full rounds
+            // ---- related carriers: append to the list, then run full rounds
             if (__any_sync(0xffffffffu, cnt != 0)) {
                 int incl = cnt;
 #pragma unroll
@@ -192,11 +156,11 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams
                     }
                 }
                 ncar += total;
-                __syncwarp();
-                int done = 0;
-                while (ncar - done >= 32) { carrier_round(done, 32); done += 32; }
-                if (done) {
-                    const int rem = ncar - done;
+                if (ncar >= 32) {
+                    __syncwarp();
+                    int done = 0;
+                    while (ncar - done >= 32) { carrier_round(done, 32); done += 32; }
+                    const int rem = ncar - done;                   // move the remainder (< 32) to the front
                     const uint32_t keep = lane < rem ? car[done + lane] : 0u;
                     __syncwarp();
                     if (lane < rem) car[lane] = keep;
@@ -205,15 +169,9 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams
                 }
             }
         }
-        if (HAS_OFF) {                         // flush the remainders
+        if (HAS_OFF) {
+            __syncwarp();
             if (ncar > 0) carrier_round(0, ncar);
-            if (npair > 0) {
-                const uint32_t pe = lane < npair ? pair[lane] : 0u;
-                if (lane < npair) {
-                    const NullSparse::OffEntry oe = P.off_ent[pe >> 2];
-                    quad += code_value(pe & 3u, mu) * oe.val * lookup_value(colp, oe.col, flip, mu);
-                }
-            }
             __syncwarp();
         }
         quad = warp_sum(quad);
@@ -274,7 +232,7 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     if (n >= (1ll << 30)) { set_error("packed scan: n too large for 30-bit sample indices"); return STAAR_ERR_ARG; }
     ScanParams P;
     P.packed = d_packed; P.stride = stride; P.n = n; P.p = p; P.impute = impute;
-    P.diag = ns.diag; P.relmask = ns.relmask; P.rel = ns.rel; P.sinfo = ns.sinfo; P.off_ent = ns.off_ent;
+    P.relmask = ns.relmask; P.rel = ns.rel; P.up_ent = ns.up_ent;
     P.Y = ns.Y; P.ldY = ns.ldY; P.ncol = (int)ns.q + 2;
     P.AF = dAF; P.MAF = dMAF; P.flip = dflip; P.mu = d_mu; P.quad = d_quad; P.Sm = d_Sm;
     int64_t blocks = std::min<int64_t>((p + kScanWarps - 1) / kScanWarps, (int64_t)ctx->sm_count * 8);
