@@ -185,29 +185,14 @@ def run_ours(args):
     seed = synth.BASE_SEED
 
     # ---- null model: built on rank 0, replicated by NCCL broadcast over NVLink once per run
+    from staarpipeline_b200 import shard
     t0 = time.perf_counter()
+    parts = None
     if rank == 0:
         nm = synth.nullmodel_sparse_grm(n, seed=seed, q=Q_COVARIATES, shuffle=True)
-        S = nm.Sigma_i.tocsc(); S.sort_indices()
-        parts = [S.data.astype(np.float64), S.indices.astype(np.int64), S.indptr.astype(np.int64),
-                 np.ascontiguousarray(nm.Sigma_iX.T).ravel(), nm.cov.ravel(order="F").copy(), nm.residuals.copy()]
-        sizes = torch.tensor([x.size for x in parts], dtype=torch.int64, device=dev)
-    else:
-        parts, sizes = None, torch.zeros(6, dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.broadcast(sizes, 0)
-        bufs = []
-        for i, sz in enumerate(sizes.tolist()):
-            dt = torch.int64 if i in (1, 2) else torch.float64
-            t = torch.from_numpy(parts[i]).to(dev) if rank == 0 else torch.empty(sz, dtype=dt, device=dev)
-            dist.broadcast(t, 0)
-            bufs.append(t.cpu().numpy())
-        parts = bufs
-    import scipy.sparse as sp
-    Sigma_i = sp.csc_matrix((parts[0], parts[1], parts[2]), shape=(n, n))
-    Sigma_iX = np.asfortranarray(parts[3].reshape(Q_COVARIATES, n).T)
-    cov = np.asfortranarray(parts[4].reshape(Q_COVARIATES, Q_COVARIATES, order="F"))
-    residuals = parts[5]
+        parts = shard.pack_nullmodel(nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+    parts = shard.broadcast_nullmodel(parts, rank, world, dev)
+    Sigma_i, Sigma_iX, cov, residuals = shard.unpack_nullmodel(parts)
     ctx = api.Context(local)
     ctx.set_nullmodel_sparse(Sigma_i, Sigma_iX, cov, residuals)
     log(f"[rank {rank}] null model ready in {time.perf_counter() - t0:.1f} s (nnz(Sigma_i) = {Sigma_i.nnz})")
@@ -215,7 +200,7 @@ def run_ours(args):
     # ---- this rank's shard of packed dosage columns, generated on the device
     t0 = time.perf_counter()
     stride = api.packed_stride(n)
-    first = rank * V
+    first = rank * V                       # weak scaling: rank r owns variants [r*V, (r+1)*V) of the N*V-variant job
     packed = torch.empty((V, stride), dtype=torch.uint8, device=dev)
     gen = 125_000
     for a in range(0, V, gen):
