@@ -102,7 +102,8 @@ struct staar_ctx {
     staar::NullSparse ns;
     staar::NullDense nd;
     // scratch
-    staar::DevBuf G, L, aux, out, tmp, tmp2, pk;
+    staar::DevBuf G, L, aux, out, tmp, tmp2, pk, ctr;
+    bool scan_warp_kernel = false;   // test hook: force the warp-per-variant scan (columns read from global memory)
     void *pinned = nullptr;
     size_t pinned_cap = 0;
     // optional per-kernel timing of the packed path (bench.py roofline)

@@ -258,7 +258,7 @@ void staar_ctx_destroy(staar_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->ns.release(); ctx->nd.release();
     ctx->G.release(); ctx->L.release(); ctx->aux.release(); ctx->out.release(); ctx->tmp.release();
-    ctx->tmp2.release(); ctx->pk.release();
+    ctx->tmp2.release(); ctx->pk.release(); ctx->ctr.release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);

@@ -182,6 +182,238 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Block-per-variant scan (the production kernel).  The warp-per-variant kernel above keeps ~10^4 columns in
+// flight at once (240 MB at n = 1e5), so its second sweep and the relatives' genotype look-ups miss L2 and the
+// column is fetched from HBM ~5x (ncu: 134 KB/variant).  Here a CTA owns one variant at a time: its 2-bit column is
+// brought into shared memory ONCE by a 1-D bulk copy (cp.async.bulk completing on an mbarrier), the next column is
+// prefetched into the second stage while this one is processed, both sweeps and every relative's genotype look-up
+// read shared memory, and only the per-sample kinship records / rows of Y (L2-resident, a few MB) are gathered
+// from global memory.  Variants are handed out by an atomic work counter (their cost varies >20x with allele
+// frequency); each variant's arithmetic is independent of which CTA runs it, so results stay bit-reproducible.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kBlkWarps = 8;
+constexpr int kGroupCap = 1024;          // related carriers one warp can find in one 1024-sample group
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ double lookup_value_smem(const uint8_t *col, int64_t k, bool flip, double mu)
+{
+    uint32_t code = ((uint32_t)col[k >> 2] >> (2 * (k & 3))) & 3u;
+    if (flip && !(code & 1u)) code ^= 2u;
+    return code_value(code, mu);
+}
+
+template <bool HAS_OFF>
+__global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P, int nstage, unsigned long long *work)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const size_t stride = P.stride;
+    uint8_t *cols = smem;
+    uint8_t *after = smem + (size_t)nstage * stride;
+    uint16_t *car = reinterpret_cast<uint16_t *>(after) + (HAS_OFF ? wib * kGroupCap : 0);
+    after += HAS_OFF ? (size_t)kBlkWarps * kGroupCap * sizeof(uint16_t) : 0;
+    double *s_sm = reinterpret_cast<double *>(after);            // [kBlkWarps][16]
+    double *s_quad = s_sm + kBlkWarps * kColsPerSlice;           // [kBlkWarps]
+    int *s_cnt = reinterpret_cast<int *>(s_quad + kBlkWarps);    // [3][kBlkWarps]
+    unsigned long long *s_work = reinterpret_cast<unsigned long long *>(s_cnt + 3 * kBlkWarps + (kBlkWarps & 1));   // [2]
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_work + 2);   // [2]
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; s++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&full[s])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](unsigned long long v, int stage) {          // thread 0 only
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&full[stage])),
+                     "r"((uint32_t)stride) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr(cols + (size_t)stage * stride)),
+                     "l"(P.packed + (size_t)v * stride), "r"((uint32_t)stride), "r"(smem_addr(&full[stage]))
+                     : "memory");
+    };
+    auto wait_full = [&](int stage, uint32_t parity) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "SCAN_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra SCAN_DONE;\n"
+            "bra SCAN_WAIT;\n"
+            "SCAN_DONE:\n"
+            "}\n" ::"r"(smem_addr(&full[stage])), "r"(parity) : "memory");
+    };
+
+    const unsigned long long pmax = (unsigned long long)P.p;
+    if (tid == 0) {
+        const unsigned long long v = atomicAdd(work, 1ull);
+        s_work[0] = v;
+        if (v < pmax) issue(v, 0);
+    }
+    __syncthreads();
+    unsigned long long cur = s_work[0];
+    int stage = 0;
+    uint32_t parity = 0u;                                        // bit s = phase parity of full[s]
+    const uint2 *rmask = reinterpret_cast<const uint2 *>(P.relmask);
+    const int nvec16 = (int)(stride >> 4), nvec8 = (int)(stride >> 3);
+
+    for (unsigned it = 1; cur < pmax; it++) {
+        if (nstage == 2 && tid == 0) {                           // prefetch the next variant's column
+            const unsigned long long v = atomicAdd(work, 1ull);
+            s_work[it & 1] = v;
+            if (v < pmax) issue(v, stage ^ 1);
+        }
+        wait_full(stage, (parity >> stage) & 1u);
+        parity ^= 1u << stage;
+        const uint8_t *col = cols + (size_t)stage * stride;
+        const int64_t i = (int64_t)cur;
+
+        // ---- sweep 1: popcounts -> AF / MAF / flip / imputation value (bit-exact integer counts)
+        int c1 = 0, c2 = 0, cm = 0;
+        {
+            const uint4 *v4 = reinterpret_cast<const uint4 *>(col);
+            for (int k = tid; k < nvec16; k += kBlkWarps * 32) {
+                const uint4 w = v4[k];
+                count_word(w.x, c1, c2, cm); count_word(w.y, c1, c2, cm);
+                count_word(w.z, c1, c2, cm); count_word(w.w, c1, c2, cm);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+                c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+                cm += __shfl_xor_sync(0xffffffffu, cm, o);
+            }
+            if (lane == 0) { s_cnt[wib] = c1; s_cnt[kBlkWarps + wib] = c2; s_cnt[2 * kBlkWarps + wib] = cm; }
+            __syncthreads();
+            c1 = c2 = cm = 0;
+#pragma unroll
+            for (int w = 0; w < kBlkWarps; w++) { c1 += s_cnt[w]; c2 += s_cnt[kBlkWarps + w]; cm += s_cnt[2 * kBlkWarps + w]; }
+        }
+        const VariantFlip vf = flip_from_counts(PackedCounts{c1, c2, cm}, P.n, P.impute);
+        const bool flip = vf.flip != 0;
+        const double mu = vf.mu;
+
+        // ---- sweep 2: missing entries and related carriers (see scan_packed_kernel); groups of 1024 samples per warp
+        double quad = 0.0, sm = 0.0;
+        const uint2 *vecs = reinterpret_cast<const uint2 *>(col);
+        const bool sweep2 = HAS_OFF || cm > 0;      // unrelated samples: only missing entries need the second sweep
+        if (sweep2)
+        for (int k0 = wib * 32; k0 < nvec8; k0 += kBlkWarps * 32) {
+            const int k = k0 + lane;
+            uint2 q2 = make_uint2(0u, 0u), r2 = make_uint2(0u, 0u);
+            if (k < nvec8) {
+                q2 = vecs[k];
+                if (HAS_OFF) r2 = __ldg(rmask + k);
+            }
+            uint32_t w[2] = {q2.x, q2.y}, sel[2], mis[2];
+            const uint32_t rm[2] = {r2.x, r2.y};
+            const int64_t base = (int64_t)k * 32;
+            int cnt = 0;
+            bool any_missing = false;
+#pragma unroll
+            for (int wi = 0; wi < 2; wi++) {
+                if (flip) {
+                    w[wi] = flip_word(w[wi]);
+                    const int64_t valid = P.n - (base + wi * 16);
+                    if (valid < 16) w[wi] &= (valid <= 0) ? 0u : ((1u << (2 * valid)) - 1u);
+                }
+                const uint32_t lo = w[wi] & 0x55555555u, hi = (w[wi] >> 1) & 0x55555555u;
+                mis[wi] = lo & hi;
+                sel[wi] = HAS_OFF ? ((lo | hi) & rm[wi] & ~(mu == 0.0 ? mis[wi] : 0u)) : 0u;
+                cnt += __popc(sel[wi]);
+                any_missing |= mis[wi] != 0u;
+            }
+            if (__any_sync(0xffffffffu, any_missing)) {
+#pragma unroll
+                for (int wi = 0; wi < 2; wi++) {
+                    const uint32_t mine = mis[wi];
+                    uint32_t who = __ballot_sync(0xffffffffu, mine != 0u);
+                    while (who) {
+                        const int src = __ffs(who) - 1;
+                        who &= who - 1;
+                        uint32_t mw = __shfl_sync(0xffffffffu, mine, src);
+                        const int64_t b0 = __shfl_sync(0xffffffffu, base, src) + wi * 16;
+                        while (mw) {
+                            const int b = __ffs(mw) - 1;
+                            mw &= mw - 1;
+                            if (lane < P.ncol) sm += __ldg(P.Y + (b0 + (b >> 1)) * P.ldY + lane);
+                        }
+                    }
+                }
+            }
+            if (!HAS_OFF) continue;
+            if (__any_sync(0xffffffffu, cnt != 0)) {
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                int pos = incl - cnt;
+#pragma unroll
+                for (int wi = 0; wi < 2; wi++) {
+                    uint32_t ss = sel[wi];
+                    while (ss) {
+                        const int b = __ffs(ss) - 1;                 // even bit position = 2 * field
+                        ss &= ss - 1;
+                        car[pos++] = (uint16_t)(((uint32_t)(lane * 32 + wi * 16 + (b >> 1)) << 2) | ((w[wi] >> b) & 3u));
+                    }
+                }
+                __syncwarp();
+                const int64_t gbase = (int64_t)k0 * 32;              // first sample of this warp's group
+                for (int first = 0; first < total; first += 32) {
+                    if (first + lane < total) {
+                        const uint32_t ce = car[first + lane];
+                        const NullSparse::CarrierRec rr = P.rel[gbase + (ce >> 2)];
+                        double s = rr.val[0] * lookup_value_smem(col, rr.col[0], flip, mu);
+                        if (rr.count > 1) s += rr.val[1] * lookup_value_smem(col, rr.col[1], flip, mu);
+                        for (uint32_t t = 2; t < rr.count; t++) {
+                            const NullSparse::OffEntry oe = P.up_ent[rr.start + t];
+                            s += oe.val * lookup_value_smem(col, oe.col, flip, mu);
+                        }
+                        quad += 2.0 * code_value(ce & 3u, mu) * s;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        quad = warp_sum(quad);
+        if (lane == 0) s_quad[wib] = quad;
+        if (lane < kColsPerSlice) s_sm[wib * kColsPerSlice + lane] = sm;
+        __syncthreads();                      // also: every read of this stage's column is complete
+        if (tid < kColsPerSlice) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kBlkWarps; w++) t += s_sm[w * kColsPerSlice + tid];
+            P.Sm[i * kColsPerSlice + tid] = (tid < P.ncol) ? t : 0.0;
+        } else if (tid == 32) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kBlkWarps; w++) t += s_quad[w];
+            P.AF[i] = vf.af; P.MAF[i] = vf.maf; P.flip[i] = vf.flip; P.mu[i] = mu; P.quad[i] = t;
+        }
+        if (nstage == 2) {
+            cur = s_work[it & 1];
+            stage ^= 1;
+            __syncthreads();                  // s_sm / s_quad / s_cnt are rewritten by the next variant
+        } else {
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned long long v = atomicAdd(work, 1ull);
+                s_work[it & 1] = v;
+                if (v < pmax) issue(v, 0);
+            }
+            __syncthreads();
+            cur = s_work[it & 1];
+        }
+    }
+}
+
 struct FinParams {
     int64_t p; int q;
     const double *mu, *quad, *Sm;
@@ -235,9 +467,29 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     P.relmask = ns.relmask; P.rel = ns.rel; P.up_ent = ns.up_ent;
     P.Y = ns.Y; P.ldY = ns.ldY; P.ncol = (int)ns.q + 2;
     P.AF = dAF; P.MAF = dMAF; P.flip = dflip; P.mu = d_mu; P.quad = d_quad; P.Sm = d_Sm;
-    int64_t blocks = std::min<int64_t>((p + kScanWarps - 1) / kScanWarps, (int64_t)ctx->sm_count * 8);
-    if (ns.nnz_offdiag > 0) scan_packed_kernel<true><<<(int)blocks, kScanWarps * 32, 0, ctx->stream>>>(P);
-    else scan_packed_kernel<false><<<(int)blocks, kScanWarps * 32, 0, ctx->stream>>>(P);
+    const bool has_off = ns.nnz_offdiag > 0;
+    // block-per-variant kernel: column(s) in shared memory, double-buffered when two fit
+    const size_t extra = (has_off ? (size_t)kBlkWarps * kGroupCap * sizeof(uint16_t) : 0) +
+                         sizeof(double) * (kBlkWarps * kColsPerSlice + kBlkWarps) + sizeof(int) * 3 * kBlkWarps + 64;
+    const size_t smem_max = 227 * 1024;
+    const int nstage = (2 * stride + extra <= smem_max) ? 2 : (stride + extra <= smem_max) ? 1 : 0;
+    if (nstage > 0 && !ctx->scan_warp_kernel) {
+        const size_t smem = (size_t)nstage * stride + extra;
+        auto kern = has_off ? scan_block_kernel<true> : scan_block_kernel<false>;
+        STAAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        STAAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlkWarps * 32, smem));
+        if (per_sm < 1) { set_error("packed scan: kernel does not fit on an SM (smem %zu B)", smem); return STAAR_ERR_CUDA; }
+        STAAR_TRY(ctx->ctr.reserve(sizeof(unsigned long long)));
+        STAAR_CUDA(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(unsigned long long), ctx->stream));
+        const int64_t blocks = std::min<int64_t>(p, (int64_t)ctx->sm_count * per_sm);
+        kern<<<(int)blocks, kBlkWarps * 32, smem, ctx->stream>>>(P, nstage, ctx->ctr.as<unsigned long long>());
+    } else {
+        // columns too long for shared memory (n > ~9e5): warp-per-variant kernel reading global memory
+        int64_t blocks = std::min<int64_t>((p + kScanWarps - 1) / kScanWarps, (int64_t)ctx->sm_count * 8);
+        if (has_off) scan_packed_kernel<true><<<(int)blocks, kScanWarps * 32, 0, ctx->stream>>>(P);
+        else scan_packed_kernel<false><<<(int)blocks, kScanWarps * 32, 0, ctx->stream>>>(P);
+    }
     ctx->launches++;
     STAAR_CUDA(cudaGetLastError());
     return STAAR_OK;
