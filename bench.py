@@ -200,6 +200,8 @@ def run_ours(args):
     # ---- this rank's shard of packed dosage columns, generated on the device
     t0 = time.perf_counter()
     stride = api.packed_stride(n)
+    order = ctx.nullmodel_sample_order()           # resident columns are in the null-model sample order
+    d_order = torch.from_numpy(order).to(dev)
     first = rank * V                       # weak scaling: rank r owns variants [r*V, (r+1)*V) of the N*V-variant job
     packed = torch.empty((V, stride), dtype=torch.uint8, device=dev)
     gen = 125_000
@@ -212,7 +214,7 @@ def run_ours(args):
         sa = torch.from_numpy(prm.store_alt).to(dev)
         torch.cuda.synchronize()
         ctx.synth_packed_device(packed[a:b].data_ptr(), stride, n, first + a, b - a, seed, th.data_ptr(), te.data_ptr(),
-                                tm.data_ptr(), sa.data_ptr())
+                                tm.data_ptr(), sa.data_ptr(), d_order.data_ptr())
     outs = torch.zeros((7, V), dtype=torch.float64, device=dev)
     optrs = [outs[i].data_ptr() for i in range(7)]
     torch.cuda.synchronize()
@@ -294,7 +296,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         p = CHUNK
-        host = torch.from_numpy(host_chunk_from_device(packed[:p], n, dev).T).pin_memory()   # (p, n) C-order, pinned
+        host = torch.from_numpy(host_chunk_from_device(packed[:p], n, dev, d_order).T).pin_memory()   # (p, n) C-order, pinned
         G = host.numpy().T                                                                    # n x p, F-order view
         out7 = [np.zeros(p) for _ in range(7)]
         for _ in range(max(1, min(args.warmup, 2))):
@@ -321,7 +323,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ref, kind, blas = load_reference()
         pc = args.cpu_chunk
-        Gc = np.asfortranarray(host_chunk_from_device(packed[:pc], n, dev))
+        Gc = np.asfortranarray(host_chunk_from_device(packed[:pc], n, dev, d_order))
         nm_like = argparse.Namespace(Sigma_i=Sigma_i, Sigma_iX=Sigma_iX, cov=cov, residuals=residuals)
         t, tested = reference_chunk(ref, Gc, nm_like)
         cpu = {"value": pc / t, "unit": "variants/s", "cores": (os.cpu_count() or 1) if blas else 1, "kind": kind,
@@ -342,12 +344,15 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def host_chunk_from_device(packed_rows, n, dev):
-    """unpack device-resident 2-bit columns into the FP64 `$dosage` matrix (n x p, F-order, NaN = missing)"""
+def host_chunk_from_device(packed_rows, n, dev, d_order):
+    """unpack device-resident 2-bit columns (null-model sample order) into the FP64 `$dosage` matrix in the caller's
+    sample order (n x p, F-order, NaN = missing)"""
     import torch
     p = packed_rows.shape[0]
     sh = torch.tensor([0, 2, 4, 6], dtype=torch.uint8, device=dev)
-    codes = ((packed_rows.unsqueeze(-1) >> sh) & 3).reshape(p, -1)[:, :n]
+    by_pos = ((packed_rows.unsqueeze(-1) >> sh) & 3).reshape(p, -1)[:, :n]
+    codes = torch.empty_like(by_pos)
+    codes[:, d_order.long()] = by_pos              # position j holds sample order[j]
     G = codes.to(torch.float64)
     G[codes == 3] = float("nan")
     return G.cpu().numpy().T          # (n, p) view of a C-order (p, n) array == F-order n x p

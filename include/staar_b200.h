@@ -143,9 +143,17 @@ int staar_individual_score_test_SPA(staar_ctx *ctx, const double *G, int64_t n, 
 /*    the operand cache inside the A-entry points.)                         */
 /* ======================================================================= */
 
-/* Packed dosage block: variant-major, 2 bits per genotype, sample j of a variant in byte j/4,
+/* Packed dosage block: variant-major, 2 bits per genotype, the sample at POSITION j of a variant in byte j/4,
  * bits 2*(j%4)..+1; codes 0/1/2 = dosage, 3 = missing.  stride_bytes >= ceil(n/4), multiple of 16;
- * bits beyond sample n-1 must be 0. */
+ * bits beyond position n-1 must be 0.
+ *
+ * Sample order.  Host-side packed columns (staar_pack_dosage_host, staar_packed_score_host,
+ * staar_individual_analysis_chunk) are in the CALLER's sample order (position j = sample j).  Columns RESIDENT in
+ * HBM for the *_device entry points are in the "null-model sample order": staar_nullmodel_set_sparse* re-orders the
+ * samples once so that every family of Sigma_i (connected component of its off-diagonal pattern) of up to 16
+ * members lies inside one 16-sample word and related samples come first; staar_nullmodel_sample_order returns the
+ * order (position -> caller's sample index; the identity for unrelated samples) and staar_packed_reorder_device
+ * converts caller-order columns already on the device. */
 size_t staar_packed_stride(int64_t n);
 
 /* host FP64 dosage (n x p, NaN / <= -1 missing) -> packed host buffer (p x stride).  Returns
@@ -162,6 +170,12 @@ int staar_nullmodel_set_sparse_device(staar_ctx *ctx, int64_t n, int64_t q,
                                       const int64_t *d_row_ptr, const int32_t *d_col, const double *d_val,
                                       const double *d_Sigma_iX, const double *d_cov, const double *d_residuals);
 
+/* order[j] = caller's sample index stored at position j of a resident packed column (length n). */
+int staar_nullmodel_sample_order(staar_ctx *ctx, int64_t n, int32_t *order);
+/* caller-order packed columns -> null-model order (device pointers, d_out != d_in, same stride). */
+int staar_packed_reorder_device(staar_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, size_t stride_bytes, int64_t n,
+                                int64_t p);
+
 #define STAAR_IMPUTE_MEAN 0
 #define STAAR_IMPUTE_MINOR 1
 
@@ -170,8 +184,9 @@ int staar_nullmodel_set_sparse_device(staar_ctx *ctx, int64_t n, int64_t q,
 int staar_packed_flip_stats_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride_bytes, int64_t n, int64_t p,
                                    int impute, double *d_AF, double *d_MAF, int32_t *d_flip, int32_t *d_nmiss);
 
-/* The fused per-variant path on resident packed columns: flip/impute + Individual_Score_Test.
- * All pointers are DEVICE pointers; outputs are 7 arrays of length p. Requires staar_nullmodel_set_sparse*. */
+/* The fused per-variant path on resident packed columns (null-model sample order): flip/impute +
+ * Individual_Score_Test.  All pointers are DEVICE pointers; outputs are 7 arrays of length p.
+ * Requires staar_nullmodel_set_sparse*. */
 int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride_bytes, int64_t n, int64_t p,
                               int impute, double *d_AF, double *d_MAF, double *d_Score, double *d_Score_se,
                               double *d_pvalue_log, double *d_Est, double *d_Est_se);
@@ -204,11 +219,13 @@ int staar_individual_analysis_chunk(staar_ctx *ctx, const double *G, int64_t n, 
                                     double *Est, double *Est_se);
 
 /* Synthetic packed dosage columns generated on the device (bench / parity subsets); per-variant
- * thresholds as in staarpipeline_b200/synth.py (device pointers, uint64 / uint8). */
+ * thresholds as in staarpipeline_b200/synth.py (device pointers, uint64 / uint8).  d_sample_order (device int32[n],
+ * may be NULL = identity): the sample whose genotype is written at each position, so a shard can be generated
+ * directly in the null-model order. */
 int staar_synth_packed_device(staar_ctx *ctx, uint8_t *d_packed, size_t stride_bytes, int64_t n,
                               int64_t first_variant, int64_t p, uint64_t seed,
                               const uint64_t *d_thr_hom, const uint64_t *d_thr_het, const uint64_t *d_thr_miss,
-                              const uint8_t *d_store_alt);
+                              const uint8_t *d_store_alt, const int32_t *d_sample_order);
 
 #ifdef __cplusplus
 }

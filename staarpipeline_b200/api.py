@@ -325,10 +325,21 @@ class Context:
                    C.c_void_p(d_nmiss))
 
     def synth_packed_device(self, d_packed: int, stride: int, n: int, first_variant: int, p: int, seed: int,
-                            d_thr_hom: int, d_thr_het: int, d_thr_miss: int, d_store_alt: int):
+                            d_thr_hom: int, d_thr_het: int, d_thr_miss: int, d_store_alt: int, d_sample_order: int = 0):
         self._call("staar_synth_packed_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n),
                    C.c_int64(first_variant), C.c_int64(p), C.c_uint64(seed), C.c_void_p(d_thr_hom),
-                   C.c_void_p(d_thr_het), C.c_void_p(d_thr_miss), C.c_void_p(d_store_alt))
+                   C.c_void_p(d_thr_het), C.c_void_p(d_thr_miss), C.c_void_p(d_store_alt),
+                   C.c_void_p(d_sample_order or None))
+
+    def nullmodel_sample_order(self) -> np.ndarray:
+        """position -> caller's sample index of RESIDENT packed columns (identity for unrelated samples)"""
+        order = np.zeros(self._n, dtype=np.int32)
+        self._call("staar_nullmodel_sample_order", C.c_int64(self._n), order.ctypes.data_as(C.POINTER(C.c_int32)))
+        return order
+
+    def packed_reorder_device(self, d_in: int, d_out: int, stride: int, n: int, p: int):
+        self._call("staar_packed_reorder_device", C.c_void_p(d_in), C.c_void_p(d_out), C.c_size_t(stride),
+                   C.c_int64(n), C.c_int64(p))
 
 
 def packed_stride(n: int) -> int:

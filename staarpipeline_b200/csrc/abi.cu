@@ -624,14 +624,48 @@ int staar_packed_score_host(staar_ctx *ctx, const uint8_t *packed, size_t stride
 {
     CHECK_CTX(ctx);
     STAAR_TRY(check_dims(n, p));
+    NullSparse &ns = ctx->ns;
+    if (!ns.set) { set_error("packed score: call staar_nullmodel_set_sparse first"); return STAAR_ERR_STATE; }
     STAAR_TRY(ctx->pk.reserve(stride * (size_t)std::max<int64_t>(p, 1)));
     STAAR_TRY(h2d(ctx, ctx->pk.p, packed, stride * (size_t)p));
+    const uint8_t *d_cols = ctx->pk.as<uint8_t>();
+    if (ns.permuted) {      // host columns are in the caller's sample order: re-order into the resident layout
+        STAAR_TRY(ctx->pk2.reserve(stride * (size_t)std::max<int64_t>(p, 1)));
+        STAAR_TRY(launch_permute_packed(ctx, d_cols, ctx->pk2.as<uint8_t>(), stride, n, p, ns.perm));
+        d_cols = ctx->pk2.as<uint8_t>();
+    }
     STAAR_TRY(ctx->out.reserve(sizeof(double) * 7 * (size_t)std::max<int64_t>(p, 1)));
     double *o = ctx->out.as<double>();
-    STAAR_TRY(staar_packed_score_device(ctx, ctx->pk.as<uint8_t>(), stride, n, p, impute, o, o + p, o + 2 * p, o + 3 * p,
-                                        o + 4 * p, o + 5 * p, o + 6 * p));
+    STAAR_TRY(staar_packed_score_device(ctx, d_cols, stride, n, p, impute, o, o + p, o + 2 * p, o + 3 * p, o + 4 * p,
+                                        o + 5 * p, o + 6 * p));
     double *dst[7] = {AF, MAF, Score, Score_se, pl, Est, Est_se};
     for (int a = 0; a < 7; a++) STAAR_TRY(d2h(ctx, dst[a], o + (size_t)a * p, sizeof(double) * p));
+    return sync(ctx);
+}
+
+int staar_nullmodel_sample_order(staar_ctx *ctx, int64_t n, int32_t *order)
+{
+    CHECK_CTX(ctx);
+    NullSparse &ns = ctx->ns;
+    if (!ns.set || ns.n != n) { set_error("sample_order: null model not set for n = %lld", (long long)n); return STAAR_ERR_STATE; }
+    if (!order) { set_error("sample_order: NULL pointer"); return STAAR_ERR_ARG; }
+    for (int64_t j = 0; j < n; j++) order[j] = ns.permuted ? ns.h_perm[j] : (int32_t)j;
+    return STAAR_OK;
+}
+
+int staar_packed_reorder_device(staar_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, size_t stride, int64_t n, int64_t p)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    NullSparse &ns = ctx->ns;
+    if (!ns.set || ns.n != n) { set_error("packed_reorder: null model not set for n = %lld", (long long)n); return STAAR_ERR_STATE; }
+    if (stride % 16 != 0 || stride < (size_t)((n + 3) / 4)) { set_error("packed stride must be a multiple of 16 and >= ceil(n/4)"); return STAAR_ERR_ARG; }
+    if (d_in == d_out) { set_error("packed_reorder: in-place re-ordering is not supported"); return STAAR_ERR_ARG; }
+    if (!ns.permuted) {
+        STAAR_CUDA(cudaMemcpyAsync(d_out, d_in, stride * (size_t)p, cudaMemcpyDeviceToDevice, ctx->stream));
+        return sync(ctx);
+    }
+    STAAR_TRY(launch_permute_packed(ctx, d_in, d_out, stride, n, p, ns.perm));
     return sync(ctx);
 }
 
@@ -669,11 +703,11 @@ int staar_individual_analysis_chunk(staar_ctx *ctx, const double *G, int64_t n, 
 
 int staar_synth_packed_device(staar_ctx *ctx, uint8_t *d_packed, size_t stride, int64_t n, int64_t first_variant,
                               int64_t p, uint64_t seed, const uint64_t *d_thr_hom, const uint64_t *d_thr_het,
-                              const uint64_t *d_thr_miss, const uint8_t *d_store_alt)
+                              const uint64_t *d_thr_miss, const uint8_t *d_store_alt, const int32_t *d_sample_order)
 {
     CHECK_CTX(ctx);
     STAAR_TRY(launch_synth_packed(ctx, d_packed, stride, n, first_variant, p, seed, d_thr_hom, d_thr_het, d_thr_miss,
-                                  d_store_alt));
+                                  d_store_alt, d_sample_order));
     return sync(ctx);
 }
 

@@ -55,18 +55,37 @@ struct NullSparse {
     int32_t *col = nullptr;       // nnz
     double *val = nullptr;        // nnz
     double *diag = nullptr;       // n   (Sigma_i[j,j])
-    // per-sample record for the carrier scan: {Sigma_i[j,j], first off-diagonal entry, #off-diagonal entries}
     struct alignas(16) SampleInfo { double diag; uint32_t off_start, off_count; };
     struct alignas(16) OffEntry { double val; int32_t col; int32_t pad; };
-    SampleInfo *sinfo = nullptr;  // n
-    OffEntry *off_ent = nullptr;  // nnz_offdiag
-    // carrier scan of the packed path (upper triangle only: each related pair j < k is visited from j and doubled):
-    // 2-bit mask (11 = sample has kinship off-diagonals with a LARGER index) in the genotype packing, one 32-byte
-    // record per sample with its first two such entries inline, and the remaining ones in `up_ent`.
+    // ---- packed path: "null-model sample order".  Samples are re-ordered once, at set-up, so that every family
+    // (connected component of Sigma_i's off-diagonal graph) of 2..16 members sits inside ONE 16-sample word of the
+    // packed column; related samples come first, unrelated ones after.  The kinship part of g' Sigma_i g then needs
+    // no genotype gathers: a lane extracts a family's 2-bit codes from the word it already holds and looks the
+    // family's contribution up in a per-family table (4^size entries, size <= 4; larger families are chunked).
+    // Families that do not fit (more than 16 members) take the "generic" record path below.
+    bool permuted = false;            // false: perm is the identity
+    std::vector<int32_t> h_perm;      // position -> original sample (empty when identity)
+    int32_t *perm = nullptr;          // device copy (nullptr when identity)
+    double *Yp = nullptr;             // Y rows in null-model order (== Y when !permuted; then not owned)
+    int64_t kin_words = 0;            // 16-sample words [0, kin_words) hold every sample with kinship off-diagonals
+    int64_t tab_words = 0;            // words [0, tab_words): table families; [tab_words, kin_words): generic families
+    uint32_t *kinmask = nullptr;      // kin_words words: bit 2f set = sample f of the word is in a table family
+    struct KinTerm { uint32_t off; uint8_t shift, size, jpos, pad; };   // value = (jpos == 255 ? 1 : code[jpos]) * lut[off + idx]
+    struct alignas(64) WordDesc { uint32_t nterm, ovf; KinTerm t[7]; };
+    WordDesc *wdesc = nullptr;        // tab_words descriptors
+    KinTerm *terms_ovf = nullptr;     // terms beyond the 7 inline ones
+    double *lut = nullptr;
+    int64_t lut_entries = 0;
+    SampleInfo *sinfo_p = nullptr;    // full kinship rows in null-model positions (missing related samples)
+    OffEntry *off_ent_p = nullptr;
+    // generic path (families of more than 16 members, or every family when the column does not fit in shared memory):
+    // 2-bit mask (11 = sample has kinship off-diagonals with a LARGER position), one 32-byte record per sample with
+    // its first two such entries inline, and the remaining ones in `up_ent`.  Positions are null-model positions.
     struct alignas(32) CarrierRec { double val[2]; int32_t col[2]; uint32_t start, count; };
     uint8_t *relmask = nullptr;   // packed_stride(n) bytes
-    CarrierRec *rel = nullptr;    // n (only when nnz_offdiag > 0)
+    CarrierRec *rel = nullptr;    // n (only when some family is generic)
     OffEntry *up_ent = nullptr;   // upper-triangle off-diagonal entries, rows concatenated
+    int64_t n_generic = 0;        // samples on the generic path
     double *SX = nullptr;         // Sigma_iX, n x q column-major (kept for the conditional test)
     // Y = [residuals | Sigma_iX | diag(Sigma_i)], row-major n x ldY (ldY = 8-padded 2+q), FP64.  The last column
     // rides along in the packed contraction (sum_j g_j s_jj); the FP64 kernels use the first 1+q columns only.
@@ -102,8 +121,7 @@ struct staar_ctx {
     staar::NullSparse ns;
     staar::NullDense nd;
     // scratch
-    staar::DevBuf G, L, aux, out, tmp, tmp2, pk, ctr;
-    bool scan_warp_kernel = false;   // test hook: force the warp-per-variant scan (columns read from global memory)
+    staar::DevBuf G, L, aux, out, tmp, tmp2, pk, pk2, ctr;
     void *pinned = nullptr;
     size_t pinned_cap = 0;
     // optional per-kernel timing of the packed path (bench.py roofline)
@@ -150,11 +168,12 @@ int launch_contract_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t strid
 int launch_finalize_packed(staar_ctx *ctx, int64_t p, const double *d_mu, const double *d_quad,
                            const double *d_Sm, const long long *d_hi, const long long *d_lo,
                            double *dScore, double *dScore_se, double *dpl, double *dEst, double *dEst_se);
-int build_sliced_operand(staar_ctx *ctx, const double *hY /* n x ldY row-major host */);
+int build_sliced_operand(staar_ctx *ctx, const double *hY /* n x ldY row-major host, natural sample order */);
+int refresh_permuted_Y(staar_ctx *ctx, const double *hY);
 // synth.cu
 int launch_synth_packed(staar_ctx *ctx, uint8_t *d_packed, size_t stride, int64_t n, int64_t first_variant, int64_t p,
                         uint64_t seed, const uint64_t *thr_hom, const uint64_t *thr_het, const uint64_t *thr_miss,
-                        const uint8_t *store_alt);
+                        const uint8_t *store_alt, const int32_t *sample_order);
 // misc.cu
 int launch_csc_to_dense(staar_ctx *ctx, const double *d_val, const int64_t *d_row, const int64_t *d_colptr,
                         int64_t n, int64_t p, double *dG);
@@ -164,6 +183,8 @@ int launch_set_Y_col0(staar_ctx *ctx, int64_t n, int ldY, const double *d_res, d
 int launch_px_adj(staar_ctx *ctx, int64_t n, const int64_t *row_ptr, const int32_t *col, const double *val,
                   const double *dA, int m, const double *dSX, int q, const double *dT1, double *dOut);
 int launch_fill_pairs(staar_ctx *ctx, int64_t pp, int k, int32_t *d_colA, int32_t *d_colB);
+int launch_permute_packed(staar_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, size_t stride, int64_t n, int64_t p,
+                          const int32_t *d_perm);
 int spa_scratch_slots(staar_ctx *ctx, int64_t p);
 
 // ------------------------------------------------------------------ device math shared by kernels

@@ -336,7 +336,11 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
         STAAR_CUDA(cudaMemcpyAsync(pulled.data(), ns.Y, sizeof(double) * pulled.size(), cudaMemcpyDeviceToHost, ctx->stream));
         STAAR_CUDA(cudaStreamSynchronize(ctx->stream));
         hY = pulled.data();
+        STAAR_TRY(refresh_permuted_Y(ctx, hY));      // the scan's missing-sample sums gather rows of Yp
     }
+    // packed columns are in null-model sample order: digit position smp <- row perm[smp] of the natural operand
+    const int32_t *hperm = ns.permuted ? ns.h_perm.data() : nullptr;
+    auto row_of = [&](int64_t smp) { return hperm ? (int64_t)hperm[smp] : smp; };
     const int64_t n_chunks = (n + kChunkSamples - 1) / kChunkSamples;
     std::vector<int8_t> frag((size_t)n_chunks * kChunkBytesB, 0);
     std::vector<double> scale(kColsPerSlice, 1.0);
@@ -352,7 +356,7 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
         if (mx > 0.0) frexp(mx, &e);                 // mx = f * 2^e, f in [0.5, 1)  =>  |Y| < 2^e
         scale[c] = ldexp(1.0, e - 54);
         for (int64_t j = 0; j < n; j++) {
-            long long X = llrint(ldexp(hY[j * ldY + c], 54 - e));     // |X| <= 2^54
+            long long X = llrint(ldexp(hY[row_of(j) * ldY + c], 54 - e));     // |X| <= 2^54; digits[] is in position order
             int8_t d[kSlices];
             for (int s = kSlices - 1; s >= 1; s--) {
                 const long long dd = ((X + 128) & 255) - 128;

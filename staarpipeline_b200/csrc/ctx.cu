@@ -56,7 +56,9 @@ void NullSparse::release()
     if (owned) {
         cudaFree(row_ptr); cudaFree(col); cudaFree(val); cudaFree(SX); cudaFree(cov);
     }
-    cudaFree(diag); cudaFree(sinfo); cudaFree(off_ent); cudaFree(relmask); cudaFree(rel); cudaFree(up_ent); cudaFree(Y); cudaFree(Yfrag); cudaFree(col_scale);
+    if (permuted) cudaFree(Yp);
+    cudaFree(diag); cudaFree(sinfo_p); cudaFree(off_ent_p); cudaFree(relmask); cudaFree(rel); cudaFree(up_ent); cudaFree(Y);
+    cudaFree(Yfrag); cudaFree(col_scale); cudaFree(perm); cudaFree(kinmask); cudaFree(wdesc); cudaFree(terms_ovf); cudaFree(lut);
     *this = NullSparse();
 }
 void NullDense::release()
@@ -97,8 +99,24 @@ uint64_t hash_sampled(const double *data, size_t count, uint64_t seed)
 }
 
 // ------------------------------------------------------------------------------------------------
-// sparse null model: CSC(uint64) host -> CSR(int64/int32) device, Y = [res | Sigma_iX] row-major, diag, flags
+// sparse null model: CSC(uint64) host -> CSR(int64/int32) device, Y = [res | Sigma_iX | diag] row-major,
+// and the packed path's "null-model sample order" with its per-family kinship tables (common.cuh).
 // ------------------------------------------------------------------------------------------------
+namespace {
+
+template <typename T> int upload_vec(staar_ctx *ctx, T **dst, const std::vector<T> &src)
+{
+    const size_t count = std::max<size_t>(src.size(), 1);
+    STAAR_CUDA(cudaMalloc(reinterpret_cast<void **>(dst), sizeof(T) * count));
+    if (!src.empty())
+        STAAR_CUDA(cudaMemcpyAsync(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice, ctx->stream));
+    return STAAR_OK;
+}
+
+struct Family { int32_t first_member; int32_t size; };   // members: fam_members[first_member .. +size), natural indices
+
+}  // namespace
+
 int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *Sv, const uint64_t *Sr,
                             const uint64_t *Sc, const double *SX, const double *cov, const double *res,
                             uint64_t fp, uint64_t res_fp, bool want_sliced)
@@ -106,7 +124,7 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
     NullSparse &ns = ctx->ns;
     ns.release();
     if (n <= 0 || q < 0) { set_error("null model: bad dimensions n=%lld q=%lld", (long long)n, (long long)q); return STAAR_ERR_ARG; }
-    if (n >= (1ll << 31)) { set_error("null model: n too large for int32 column indices"); return STAAR_ERR_ARG; }
+    if (n >= (1ll << 30)) { set_error("null model: n too large for 30-bit sample indices"); return STAAR_ERR_ARG; }
     const int64_t nnz = (int64_t)Sc[n];
     // CSC -> CSR (transpose; exact for any matrix, and Sigma_i is symmetric anyway)
     std::vector<int64_t> row_ptr(n + 1, 0);
@@ -117,28 +135,25 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
     for (int64_t r = 0; r < n; r++) row_ptr[r + 1] += row_ptr[r];
     std::vector<int32_t> col(nnz);
     std::vector<double> val(nnz);
-    std::vector<int64_t> pos(row_ptr.begin(), row_ptr.end() - 1);
+    std::vector<int64_t> wpos(row_ptr.begin(), row_ptr.end() - 1);
     std::vector<double> diag(n, 0.0);
     int64_t nnz_off = 0;
+    // union-find over the off-diagonal graph: families = connected components
+    std::vector<int32_t> parent(n);
+    for (int64_t j = 0; j < n; j++) parent[j] = (int32_t)j;
+    auto find = [&](int32_t x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
     for (int64_t c = 0; c < n; c++)
         for (uint64_t e = Sc[c]; e < Sc[c + 1]; e++) {
             const int64_t r = (int64_t)Sr[e];
-            const int64_t d = pos[r]++;
+            const int64_t d = wpos[r]++;
             col[d] = (int32_t)c; val[d] = Sv[e];
             if (r == c) diag[r] += Sv[e];
-            else if (Sv[e] != 0.0) nnz_off++;
+            else if (Sv[e] != 0.0) {
+                nnz_off++;
+                const int32_t a = find((int32_t)r), b = find((int32_t)c);
+                if (a != b) parent[std::max(a, b)] = std::min(a, b);
+            }
         }
-    std::vector<NullSparse::SampleInfo> sinfo(n);
-    std::vector<NullSparse::OffEntry> off_ent(std::max<int64_t>(nnz_off, 1));
-    {
-        int64_t o = 0;
-        for (int64_t r = 0; r < n; r++) {
-            sinfo[r].diag = diag[r]; sinfo[r].off_start = (uint32_t)o;
-            for (int64_t e = row_ptr[r]; e < row_ptr[r + 1]; e++)
-                if (col[e] != r && val[e] != 0.0) { off_ent[o].val = val[e]; off_ent[o].col = col[e]; off_ent[o].pad = 0; o++; }
-            sinfo[r].off_count = (uint32_t)(o - sinfo[r].off_start);
-        }
-    }
     const int ldY = (int)(((2 + q) + 7) / 8 * 8);
     std::vector<double> Y((size_t)n * ldY, 0.0);
     for (int64_t j = 0; j < n; j++) {
@@ -147,58 +162,250 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
         Y[(size_t)j * ldY + 1 + q] = diag[j];
     }
     ns.n = n; ns.q = q; ns.nnz = nnz; ns.nnz_offdiag = nnz_off; ns.ldY = ldY; ns.owned = true;
-    STAAR_CUDA(cudaMalloc(&ns.row_ptr, sizeof(int64_t) * (n + 1)));
-    STAAR_CUDA(cudaMalloc(&ns.col, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
-    STAAR_CUDA(cudaMalloc(&ns.val, sizeof(double) * std::max<int64_t>(nnz, 1)));
-    STAAR_CUDA(cudaMalloc(&ns.diag, sizeof(double) * n));
-    // relatives mask + inline records for the packed carrier scan (upper triangle)
+
+    // ---- families and the null-model sample order --------------------------------------------------------
     const size_t pstride = staar_packed_stride(n);
+    const bool tables_ok = nnz_off > 0 && pstride + 4096 <= 227 * 1024;     // column must fit in shared memory
+    std::vector<int32_t> fam_members;            // natural indices, grouped by family (multi-member families only)
+    std::vector<Family> fams;
+    std::vector<int32_t> singles;
+    if (nnz_off > 0) {
+        std::vector<int32_t> root(n), count(n, 0), start(n, -1);
+        for (int64_t j = 0; j < n; j++) { root[j] = find((int32_t)j); count[root[j]]++; }
+        int32_t off = 0;
+        for (int64_t j = 0; j < n; j++)
+            if (root[j] == j && count[j] > 1) { start[j] = off; fams.push_back(Family{off, count[j]}); off += count[j]; }
+        fam_members.resize(off);
+        std::vector<int32_t> fill(n, 0);
+        for (int64_t j = 0; j < n; j++) {
+            const int32_t r = root[j];
+            if (count[r] > 1) fam_members[start[r] + fill[r]++] = (int32_t)j;   // ascending natural index within a family
+            else singles.push_back((int32_t)j);
+        }
+    }
+    // bins of 16 positions: best-fit decreasing over families of 2..16 members
+    struct Bin { std::vector<int32_t> fam; int used = 0; };
+    std::vector<Bin> bins;
+    std::vector<int32_t> generic_fams;
+    if (tables_ok) {
+        std::vector<int32_t> order;
+        for (size_t f = 0; f < fams.size(); f++) (fams[f].size <= 16 ? order : generic_fams).push_back((int32_t)f);
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return fams[a].size > fams[b].size; });
+        std::vector<std::vector<int32_t>> open(17);                 // open[r] = bins with r free positions
+        for (int32_t f : order) {
+            const int sz = fams[f].size;
+            int r = sz;
+            while (r <= 16 && open[r].empty()) r++;
+            int32_t b;
+            if (r <= 16) { b = open[r].back(); open[r].pop_back(); }
+            else { b = (int32_t)bins.size(); bins.emplace_back(); r = 16; }
+            bins[b].fam.push_back(f); bins[b].used += sz;
+            if (r - sz > 0) open[r - sz].push_back(b);
+        }
+    } else {
+        for (size_t f = 0; f < fams.size(); f++) generic_fams.push_back((int32_t)f);
+    }
+    // bins that can be topped up with unrelated samples become table words; the others go generic
+    std::vector<int32_t> bin_order(bins.size());
+    for (size_t b = 0; b < bins.size(); b++) bin_order[b] = (int32_t)b;
+    std::stable_sort(bin_order.begin(), bin_order.end(), [&](int32_t a, int32_t b) { return bins[a].used > bins[b].used; });
+    std::vector<int32_t> perm;                    // position -> natural index
+    perm.reserve(n);
+    std::vector<int32_t> table_bins;
+    {
+        size_t reserved = 0;                      // unrelated samples promised to earlier bins
+        for (int32_t b : bin_order) {
+            const size_t gap = (size_t)(16 - bins[b].used);
+            if (gap <= singles.size() - reserved) { table_bins.push_back(b); reserved += gap; }
+            else for (int32_t f : bins[b].fam) generic_fams.push_back(f);
+        }
+    }
+    size_t single_next = 0;
+    struct Placed { int32_t fam; int64_t pos0; };
+    std::vector<Placed> table_placed, generic_placed;
+    const bool permute = tables_ok && !table_bins.empty();
+    if (permute) {
+        for (int32_t b : table_bins) {
+            for (int32_t f : bins[b].fam) {
+                table_placed.push_back(Placed{f, (int64_t)perm.size()});
+                for (int m = 0; m < fams[f].size; m++) perm.push_back(fam_members[fams[f].first_member + m]);
+            }
+            for (int g = bins[b].used; g < 16; g++) perm.push_back(singles[single_next++]);
+        }
+        const int64_t tab_samples = (int64_t)perm.size();
+        for (int32_t f : generic_fams) {
+            generic_placed.push_back(Placed{f, (int64_t)perm.size()});
+            for (int m = 0; m < fams[f].size; m++) perm.push_back(fam_members[fams[f].first_member + m]);
+        }
+        ns.tab_words = tab_samples / 16;                                   // table words come first: [0, tab_words)
+        ns.kin_words = ((int64_t)perm.size() + 15) / 16;
+        while (single_next < singles.size()) perm.push_back(singles[single_next++]);
+    } else {
+        // identity order; every family on the generic path (positions == natural indices)
+        for (size_t f = 0; f < fams.size(); f++) generic_placed.push_back(Placed{(int32_t)f, -1});
+        ns.tab_words = 0;
+        int64_t last = -1;
+        for (int32_t j : fam_members) last = std::max<int64_t>(last, j);
+        ns.kin_words = nnz_off > 0 ? last / 16 + 1 : 0;
+    }
+    if (permute && (int64_t)perm.size() != n) { set_error("internal: sample order is not a permutation"); return STAAR_ERR_ARG; }
+    std::vector<int32_t> inv;
+    if (permute) { inv.resize(n); for (int64_t pz = 0; pz < n; pz++) inv[perm[pz]] = (int32_t)pz; }
+    auto pos_of = [&](int32_t natural) { return permute ? inv[natural] : natural; };
+    auto nat_of = [&](int64_t pz) { return permute ? perm[pz] : (int32_t)pz; };
+    ns.permuted = permute;
+
+    // ---- per-position kinship rows (both directions): corrections for missing related samples ------------
+    std::vector<NullSparse::SampleInfo> sinfo(n);
+    std::vector<NullSparse::OffEntry> off_ent;
+    off_ent.reserve(std::max<int64_t>(nnz_off, 1));
+    for (int64_t pz = 0; pz < n; pz++) {
+        const int32_t r = nat_of(pz);
+        sinfo[pz].diag = diag[r]; sinfo[pz].off_start = (uint32_t)off_ent.size();
+        for (int64_t e = row_ptr[r]; e < row_ptr[r + 1]; e++)
+            if (col[e] != r && val[e] != 0.0) off_ent.push_back(NullSparse::OffEntry{val[e], pos_of(col[e]), 0});
+        sinfo[pz].off_count = (uint32_t)(off_ent.size() - sinfo[pz].off_start);
+    }
+    // ---- table families: masks, word descriptors, look-up tables ------------------------------------------
+    std::vector<uint32_t> kinmask((size_t)std::max<int64_t>(ns.kin_words, 1), 0u);
+    std::vector<NullSparse::WordDesc> wdesc((size_t)std::max<int64_t>(ns.tab_words, 1));
+    memset(wdesc.data(), 0, sizeof(NullSparse::WordDesc) * wdesc.size());
+    std::vector<NullSparse::KinTerm> ovf;
+    std::vector<double> lut;
+    {
+        std::vector<std::vector<NullSparse::KinTerm>> word_terms((size_t)ns.tab_words);
+        double S[16][16];
+        for (const Placed &pl : table_placed) {
+            const int f = fams[pl.fam].size;
+            const int64_t word = pl.pos0 / 16;
+            const int o0 = (int)(pl.pos0 % 16);
+            for (int a = 0; a < f; a++) {
+                for (int b2 = 0; b2 < f; b2++) S[a][b2] = 0.0;
+                kinmask[word] |= 1u << (2 * (o0 + a));
+                const NullSparse::SampleInfo &si = sinfo[pl.pos0 + a];
+                for (uint32_t t = 0; t < si.off_count; t++) {
+                    const NullSparse::OffEntry &oe = off_ent[si.off_start + t];
+                    S[a][oe.col - pl.pos0] += oe.val;
+                }
+            }
+            // chunks of <= 4 members, as even as possible
+            const int nch = (f + 3) / 4, base = f / nch, extra = f % nch;
+            int c0[5];
+            c0[0] = 0;
+            for (int c = 0; c < nch; c++) c0[c + 1] = c0[c] + base + (c < extra ? 1 : 0);
+            auto codeval = [](int idx, int m) { const int c = (idx >> (2 * m)) & 3; return c == 3 ? 0.0 : (double)c; };
+            for (int A = 0; A < nch; A++) {
+                const int a0 = c0[A], sa = c0[A + 1] - c0[A];
+                if (sa >= 2) {                                         // pairs inside the chunk
+                    NullSparse::KinTerm t{(uint32_t)lut.size(), (uint8_t)(o0 + a0), (uint8_t)sa, 255, 0};
+                    for (int idx = 0; idx < (1 << (2 * sa)); idx++) {
+                        double v = 0.0;
+                        for (int m = 0; m < sa; m++)
+                            for (int m2 = m + 1; m2 < sa; m2++) v += 2.0 * S[a0 + m][a0 + m2] * codeval(idx, m) * codeval(idx, m2);
+                        lut.push_back(v);
+                    }
+                    word_terms[word].push_back(t);
+                }
+                for (int B = A + 1; B < nch; B++) {                    // member j of chunk A against chunk B
+                    const int b0 = c0[B], sb = c0[B + 1] - c0[B];
+                    for (int j = a0; j < a0 + sa; j++) {
+                        bool any = false;
+                        for (int m = 0; m < sb; m++) any |= S[j][b0 + m] != 0.0;
+                        if (!any) continue;
+                        NullSparse::KinTerm t{(uint32_t)lut.size(), (uint8_t)(o0 + b0), (uint8_t)sb, (uint8_t)(o0 + j), 0};
+                        for (int idx = 0; idx < (1 << (2 * sb)); idx++) {
+                            double v = 0.0;
+                            for (int m = 0; m < sb; m++) v += 2.0 * S[j][b0 + m] * codeval(idx, m);
+                            lut.push_back(v);
+                        }
+                        word_terms[word].push_back(t);
+                    }
+                }
+            }
+        }
+        for (int64_t w = 0; w < ns.tab_words; w++) {
+            const auto &tv = word_terms[w];
+            wdesc[w].nterm = (uint32_t)tv.size();
+            wdesc[w].ovf = (uint32_t)ovf.size();
+            for (size_t t = 0; t < tv.size(); t++) {
+                if (t < 7) wdesc[w].t[t] = tv[t];
+                else ovf.push_back(tv[t]);
+            }
+        }
+    }
+    ns.lut_entries = (int64_t)lut.size();
+    // ---- generic families: upper-triangle records in positions -------------------------------------------
     std::vector<uint8_t> relmask(pstride, 0);
     std::vector<NullSparse::CarrierRec> rel;
     std::vector<NullSparse::OffEntry> up_ent;
-    if (nnz_off > 0) {
+    ns.n_generic = 0;
+    if (!generic_placed.empty()) {
         rel.resize(n);
-        for (int64_t r = 0; r < n; r++) {
-            NullSparse::CarrierRec &rr = rel[r];
-            memset(&rr, 0, sizeof rr);
-            rr.start = (uint32_t)up_ent.size();
-            for (uint32_t t = 0; t < sinfo[r].off_count; t++) {
-                const NullSparse::OffEntry &oe = off_ent[sinfo[r].off_start + t];
-                if (oe.col <= r) continue;
-                if (rr.count < 2) { rr.val[rr.count] = oe.val; rr.col[rr.count] = oe.col; }
-                up_ent.push_back(oe);
-                rr.count++;
+        memset(rel.data(), 0, sizeof(NullSparse::CarrierRec) * rel.size());
+        for (const Placed &pl : generic_placed) {
+            for (int m = 0; m < fams[pl.fam].size; m++) {
+                const int64_t pz = pos_of(fam_members[fams[pl.fam].first_member + m]);
+                NullSparse::CarrierRec &rr = rel[pz];
+                rr.start = (uint32_t)up_ent.size();
+                const NullSparse::SampleInfo &si = sinfo[pz];
+                for (uint32_t t = 0; t < si.off_count; t++) {
+                    const NullSparse::OffEntry &oe = off_ent[si.off_start + t];
+                    if (oe.col <= pz) continue;
+                    if (rr.count < 2) { rr.val[rr.count] = oe.val; rr.col[rr.count] = oe.col; }
+                    up_ent.push_back(oe);
+                    rr.count++;
+                }
+                if (rr.count > 0) relmask[pz >> 2] |= (uint8_t)(3u << (2 * (pz & 3)));
+                ns.n_generic++;
             }
-            if (rr.count > 0) relmask[r >> 2] |= (uint8_t)(3u << (2 * (r & 3)));
         }
-        if (up_ent.empty()) up_ent.resize(1);
-        STAAR_CUDA(cudaMalloc(&ns.rel, sizeof(NullSparse::CarrierRec) * n));
-        STAAR_CUDA(cudaMemcpyAsync(ns.rel, rel.data(), sizeof(NullSparse::CarrierRec) * n, cudaMemcpyHostToDevice, ctx->stream));
-        STAAR_CUDA(cudaMalloc(&ns.up_ent, sizeof(NullSparse::OffEntry) * up_ent.size()));
-        STAAR_CUDA(cudaMemcpyAsync(ns.up_ent, up_ent.data(), sizeof(NullSparse::OffEntry) * up_ent.size(), cudaMemcpyHostToDevice, ctx->stream));
-        STAAR_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    STAAR_CUDA(cudaMalloc(&ns.relmask, pstride));
-    STAAR_CUDA(cudaMemcpyAsync(ns.relmask, relmask.data(), pstride, cudaMemcpyHostToDevice, ctx->stream));
-    STAAR_CUDA(cudaMalloc(&ns.sinfo, sizeof(NullSparse::SampleInfo) * n));
-    STAAR_CUDA(cudaMalloc(&ns.off_ent, sizeof(NullSparse::OffEntry) * off_ent.size()));
+    // ---- Y rows in null-model order ----------------------------------------------------------------------
+    if (permute) ns.h_perm = perm;
+
+    cudaStream_t st = ctx->stream;
+    STAAR_TRY(upload_vec(ctx, &ns.row_ptr, row_ptr));
+    STAAR_TRY(upload_vec(ctx, &ns.col, col));
+    STAAR_TRY(upload_vec(ctx, &ns.val, val));
+    STAAR_TRY(upload_vec(ctx, &ns.diag, diag));
+    STAAR_TRY(upload_vec(ctx, &ns.sinfo_p, sinfo));
+    STAAR_TRY(upload_vec(ctx, &ns.off_ent_p, off_ent));
+    STAAR_TRY(upload_vec(ctx, &ns.kinmask, kinmask));
+    STAAR_TRY(upload_vec(ctx, &ns.wdesc, wdesc));
+    STAAR_TRY(upload_vec(ctx, &ns.terms_ovf, ovf));
+    STAAR_TRY(upload_vec(ctx, &ns.lut, lut));
+    STAAR_TRY(upload_vec(ctx, &ns.relmask, relmask));
+    if (!rel.empty()) {
+        STAAR_TRY(upload_vec(ctx, &ns.rel, rel));
+        STAAR_TRY(upload_vec(ctx, &ns.up_ent, up_ent));
+    }
+    if (permute) STAAR_TRY(upload_vec(ctx, &ns.perm, perm));
+    STAAR_TRY(upload_vec(ctx, &ns.Y, Y));
     STAAR_CUDA(cudaMalloc(&ns.SX, sizeof(double) * std::max<int64_t>(n * q, 1)));
     STAAR_CUDA(cudaMalloc(&ns.cov, sizeof(double) * std::max<int64_t>(q * q, 1)));
-    STAAR_CUDA(cudaMalloc(&ns.Y, sizeof(double) * (size_t)n * ldY));
-    cudaStream_t st = ctx->stream;
-    STAAR_CUDA(cudaMemcpyAsync(ns.row_ptr, row_ptr.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
-    STAAR_CUDA(cudaMemcpyAsync(ns.col, col.data(), sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, st));
-    STAAR_CUDA(cudaMemcpyAsync(ns.val, val.data(), sizeof(double) * nnz, cudaMemcpyHostToDevice, st));
-    STAAR_CUDA(cudaMemcpyAsync(ns.diag, diag.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    STAAR_CUDA(cudaMemcpyAsync(ns.sinfo, sinfo.data(), sizeof(NullSparse::SampleInfo) * n, cudaMemcpyHostToDevice, st));
-    STAAR_CUDA(cudaMemcpyAsync(ns.off_ent, off_ent.data(), sizeof(NullSparse::OffEntry) * off_ent.size(), cudaMemcpyHostToDevice, st));
     STAAR_CUDA(cudaMemcpyAsync(ns.SX, SX, sizeof(double) * n * q, cudaMemcpyHostToDevice, st));
     STAAR_CUDA(cudaMemcpyAsync(ns.cov, cov, sizeof(double) * q * q, cudaMemcpyHostToDevice, st));
-    STAAR_CUDA(cudaMemcpyAsync(ns.Y, Y.data(), sizeof(double) * (size_t)n * ldY, cudaMemcpyHostToDevice, st));
+    if (permute) STAAR_CUDA(cudaMalloc(&ns.Yp, sizeof(double) * (size_t)n * ldY));
+    else ns.Yp = ns.Y;
     STAAR_CUDA(cudaStreamSynchronize(st));
     ns.fingerprint = fp; ns.res_fingerprint = res_fp;
     ns.set = true;
+    STAAR_TRY(refresh_permuted_Y(ctx, Y.data()));
     if (want_sliced) STAAR_TRY(build_sliced_operand(ctx, Y.data()));
+    return STAAR_OK;
+}
+
+// Yp <- rows of the (natural-order) host operand in null-model order; no-op when the order is the identity
+int refresh_permuted_Y(staar_ctx *ctx, const double *hY)
+{
+    NullSparse &ns = ctx->ns;
+    if (!ns.permuted) return STAAR_OK;
+    const int64_t n = ns.n;
+    const int ldY = ns.ldY;
+    std::vector<double> Yp((size_t)n * ldY);
+    for (int64_t pz = 0; pz < n; pz++) memcpy(&Yp[(size_t)pz * ldY], hY + (size_t)ns.h_perm[pz] * ldY, sizeof(double) * ldY);
+    STAAR_CUDA(cudaMemcpyAsync(ns.Yp, Yp.data(), sizeof(double) * Yp.size(), cudaMemcpyHostToDevice, ctx->stream));
+    STAAR_CUDA(cudaStreamSynchronize(ctx->stream));
     return STAAR_OK;
 }
 
@@ -258,7 +465,7 @@ void staar_ctx_destroy(staar_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->ns.release(); ctx->nd.release();
     ctx->G.release(); ctx->L.release(); ctx->aux.release(); ctx->out.release(); ctx->tmp.release();
-    ctx->tmp2.release(); ctx->pk.release(); ctx->ctr.release();
+    ctx->tmp2.release(); ctx->pk.release(); ctx->pk2.release(); ctx->ctr.release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);

@@ -73,6 +73,44 @@ __global__ void fill_pairs_kernel(int64_t pp, int k, int32_t *__restrict__ colA,
     }
 }
 
+// natural sample order -> null-model sample order for packed 2-bit columns: one CTA per variant, the source column is
+// staged in shared memory and every thread assembles whole 16-sample output words (out position j <- source perm[j])
+__global__ void __launch_bounds__(256) permute_packed_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
+                                                             size_t stride, int64_t n, int64_t p,
+                                                             const int32_t *__restrict__ perm)
+{
+    extern __shared__ __align__(16) uint8_t s_col[];
+    const int nvec16 = (int)(stride >> 4), nwords = (int)(stride >> 2);
+    for (int64_t i = blockIdx.x; i < p; i += gridDim.x) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(in + (size_t)i * stride);
+        for (int k = threadIdx.x; k < nvec16; k += blockDim.x) reinterpret_cast<uint4 *>(s_col)[k] = __ldg(src + k);
+        __syncthreads();
+        uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)i * stride);
+        for (int k = threadIdx.x; k < nwords; k += blockDim.x) {
+            const int64_t base = (int64_t)k * 16;
+            uint32_t w = 0u;
+            if (base + 16 <= n) {
+                const int4 *pp = reinterpret_cast<const int4 *>(perm + base);
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    const int4 q4 = __ldg(pp + v);
+                    const int sj[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                    for (int f = 0; f < 4; f++)
+                        w |= (((uint32_t)s_col[sj[f] >> 2] >> (2 * (sj[f] & 3))) & 3u) << (2 * (4 * v + f));
+                }
+            } else {
+                for (int f = 0; f < 16 && base + f < n; f++) {
+                    const int sj = __ldg(perm + base + f);
+                    w |= (((uint32_t)s_col[sj >> 2] >> (2 * (sj & 3))) & 3u) << (2 * f);
+                }
+            }
+            dst[k] = w;
+        }
+        __syncthreads();
+    }
+}
+
 inline int grid_for(staar_ctx *ctx, int64_t work, int threads)
 {
     return (int)std::max<int64_t>(1, std::min<int64_t>((work + threads - 1) / threads, (int64_t)ctx->sm_count * 16));
@@ -112,6 +150,23 @@ int launch_px_adj(staar_ctx *ctx, int64_t n, const int64_t *row_ptr, const int32
                   const double *dA, int m, const double *dSX, int q, const double *dT1, double *dOut)
 {
     px_adj_kernel<<<grid_for(ctx, n * m, 256), 256, 0, ctx->stream>>>(n, row_ptr, col, val, dA, m, dSX, q, dT1, dOut);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+int launch_permute_packed(staar_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, size_t stride, int64_t n, int64_t p,
+                          const int32_t *d_perm)
+{
+    if (p == 0) return STAAR_OK;
+    if (stride > 227 * 1024) { set_error("permute_packed: column of %zu bytes does not fit in shared memory", stride); return STAAR_ERR_ARG; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        STAAR_CUDA(cudaFuncSetAttribute(permute_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int grid = (int)std::min<int64_t>(p, (int64_t)ctx->sm_count * 4);
+    permute_packed_kernel<<<grid, 256, stride, ctx->stream>>>(d_in, d_out, stride, n, p, d_perm);
     ctx->launches++;
     STAAR_CUDA(cudaGetLastError());
     return STAAR_OK;

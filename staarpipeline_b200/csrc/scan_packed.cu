@@ -23,10 +23,19 @@ namespace {
 
 struct ScanParams {
     const uint8_t *packed; size_t stride; int64_t n, p; int impute;
-    const uint8_t *relmask;                // 2-bit mask, 11 = sample has kinship off-diagonals with a larger index
+    // generic kinship path (positions in null-model order)
+    const uint8_t *relmask;                // 2-bit mask, 11 = sample has kinship off-diagonals with a larger position
     const NullSparse::CarrierRec *rel;     // per-sample record: first two such entries inline (32 B)
     const NullSparse::OffEntry *up_ent;    // all upper-triangle entries (rows with more than two)
-    const double *Y; int ldY, ncol;
+    // table kinship path: families inside one 16-sample word
+    int64_t tab_words, kin_words;
+    const uint32_t *kinmask;
+    const NullSparse::WordDesc *wdesc;
+    const NullSparse::KinTerm *terms_ovf;
+    const double *lut;
+    const NullSparse::SampleInfo *sinfo;   // full kinship rows per position (missing related samples)
+    const NullSparse::OffEntry *off_ent;
+    const double *Y; int ldY, ncol;        // Y rows in null-model order
     double *AF, *MAF; int32_t *flip; double *mu, *quad, *Sm;
 };
 
@@ -194,32 +203,28 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams
 // frequency); each variant's arithmetic is independent of which CTA runs it, so results stay bit-reproducible.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kBlkWarps = 8;
-constexpr int kGroupCap = 1024;          // related carriers one warp can find in one 1024-sample group
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ double lookup_value_smem(const uint8_t *col, int64_t k, bool flip, double mu)
+// post-flip 2-bit code of the sample at position k of a column held in shared memory
+__device__ __forceinline__ uint32_t code_smem(const uint8_t *col, int64_t k, bool flip)
 {
     uint32_t code = ((uint32_t)col[k >> 2] >> (2 * (k & 3))) & 3u;
     if (flip && !(code & 1u)) code ^= 2u;
-    return code_value(code, mu);
+    return code;
 }
 
-template <bool HAS_OFF>
 __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P, int nstage, unsigned long long *work)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const size_t stride = P.stride;
     uint8_t *cols = smem;
-    uint8_t *after = smem + (size_t)nstage * stride;
-    uint16_t *car = reinterpret_cast<uint16_t *>(after) + (HAS_OFF ? wib * kGroupCap : 0);
-    after += HAS_OFF ? (size_t)kBlkWarps * kGroupCap * sizeof(uint16_t) : 0;
-    double *s_sm = reinterpret_cast<double *>(after);            // [kBlkWarps][16]
-    double *s_quad = s_sm + kBlkWarps * kColsPerSlice;           // [kBlkWarps]
-    int *s_cnt = reinterpret_cast<int *>(s_quad + kBlkWarps);    // [3][kBlkWarps]
-    unsigned long long *s_work = reinterpret_cast<unsigned long long *>(s_cnt + 3 * kBlkWarps + (kBlkWarps & 1));   // [2]
-    uint64_t *full = reinterpret_cast<uint64_t *>(s_work + 2);   // [2]
+    double *s_sm = reinterpret_cast<double *>(smem + (size_t)nstage * stride);   // [kBlkWarps][16]
+    double *s_quad = s_sm + kBlkWarps * kColsPerSlice;                           // [kBlkWarps]
+    int *s_cnt = reinterpret_cast<int *>(s_quad + kBlkWarps);                    // [3][kBlkWarps]
+    unsigned long long *s_work = reinterpret_cast<unsigned long long *>(s_cnt + 3 * kBlkWarps);   // [2]
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_work + 2);                   // [2]
 
     if (tid == 0) {
         for (int s = 0; s < 2; s++)
@@ -258,8 +263,9 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
     unsigned long long cur = s_work[0];
     int stage = 0;
     uint32_t parity = 0u;                                        // bit s = phase parity of full[s]
-    const uint2 *rmask = reinterpret_cast<const uint2 *>(P.relmask);
-    const int nvec16 = (int)(stride >> 4), nvec8 = (int)(stride >> 3);
+    const int nvec16 = (int)(stride >> 4);
+    const uint32_t *rmask32 = reinterpret_cast<const uint32_t *>(P.relmask);
+    const int kin_words = (int)P.kin_words, tab_words = (int)P.tab_words;
 
     for (unsigned it = 1; cur < pmax; it++) {
         if (nstage == 2 && tid == 0) {                           // prefetch the next variant's column
@@ -272,14 +278,45 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         const uint8_t *col = cols + (size_t)stage * stride;
         const int64_t i = (int64_t)cur;
 
-        // ---- sweep 1: popcounts -> AF / MAF / flip / imputation value (bit-exact integer counts)
+        // ---- sweep 1: popcounts -> AF / MAF / flip / imputation value (bit-exact integer counts), and the column
+        //      sums of Y over missing samples (independent of the flip): lane c accumulates column c
         int c1 = 0, c2 = 0, cm = 0;
+        double sm = 0.0;
         {
             const uint4 *v4 = reinterpret_cast<const uint4 *>(col);
-            for (int k = tid; k < nvec16; k += kBlkWarps * 32) {
-                const uint4 w = v4[k];
-                count_word(w.x, c1, c2, cm); count_word(w.y, c1, c2, cm);
-                count_word(w.z, c1, c2, cm); count_word(w.w, c1, c2, cm);
+            for (int k0 = wib * 32; k0 < nvec16; k0 += kBlkWarps * 32) {
+                const int k = k0 + lane;
+                uint4 q4 = make_uint4(0u, 0u, 0u, 0u);
+                if (k < nvec16) q4 = v4[k];
+                const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+                uint32_t mis[4];
+                uint32_t anym = 0u;
+#pragma unroll
+                for (int wi = 0; wi < 4; wi++) {
+                    const uint32_t lo = w[wi] & 0x55555555u, hi = (w[wi] >> 1) & 0x55555555u;
+                    mis[wi] = lo & hi;
+                    c1 += __popc(lo & ~hi);
+                    c2 += __popc(hi & ~lo);
+                    anym |= mis[wi];
+                }
+                if (__any_sync(0xffffffffu, anym != 0u)) {
+#pragma unroll
+                    for (int wi = 0; wi < 4; wi++) {
+                        cm += __popc(mis[wi]);
+                        uint32_t who = __ballot_sync(0xffffffffu, mis[wi] != 0u);
+                        while (who) {
+                            const int src = __ffs(who) - 1;
+                            who &= who - 1;
+                            uint32_t mw = __shfl_sync(0xffffffffu, mis[wi], src);
+                            const int64_t b0 = ((int64_t)(k0 + src) * 4 + wi) * 16;       // first sample of that word
+                            while (mw) {
+                                const int b = __ffs(mw) - 1;
+                                mw &= mw - 1;
+                                if (lane < P.ncol) sm += __ldg(P.Y + (b0 + (b >> 1)) * P.ldY + lane);
+                            }
+                        }
+                    }
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -288,6 +325,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
                 cm += __shfl_xor_sync(0xffffffffu, cm, o);
             }
             if (lane == 0) { s_cnt[wib] = c1; s_cnt[kBlkWarps + wib] = c2; s_cnt[2 * kBlkWarps + wib] = cm; }
+            if (lane < kColsPerSlice) s_sm[wib * kColsPerSlice + lane] = sm;
             __syncthreads();
             c1 = c2 = cm = 0;
 #pragma unroll
@@ -297,94 +335,79 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         const bool flip = vf.flip != 0;
         const double mu = vf.mu;
 
-        // ---- sweep 2: missing entries and related carriers (see scan_packed_kernel); groups of 1024 samples per warp
-        double quad = 0.0, sm = 0.0;
-        const uint2 *vecs = reinterpret_cast<const uint2 *>(col);
-        const bool sweep2 = HAS_OFF || cm > 0;      // unrelated samples: only missing entries need the second sweep
-        if (sweep2)
-        for (int k0 = wib * 32; k0 < nvec8; k0 += kBlkWarps * 32) {
-            const int k = k0 + lane;
-            uint2 q2 = make_uint2(0u, 0u), r2 = make_uint2(0u, 0u);
-            if (k < nvec8) {
-                q2 = vecs[k];
-                if (HAS_OFF) r2 = __ldg(rmask + k);
+        // ---- sweep 2: kinship off-diagonal part of g' Sigma_i g over the related prefix of the column, one
+        //      16-sample word per thread.  Table words: family codes -> look-up; generic words: per-carrier records.
+        double quad = 0.0;
+        const uint32_t *col32 = reinterpret_cast<const uint32_t *>(col);
+        for (int k = tid; k < kin_words; k += kBlkWarps * 32) {
+            const uint32_t w = col32[k];
+            const uint32_t lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+            const uint32_t mis = lo & hi;
+            uint32_t wf = w;
+            if (flip) {
+                wf = w ^ ((~lo & 0x55555555u) << 1);
+                const int64_t valid = P.n - (int64_t)k * 16;         // padding codes would flip to 2
+                if (valid < 16) wf &= (valid <= 0) ? 0u : ((1u << (2 * valid)) - 1u);
             }
-            uint32_t w[2] = {q2.x, q2.y}, sel[2], mis[2];
-            const uint32_t rm[2] = {r2.x, r2.y};
-            const int64_t base = (int64_t)k * 32;
-            int cnt = 0;
-            bool any_missing = false;
-#pragma unroll
-            for (int wi = 0; wi < 2; wi++) {
-                if (flip) {
-                    w[wi] = flip_word(w[wi]);
-                    const int64_t valid = P.n - (base + wi * 16);
-                    if (valid < 16) w[wi] &= (valid <= 0) ? 0u : ((1u << (2 * valid)) - 1u);
-                }
-                const uint32_t lo = w[wi] & 0x55555555u, hi = (w[wi] >> 1) & 0x55555555u;
-                mis[wi] = lo & hi;
-                sel[wi] = HAS_OFF ? ((lo | hi) & rm[wi] & ~(mu == 0.0 ? mis[wi] : 0u)) : 0u;
-                cnt += __popc(sel[wi]);
-                any_missing |= mis[wi] != 0u;
-            }
-            if (__any_sync(0xffffffffu, any_missing)) {
-#pragma unroll
-                for (int wi = 0; wi < 2; wi++) {
-                    const uint32_t mine = mis[wi];
-                    uint32_t who = __ballot_sync(0xffffffffu, mine != 0u);
-                    while (who) {
-                        const int src = __ffs(who) - 1;
-                        who &= who - 1;
-                        uint32_t mw = __shfl_sync(0xffffffffu, mine, src);
-                        const int64_t b0 = __shfl_sync(0xffffffffu, base, src) + wi * 16;
-                        while (mw) {
-                            const int b = __ffs(mw) - 1;
-                            mw &= mw - 1;
-                            if (lane < P.ncol) sm += __ldg(P.Y + (b0 + (b >> 1)) * P.ldY + lane);
+            const int64_t base = (int64_t)k * 16;
+            if (k < tab_words) {
+                const uint32_t wz = wf & ~(mis * 3u);                // missing -> 0: tables hold non-missing pairs only
+                const uint32_t km = __ldg(P.kinmask + k);
+                const uint32_t hit = (wz | (wz >> 1)) & km;
+                if (hit & (hit - 1u)) {                              // at least two related carriers in this word
+                    const uint2 *dp = reinterpret_cast<const uint2 *>(P.wdesc + k);
+                    const uint2 hdr = __ldg(dp);
+                    for (uint32_t t = 0; t < hdr.x; t++) {
+                        const uint2 tr = t < 7u ? __ldg(dp + 1 + t)
+                                                : __ldg(reinterpret_cast<const uint2 *>(P.terms_ovf) + hdr.y + (t - 7u));
+                        const uint32_t shift = tr.y & 0xffu, size = (tr.y >> 8) & 0xffu, jpos = (tr.y >> 16) & 0xffu;
+                        const uint32_t idx = (wz >> (2u * shift)) & ((1u << (2u * size)) - 1u);
+                        if (jpos == 255u) {
+                            const uint32_t nzb = (idx | (idx >> 1)) & 0x55u;
+                            if (nzb & (nzb - 1u)) quad += __ldg(P.lut + tr.x + idx);
+                        } else {
+                            const uint32_t gj = (wz >> (2u * jpos)) & 3u;
+                            if (gj != 0u && idx != 0u) quad += (double)gj * __ldg(P.lut + tr.x + idx);
                         }
                     }
                 }
-            }
-            if (!HAS_OFF) continue;
-            if (__any_sync(0xffffffffu, cnt != 0)) {
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                int pos = incl - cnt;
-#pragma unroll
-                for (int wi = 0; wi < 2; wi++) {
-                    uint32_t ss = sel[wi];
-                    while (ss) {
-                        const int b = __ffs(ss) - 1;                 // even bit position = 2 * field
-                        ss &= ss - 1;
-                        car[pos++] = (uint16_t)(((uint32_t)(lane * 32 + wi * 16 + (b >> 1)) << 2) | ((w[wi] >> b) & 3u));
-                    }
-                }
-                __syncwarp();
-                const int64_t gbase = (int64_t)k0 * 32;              // first sample of this warp's group
-                for (int first = 0; first < total; first += 32) {
-                    if (first + lane < total) {
-                        const uint32_t ce = car[first + lane];
-                        const NullSparse::CarrierRec rr = P.rel[gbase + (ce >> 2)];
-                        double s = rr.val[0] * lookup_value_smem(col, rr.col[0], flip, mu);
-                        if (rr.count > 1) s += rr.val[1] * lookup_value_smem(col, rr.col[1], flip, mu);
-                        for (uint32_t t = 2; t < rr.count; t++) {
-                            const NullSparse::OffEntry oe = P.up_ent[rr.start + t];
-                            s += oe.val * lookup_value_smem(col, oe.col, flip, mu);
+                uint32_t mk = mis & km;                              // missing related samples (imputed to mu)
+                if (mu != 0.0)
+                    while (mk) {
+                        const int b = __ffs(mk) - 1;
+                        mk &= mk - 1;
+                        const int64_t j = base + (b >> 1);
+                        const NullSparse::SampleInfo si = P.sinfo[j];
+                        double sacc = 0.0;
+                        for (uint32_t t = 0; t < si.off_count; t++) {
+                            const NullSparse::OffEntry oe = P.off_ent[si.off_start + t];
+                            const uint32_t c = code_smem(col, oe.col, flip);
+                            // a pair of two missing samples is counted once, from its smaller position
+                            const double v = c == 3u ? ((int64_t)oe.col > j ? mu : 0.0) : (double)c;
+                            sacc += oe.val * v;
                         }
-                        quad += 2.0 * code_value(ce & 3u, mu) * s;
+                        quad += 2.0 * mu * sacc;
                     }
+            } else {
+                uint32_t sel = (wf | (wf >> 1)) & 0x55555555u & __ldg(rmask32 + k);
+                if (mu == 0.0) sel &= ~mis;
+                while (sel) {
+                    const int b = __ffs(sel) - 1;
+                    sel &= sel - 1;
+                    const NullSparse::CarrierRec rr = P.rel[base + (b >> 1)];
+                    double sacc = 0.0;
+                    for (uint32_t t = 0; t < rr.count; t++) {
+                        double sv; int32_t sc;
+                        if (t < 2u) { sv = rr.val[t]; sc = rr.col[t]; }
+                        else { const NullSparse::OffEntry oe = P.up_ent[rr.start + t]; sv = oe.val; sc = oe.col; }
+                        sacc += sv * code_value(code_smem(col, sc, flip), mu);
+                    }
+                    quad += 2.0 * code_value((wf >> b) & 3u, mu) * sacc;
                 }
-                __syncwarp();
             }
         }
         quad = warp_sum(quad);
         if (lane == 0) s_quad[wib] = quad;
-        if (lane < kColsPerSlice) s_sm[wib * kColsPerSlice + lane] = sm;
         __syncthreads();                      // also: every read of this stage's column is complete
         if (tid < kColsPerSlice) {
             double t = 0.0;
@@ -465,29 +488,30 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     ScanParams P;
     P.packed = d_packed; P.stride = stride; P.n = n; P.p = p; P.impute = impute;
     P.relmask = ns.relmask; P.rel = ns.rel; P.up_ent = ns.up_ent;
-    P.Y = ns.Y; P.ldY = ns.ldY; P.ncol = (int)ns.q + 2;
+    P.tab_words = ns.tab_words; P.kin_words = ns.kin_words; P.kinmask = ns.kinmask; P.wdesc = ns.wdesc;
+    P.terms_ovf = ns.terms_ovf; P.lut = ns.lut; P.sinfo = ns.sinfo_p; P.off_ent = ns.off_ent_p;
+    P.Y = ns.Yp; P.ldY = ns.ldY; P.ncol = (int)ns.q + 2;
     P.AF = dAF; P.MAF = dMAF; P.flip = dflip; P.mu = d_mu; P.quad = d_quad; P.Sm = d_Sm;
-    const bool has_off = ns.nnz_offdiag > 0;
     // block-per-variant kernel: column(s) in shared memory, double-buffered when two fit
-    const size_t extra = (has_off ? (size_t)kBlkWarps * kGroupCap * sizeof(uint16_t) : 0) +
-                         sizeof(double) * (kBlkWarps * kColsPerSlice + kBlkWarps) + sizeof(int) * 3 * kBlkWarps + 64;
+    const size_t extra = sizeof(double) * (kBlkWarps * kColsPerSlice + kBlkWarps) + sizeof(int) * 3 * kBlkWarps + 64;
     const size_t smem_max = 227 * 1024;
     const int nstage = (2 * stride + extra <= smem_max) ? 2 : (stride + extra <= smem_max) ? 1 : 0;
-    if (nstage > 0 && !ctx->scan_warp_kernel) {
+    if (nstage > 0) {
         const size_t smem = (size_t)nstage * stride + extra;
-        auto kern = has_off ? scan_block_kernel<true> : scan_block_kernel<false>;
-        STAAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        STAAR_CUDA(cudaFuncSetAttribute(scan_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        STAAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlkWarps * 32, smem));
+        STAAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_block_kernel, kBlkWarps * 32, smem));
         if (per_sm < 1) { set_error("packed scan: kernel does not fit on an SM (smem %zu B)", smem); return STAAR_ERR_CUDA; }
         STAAR_TRY(ctx->ctr.reserve(sizeof(unsigned long long)));
         STAAR_CUDA(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(unsigned long long), ctx->stream));
         const int64_t blocks = std::min<int64_t>(p, (int64_t)ctx->sm_count * per_sm);
-        kern<<<(int)blocks, kBlkWarps * 32, smem, ctx->stream>>>(P, nstage, ctx->ctr.as<unsigned long long>());
+        scan_block_kernel<<<(int)blocks, kBlkWarps * 32, smem, ctx->stream>>>(P, nstage, ctx->ctr.as<unsigned long long>());
     } else {
-        // columns too long for shared memory (n > ~9e5): warp-per-variant kernel reading global memory
+        // columns too long for shared memory (n > ~9e5): warp-per-variant kernel reading global memory; the null
+        // model was then set up with every family on the generic path and the identity sample order
+        if (ns.tab_words > 0) { set_error("packed scan: stride %zu does not fit in shared memory", stride); return STAAR_ERR_ARG; }
         int64_t blocks = std::min<int64_t>((p + kScanWarps - 1) / kScanWarps, (int64_t)ctx->sm_count * 8);
-        if (has_off) scan_packed_kernel<true><<<(int)blocks, kScanWarps * 32, 0, ctx->stream>>>(P);
+        if (ns.nnz_offdiag > 0) scan_packed_kernel<true><<<(int)blocks, kScanWarps * 32, 0, ctx->stream>>>(P);
         else scan_packed_kernel<false><<<(int)blocks, kScanWarps * 32, 0, ctx->stream>>>(P);
     }
     ctx->launches++;

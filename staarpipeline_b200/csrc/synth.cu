@@ -19,7 +19,7 @@ __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t variant, ui
 __global__ void synth_packed_kernel(uint8_t *__restrict__ packed, size_t stride, int64_t n, int64_t first_variant,
                                     int64_t p, uint64_t seed, const uint64_t *__restrict__ thr_hom,
                                     const uint64_t *__restrict__ thr_het, const uint64_t *__restrict__ thr_miss,
-                                    const uint8_t *__restrict__ store_alt)
+                                    const uint8_t *__restrict__ store_alt, const int32_t *__restrict__ order)
 {
     const int64_t words_per_col = (int64_t)(stride >> 2);
     const int64_t total = p * words_per_col;
@@ -30,8 +30,9 @@ __global__ void synth_packed_kernel(uint8_t *__restrict__ packed, size_t stride,
         const bool alt_stored = store_alt[i] != 0;
         uint32_t w = 0;
         for (int f = 0; f < 16; f++) {
-            const int64_t j = wi * 16 + f;
-            if (j >= n) break;
+            const int64_t pos = wi * 16 + f;
+            if (pos >= n) break;
+            const int64_t j = order ? (int64_t)order[pos] : pos;     // the sample stored at this position
             const uint64_t u = hash_u32(seed, v, (uint64_t)j, 0), u2 = hash_u32(seed, v, (uint64_t)j, 4);
             uint32_t alt = (u < th ? 1u : 0u) + (u < te ? 1u : 0u);
             uint32_t code = alt_stored ? alt : 2u - alt;
@@ -46,13 +47,13 @@ __global__ void synth_packed_kernel(uint8_t *__restrict__ packed, size_t stride,
 
 int launch_synth_packed(staar_ctx *ctx, uint8_t *d_packed, size_t stride, int64_t n, int64_t first_variant, int64_t p,
                         uint64_t seed, const uint64_t *thr_hom, const uint64_t *thr_het, const uint64_t *thr_miss,
-                        const uint8_t *store_alt)
+                        const uint8_t *store_alt, const int32_t *sample_order)
 {
     if (p == 0) return STAAR_OK;
     const int64_t total = p * (int64_t)(stride >> 2);
     int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 32);
     synth_packed_kernel<<<blocks, 256, 0, ctx->stream>>>(d_packed, stride, n, first_variant, p, seed, thr_hom, thr_het,
-                                                         thr_miss, store_alt);
+                                                         thr_miss, store_alt, sample_order);
     ctx->launches++;
     STAAR_CUDA(cudaGetLastError());
     return STAAR_OK;

@@ -152,6 +152,42 @@ def test_packed_score_vs_oracle(gpu_ctx, oracle, n, p, q, related, impute):
     assert zero.any() and np.array_equal(got["Score_se"] == 0, zero)
 
 
+def test_packed_kinship_paths(gpu_ctx, oracle):
+    """Kinship term of the packed path on every route: table families (sizes 2-16, chunked above 4), a family of more
+    than 16 members (generic record path), heavy missingness among relatives, mean and minor imputation."""
+    from staarpipeline_b200 import synth
+    from staarpipeline_b200.api import IMPUTE_MEAN, IMPUTE_MINOR
+    n, q = 1500, 4
+    rng = np.random.default_rng(123)
+    sizes = [2] * 60 + [3] * 40 + [4] * 30 + [5] * 10 + [6] * 10 + [7, 9, 11, 13, 16, 16, 21, 40]
+    perm = rng.permutation(n)
+    rows, cols, vals, pos = [], [], [], 0
+    for s_ in sizes:
+        A = rng.normal(size=(s_, s_)); Sig = A @ A.T / s_ + np.eye(s_)
+        inv = np.linalg.inv(Sig)
+        idx = perm[pos:pos + s_]; pos += s_
+        r, c = np.meshgrid(idx, idx, indexing="ij")
+        rows.append(r.ravel()); cols.append(c.ravel()); vals.append(inv.ravel())
+    for j in perm[pos:]:
+        rows.append(np.array([j])); cols.append(np.array([j])); vals.append(np.array([1.0 + rng.random()]))
+    Sigma_i = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+    X = synth.covariates(n, rng, q)
+    Sigma_iX = np.asfortranarray(Sigma_i @ X)
+    cov = np.asfortranarray(np.linalg.inv(X.T @ Sigma_iX))
+    res = np.asarray(Sigma_i @ rng.normal(size=n)).ravel()
+    G0 = cases.raw_dosage(n, 80, seed=5)
+    G0[rng.random(G0.shape) < 0.05] = np.nan                      # 5 % missing everywhere, relatives included
+    codes = np.where(np.isnan(G0) | (G0 <= -1), 3, G0).astype(np.uint8)
+    packed = synth.pack_codes(np.asfortranarray(codes))
+    gpu_ctx.set_nullmodel_sparse(Sigma_i, Sigma_iX, cov, res)
+    for impute, flag in (("mean", IMPUTE_MEAN), ("minor", IMPUTE_MINOR)):
+        fl = getattr(oracle, f"matrix_flip_{impute}")(G0)
+        want = oracle.Individual_Score_Test(fl["Geno"], Sigma_i, Sigma_iX, cov, res)
+        got = gpu_ctx.packed_score_host(packed, n, flag)
+        assert np.array_equal(got["AF"], fl["AF"]) and np.array_equal(got["MAF"], fl["MAF"])
+        assert_stats_close({k: got[k] for k in want}, want, score_floor(fl["Geno"], res))
+
+
 def test_host_packer_matches_numpy(oracle):
     from staarpipeline_b200 import api, synth
     G0 = cases.raw_dosage(333, 21)
@@ -176,6 +212,46 @@ def test_device_generator_matches_host(gpu_ctx):
                                 tm.data_ptr(), sa.data_ptr())
     want = synth.pack_codes(synth.dosage_codes(n, first, p, params=prm), stride)
     assert np.array_equal(out.cpu().numpy(), want)
+    # generated directly in a given sample order == generated in natural order, then re-ordered
+    order = np.random.default_rng(0).permutation(n).astype(np.int32)
+    d_order = torch.from_numpy(order).to(dev)
+    gpu_ctx.synth_packed_device(out.data_ptr(), stride, n, first, p, synth.BASE_SEED, th.data_ptr(), te.data_ptr(),
+                                tm.data_ptr(), sa.data_ptr(), d_order.data_ptr())
+    codes = synth.dosage_codes(n, first, p, params=prm)
+    assert np.array_equal(out.cpu().numpy(), synth.pack_codes(np.asfortranarray(codes[order]), stride))
+
+
+def test_resident_order_and_reorder(gpu_ctx, oracle):
+    """Resident columns are in the null-model sample order: families inside 16-sample words, a true permutation;
+    re-ordering caller-order columns on the device + the resident entry point == the host entry point, bit for bit."""
+    import torch
+    from staarpipeline_b200 import api, synth
+    n, p, q = 3000, 64, 6
+    nm, G0, packed, want, Gf = _packed_case(oracle, n, p, q, seed=77, related=True)
+    gpu_ctx.set_nullmodel_sparse(nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+    order = gpu_ctx.nullmodel_sample_order()
+    assert np.array_equal(np.sort(order), np.arange(n))
+    # every related pair whose members are both in the table region shares a word
+    S = sp.coo_matrix(nm.Sigma_i)
+    pos = np.empty(n, dtype=np.int64); pos[order] = np.arange(n)
+    off = S.row != S.col
+    same_word = pos[S.row[off]] // 16 == pos[S.col[off]] // 16
+    assert same_word.mean() > 0.99
+    host = gpu_ctx.packed_score_host(packed, n, api.IMPUTE_MEAN)
+    dev = torch.device("cuda:0")
+    P, stride = packed.shape
+    d_in = torch.from_numpy(packed).to(dev)
+    d_out = torch.zeros_like(d_in)
+    outs = torch.zeros((7, P), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    gpu_ctx.packed_reorder_device(d_in.data_ptr(), d_out.data_ptr(), stride, n, P)
+    codes = np.where(np.isnan(G0) | (G0 <= -1), 3, G0).astype(np.uint8)
+    assert np.array_equal(d_out.cpu().numpy(), synth.pack_codes(np.asfortranarray(codes[order]), stride))
+    gpu_ctx.packed_score_device(d_out.data_ptr(), stride, n, P, api.IMPUTE_MEAN, [outs[i].data_ptr() for i in range(7)])
+    gpu_ctx.synchronize()
+    res = outs.cpu().numpy()
+    for i, k in enumerate(("AF", "MAF", "Score", "Score_se", "pvalue_log", "Est", "Est_se")):
+        assert np.array_equal(res[i], host[k], equal_nan=True), k
 
 
 def test_packed_contraction_is_exact_integer(gpu_ctx, oracle):
