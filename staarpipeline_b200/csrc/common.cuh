@@ -59,21 +59,24 @@ struct NullSparse {
     struct alignas(16) OffEntry { double val; int32_t col; int32_t pad; };
     // ---- packed path: "null-model sample order".  Samples are re-ordered once, at set-up, so that every family
     // (connected component of Sigma_i's off-diagonal graph) of 2..16 members sits inside ONE 16-sample word of the
-    // packed column; related samples come first, unrelated ones after.  The kinship part of g' Sigma_i g then needs
-    // no genotype gathers: a lane extracts a family's 2-bit codes from the word it already holds and looks the
-    // family's contribution up in a per-family table (4^size entries, size <= 4; larger families are chunked).
-    // Families that do not fit (more than 16 members) take the "generic" record path below.
+    // packed column, families of <= 4 members inside one aligned 4-sample group; related samples come first,
+    // unrelated ones after.  The kinship part of g' Sigma_i g then needs no genotype gathers: a lane takes the byte
+    // of a group (four 2-bit codes) from the word it already holds and looks the group's contribution up in that
+    // group's table (<= 256 entries); families of 5..16 members add member x later-chunk terms ("cross" words).
+    // Families of more than 16 members take the "generic" record path below.
     bool permuted = false;            // false: perm is the identity
     std::vector<int32_t> h_perm;      // position -> original sample (empty when identity)
     int32_t *perm = nullptr;          // device copy (nullptr when identity)
     double *Yp = nullptr;             // Y rows in null-model order (== Y when !permuted; then not owned)
     int64_t kin_words = 0;            // 16-sample words [0, kin_words) hold every sample with kinship off-diagonals
-    int64_t tab_words = 0;            // words [0, tab_words): table families; [tab_words, kin_words): generic families
-    uint32_t *kinmask = nullptr;      // kin_words words: bit 2f set = sample f of the word is in a table family
-    struct KinTerm { uint32_t off; uint8_t shift, size, jpos, pad; };   // value = (jpos == 255 ? 1 : code[jpos]) * lut[off + idx]
-    struct alignas(64) WordDesc { uint32_t nterm, ovf; KinTerm t[7]; };
-    WordDesc *wdesc = nullptr;        // tab_words descriptors
-    KinTerm *terms_ovf = nullptr;     // terms beyond the 7 inline ones
+    int64_t tab_words = 0;            // words [0, tab_words): table words; [tab_words, kin_words): generic families
+    int64_t x_words = 0;              // words [0, x_words) additionally carry cross terms (families of 5..16 members)
+    uint32_t *gdesc = nullptr;        // 4 per table word: (table offset / 16) << 8 | code mask of the group's related slots
+    // cross term: value = code(word >> jshift2) * lut[off + ((word >> shift2) & mask)]
+    struct KinTerm { uint32_t off; uint8_t shift2, mask, jshift2, pad; };
+    struct WordDesc { uint32_t start, count; };
+    WordDesc *wdesc = nullptr;        // x_words descriptors
+    KinTerm *xterms = nullptr;
     double *lut = nullptr;
     int64_t lut_entries = 0;
     SampleInfo *sinfo_p = nullptr;    // full kinship rows in null-model positions (missing related samples)

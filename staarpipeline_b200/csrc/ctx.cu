@@ -58,7 +58,7 @@ void NullSparse::release()
     }
     if (permuted) cudaFree(Yp);
     cudaFree(diag); cudaFree(sinfo_p); cudaFree(off_ent_p); cudaFree(relmask); cudaFree(rel); cudaFree(up_ent); cudaFree(Y);
-    cudaFree(Yfrag); cudaFree(col_scale); cudaFree(perm); cudaFree(kinmask); cudaFree(wdesc); cudaFree(terms_ovf); cudaFree(lut);
+    cudaFree(Yfrag); cudaFree(col_scale); cudaFree(perm); cudaFree(gdesc); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut);
     *this = NullSparse();
 }
 void NullDense::release()
@@ -183,54 +183,85 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
             else singles.push_back((int32_t)j);
         }
     }
-    // bins of 16 positions: best-fit decreasing over families of 2..16 members
-    struct Bin { std::vector<int32_t> fam; int used = 0; };
-    std::vector<Bin> bins;
+    // ---- layout: 16-sample words of four 4-sample groups.  A family of <= 4 members lives inside one group (its
+    // members first, unrelated samples fill the rest; two pairs share a group); a family of 5..16 members takes
+    // consecutive groups of one word in chunks of 4.  Words holding such a family come first ("cross" words: they
+    // also need member x chunk terms); every within-group pair is covered by that group's look-up table.
+    struct Item { std::vector<int32_t> fam; int groups; };      // groups of 4 slots this item occupies in a word
+    std::vector<Item> items;
     std::vector<int32_t> generic_fams;
+    size_t singles_needed = 0;
     if (tables_ok) {
-        std::vector<int32_t> order;
-        for (size_t f = 0; f < fams.size(); f++) (fams[f].size <= 16 ? order : generic_fams).push_back((int32_t)f);
-        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return fams[a].size > fams[b].size; });
-        std::vector<std::vector<int32_t>> open(17);                 // open[r] = bins with r free positions
-        for (int32_t f : order) {
+        std::vector<int32_t> pairs;
+        for (size_t f = 0; f < fams.size(); f++) {
             const int sz = fams[f].size;
-            int r = sz;
-            while (r <= 16 && open[r].empty()) r++;
-            int32_t b;
-            if (r <= 16) { b = open[r].back(); open[r].pop_back(); }
-            else { b = (int32_t)bins.size(); bins.emplace_back(); r = 16; }
-            bins[b].fam.push_back(f); bins[b].used += sz;
-            if (r - sz > 0) open[r - sz].push_back(b);
+            if (sz > 16) generic_fams.push_back((int32_t)f);
+            else if (sz == 2) pairs.push_back((int32_t)f);
+            else items.push_back(Item{{(int32_t)f}, (sz + 3) / 4});
         }
+        for (size_t i = 0; i + 1 < pairs.size(); i += 2) items.push_back(Item{{pairs[i], pairs[i + 1]}, 1});
+        if (pairs.size() & 1) items.push_back(Item{{pairs.back()}, 1});
     } else {
         for (size_t f = 0; f < fams.size(); f++) generic_fams.push_back((int32_t)f);
     }
-    // bins that can be topped up with unrelated samples become table words; the others go generic
-    std::vector<int32_t> bin_order(bins.size());
-    for (size_t b = 0; b < bins.size(); b++) bin_order[b] = (int32_t)b;
-    std::stable_sort(bin_order.begin(), bin_order.end(), [&](int32_t a, int32_t b) { return bins[a].used > bins[b].used; });
-    std::vector<int32_t> perm;                    // position -> natural index
-    perm.reserve(n);
-    std::vector<int32_t> table_bins;
+    // bins = words of 4 groups, best-fit decreasing by group count; multi-group items first
+    struct Bin { std::vector<int32_t> item; int used = 0; bool cross = false; };
+    std::vector<Bin> bins;
     {
-        size_t reserved = 0;                      // unrelated samples promised to earlier bins
-        for (int32_t b : bin_order) {
-            const size_t gap = (size_t)(16 - bins[b].used);
-            if (gap <= singles.size() - reserved) { table_bins.push_back(b); reserved += gap; }
-            else for (int32_t f : bins[b].fam) generic_fams.push_back(f);
+        std::vector<int32_t> order(items.size());
+        for (size_t i = 0; i < items.size(); i++) order[i] = (int32_t)i;
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return items[a].groups > items[b].groups; });
+        std::vector<std::vector<int32_t>> open(5);                  // open[r] = bins with r free groups
+        for (int32_t it : order) {
+            const int g = items[it].groups;
+            int r = g;
+            while (r <= 4 && open[r].empty()) r++;
+            int32_t b;
+            if (r <= 4) { b = open[r].back(); open[r].pop_back(); }
+            else { b = (int32_t)bins.size(); bins.emplace_back(); r = 4; }
+            bins[b].item.push_back(it); bins[b].used += g; bins[b].cross |= g > 1;
+            if (r - g > 0) open[r - g].push_back(b);
         }
     }
+    auto bin_members = [&](const Bin &b) { int m = 0; for (int32_t it : b.item) for (int32_t f : items[it].fam) m += fams[f].size; return m; };
+    // words that cannot be topped up with unrelated samples go generic (cohorts where nearly everyone is related)
+    std::vector<int32_t> bin_order(bins.size());
+    for (size_t b = 0; b < bins.size(); b++) bin_order[b] = (int32_t)b;
+    std::stable_sort(bin_order.begin(), bin_order.end(), [&](int32_t a, int32_t b) {
+        if (bins[a].cross != bins[b].cross) return bins[a].cross;              // cross words first
+        return bin_members(bins[a]) > bin_members(bins[b]);
+    });
+    std::vector<int32_t> table_bins;
+    {
+        size_t reserved = 0;
+        for (int32_t b : bin_order) {
+            const size_t gap = (size_t)(16 - bin_members(bins[b]));
+            if (gap <= singles.size() - reserved) { table_bins.push_back(b); reserved += gap; }
+            else for (int32_t it : bins[b].item) for (int32_t f : items[it].fam) generic_fams.push_back(f);
+        }
+        singles_needed = reserved;
+    }
+    (void)singles_needed;
+    std::vector<int32_t> perm;                    // position -> natural index
+    perm.reserve(n);
     size_t single_next = 0;
     struct Placed { int32_t fam; int64_t pos0; };
     std::vector<Placed> table_placed, generic_placed;
     const bool permute = tables_ok && !table_bins.empty();
+    ns.x_words = 0;
     if (permute) {
         for (int32_t b : table_bins) {
-            for (int32_t f : bins[b].fam) {
-                table_placed.push_back(Placed{f, (int64_t)perm.size()});
-                for (int m = 0; m < fams[f].size; m++) perm.push_back(fam_members[fams[f].first_member + m]);
+            const int64_t word0 = (int64_t)perm.size();
+            for (int32_t it : bins[b].item) {
+                // an item starts on a group boundary; families of one item are laid out back to back
+                for (int32_t f : items[it].fam) {
+                    table_placed.push_back(Placed{f, (int64_t)perm.size()});
+                    for (int m = 0; m < fams[f].size; m++) perm.push_back(fam_members[fams[f].first_member + m]);
+                }
+                while (((int64_t)perm.size() - word0) % 4 != 0) perm.push_back(singles[single_next++]);
             }
-            for (int g = bins[b].used; g < 16; g++) perm.push_back(singles[single_next++]);
+            while ((int64_t)perm.size() - word0 < 16) perm.push_back(singles[single_next++]);
+            if (bins[b].cross) ns.x_words = (int64_t)perm.size() / 16;
         }
         const int64_t tab_samples = (int64_t)perm.size();
         for (int32_t f : generic_fams) {
@@ -266,71 +297,85 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
             if (col[e] != r && val[e] != 0.0) off_ent.push_back(NullSparse::OffEntry{val[e], pos_of(col[e]), 0});
         sinfo[pz].off_count = (uint32_t)(off_ent.size() - sinfo[pz].off_start);
     }
-    // ---- table families: masks, word descriptors, look-up tables ------------------------------------------
-    std::vector<uint32_t> kinmask((size_t)std::max<int64_t>(ns.kin_words, 1), 0u);
-    std::vector<NullSparse::WordDesc> wdesc((size_t)std::max<int64_t>(ns.tab_words, 1));
+    // ---- table words: one look-up table per 4-sample group (all related pairs inside the group), and for words
+    //      holding a family of more than 4 members the member x later-chunk terms ----------------------------
+    std::vector<uint32_t> gdesc((size_t)std::max<int64_t>(ns.tab_words, 1) * 4, 0u);   // (lut offset / 16) << 8 | code mask
+    std::vector<NullSparse::WordDesc> wdesc((size_t)std::max<int64_t>(ns.x_words, 1));
     memset(wdesc.data(), 0, sizeof(NullSparse::WordDesc) * wdesc.size());
-    std::vector<NullSparse::KinTerm> ovf;
-    std::vector<double> lut;
+    std::vector<NullSparse::KinTerm> xterms;
+    std::vector<double> lut(256, 0.0);            // offset 0 = an all-zero table (groups without related pairs)
     {
-        std::vector<std::vector<NullSparse::KinTerm>> word_terms((size_t)ns.tab_words);
-        double S[16][16];
-        for (const Placed &pl : table_placed) {
-            const int f = fams[pl.fam].size;
-            const int64_t word = pl.pos0 / 16;
-            const int o0 = (int)(pl.pos0 % 16);
-            for (int a = 0; a < f; a++) {
-                for (int b2 = 0; b2 < f; b2++) S[a][b2] = 0.0;
-                kinmask[word] |= 1u << (2 * (o0 + a));
-                const NullSparse::SampleInfo &si = sinfo[pl.pos0 + a];
-                for (uint32_t t = 0; t < si.off_count; t++) {
-                    const NullSparse::OffEntry &oe = off_ent[si.off_start + t];
-                    S[a][oe.col - pl.pos0] += oe.val;
+        auto codeval = [](int idx, int m) { const int c = (idx >> (2 * m)) & 3; return c == 3 ? 0.0 : (double)c; };
+        // kinship entry between two positions (0 when unrelated)
+        auto s_between = [&](int64_t a, int64_t b2) {
+            const NullSparse::SampleInfo &si = sinfo[a];
+            double v = 0.0;
+            for (uint32_t t = 0; t < si.off_count; t++) if (off_ent[si.off_start + t].col == b2) v += off_ent[si.off_start + t].val;
+            return v;
+        };
+        for (int64_t g = 0; g < ns.tab_words * 4; g++) {
+            const int64_t p0 = g * 4;
+            double S[4][4];
+            int hi = -1;                                             // highest slot holding a related sample
+            uint32_t mask = 0u;
+            bool any_pair = false;
+            for (int a = 0; a < 4; a++) {
+                if (p0 + a < n && sinfo[p0 + a].off_count > 0) { hi = a; mask |= 3u << (2 * a); }
+                for (int b2 = 0; b2 < 4; b2++) {
+                    S[a][b2] = (a != b2 && p0 + a < n && p0 + b2 < n) ? s_between(p0 + a, p0 + b2) : 0.0;
+                    any_pair |= S[a][b2] != 0.0;
                 }
             }
-            // chunks of <= 4 members, as even as possible
-            const int nch = (f + 3) / 4, base = f / nch, extra = f % nch;
-            int c0[5];
-            c0[0] = 0;
-            for (int c = 0; c < nch; c++) c0[c + 1] = c0[c] + base + (c < extra ? 1 : 0);
-            auto codeval = [](int idx, int m) { const int c = (idx >> (2 * m)) & 3; return c == 3 ? 0.0 : (double)c; };
-            for (int A = 0; A < nch; A++) {
-                const int a0 = c0[A], sa = c0[A + 1] - c0[A];
-                if (sa >= 2) {                                         // pairs inside the chunk
-                    NullSparse::KinTerm t{(uint32_t)lut.size(), (uint8_t)(o0 + a0), (uint8_t)sa, 255, 0};
-                    for (int idx = 0; idx < (1 << (2 * sa)); idx++) {
-                        double v = 0.0;
-                        for (int m = 0; m < sa; m++)
-                            for (int m2 = m + 1; m2 < sa; m2++) v += 2.0 * S[a0 + m][a0 + m2] * codeval(idx, m) * codeval(idx, m2);
-                        lut.push_back(v);
-                    }
-                    word_terms[word].push_back(t);
-                }
-                for (int B = A + 1; B < nch; B++) {                    // member j of chunk A against chunk B
-                    const int b0 = c0[B], sb = c0[B + 1] - c0[B];
-                    for (int j = a0; j < a0 + sa; j++) {
+            if (hi < 0) continue;                                    // only unrelated samples in this group
+            gdesc[g] = mask;                                         // table offset 0: the all-zero table
+            if (!any_pair) continue;                                 // e.g. the lone last member of a 5-member family
+            const int entries = 1 << (2 * (hi + 1));
+            if (lut.size() / 16 >= (1u << 24)) { set_error("kinship tables exceed 2^28 entries"); return STAAR_ERR_ARG; }
+            gdesc[g] |= (uint32_t)((lut.size() / 16) << 8);
+            for (int idx = 0; idx < entries; idx++) {
+                double v = 0.0;
+                for (int m = 0; m <= hi; m++)
+                    for (int m2 = m + 1; m2 <= hi; m2++) v += 2.0 * S[m][m2] * codeval(idx, m) * codeval(idx, m2);
+                lut.push_back(v);
+            }
+            while (lut.size() % 16) lut.push_back(0.0);
+        }
+        // cross terms of a family of 5..16 members: for every pair of chunks the LARGER chunk indexes a table
+        // (<= 256 entries) per member of the smaller one:  sum_j code_j * T_j[codes of the other chunk]
+        std::vector<std::vector<NullSparse::KinTerm>> word_terms((size_t)ns.x_words);
+        for (const Placed &pl : table_placed) {
+            const int f = fams[pl.fam].size;
+            if (f <= 4) continue;
+            const int64_t word = pl.pos0 / 16;
+            const int o0 = (int)(pl.pos0 % 16);                      // multiple of 4: chunks coincide with groups
+            if (word >= ns.x_words || o0 % 4 != 0) { set_error("internal: large family not on a cross word"); return STAAR_ERR_ARG; }
+            const int nch = (f + 3) / 4;
+            for (int A = 0; A < nch; A++)
+                for (int B = A + 1; B < nch; B++) {
+                    const int sa = std::min(4, f - 4 * A), sb = std::min(4, f - 4 * B);
+                    const int I = sa >= sb ? A : B, M = sa >= sb ? B : A;          // index chunk, multiplier chunk
+                    const int si_ = std::min(4, f - 4 * I), smul = std::min(4, f - 4 * M);
+                    for (int j = 4 * M; j < 4 * M + smul; j++) {
+                        double sj[4] = {0, 0, 0, 0};
                         bool any = false;
-                        for (int m = 0; m < sb; m++) any |= S[j][b0 + m] != 0.0;
+                        for (int m = 0; m < si_; m++) { sj[m] = s_between(pl.pos0 + j, pl.pos0 + 4 * I + m); any |= sj[m] != 0.0; }
                         if (!any) continue;
-                        NullSparse::KinTerm t{(uint32_t)lut.size(), (uint8_t)(o0 + b0), (uint8_t)sb, (uint8_t)(o0 + j), 0};
-                        for (int idx = 0; idx < (1 << (2 * sb)); idx++) {
+                        NullSparse::KinTerm t{(uint32_t)lut.size(), (uint8_t)(2 * (o0 + 4 * I)), (uint8_t)((1 << (2 * si_)) - 1),
+                                              (uint8_t)(2 * (o0 + j)), 0};
+                        for (int idx = 0; idx < (1 << (2 * si_)); idx++) {
                             double v = 0.0;
-                            for (int m = 0; m < sb; m++) v += 2.0 * S[j][b0 + m] * codeval(idx, m);
+                            for (int m = 0; m < si_; m++) v += 2.0 * sj[m] * codeval(idx, m);
                             lut.push_back(v);
                         }
+                        while (lut.size() % 16) lut.push_back(0.0);
                         word_terms[word].push_back(t);
                     }
                 }
-            }
         }
-        for (int64_t w = 0; w < ns.tab_words; w++) {
-            const auto &tv = word_terms[w];
-            wdesc[w].nterm = (uint32_t)tv.size();
-            wdesc[w].ovf = (uint32_t)ovf.size();
-            for (size_t t = 0; t < tv.size(); t++) {
-                if (t < 7) wdesc[w].t[t] = tv[t];
-                else ovf.push_back(tv[t]);
-            }
+        for (int64_t w = 0; w < ns.x_words; w++) {
+            wdesc[w].start = (uint32_t)xterms.size();
+            wdesc[w].count = (uint32_t)word_terms[w].size();
+            xterms.insert(xterms.end(), word_terms[w].begin(), word_terms[w].end());
         }
     }
     ns.lut_entries = (int64_t)lut.size();
@@ -370,9 +415,9 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
     STAAR_TRY(upload_vec(ctx, &ns.diag, diag));
     STAAR_TRY(upload_vec(ctx, &ns.sinfo_p, sinfo));
     STAAR_TRY(upload_vec(ctx, &ns.off_ent_p, off_ent));
-    STAAR_TRY(upload_vec(ctx, &ns.kinmask, kinmask));
+    STAAR_TRY(upload_vec(ctx, &ns.gdesc, gdesc));
     STAAR_TRY(upload_vec(ctx, &ns.wdesc, wdesc));
-    STAAR_TRY(upload_vec(ctx, &ns.terms_ovf, ovf));
+    STAAR_TRY(upload_vec(ctx, &ns.xterms, xterms));
     STAAR_TRY(upload_vec(ctx, &ns.lut, lut));
     STAAR_TRY(upload_vec(ctx, &ns.relmask, relmask));
     if (!rel.empty()) {

@@ -28,10 +28,10 @@ struct ScanParams {
     const NullSparse::CarrierRec *rel;     // per-sample record: first two such entries inline (32 B)
     const NullSparse::OffEntry *up_ent;    // all upper-triangle entries (rows with more than two)
     // table kinship path: families inside one 16-sample word
-    int64_t tab_words, kin_words;
-    const uint32_t *kinmask;
+    int64_t tab_words, kin_words, x_words;
+    const uint32_t *gdesc;                 // 4 per table word: (table offset / 16) << 8 | code mask of related slots
     const NullSparse::WordDesc *wdesc;
-    const NullSparse::KinTerm *terms_ovf;
+    const NullSparse::KinTerm *xterms;
     const double *lut;
     const NullSparse::SampleInfo *sinfo;   // full kinship rows per position (missing related samples)
     const NullSparse::OffEntry *off_ent;
@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams
 // frequency); each variant's arithmetic is independent of which CTA runs it, so results stay bit-reproducible.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kBlkWarps = 8;
+constexpr int kQueueCap = 128;           // per-warp queue of sample positions (missing samples); flushed when nearly full
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -220,7 +221,8 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const size_t stride = P.stride;
     uint8_t *cols = smem;
-    double *s_sm = reinterpret_cast<double *>(smem + (size_t)nstage * stride);   // [kBlkWarps][16]
+    uint32_t *wq = reinterpret_cast<uint32_t *>(smem + (size_t)nstage * stride) + wib * kQueueCap;   // this warp's queue
+    double *s_sm = reinterpret_cast<double *>(smem + (size_t)nstage * stride + sizeof(uint32_t) * kBlkWarps * kQueueCap);
     double *s_quad = s_sm + kBlkWarps * kColsPerSlice;                           // [kBlkWarps]
     int *s_cnt = reinterpret_cast<int *>(s_quad + kBlkWarps);                    // [3][kBlkWarps]
     unsigned long long *s_work = reinterpret_cast<unsigned long long *>(s_cnt + 3 * kBlkWarps);   // [2]
@@ -265,7 +267,11 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
     uint32_t parity = 0u;                                        // bit s = phase parity of full[s]
     const int nvec16 = (int)(stride >> 4);
     const uint32_t *rmask32 = reinterpret_cast<const uint32_t *>(P.relmask);
-    const int kin_words = (int)P.kin_words, tab_words = (int)P.tab_words;
+    const int kin_words = (int)P.kin_words, tab_words = (int)P.tab_words, x_words = (int)P.x_words;
+    const int n32 = (int)P.n;
+    const int tail_word = n32 >> 4;                              // first word with padding positions
+    const uint32_t tail_mask = (1u << (2 * (n32 & 15))) - 1u;    // valid codes of that word
+    const int ycol = lane & 15;
 
     for (unsigned it = 1; cur < pmax; it++) {
         if (nstage == 2 && tid == 0) {                           // prefetch the next variant's column
@@ -279,118 +285,153 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         const int64_t i = (int64_t)cur;
 
         // ---- sweep 1: popcounts -> AF / MAF / flip / imputation value (bit-exact integer counts), and the column
-        //      sums of Y over missing samples (independent of the flip): lane c accumulates column c
-        int c1 = 0, c2 = 0, cm = 0;
+        //      sums of Y over missing samples (independent of the flip).  Missing positions go to the warp's queue;
+        //      a flush reads two rows of Y per warp instruction (half-warp h: entries h, h+2, ...; lane c: column c).
+        int clo = 0, chi = 0, cm = 0;                            // popcounts of low bits, high bits, both (missing)
         double sm = 0.0;
+        int qn = 0;
+        auto flush_missing = [&]() {
+            __syncwarp();
+            if (ycol < P.ncol) {
+#pragma unroll 4
+                for (int e = lane >> 4; e < qn; e += 2) sm += __ldg(P.Y + (int64_t)wq[e] * P.ldY + ycol);
+            }
+            __syncwarp();
+            qn = 0;
+        };
         {
             const uint4 *v4 = reinterpret_cast<const uint4 *>(col);
             for (int k0 = wib * 32; k0 < nvec16; k0 += kBlkWarps * 32) {
                 const int k = k0 + lane;
                 uint4 q4 = make_uint4(0u, 0u, 0u, 0u);
                 if (k < nvec16) q4 = v4[k];
-                const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
-                uint32_t mis[4];
-                uint32_t anym = 0u;
-#pragma unroll
-                for (int wi = 0; wi < 4; wi++) {
-                    const uint32_t lo = w[wi] & 0x55555555u, hi = (w[wi] >> 1) & 0x55555555u;
-                    mis[wi] = lo & hi;
-                    c1 += __popc(lo & ~hi);
-                    c2 += __popc(hi & ~lo);
-                    anym |= mis[wi];
-                }
+                const uint32_t m0 = q4.x & (q4.x >> 1) & 0x55555555u, m1 = q4.y & (q4.y >> 1) & 0x55555555u;
+                const uint32_t m2 = q4.z & (q4.z >> 1) & 0x55555555u, m3 = q4.w & (q4.w >> 1) & 0x55555555u;
+                clo += __popc(q4.x & 0x55555555u) + __popc(q4.y & 0x55555555u) + __popc(q4.z & 0x55555555u) + __popc(q4.w & 0x55555555u);
+                chi += __popc(q4.x & 0xaaaaaaaau) + __popc(q4.y & 0xaaaaaaaau) + __popc(q4.z & 0xaaaaaaaau) + __popc(q4.w & 0xaaaaaaaau);
+                const uint32_t anym = m0 | m1 | m2 | m3;
                 if (__any_sync(0xffffffffu, anym != 0u)) {
-#pragma unroll
-                    for (int wi = 0; wi < 4; wi++) {
-                        cm += __popc(mis[wi]);
-                        uint32_t who = __ballot_sync(0xffffffffu, mis[wi] != 0u);
-                        while (who) {
-                            const int src = __ffs(who) - 1;
-                            who &= who - 1;
-                            uint32_t mw = __shfl_sync(0xffffffffu, mis[wi], src);
-                            const int64_t b0 = ((int64_t)(k0 + src) * 4 + wi) * 16;       // first sample of that word
-                            while (mw) {
-                                const int b = __ffs(mw) - 1;
-                                mw &= mw - 1;
-                                if (lane < P.ncol) sm += __ldg(P.Y + (b0 + (b >> 1)) * P.ldY + lane);
-                            }
+                    cm += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+                    // bit 2f + w of each half = sample f of word w (w = 0,1 in the low half, 2,3 in the high half)
+                    unsigned long long bits = (unsigned long long)(m0 | (m1 << 1)) | ((unsigned long long)(m2 | (m3 << 1)) << 32);
+                    const int64_t first = (int64_t)k * 64;
+                    while (__any_sync(0xffffffffu, bits != 0ull)) {
+                        // decode: bit b -> word 2*(b>>5) + (b&1), sample (b&31)>>1 ; store the absolute position
+                        const bool has = bits != 0ull;
+                        const uint32_t bal = __ballot_sync(0xffffffffu, has);
+                        if (has) {
+                            const int b = __ffsll((long long)bits) - 1;
+                            bits &= bits - 1ull;
+                            const int word = 2 * (b >> 5) + (b & 1), smp = (b & 31) >> 1;
+                            wq[qn + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)(first + word * 16 + smp);
                         }
+                        qn += __popc(bal);
+                        if (qn > kQueueCap - 32) flush_missing();
                     }
                 }
             }
+            if (qn > 0) flush_missing();
+            sm += __shfl_xor_sync(0xffffffffu, sm, 16);            // the two half-warps' partial sums (fixed order)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-                c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+                clo += __shfl_xor_sync(0xffffffffu, clo, o);
+                chi += __shfl_xor_sync(0xffffffffu, chi, o);
                 cm += __shfl_xor_sync(0xffffffffu, cm, o);
             }
-            if (lane == 0) { s_cnt[wib] = c1; s_cnt[kBlkWarps + wib] = c2; s_cnt[2 * kBlkWarps + wib] = cm; }
+            if (lane == 0) { s_cnt[wib] = clo; s_cnt[kBlkWarps + wib] = chi; s_cnt[2 * kBlkWarps + wib] = cm; }
             if (lane < kColsPerSlice) s_sm[wib * kColsPerSlice + lane] = sm;
             __syncthreads();
-            c1 = c2 = cm = 0;
+            clo = chi = cm = 0;
 #pragma unroll
-            for (int w = 0; w < kBlkWarps; w++) { c1 += s_cnt[w]; c2 += s_cnt[kBlkWarps + w]; cm += s_cnt[2 * kBlkWarps + w]; }
+            for (int w = 0; w < kBlkWarps; w++) { clo += s_cnt[w]; chi += s_cnt[kBlkWarps + w]; cm += s_cnt[2 * kBlkWarps + w]; }
         }
-        const VariantFlip vf = flip_from_counts(PackedCounts{c1, c2, cm}, P.n, P.impute);
-        const bool flip = vf.flip != 0;
-        const double mu = vf.mu;
+        const int c1 = clo - cm, c2 = chi - cm;
+        // flip decision in exact integers (every thread; the FP64 divisions stay off the critical path):
+        //   mean : AF = sum/2/num > 0.5  <=>  sum > num          (|AF - 0.5| >= 1/(4 num) >> ulp, division is monotone)
+        //   minor: fill = AF > 0.5 ? 2 : 0;  AF' = (sum + fill cm)/2/n > 0.5  <=>  sum + fill cm > n
+        const PackedCounts pc{c1, c2, cm};
+        const long long gsum = (long long)c1 + 2ll * c2, gnum = (long long)P.n - cm;
+        bool flip, mu_zero;
+        if (P.impute == STAAR_IMPUTE_MEAN) {
+            flip = gsum > gnum;
+            mu_zero = flip ? (gsum == 2 * gnum) : (gsum == 0);      // mu = 2 AF or 2 - 2 AF
+        } else {
+            const long long fill = gsum > gnum ? 2 : 0;
+            flip = gsum + fill * cm > (long long)P.n;
+            mu_zero = flip ? (fill == 2) : (fill == 0);            // mu = fill or 2 - fill
+        }
+        auto mu_of = [&]() { return flip_from_counts(pc, P.n, P.impute).mu; };   // rare paths only
 
         // ---- sweep 2: kinship off-diagonal part of g' Sigma_i g over the related prefix of the column, one
-        //      16-sample word per thread.  Table words: family codes -> look-up; generic words: per-carrier records.
+        //      16-sample word per thread.  Table words: a 4-sample group's codes index that group's table; generic
+        //      words: per-carrier records.  Missing related samples are queued and corrected afterwards.
         double quad = 0.0;
         const uint32_t *col32 = reinterpret_cast<const uint32_t *>(col);
-        for (int k = tid; k < kin_words; k += kBlkWarps * 32) {
-            const uint32_t w = col32[k];
-            const uint32_t lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
-            const uint32_t mis = lo & hi;
-            uint32_t wf = w;
-            if (flip) {
-                wf = w ^ ((~lo & 0x55555555u) << 1);
-                const int64_t valid = P.n - (int64_t)k * 16;         // padding codes would flip to 2
-                if (valid < 16) wf &= (valid <= 0) ? 0u : ((1u << (2 * valid)) - 1u);
+        const uint32_t flipmask = flip ? 0x55555555u : 0u;
+        qn = 0;
+        auto flush_related_missing = [&]() {
+            __syncwarp();
+            if (qn > 0) {
+                const double mu = mu_of();
+                for (int e = lane; e < qn; e += 32) {
+                    const int64_t j = (int64_t)wq[e];
+                    const NullSparse::SampleInfo si = P.sinfo[j];
+                    double sacc = 0.0;
+                    for (uint32_t t = 0; t < si.off_count; t++) {
+                        const NullSparse::OffEntry oe = P.off_ent[si.off_start + t];
+                        const uint32_t c = code_smem(col, oe.col, flip);
+                        // a pair of two missing samples is counted once, from its smaller position
+                        const double v = c == 3u ? ((int64_t)oe.col > j ? mu : 0.0) : (double)c;
+                        sacc += oe.val * v;
+                    }
+                    quad += 2.0 * mu * sacc;
+                }
             }
-            const int64_t base = (int64_t)k * 16;
-            if (k < tab_words) {
+            __syncwarp();
+            qn = 0;
+        };
+        for (int k0 = wib * 32; k0 < kin_words; k0 += kBlkWarps * 32) {
+            const int k = k0 + lane;
+            const bool live = k < kin_words;
+            const uint32_t w = live ? col32[k] : 0u;
+            const uint32_t lo = w & 0x55555555u;
+            const uint32_t mis = lo & (w >> 1);
+            uint32_t wf = w ^ ((~lo & flipmask) << 1);               // g -> 2 - g on the codes 0 and 2
+            if (k >= tail_word) wf &= (k == tail_word) ? tail_mask : 0u;   // padding codes would flip to 2
+            unsigned long long relmiss = 0ull;
+            if (k0 < tab_words) {                                    // warp-uniform: table words
                 const uint32_t wz = wf & ~(mis * 3u);                // missing -> 0: tables hold non-missing pairs only
-                const uint32_t km = __ldg(P.kinmask + k);
-                const uint32_t hit = (wz | (wz >> 1)) & km;
-                if (hit & (hit - 1u)) {                              // at least two related carriers in this word
-                    const uint2 *dp = reinterpret_cast<const uint2 *>(P.wdesc + k);
-                    const uint2 hdr = __ldg(dp);
-                    for (uint32_t t = 0; t < hdr.x; t++) {
-                        const uint2 tr = t < 7u ? __ldg(dp + 1 + t)
-                                                : __ldg(reinterpret_cast<const uint2 *>(P.terms_ovf) + hdr.y + (t - 7u));
-                        const uint32_t shift = tr.y & 0xffu, size = (tr.y >> 8) & 0xffu, jpos = (tr.y >> 16) & 0xffu;
-                        const uint32_t idx = (wz >> (2u * shift)) & ((1u << (2u * size)) - 1u);
-                        if (jpos == 255u) {
-                            const uint32_t nzb = (idx | (idx >> 1)) & 0x55u;
-                            if (nzb & (nzb - 1u)) quad += __ldg(P.lut + tr.x + idx);
-                        } else {
-                            const uint32_t gj = (wz >> (2u * jpos)) & 3u;
+                uint4 gd = make_uint4(0u, 0u, 0u, 0u);
+                if (k < tab_words) gd = __ldg(reinterpret_cast<const uint4 *>(P.gdesc) + k);
+                const uint32_t km = __byte_perm(__byte_perm(gd.x, gd.y, 0x0040), __byte_perm(gd.z, gd.w, 0x0040), 0x5410);
+                const uint32_t hit = (wz | (wz >> 1)) & km & 0x55555555u;
+                const bool two = (hit & (hit - 1u)) != 0u;          // at least two related carriers in this word
+                if (__any_sync(0xffffffffu, two)) {
+                    const uint32_t g4[4] = {gd.x, gd.y, gd.z, gd.w};
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {                    // all related pairs inside a 4-sample group: one table
+                        const uint32_t idx = (wz >> (8 * g)) & g4[g] & 0xffu;
+                        const uint32_t nzb = (idx | (idx >> 1)) & 0x55u;
+                        if (nzb & (nzb - 1u)) quad += __ldg(P.lut + (g4[g] >> 8) * 16u + idx);
+                    }
+                    if (k < x_words && two) {                        // families of 5..16 members: member x other chunk
+                        const uint2 wd = __ldg(reinterpret_cast<const uint2 *>(P.wdesc) + k);
+                        const uint2 *tp = reinterpret_cast<const uint2 *>(P.xterms) + wd.x;
+                        for (uint32_t t = 0; t < wd.y; t++) {
+                            const uint2 tr = __ldg(tp + t);
+                            const uint32_t idx = (wz >> (tr.y & 0xffu)) & ((tr.y >> 8) & 0xffu);
+                            const uint32_t gj = (wz >> ((tr.y >> 16) & 0xffu)) & 3u;
                             if (gj != 0u && idx != 0u) quad += (double)gj * __ldg(P.lut + tr.x + idx);
                         }
                     }
                 }
-                uint32_t mk = mis & km;                              // missing related samples (imputed to mu)
-                if (mu != 0.0)
-                    while (mk) {
-                        const int b = __ffs(mk) - 1;
-                        mk &= mk - 1;
-                        const int64_t j = base + (b >> 1);
-                        const NullSparse::SampleInfo si = P.sinfo[j];
-                        double sacc = 0.0;
-                        for (uint32_t t = 0; t < si.off_count; t++) {
-                            const NullSparse::OffEntry oe = P.off_ent[si.off_start + t];
-                            const uint32_t c = code_smem(col, oe.col, flip);
-                            // a pair of two missing samples is counted once, from its smaller position
-                            const double v = c == 3u ? ((int64_t)oe.col > j ? mu : 0.0) : (double)c;
-                            sacc += oe.val * v;
-                        }
-                        quad += 2.0 * mu * sacc;
-                    }
-            } else {
+                if (!mu_zero) relmiss = (unsigned long long)(mis & km);   // bit 2f = sample f (imputed to mu != 0)
+            }
+            if (k0 + 31 >= tab_words && live && k >= tab_words) {   // generic words (a step may straddle the boundary)
                 uint32_t sel = (wf | (wf >> 1)) & 0x55555555u & __ldg(rmask32 + k);
-                if (mu == 0.0) sel &= ~mis;
+                if (mu_zero) sel &= ~mis;
+                const double mu = sel ? mu_of() : 0.0;
+                const int64_t base = (int64_t)k * 16;
                 while (sel) {
                     const int b = __ffs(sel) - 1;
                     sel &= sel - 1;
@@ -405,7 +446,20 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
                     quad += 2.0 * code_value((wf >> b) & 3u, mu) * sacc;
                 }
             }
+            // queue the missing related samples of table words (warp-uniform loop; usually not entered)
+            while (__any_sync(0xffffffffu, relmiss != 0ull)) {
+                const bool has = relmiss != 0ull;
+                const uint32_t bal = __ballot_sync(0xffffffffu, has);
+                if (has) {
+                    const int b = __ffsll((long long)relmiss) - 1;
+                    relmiss &= relmiss - 1ull;
+                    wq[qn + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)(k * 16 + (b >> 1));
+                }
+                qn += __popc(bal);
+                if (qn > kQueueCap - 32) flush_related_missing();
+            }
         }
+        flush_related_missing();
         quad = warp_sum(quad);
         if (lane == 0) s_quad[wib] = quad;
         __syncthreads();                      // also: every read of this stage's column is complete
@@ -418,7 +472,8 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             double t = 0.0;
 #pragma unroll
             for (int w = 0; w < kBlkWarps; w++) t += s_quad[w];
-            P.AF[i] = vf.af; P.MAF[i] = vf.maf; P.flip[i] = vf.flip; P.mu[i] = mu; P.quad[i] = t;
+            const VariantFlip vf = flip_from_counts(pc, P.n, P.impute);
+            P.AF[i] = vf.af; P.MAF[i] = vf.maf; P.flip[i] = flip ? 1 : 0; P.mu[i] = vf.mu; P.quad[i] = t;
         }
         if (nstage == 2) {
             cur = s_work[it & 1];
@@ -488,12 +543,13 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     ScanParams P;
     P.packed = d_packed; P.stride = stride; P.n = n; P.p = p; P.impute = impute;
     P.relmask = ns.relmask; P.rel = ns.rel; P.up_ent = ns.up_ent;
-    P.tab_words = ns.tab_words; P.kin_words = ns.kin_words; P.kinmask = ns.kinmask; P.wdesc = ns.wdesc;
-    P.terms_ovf = ns.terms_ovf; P.lut = ns.lut; P.sinfo = ns.sinfo_p; P.off_ent = ns.off_ent_p;
+    P.tab_words = ns.tab_words; P.kin_words = ns.kin_words; P.x_words = ns.x_words; P.gdesc = ns.gdesc; P.wdesc = ns.wdesc;
+    P.xterms = ns.xterms; P.lut = ns.lut; P.sinfo = ns.sinfo_p; P.off_ent = ns.off_ent_p;
     P.Y = ns.Yp; P.ldY = ns.ldY; P.ncol = (int)ns.q + 2;
     P.AF = dAF; P.MAF = dMAF; P.flip = dflip; P.mu = d_mu; P.quad = d_quad; P.Sm = d_Sm;
     // block-per-variant kernel: column(s) in shared memory, double-buffered when two fit
-    const size_t extra = sizeof(double) * (kBlkWarps * kColsPerSlice + kBlkWarps) + sizeof(int) * 3 * kBlkWarps + 64;
+    const size_t extra = sizeof(uint32_t) * kBlkWarps * kQueueCap + sizeof(double) * (kBlkWarps * kColsPerSlice + kBlkWarps) +
+                         sizeof(int) * 3 * kBlkWarps + 64;
     const size_t smem_max = 227 * 1024;
     const int nstage = (2 * stride + extra <= smem_max) ? 2 : (stride + extra <= smem_max) ? 1 : 0;
     if (nstage > 0) {
