@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams
 // frequency); each variant's arithmetic is independent of which CTA runs it, so results stay bit-reproducible.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kBlkWarps = 8;
-constexpr int kQueueCap = 128;           // per-warp queue of sample positions (missing samples); flushed when nearly full
+constexpr int kQueueCap = 96;            // per-warp queue of missing-sample positions; flushed when nearly full
+constexpr int kRelQueueCap = 64;         // per-warp queue of missing positions inside the table region (kept per variant)
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -221,11 +222,12 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const size_t stride = P.stride;
     uint8_t *cols = smem;
-    uint32_t *wq = reinterpret_cast<uint32_t *>(smem + (size_t)nstage * stride) + wib * kQueueCap;   // this warp's queue
-    double *s_sm = reinterpret_cast<double *>(smem + (size_t)nstage * stride + sizeof(uint32_t) * kBlkWarps * kQueueCap);
+    uint32_t *wq = reinterpret_cast<uint32_t *>(smem + (size_t)nstage * stride) + wib * (kQueueCap + kRelQueueCap);   // this warp's queues
+    uint32_t *rq = wq + kQueueCap;
+    double *s_sm = reinterpret_cast<double *>(smem + (size_t)nstage * stride + sizeof(uint32_t) * kBlkWarps * (kQueueCap + kRelQueueCap));
     double *s_quad = s_sm + kBlkWarps * kColsPerSlice;                           // [kBlkWarps]
-    int *s_cnt = reinterpret_cast<int *>(s_quad + kBlkWarps);                    // [3][kBlkWarps]
-    unsigned long long *s_work = reinterpret_cast<unsigned long long *>(s_cnt + 3 * kBlkWarps);   // [2]
+    int *s_cnt = reinterpret_cast<int *>(s_quad + kBlkWarps);                    // [4][kBlkWarps]
+    unsigned long long *s_work = reinterpret_cast<unsigned long long *>(s_cnt + 4 * kBlkWarps);   // [2]
     uint64_t *full = reinterpret_cast<uint64_t *>(s_work + 2);                   // [2]
 
     if (tid == 0) {
@@ -272,6 +274,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
     const int tail_word = n32 >> 4;                              // first word with padding positions
     const uint32_t tail_mask = (1u << (2 * (n32 & 15))) - 1u;    // valid codes of that word
     const int ycol = lane & 15;
+    const uint32_t tab_samples = (uint32_t)tab_words * 16u;
 
     for (unsigned it = 1; cur < pmax; it++) {
         if (nstage == 2 && tid == 0) {                           // prefetch the next variant's column
@@ -286,15 +289,25 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
 
         // ---- sweep 1: popcounts -> AF / MAF / flip / imputation value (bit-exact integer counts), and the column
         //      sums of Y over missing samples (independent of the flip).  Missing positions go to the warp's queue;
-        //      a flush reads two rows of Y per warp instruction (half-warp h: entries h, h+2, ...; lane c: column c).
+        //      a flush reads two rows of Y per warp instruction (half-warp h: entries h, h+2, ...; lane c: column c)
+        //      and keeps the positions inside the table region in a second queue for the kinship correction.
         int clo = 0, chi = 0, cm = 0;                            // popcounts of low bits, high bits, both (missing)
         double sm = 0.0;
-        int qn = 0;
+        int qn = 0, rn = 0;
+        bool rq_over = false;
         auto flush_missing = [&]() {
             __syncwarp();
             if (ycol < P.ncol) {
 #pragma unroll 4
                 for (int e = lane >> 4; e < qn; e += 2) sm += __ldg(P.Y + (int64_t)wq[e] * P.ldY + ycol);
+            }
+            for (int e0 = 0; e0 < qn; e0 += 32) {                // warp-uniform trip count
+                const uint32_t pos = e0 + lane < qn ? wq[e0 + lane] : 0xffffffffu;
+                const bool keep = pos < tab_samples;
+                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                if (rn + __popc(bal) > kRelQueueCap) { rq_over = true; break; }
+                if (keep) rq[rn + __popc(bal & ((1u << lane) - 1u))] = pos;
+                rn += __popc(bal);
             }
             __syncwarp();
             qn = 0;
@@ -309,25 +322,23 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
                 const uint32_t m2 = q4.z & (q4.z >> 1) & 0x55555555u, m3 = q4.w & (q4.w >> 1) & 0x55555555u;
                 clo += __popc(q4.x & 0x55555555u) + __popc(q4.y & 0x55555555u) + __popc(q4.z & 0x55555555u) + __popc(q4.w & 0x55555555u);
                 chi += __popc(q4.x & 0xaaaaaaaau) + __popc(q4.y & 0xaaaaaaaau) + __popc(q4.z & 0xaaaaaaaau) + __popc(q4.w & 0xaaaaaaaau);
-                const uint32_t anym = m0 | m1 | m2 | m3;
-                if (__any_sync(0xffffffffu, anym != 0u)) {
-                    cm += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-                    // bit 2f + w of each half = sample f of word w (w = 0,1 in the low half, 2,3 in the high half)
-                    unsigned long long bits = (unsigned long long)(m0 | (m1 << 1)) | ((unsigned long long)(m2 | (m3 << 1)) << 32);
-                    const int64_t first = (int64_t)k * 64;
-                    while (__any_sync(0xffffffffu, bits != 0ull)) {
-                        // decode: bit b -> word 2*(b>>5) + (b&1), sample (b&31)>>1 ; store the absolute position
-                        const bool has = bits != 0ull;
-                        const uint32_t bal = __ballot_sync(0xffffffffu, has);
-                        if (has) {
-                            const int b = __ffsll((long long)bits) - 1;
-                            bits &= bits - 1ull;
-                            const int word = 2 * (b >> 5) + (b & 1), smp = (b & 31) >> 1;
-                            wq[qn + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)(first + word * 16 + smp);
+                // bit 2f + w of a half = sample f of word w (low half: words 0,1; high half: words 2,3)
+                uint32_t blo = m0 | (m1 << 1), bhi = m2 | (m3 << 1);
+                uint32_t bal = __ballot_sync(0xffffffffu, (blo | bhi) != 0u);
+                if (bal) {
+                    cm += __popc(blo) + __popc(bhi);
+                    const uint32_t first = (uint32_t)k * 64u;
+                    do {                                          // round r: the r-th missing sample of every lane
+                        if (blo | bhi) {
+                            int b, half;
+                            if (blo) { b = __ffs(blo) - 1; blo &= blo - 1u; half = 0; }
+                            else { b = __ffs(bhi) - 1; bhi &= bhi - 1u; half = 2; }
+                            wq[qn + __popc(bal & ((1u << lane) - 1u))] = first + (uint32_t)((half + (b & 1)) * 16 + (b >> 1));
                         }
                         qn += __popc(bal);
                         if (qn > kQueueCap - 32) flush_missing();
-                    }
+                        bal = __ballot_sync(0xffffffffu, (blo | bhi) != 0u);
+                    } while (bal);
                 }
             }
             if (qn > 0) flush_missing();
@@ -338,12 +349,16 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
                 chi += __shfl_xor_sync(0xffffffffu, chi, o);
                 cm += __shfl_xor_sync(0xffffffffu, cm, o);
             }
-            if (lane == 0) { s_cnt[wib] = clo; s_cnt[kBlkWarps + wib] = chi; s_cnt[2 * kBlkWarps + wib] = cm; }
+            if (lane == 0) { s_cnt[wib] = clo; s_cnt[kBlkWarps + wib] = chi; s_cnt[2 * kBlkWarps + wib] = cm; s_cnt[3 * kBlkWarps + wib] = rq_over; }
             if (lane < kColsPerSlice) s_sm[wib * kColsPerSlice + lane] = sm;
             __syncthreads();
             clo = chi = cm = 0;
+            int over = 0;
 #pragma unroll
-            for (int w = 0; w < kBlkWarps; w++) { clo += s_cnt[w]; chi += s_cnt[kBlkWarps + w]; cm += s_cnt[2 * kBlkWarps + w]; }
+            for (int w = 0; w < kBlkWarps; w++) {
+                clo += s_cnt[w]; chi += s_cnt[kBlkWarps + w]; cm += s_cnt[2 * kBlkWarps + w]; over |= s_cnt[3 * kBlkWarps + w];
+            }
+            rq_over = over != 0;                                  // block-wide: some warp could not keep its positions
         }
         const int c1 = clo - cm, c2 = chi - cm;
         // flip decision in exact integers (every thread; the FP64 divisions stay off the critical path):
@@ -363,103 +378,98 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         auto mu_of = [&]() { return flip_from_counts(pc, P.n, P.impute).mu; };   // rare paths only
 
         // ---- sweep 2: kinship off-diagonal part of g' Sigma_i g over the related prefix of the column, one
-        //      16-sample word per thread.  Table words: a 4-sample group's codes index that group's table; generic
-        //      words: per-carrier records.  Missing related samples are queued and corrected afterwards.
+        //      16-sample word per thread.
         double quad = 0.0;
         const uint32_t *col32 = reinterpret_cast<const uint32_t *>(col);
         const uint32_t flipmask = flip ? 0x55555555u : 0u;
-        qn = 0;
-        auto flush_related_missing = [&]() {
-            __syncwarp();
-            if (qn > 0) {
-                const double mu = mu_of();
-                for (int e = lane; e < qn; e += 32) {
-                    const int64_t j = (int64_t)wq[e];
-                    const NullSparse::SampleInfo si = P.sinfo[j];
-                    double sacc = 0.0;
-                    for (uint32_t t = 0; t < si.off_count; t++) {
-                        const NullSparse::OffEntry oe = P.off_ent[si.off_start + t];
-                        const uint32_t c = code_smem(col, oe.col, flip);
-                        // a pair of two missing samples is counted once, from its smaller position
-                        const double v = c == 3u ? ((int64_t)oe.col > j ? mu : 0.0) : (double)c;
-                        sacc += oe.val * v;
-                    }
-                    quad += 2.0 * mu * sacc;
-                }
+        // correction for a missing related sample j of a table word (imputed to mu; the tables see it as 0)
+        auto related_missing = [&](int64_t j, double mu) {
+            const NullSparse::SampleInfo si = P.sinfo[j];
+            double sacc = 0.0;
+            for (uint32_t t = 0; t < si.off_count; t++) {
+                const NullSparse::OffEntry oe = P.off_ent[si.off_start + t];
+                const uint32_t c = code_smem(col, oe.col, flip);
+                // a pair of two missing samples is counted once, from its smaller position
+                const double v = c == 3u ? ((int64_t)oe.col > j ? mu : 0.0) : (double)c;
+                sacc += oe.val * v;
             }
-            __syncwarp();
-            qn = 0;
+            quad += 2.0 * mu * sacc;
         };
-        for (int k0 = wib * 32; k0 < kin_words; k0 += kBlkWarps * 32) {
+        // (a) table words [0, tab_words): full words of real samples; a 4-sample group's codes index that group's table
+        for (int k0 = wib * 32; k0 < tab_words; k0 += kBlkWarps * 32) {
             const int k = k0 + lane;
-            const bool live = k < kin_words;
-            const uint32_t w = live ? col32[k] : 0u;
+            uint32_t w = 0u;
+            uint4 gd = make_uint4(0u, 0u, 0u, 0u);
+            if (k < tab_words) { w = col32[k]; gd = __ldg(reinterpret_cast<const uint4 *>(P.gdesc) + k); }
             const uint32_t lo = w & 0x55555555u;
             const uint32_t mis = lo & (w >> 1);
-            uint32_t wf = w ^ ((~lo & flipmask) << 1);               // g -> 2 - g on the codes 0 and 2
-            if (k >= tail_word) wf &= (k == tail_word) ? tail_mask : 0u;   // padding codes would flip to 2
-            unsigned long long relmiss = 0ull;
-            if (k0 < tab_words) {                                    // warp-uniform: table words
-                const uint32_t wz = wf & ~(mis * 3u);                // missing -> 0: tables hold non-missing pairs only
-                uint4 gd = make_uint4(0u, 0u, 0u, 0u);
-                if (k < tab_words) gd = __ldg(reinterpret_cast<const uint4 *>(P.gdesc) + k);
-                const uint32_t km = __byte_perm(__byte_perm(gd.x, gd.y, 0x0040), __byte_perm(gd.z, gd.w, 0x0040), 0x5410);
-                const uint32_t hit = (wz | (wz >> 1)) & km & 0x55555555u;
-                const bool two = (hit & (hit - 1u)) != 0u;          // at least two related carriers in this word
-                if (__any_sync(0xffffffffu, two)) {
-                    const uint32_t g4[4] = {gd.x, gd.y, gd.z, gd.w};
+            const uint32_t wf = w ^ ((~lo & flipmask) << 1);         // g -> 2 - g on the codes 0 and 2
+            const uint32_t km = __byte_perm(__byte_perm(gd.x, gd.y, 0x0040), __byte_perm(gd.z, gd.w, 0x0040), 0x5410);
+            const uint32_t wz = wf & ~(mis * 3u) & km;               // related, non-missing codes (tables hold such pairs)
+            const uint32_t hit = (wz | (wz >> 1)) & 0x55555555u;     // carriers: bits 0,2,4,6 of every group byte
+            // per byte: clear the lowest carrier bit (bit 7 guards the borrow): non-zero byte <=> >= 2 carriers in the group
+            const uint32_t two = hit & ((hit | 0x80808080u) - 0x01010101u);
+            const bool cross = k < x_words && (hit & (hit - 1u)) != 0u;   // >= 2 carriers anywhere in a cross word
+            if (__any_sync(0xffffffffu, two != 0u || cross)) {
+                const uint32_t g4[4] = {gd.x, gd.y, gd.z, gd.w};
 #pragma unroll
-                    for (int g = 0; g < 4; g++) {                    // all related pairs inside a 4-sample group: one table
-                        const uint32_t idx = (wz >> (8 * g)) & g4[g] & 0xffu;
-                        const uint32_t nzb = (idx | (idx >> 1)) & 0x55u;
-                        if (nzb & (nzb - 1u)) quad += __ldg(P.lut + (g4[g] >> 8) * 16u + idx);
-                    }
-                    if (k < x_words && two) {                        // families of 5..16 members: member x other chunk
-                        const uint2 wd = __ldg(reinterpret_cast<const uint2 *>(P.wdesc) + k);
-                        const uint2 *tp = reinterpret_cast<const uint2 *>(P.xterms) + wd.x;
-                        for (uint32_t t = 0; t < wd.y; t++) {
-                            const uint2 tr = __ldg(tp + t);
-                            const uint32_t idx = (wz >> (tr.y & 0xffu)) & ((tr.y >> 8) & 0xffu);
-                            const uint32_t gj = (wz >> ((tr.y >> 16) & 0xffu)) & 3u;
-                            if (gj != 0u && idx != 0u) quad += (double)gj * __ldg(P.lut + tr.x + idx);
-                        }
-                    }
+                for (int g = 0; g < 4; g++) {                        // entry 0 of the table at offset 0 is 0.0
+                    const uint32_t idx = (wz >> (8 * g)) & 0xffu;
+                    const uint32_t off = (two & (0xffu << (8 * g))) ? (g4[g] >> 8) * 16u + idx : 0u;
+                    quad += __ldg(P.lut + off);
                 }
-                if (!mu_zero) relmiss = (unsigned long long)(mis & km);   // bit 2f = sample f (imputed to mu != 0)
-            }
-            if (k0 + 31 >= tab_words && live && k >= tab_words) {   // generic words (a step may straddle the boundary)
-                uint32_t sel = (wf | (wf >> 1)) & 0x55555555u & __ldg(rmask32 + k);
-                if (mu_zero) sel &= ~mis;
-                const double mu = sel ? mu_of() : 0.0;
-                const int64_t base = (int64_t)k * 16;
-                while (sel) {
-                    const int b = __ffs(sel) - 1;
-                    sel &= sel - 1;
-                    const NullSparse::CarrierRec rr = P.rel[base + (b >> 1)];
-                    double sacc = 0.0;
-                    for (uint32_t t = 0; t < rr.count; t++) {
-                        double sv; int32_t sc;
-                        if (t < 2u) { sv = rr.val[t]; sc = rr.col[t]; }
-                        else { const NullSparse::OffEntry oe = P.up_ent[rr.start + t]; sv = oe.val; sc = oe.col; }
-                        sacc += sv * code_value(code_smem(col, sc, flip), mu);
+                if (cross) {                                         // families of 5..16 members: member x other chunk
+                    const uint2 wd = __ldg(reinterpret_cast<const uint2 *>(P.wdesc) + k);
+                    const uint2 *tp = reinterpret_cast<const uint2 *>(P.xterms) + wd.x;
+                    for (uint32_t t = 0; t < wd.y; t++) {
+                        const uint2 tr = __ldg(tp + t);
+                        const uint32_t idx = (wz >> (tr.y & 0xffu)) & ((tr.y >> 8) & 0xffu);
+                        const uint32_t gj = (wz >> ((tr.y >> 16) & 0xffu)) & 3u;
+                        if (gj != 0u && idx != 0u) quad += (double)gj * __ldg(P.lut + tr.x + idx);
                     }
-                    quad += 2.0 * code_value((wf >> b) & 3u, mu) * sacc;
                 }
             }
-            // queue the missing related samples of table words (warp-uniform loop; usually not entered)
-            while (__any_sync(0xffffffffu, relmiss != 0ull)) {
-                const bool has = relmiss != 0ull;
-                const uint32_t bal = __ballot_sync(0xffffffffu, has);
-                if (has) {
-                    const int b = __ffsll((long long)relmiss) - 1;
-                    relmiss &= relmiss - 1ull;
-                    wq[qn + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)(k * 16 + (b >> 1));
+            if (rq_over && !mu_zero) {                               // slow path: the position queues overflowed
+                uint32_t mk = mis & km;
+                if (mk) {
+                    const double mu = mu_of();
+                    while (mk) {
+                        const int b = __ffs(mk) - 1;
+                        mk &= mk - 1u;
+                        related_missing((int64_t)k * 16 + (b >> 1), mu);
+                    }
                 }
-                qn += __popc(bal);
-                if (qn > kQueueCap - 32) flush_related_missing();
             }
         }
-        flush_related_missing();
+        if (!rq_over && !mu_zero && rn > 0) {                        // missing samples queued in sweep 1 (this warp's)
+            const double mu = mu_of();
+            for (int e = lane; e < rn; e += 32) related_missing((int64_t)rq[e], mu);
+        }
+        // (b) generic words [tab_words, kin_words): per-carrier records (families of more than 16 members)
+        for (int k = tab_words + tid; k < kin_words; k += kBlkWarps * 32) {
+            const uint32_t w = col32[k];
+            const uint32_t lo = w & 0x55555555u;
+            const uint32_t mis = lo & (w >> 1);
+            uint32_t wf = w ^ ((~lo & flipmask) << 1);
+            if (k >= tail_word) wf &= (k == tail_word) ? tail_mask : 0u;   // padding codes would flip to 2
+            uint32_t sel = (wf | (wf >> 1)) & 0x55555555u & __ldg(rmask32 + k);
+            if (mu_zero) sel &= ~mis;
+            const double mu = sel ? mu_of() : 0.0;
+            const int64_t base = (int64_t)k * 16;
+            while (sel) {
+                const int b = __ffs(sel) - 1;
+                sel &= sel - 1;
+                const NullSparse::CarrierRec rr = P.rel[base + (b >> 1)];
+                double sacc = 0.0;
+                for (uint32_t t = 0; t < rr.count; t++) {
+                    double sv; int32_t sc;
+                    if (t < 2u) { sv = rr.val[t]; sc = rr.col[t]; }
+                    else { const NullSparse::OffEntry oe = P.up_ent[rr.start + t]; sv = oe.val; sc = oe.col; }
+                    sacc += sv * code_value(code_smem(col, sc, flip), mu);
+                }
+                quad += 2.0 * code_value((wf >> b) & 3u, mu) * sacc;
+            }
+        }
         quad = warp_sum(quad);
         if (lane == 0) s_quad[wib] = quad;
         __syncthreads();                      // also: every read of this stage's column is complete
@@ -548,8 +558,8 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     P.Y = ns.Yp; P.ldY = ns.ldY; P.ncol = (int)ns.q + 2;
     P.AF = dAF; P.MAF = dMAF; P.flip = dflip; P.mu = d_mu; P.quad = d_quad; P.Sm = d_Sm;
     // block-per-variant kernel: column(s) in shared memory, double-buffered when two fit
-    const size_t extra = sizeof(uint32_t) * kBlkWarps * kQueueCap + sizeof(double) * (kBlkWarps * kColsPerSlice + kBlkWarps) +
-                         sizeof(int) * 3 * kBlkWarps + 64;
+    const size_t extra = sizeof(uint32_t) * kBlkWarps * (kQueueCap + kRelQueueCap) +
+                         sizeof(double) * (kBlkWarps * kColsPerSlice + kBlkWarps) + sizeof(int) * 4 * kBlkWarps + 64;
     const size_t smem_max = 227 * 1024;
     const int nstage = (2 * stride + extra <= smem_max) ? 2 : (stride + extra <= smem_max) ? 1 : 0;
     if (nstage > 0) {
