@@ -100,6 +100,7 @@ struct NullSparse {
     int64_t n_chunks = 0;
     int8_t *Yfrag = nullptr;      // n_chunks * kChunkBytesB
     double *col_scale = nullptr;  // kColsPerSlice: 2^(e_c - 54)
+    long long *col_total = nullptr;   // 2 x kColsPerSlice: exact column sums of the fixed-point operand, hi | lo (X = hi 2^24 + lo)
     uint64_t fingerprint = 0;     // content hash of (Sigma_i, Sigma_iX, cov): cache key of the frozen-signature entry points
     uint64_t res_fingerprint = 0; // content hash of the residual vector currently in column 0 of Y
     void release();
@@ -167,8 +168,8 @@ int launch_spa(staar_ctx *ctx, const double *dG, int64_t n, int64_t p, const dou
 int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
                        double *dAF, double *dMAF, int32_t *dflip, double *d_mu, double *d_quad, double *d_Sm);
 int launch_contract_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p,
-                           const int32_t *d_flip, long long *d_hi, long long *d_lo);
-int launch_finalize_packed(staar_ctx *ctx, int64_t p, const double *d_mu, const double *d_quad,
+                           long long *d_hi, long long *d_lo);
+int launch_finalize_packed(staar_ctx *ctx, int64_t p, const int32_t *d_flip, const double *d_mu, const double *d_quad,
                            const double *d_Sm, const long long *d_hi, const long long *d_lo,
                            double *dScore, double *dScore_se, double *dpl, double *dEst, double *dEst_se);
 int build_sliced_operand(staar_ctx *ctx, const double *hY /* n x ldY row-major host, natural sample order */);

@@ -12,7 +12,9 @@
 // The 7 partial results are recombined in 64-bit integer arithmetic, so the contraction is bit-reproducible for any
 // tiling / split / GPU count, a monomorphic column gives an exact 0 (the reference's Cov_ii == 0 branch), and the
 // only rounding left is the 2^-54 truncation of Y (relative to the column maximum) — far inside the 1e-10 budget.
-// The flip to the minor allele (decided by scan_packed.cu) is applied to the 2-bit codes in registers.
+// The kernel contracts the RAW 2-bit codes (0, 1, 2 and 3 = missing, taken as the value 3): the flip to the minor
+// allele g -> 2 - g and the imputation of missing entries are linear in these exact integer sums and are applied
+// analytically by finalize_packed_kernel (scan_packed.cu), so the contraction does not depend on the scan.
 //
 // Kernel: M = variants (2 m16 tiles per warp, 8 warps per CTA), N = 7 slices x 16 columns = 14 n8 tiles (+1 tile:
 // the hom-minor indicator [g == 2] against the 7 digit slices of diag(Sigma_i), for sum_j s_jj g_j^2),
@@ -86,18 +88,16 @@ __device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1,
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// field f (0..3) of each of the 4 bytes of w as 4 int8 lanes; code 3 (missing) -> 0
+// field f (0..3) of each of the 4 bytes of w as 4 int8 lanes (raw codes 0..3)
 __device__ __forceinline__ uint32_t fields_to_s8(uint32_t w, int f)
 {
-    uint32_t t = (w >> (2 * f)) & 0x03030303u;
-    const uint32_t m = t & (t >> 1);          // 1 where the code is 3
-    return t ^ (m * 3u);
+    return (w >> (2 * f)) & 0x03030303u;
 }
 
 // grid = (ceil(p / 256), ksplit).  out_hi / out_lo: p x 16 int64, zero-initialised when ksplit > 1.
 __global__ void __launch_bounds__(kWarpsC * 32, 1)
 contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
-                       const int32_t *__restrict__ flip, const int8_t *__restrict__ Yfrag,
+                       const int8_t *__restrict__ Yfrag,
                        int64_t n_chunks, int64_t chunks_per_split, long long *__restrict__ out_hi,
                        long long *__restrict__ out_lo, int use_atomics)
 {
@@ -141,14 +141,13 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
     // this lane's four genotype rows: (mt, half) -> variant v0 + mt*16 + half*8 + g
     const int64_t v0 = (int64_t)blockIdx.x * kVarPerCta + warp * (kMT * 16);
     const uint8_t *rowp[kMT][2];
-    bool rok[kMT][2], rflip[kMT][2];
+    bool rok[kMT][2];
 #pragma unroll
     for (int mt = 0; mt < kMT; mt++)
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int64_t v = v0 + mt * 16 + h * 8 + g;
             rok[mt][h] = v < p;
-            rflip[mt][h] = rok[mt][h] && flip[v] != 0;
             rowp[mt][h] = packed + (size_t)(rok[mt][h] ? v : 0) * stride;
         }
     auto load_A = [&](int64_t kc, uint4 (&dst)[kMT][2]) {
@@ -174,17 +173,11 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
         for (int e = 0; e < 4; e++) acc2[mt][e] = 0;
     }
 
-    // g -> 2-g in the bit domain once a prefetched chunk becomes current; codes flipped beyond sample n-1 (and in
-    // the zero rows of out-of-range variants) meet all-zero digits
     auto adopt = [&](uint4 (&cur)[kMT][2], const uint4 (&nxt)[kMT][2]) {
 #pragma unroll
         for (int mt = 0; mt < kMT; mt++)
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                uint4 w = nxt[mt][h];
-                if (rflip[mt][h]) { w.x = flip_word(w.x); w.y = flip_word(w.y); w.z = flip_word(w.z); w.w = flip_word(w.w); }
-                cur[mt][h] = w;
-            }
+            for (int h = 0; h < 2; h++) cur[mt][h] = nxt[mt][h];
     };
     uint4 Acur[kMT][2], Anext[kMT][2];
     if (nkc > 0) { load_A(kc_begin, Anext); adopt(Acur, Anext); }
@@ -220,7 +213,7 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
                     imma16832(acc[mt][2 * jj + 1], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b.z, b.w);
                 }
             }
-            // hom-minor indicator (g^2 - g = 2 [g == 2]) against the digit slices of diag(Sigma_i): one more n-tile
+            // indicator [code >= 2] against the digit slices of diag(Sigma_i): one more n-tile (g^2 - g = 2 [g == 2])
             const uint2 b14 = reinterpret_cast<const uint2 *>(sb + (size_t)s * kStepBytesB + (kNT / 2) * 512)[lane];
 #pragma unroll
             for (int mt = 0; mt < kMT; mt++)
@@ -284,7 +277,7 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
 }  // namespace
 
 int launch_contract_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p,
-                           const int32_t *d_flip, long long *d_hi, long long *d_lo)
+                           long long *d_hi, long long *d_lo)
 {
     if (p == 0) return STAAR_OK;
     const NullSparse &ns = ctx->ns;
@@ -307,7 +300,7 @@ int launch_contract_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t strid
         attr_set = true;
     }
     dim3 grid((unsigned)vt, (unsigned)ksplit);
-    contract_packed_kernel<<<grid, kWarpsC * 32, smem, ctx->stream>>>(d_packed, stride, p, d_flip, ns.Yfrag, n_chunks, cps, d_hi,
+    contract_packed_kernel<<<grid, kWarpsC * 32, smem, ctx->stream>>>(d_packed, stride, p, ns.Yfrag, n_chunks, cps, d_hi,
                                                                       d_lo, ksplit > 1 ? 1 : 0);
     ctx->launches++;
     STAAR_CUDA(cudaGetLastError());
@@ -327,8 +320,8 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
     const int64_t n = ns.n;
     const int ncol = (int)ns.q + 2, ldY = ns.ldY;      // [r | Sigma_iX | diag(Sigma_i)]
     ns.sliced = false;
-    cudaFree(ns.Yfrag); cudaFree(ns.col_scale);
-    ns.Yfrag = nullptr; ns.col_scale = nullptr;
+    cudaFree(ns.Yfrag); cudaFree(ns.col_scale); cudaFree(ns.col_total);
+    ns.Yfrag = nullptr; ns.col_scale = nullptr; ns.col_total = nullptr;
     if (ncol > kColsPerSlice - 1) return STAAR_OK;  // wider designs take the FP64 path (slot 15 is reserved)
     std::vector<double> pulled;
     if (!hY) {                                      // current operand (incl. an updated residual column) from HBM
@@ -345,6 +338,7 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
     std::vector<int8_t> frag((size_t)n_chunks * kChunkBytesB, 0);
     std::vector<double> scale(kColsPerSlice, 1.0);
     std::vector<int8_t> digits((size_t)n * kSlices);
+    std::vector<long long> tot(2 * kColsPerSlice, 0);          // exact column totals of the fixed-point operand: hi | lo
     for (int c = 0; c < ncol; c++) {
         double mx = 0.0;
         for (int64_t j = 0; j < n; j++) {
@@ -365,6 +359,10 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
             }
             d[0] = (int8_t)X;                                          // |X| <= 65 here
             for (int s = 0; s < kSlices; s++) digits[(size_t)j * kSlices + s] = d[s];
+            long long hi = 0, lo = 0;                                  // same split as the kernel: X = hi * 2^24 + lo
+            for (int s = 0; s < 4; s++) hi = hi * 256 + d[s];
+            for (int s = 4; s < kSlices; s++) lo = lo * 256 + d[s];
+            tot[c] += hi; tot[kColsPerSlice + c] += lo;
         }
         const int cg = c / 8, g = c % 8;
         for (int64_t kc = 0; kc < n_chunks; kc++)
@@ -399,6 +397,8 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
     }
     STAAR_CUDA(cudaMalloc(&ns.Yfrag, frag.size()));
     STAAR_CUDA(cudaMalloc(&ns.col_scale, sizeof(double) * kColsPerSlice));
+    STAAR_CUDA(cudaMalloc(&ns.col_total, sizeof(long long) * 2 * kColsPerSlice));
+    STAAR_CUDA(cudaMemcpyAsync(ns.col_total, tot.data(), sizeof(long long) * tot.size(), cudaMemcpyHostToDevice, ctx->stream));
     STAAR_CUDA(cudaMemcpyAsync(ns.Yfrag, frag.data(), frag.size(), cudaMemcpyHostToDevice, ctx->stream));
     STAAR_CUDA(cudaMemcpyAsync(ns.col_scale, scale.data(), sizeof(double) * kColsPerSlice, cudaMemcpyHostToDevice, ctx->stream));
     STAAR_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -58,7 +58,7 @@ void NullSparse::release()
     }
     if (permuted) cudaFree(Yp);
     cudaFree(diag); cudaFree(sinfo_p); cudaFree(off_ent_p); cudaFree(relmask); cudaFree(rel); cudaFree(up_ent); cudaFree(Y);
-    cudaFree(Yfrag); cudaFree(col_scale); cudaFree(perm); cudaFree(gdesc); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut);
+    cudaFree(Yfrag); cudaFree(col_scale); cudaFree(col_total); cudaFree(perm); cudaFree(gdesc); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut);
     *this = NullSparse();
 }
 void NullDense::release()

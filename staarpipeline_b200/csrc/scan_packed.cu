@@ -185,7 +185,9 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams
         }
         quad = warp_sum(quad);
         if (lane == 0) {
-            P.AF[i] = vf.af; P.MAF[i] = vf.maf; P.flip[i] = vf.flip; P.mu[i] = mu; P.quad[i] = quad;
+            const int c0 = (int)(P.n - pc.c1 - pc.c2 - pc.cm);
+            const int mono = (pc.c1 == 0 && (pc.c2 == 0 || c0 == 0)) ? 2 : 0;
+            P.AF[i] = vf.af; P.MAF[i] = vf.maf; P.flip[i] = vf.flip | mono; P.mu[i] = mu; P.quad[i] = quad;
         }
         if (lane < kColsPerSlice) P.Sm[i * kColsPerSlice + lane] = (lane < P.ncol) ? sm : 0.0;
     }
@@ -483,7 +485,10 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
 #pragma unroll
             for (int w = 0; w < kBlkWarps; w++) t += s_quad[w];
             const VariantFlip vf = flip_from_counts(pc, P.n, P.impute);
-            P.AF[i] = vf.af; P.MAF[i] = vf.maf; P.flip[i] = flip ? 1 : 0; P.mu[i] = vf.mu; P.quad[i] = t;
+            // bit 1: every genotype is 0 after flip and imputation (the reference's exact Cov == 0 branch)
+            const int c0 = (int)(P.n - c1 - c2 - cm);
+            const int mono = (c1 == 0 && (c2 == 0 || c0 == 0)) ? 2 : 0;
+            P.AF[i] = vf.af; P.MAF[i] = vf.maf; P.flip[i] = (flip ? 1 : 0) | mono; P.mu[i] = vf.mu; P.quad[i] = t;
         }
         if (nstage == 2) {
             cur = s_work[it & 1];
@@ -504,21 +509,38 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
 
 struct FinParams {
     int64_t p; int q;
+    const int32_t *flip;
     const double *mu, *quad, *Sm;
-    const long long *hi, *lo;
+    const long long *hi, *lo, *tot;
     const double *scale, *cov;
     double *Score, *Score_se, *pl, *Est, *Est_se;
 };
 
+// The contraction delivers, per variant and column c, the exact integers R_c = sum_j code_j X_jc over the RAW codes
+// (missing = 3) and I = sum_j [code_j >= 2] X_jd for the diag(Sigma_i) column d; the scan delivers the FP64 column
+// sums Sm_c over missing samples, the flip decision, the imputation value mu and the kinship off-diagonal part.
+// With T_c = sum_j X_jc (exact, set-up time) the genotype the reference tests (flipped, imputed) gives
+//   no flip: G'y_c = R_c - 3 M_c + mu M_c                 g'diag g = R_d + 2 I - 5 M_d + mu^2 M_d
+//   flip   : G'y_c = 2 T_c - R_c + M_c + mu M_c           g'diag g = 4 T_d - 3 R_d + 2 I + 3 M_d + mu^2 M_d
+// (integer parts combined exactly in 64-bit, M_c = Sm_c).  A variant whose genotypes are all 0 after flip and
+// imputation takes the reference's exact Cov == 0 branch from the integer counts (bit 1 of flip[]).
 __global__ void __launch_bounds__(128) finalize_packed_kernel(FinParams P)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.p; i += (int64_t)gridDim.x * blockDim.x) {
+        const int fl = P.flip[i];
+        const bool flip = (fl & 1) != 0, mono = (fl & 2) != 0;
         const double mu = P.mu[i];
+        if (mono) {
+            P.Score[i] = 0.0;
+            single_trait_stats(0.0, 0.0, P.Score_se[i], P.pl[i], P.Est[i], P.Est_se[i]);
+            continue;
+        }
         double L[kColsPerSlice];
+        const double wm = flip ? mu + 1.0 : mu - 3.0;
         for (int c = 0; c <= P.q; c++) {
-            // the integer contraction saw the (already flipped) codes with missing as 0; add mu * sum_missing(y)
-            const long long hi = P.hi[i * 16 + c], lo = P.lo[i * 16 + c];
-            L[c] = ((double)hi * 16777216.0 + (double)lo) * P.scale[c] + mu * P.Sm[i * kColsPerSlice + c];
+            long long hi = P.hi[i * 16 + c], lo = P.lo[i * 16 + c];
+            if (flip) { hi = 2 * P.tot[c] - hi; lo = 2 * P.tot[kColsPerSlice + c] - lo; }
+            L[c] = ((double)hi * 16777216.0 + (double)lo) * P.scale[c] + wm * P.Sm[i * kColsPerSlice + c];
         }
         const double U = L[0];
         double tct = 0.0;
@@ -527,15 +549,13 @@ __global__ void __launch_bounds__(128) finalize_packed_kernel(FinParams P)
             for (int a = 0; a < P.q; a++) xb += L[1 + a] * P.cov[a + b * P.q];
             tct += xb * L[1 + b];
         }
-        // g' Sigma_i g = sum_j s_jj g_j (column q+1 of the contraction, non-missing samples)
-        //                + 2 s_jj over hom-minor carriers (g^2 - g = 2 [g == 2]; extra tile of the contraction)
-        //                + kinship off-diagonals over related carriers  (scan_packed_kernel)
-        //                + mu^2 * sum_missing s_jj
-        const long long shi = P.hi[i * 16 + P.q + 1], slo = P.lo[i * 16 + P.q + 1];
-        const double dlin = ((double)shi * 16777216.0 + (double)slo) * P.scale[P.q + 1];
-        // slot 15: sum over hom-minor carriers of s_jj (exact integer, [g == 2] tile of the contraction)
-        const double s2 = ((double)P.hi[i * 16 + 15] * 16777216.0 + (double)P.lo[i * 16 + 15]) * P.scale[P.q + 1];
-        const double quad = dlin + 2.0 * s2 + P.quad[i] + mu * mu * P.Sm[i * kColsPerSlice + P.q + 1];
+        const int d = P.q + 1;
+        const long long rhi = P.hi[i * 16 + d], rlo = P.lo[i * 16 + d], ihi = P.hi[i * 16 + 15], ilo = P.lo[i * 16 + 15];
+        long long qhi, qlo;
+        if (flip) { qhi = 4 * P.tot[d] - 3 * rhi + 2 * ihi; qlo = 4 * P.tot[kColsPerSlice + d] - 3 * rlo + 2 * ilo; }
+        else { qhi = rhi + 2 * ihi; qlo = rlo + 2 * ilo; }
+        const double smd = P.Sm[i * kColsPerSlice + d];
+        const double quad = ((double)qhi * 16777216.0 + (double)qlo) * P.scale[d] + ((flip ? 3.0 : -5.0) + mu * mu) * smd + P.quad[i];
         const double C = quad - tct;
         P.Score[i] = U;
         single_trait_stats(U, C, P.Score_se[i], P.pl[i], P.Est[i], P.Est_se[i]);
@@ -585,15 +605,15 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     return STAAR_OK;
 }
 
-int launch_finalize_packed(staar_ctx *ctx, int64_t p, const double *d_mu, const double *d_quad,
+int launch_finalize_packed(staar_ctx *ctx, int64_t p, const int32_t *d_flip, const double *d_mu, const double *d_quad,
                            const double *d_Sm, const long long *d_hi, const long long *d_lo, double *dScore,
                            double *dScore_se, double *dpl, double *dEst, double *dEst_se)
 {
     if (p == 0) return STAAR_OK;
     const NullSparse &ns = ctx->ns;
     FinParams P;
-    P.p = p; P.q = (int)ns.q; P.mu = d_mu; P.quad = d_quad; P.Sm = d_Sm;
-    P.hi = d_hi; P.lo = d_lo; P.scale = ns.col_scale; P.cov = ns.cov;
+    P.p = p; P.q = (int)ns.q; P.flip = d_flip; P.mu = d_mu; P.quad = d_quad; P.Sm = d_Sm;
+    P.hi = d_hi; P.lo = d_lo; P.tot = ns.col_total; P.scale = ns.col_scale; P.cov = ns.cov;
     P.Score = dScore; P.Score_se = dScore_se; P.pl = dpl; P.Est = dEst; P.Est_se = dEst_se;
     int blocks = (int)std::min<int64_t>((p + 127) / 128, (int64_t)ctx->sm_count * 8);
     finalize_packed_kernel<<<blocks, 128, 0, ctx->stream>>>(P);

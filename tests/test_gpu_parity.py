@@ -256,7 +256,8 @@ def test_resident_order_and_reorder(gpu_ctx, oracle):
 
 def test_packed_contraction_is_exact_integer(gpu_ctx, oracle):
     """K2 (packed): the INT8-sliced tensor-core contraction must equal, bit for bit, the integer sum
-    sum_j g_j * round(Y[j,c] * 2^(54-e_c)) — including the hom-minor slot and the split-K (atomic) path."""
+    sum_j code_j * round(Y[j,c] * 2^(54-e_c)) over the RAW 2-bit codes (missing = 3) — including the [code >= 2]
+    indicator slot and the split-K (atomic) path; flip and imputation are applied analytically afterwards."""
     import math
     from staarpipeline_b200 import synth
     from staarpipeline_b200.api import IMPUTE_MEAN
@@ -267,14 +268,13 @@ def test_packed_contraction_is_exact_integer(gpu_ctx, oracle):
         P = packed.shape[0]
         d = gpu_ctx.packed_debug_dump(P)
         Y = np.column_stack([nm.residuals, nm.Sigma_iX, nm.Sigma_i.diagonal()])
-        miss = np.isnan(G0) | (G0 <= -1)
-        Gint = np.where(miss, 0.0, Gf).astype(np.int64)                 # post-flip codes, missing -> 0
+        codes = np.where(np.isnan(G0) | (G0 <= -1), 3, G0).astype(np.int64)     # raw stored codes
         got = d["hi"].astype(object) * (1 << 24) + d["lo"].astype(object)
         for c in range(q + 2):
             e = math.frexp(np.abs(Y[:, c]).max())[1]
             assert d["col_scale"][c] == math.ldexp(1.0, e - 54)
             X = np.array([int(np.rint(math.ldexp(float(y), 54 - e))) for y in Y[:, c]], dtype=object)
-            assert list(got[:, c]) == list((Gint.astype(object) * X[:, None]).sum(axis=0)), f"column {c}"
-            if c == q + 1:                                              # hom-minor slot
-                assert list(got[:, 15]) == list(((Gint == 2).astype(object) * X[:, None]).sum(axis=0))
-        assert np.array_equal(d["flip"] != 0, oracle.matrix_flip_mean(G0)["AF"] > 0.5)
+            assert list(got[:, c]) == list((codes.astype(object) * X[:, None]).sum(axis=0)), f"column {c}"
+            if c == q + 1:                                              # indicator slot
+                assert list(got[:, 15]) == list(((codes >= 2).astype(object) * X[:, None]).sum(axis=0))
+        assert np.array_equal((d["flip"] & 1) != 0, oracle.matrix_flip_mean(G0)["AF"] > 0.5)
