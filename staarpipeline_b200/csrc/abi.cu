@@ -572,7 +572,8 @@ int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t st
     if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     STAAR_TRY(launch_scan_packed(ctx, d_packed, stride, n, p, impute, d_AF, d_MAF, dflip, dmu, dquad, dSm));
     if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-    STAAR_TRY(launch_contract_packed(ctx, d_packed, stride, n, p, dhi, dlo));
+    if (ctx->use_mma_sync) STAAR_TRY(launch_contract_packed(ctx, d_packed, stride, n, p, dhi, dlo));
+    else STAAR_TRY(launch_contract_tc(ctx, d_packed, stride, n, p, dhi, dlo));
     if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
     STAAR_TRY(launch_finalize_packed(ctx, p, dflip, dmu, dquad, dSm, dhi, dlo, d_Score, d_Score_se, d_pl, d_Est, d_Est_se));
     if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));

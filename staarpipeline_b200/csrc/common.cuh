@@ -98,7 +98,8 @@ struct NullSparse {
     // exact INT8 slices of Y in IMMA-fragment-major order, and their exact column sums
     bool sliced = false;
     int64_t n_chunks = 0;
-    int8_t *Yfrag = nullptr;      // n_chunks * kChunkBytesB
+    int8_t *Yfrag = nullptr;      // n_chunks * kChunkBytesB (mma.sync fragment-major order)
+    int8_t *Ytc = nullptr;        // n_chunks * kChunkBytesB (tcgen05 canonical K-major core-matrix order)
     double *col_scale = nullptr;  // kColsPerSlice: 2^(e_c - 54)
     long long *col_total = nullptr;   // 2 x kColsPerSlice: exact column sums of the fixed-point operand, hi | lo (X = hi 2^24 + lo)
     uint64_t fingerprint = 0;     // content hash of (Sigma_i, Sigma_iX, cov): cache key of the frozen-signature entry points
@@ -126,6 +127,7 @@ struct staar_ctx {
     staar::NullDense nd;
     // scratch
     staar::DevBuf G, L, aux, out, tmp, tmp2, pk, pk2, ctr;
+    bool use_mma_sync = false;       // STAAR_B200_CONTRACT=mma: legacy mma.sync contraction instead of tcgen05
     void *pinned = nullptr;
     size_t pinned_cap = 0;
     // optional per-kernel timing of the packed path (bench.py roofline)
@@ -173,6 +175,9 @@ int launch_finalize_packed(staar_ctx *ctx, int64_t p, const int32_t *d_flip, con
                            const double *d_Sm, const long long *d_hi, const long long *d_lo,
                            double *dScore, double *dScore_se, double *dpl, double *dEst, double *dEst_se);
 int build_sliced_operand(staar_ctx *ctx, const double *hY /* n x ldY row-major host, natural sample order */);
+int build_tc_operand(staar_ctx *ctx, const int8_t *digits, int ncol);
+int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, long long *d_hi,
+                       long long *d_lo);
 int refresh_permuted_Y(staar_ctx *ctx, const double *hY);
 // synth.cu
 int launch_synth_packed(staar_ctx *ctx, uint8_t *d_packed, size_t stride, int64_t n, int64_t first_variant, int64_t p,

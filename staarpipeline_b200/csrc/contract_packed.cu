@@ -320,8 +320,8 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
     const int64_t n = ns.n;
     const int ncol = (int)ns.q + 2, ldY = ns.ldY;      // [r | Sigma_iX | diag(Sigma_i)]
     ns.sliced = false;
-    cudaFree(ns.Yfrag); cudaFree(ns.col_scale); cudaFree(ns.col_total);
-    ns.Yfrag = nullptr; ns.col_scale = nullptr; ns.col_total = nullptr;
+    cudaFree(ns.Yfrag); cudaFree(ns.col_scale); cudaFree(ns.col_total); cudaFree(ns.Ytc);
+    ns.Yfrag = nullptr; ns.col_scale = nullptr; ns.col_total = nullptr; ns.Ytc = nullptr;
     if (ncol > kColsPerSlice - 1) return STAAR_OK;  // wider designs take the FP64 path (slot 15 is reserved)
     std::vector<double> pulled;
     if (!hY) {                                      // current operand (incl. an updated residual column) from HBM
@@ -338,6 +338,7 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
     std::vector<int8_t> frag((size_t)n_chunks * kChunkBytesB, 0);
     std::vector<double> scale(kColsPerSlice, 1.0);
     std::vector<int8_t> digits((size_t)n * kSlices);
+    std::vector<int8_t> alldigits((size_t)n * kColsPerSlice * kSlices, 0);   // [position][column][slice] for the tcgen05 image
     std::vector<long long> tot(2 * kColsPerSlice, 0);          // exact column totals of the fixed-point operand: hi | lo
     for (int c = 0; c < ncol; c++) {
         double mx = 0.0;
@@ -358,7 +359,10 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
                 X = (X - dd) >> 8;
             }
             d[0] = (int8_t)X;                                          // |X| <= 65 here
-            for (int s = 0; s < kSlices; s++) digits[(size_t)j * kSlices + s] = d[s];
+            for (int s = 0; s < kSlices; s++) {
+                digits[(size_t)j * kSlices + s] = d[s];
+                alldigits[((size_t)j * kColsPerSlice + c) * kSlices + s] = d[s];
+            }
             long long hi = 0, lo = 0;                                  // same split as the kernel: X = hi * 2^24 + lo
             for (int s = 0; s < 4; s++) hi = hi * 256 + d[s];
             for (int s = 4; s < kSlices; s++) lo = lo * 256 + d[s];
@@ -402,6 +406,7 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
     STAAR_CUDA(cudaMemcpyAsync(ns.Yfrag, frag.data(), frag.size(), cudaMemcpyHostToDevice, ctx->stream));
     STAAR_CUDA(cudaMemcpyAsync(ns.col_scale, scale.data(), sizeof(double) * kColsPerSlice, cudaMemcpyHostToDevice, ctx->stream));
     STAAR_CUDA(cudaStreamSynchronize(ctx->stream));
+    STAAR_TRY(build_tc_operand(ctx, alldigits.data(), ncol));
     ns.n_chunks = n_chunks;
     ns.sliced = true;
     return STAAR_OK;

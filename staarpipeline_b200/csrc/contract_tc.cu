@@ -1,0 +1,371 @@
+// contract_tc.cu — K2 for packed dosages on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a.
+//
+// Same contract as contract_packed.cu (the mma.sync version): for every variant the EXACT integers
+//     R_c = sum_j code_j * X_jc   (c = residuals | Sigma_iX | diag(Sigma_i); raw 2-bit codes, missing = 3)
+//     I   = sum_j [code_j >= 2] * X_jd                                  (d = the diag(Sigma_i) column)
+// with X the 54-bit fixed-point image of Y split into 7 balanced base-256 digits (see contract_packed.cu), i.e. the
+// first factor of every Cov in the reference (trans(residuals)*G, trans(Sigma_iX)*G; src/Individual_Score_Test.cpp:17,42).
+//
+// Mapping onto tcgen05.mma.cta_group::1.kind::i8 (int8 x int8 -> int32 accumulators in TMEM):
+//   M = 128 variants per CTA (TMEM lane = variant), K = samples (32 per instruction), N = 112 = 7 digit slices x 16
+//   columns for the main product and N = 8 for the [code >= 2] indicator against the 7 slices of diag(Sigma_i).
+//   * B (digits) is pre-arranged at null-model set-up in the canonical K-major, non-swizzled core-matrix layout, so a
+//     256-sample k-block (30 KiB) is ONE cp.async.bulk from L2 into a 4-stage shared-memory ring (mbarrier tx-count).
+//   * A (genotypes) never exists as int8 in memory: each of 128 "expander" threads owns one variant row, streams its
+//     2-bit column HBM -> shared memory with cp.async (4 k-blocks ahead), expands 2-bit -> int8 with shift/mask in
+//     registers (no flip, no missing fix-up: both are applied analytically by the finaliser) and writes the int8 tile
+//     straight into TMEM with tcgen05.st; the MMA reads A from TMEM (".ts" form), so shared-memory bandwidth is
+//     spent on B only.
+//   * One elected thread issues the MMAs; tcgen05.commit releases the A (TMEM) and B (smem) stages to the expanders and
+//     the bulk-copy producer through mbarriers; the expander warps read the accumulators back with tcgen05.ld and
+//     recombine the 7 digit sums per (variant, column) in 64-bit integers.
+// Roles: warps 0-3 expanders + epilogue (TMEM lane quarter = warp id), warp 4 MMA issuer + TMEM allocator, warp 5
+// bulk-copy producer.  Every genotype byte is read from HBM exactly once per launch.
+#include "common.cuh"
+#include "packed.cuh"
+
+namespace staar {
+
+namespace {
+
+constexpr int kTcRows = 128;                 // variants per CTA
+constexpr int kTcThreads = 192;
+constexpr int kStagesA = 3;                  // TMEM stages of the expanded A tiles
+constexpr int kStagesB = 4;                  // shared-memory stages of the digit operand
+constexpr int kMainBytes = 8 * 2 * 14 * 128; // per k-block: 8 k-steps x 2 k-chunks x 14 row groups x (8 rows x 16 B)
+constexpr int kIndBytes = 8 * 2 * 128;       // per k-block: 8 k-steps x 2 k-chunks x (8 rows x 16 B)
+static_assert(kMainBytes + kIndBytes == kChunkBytesB, "tcgen05 and mma.sync digit layouts have the same size");
+constexpr int kRing = 4;                     // per-thread ring of raw 64-byte genotype slices (cp.async)
+constexpr int kSlot = 80;                    // 64 B + 16 B pad: conflict-free 128-bit reads of one's own slot
+constexpr int kColD = 0, kColD2 = 112, kColA = 128;   // TMEM columns: accumulators, indicator accumulators, A stages
+
+__device__ __forceinline__ uint32_t s_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TC_DONE;\n"
+        "bra TC_WAIT;\n"
+        "TC_DONE:\n"
+        "}\n" ::"r"(s_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(s_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s_addr(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_addr(bar)) : "memory");
+}
+
+// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B (128 B contiguous);
+// lbo = byte distance between the two 16-byte k-chunks, sbo = byte distance between 8-row groups
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor for kind::i8: D = s32, A = B = signed int8, both K-major, dense
+__host__ __device__ constexpr uint32_t idesc_i8(int M, int N)
+{
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+        "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+        "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+// grid = ceil(p / 128); out_hi / out_lo: p x 16 int64 (slot 15 = indicator sum), X = hi * 2^24 + lo
+__global__ void __launch_bounds__(kTcThreads, 1)
+contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p, const int8_t *__restrict__ Ytc,
+                   int64_t n_kblocks, long long *__restrict__ out_hi, long long *__restrict__ out_lo)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *sB = smem;                                                       // kStagesB x kChunkBytesB
+    uint8_t *sG = smem + (size_t)kStagesB * kChunkBytesB;                     // kRing x 128 x kSlot
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sG + (size_t)kRing * kTcRows * kSlot);
+    uint64_t *a_full = bars, *a_empty = bars + kStagesA;
+    uint64_t *b_full = bars + 2 * kStagesA, *b_empty = b_full + kStagesB;
+    uint64_t *d_full = b_empty + kStagesB;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStagesA; s++) { bar_init(&a_full[s], kTcRows); bar_init(&a_empty[s], 1); }
+        for (int s = 0; s < kStagesB; s++) { bar_init(&b_full[s], 1); bar_init(&b_empty[s], 1); }
+        bar_init(d_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {                                                          // whole warp: allocate all 512 TMEM columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        // ===================================================================== expanders (one variant row each)
+        const int row = threadIdx.x;                                         // TMEM lane
+        const int64_t v = (int64_t)blockIdx.x * kTcRows + row;
+        const bool rok = v < p;
+        const uint8_t *rowp = packed + (size_t)(rok ? v : 0) * stride;
+        uint8_t *slot0 = sG + (size_t)row * kSlot;
+        auto fetch = [&](int64_t kb) {                                       // raw 64 bytes of k-block kb -> ring slot
+            uint8_t *dst = slot0 + (size_t)(kb % kRing) * (kTcRows * kSlot);
+            const size_t off = (size_t)kb * 64;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const bool ok = rok && off + 16 * c + 16 <= stride;
+                cp_async16(dst + 16 * c, ok ? rowp + off + 16 * c : packed, ok ? 16u : 0u);   // zero fill outside the column
+            }
+        };
+        for (int64_t kb = 0; kb < kRing - 1; kb++) {
+            if (kb < n_kblocks) fetch(kb);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int64_t kb = 0; kb < n_kblocks; kb++) {
+            if (kb + kRing - 1 < n_kblocks) fetch(kb + kRing - 1);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(kRing - 1) : "memory");
+            const uint4 *src = reinterpret_cast<const uint4 *>(slot0 + (size_t)(kb % kRing) * (kTcRows * kSlot));
+            uint32_t w[16];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint4 q = src[c];
+                w[4 * c] = q.x; w[4 * c + 1] = q.y; w[4 * c + 2] = q.z; w[4 * c + 3] = q.w;
+            }
+            const int sa = (int)(kb % kStagesA);
+            bar_wait(&a_empty[sa], (uint32_t)(((kb / kStagesA) & 1) ^ 1));  // MMAs that read this TMEM stage are done
+            tc_fence_after();
+            const uint32_t a1 = lane_base + kColA + sa * 128, a2 = a1 + 64;
+            // K index 4c + y of k-step ks <-> sample 32 ks + 16 (c >> 2) + 4 y + (c & 3): column c of a k-step is field
+            // (c & 3) of word 2 ks + (c >> 2); the digit operand is laid out with the same map (build_tc_operand)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t x[32];
+#pragma unroll
+                for (int c = 0; c < 32; c++) x[c] = (w[8 * h + (c >> 2)] >> (2 * (c & 3))) & 0x03030303u;
+                tmem_st32(a1 + 32 * h, x);
+#pragma unroll
+                for (int c = 0; c < 32; c++) x[c] = (w[8 * h + (c >> 2)] >> (2 * (c & 3) + 1)) & 0x01010101u;
+                tmem_st32(a2 + 32 * h, x);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            bar_arrive(&a_full[sa]);
+        }
+        // ===================================================================== epilogue: TMEM -> 64-bit recombination
+        bar_wait(d_full, 0u);
+        tc_fence_after();
+        int acc[112];
+        {
+            int t32[32];
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                tmem_ld32(lane_base + kColD + 32 * b, t32);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int e = 0; e < 32; e++) acc[32 * b + e] = t32[e];
+            }
+            int t16[16];
+            tmem_ld16(lane_base + kColD + 96, t16);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int e = 0; e < 16; e++) acc[96 + e] = t16[e];
+        }
+        int ind[8];
+        tmem_ld8(lane_base + kColD2, ind);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (rok) {
+#pragma unroll
+            for (int c = 0; c < 15; c++) {                                   // accumulator column = 16 * slice + c
+                long long hi = 0, lo = 0;
+#pragma unroll
+                for (int sl = 0; sl < 4; sl++) hi = hi * 256 + (long long)acc[16 * sl + c];
+#pragma unroll
+                for (int sl = 4; sl < kSlices; sl++) lo = lo * 256 + (long long)acc[16 * sl + c];
+                out_hi[v * 16 + c] = hi;
+                out_lo[v * 16 + c] = lo;
+            }
+            long long hi = 0, lo = 0;
+#pragma unroll
+            for (int sl = 0; sl < 4; sl++) hi = hi * 256 + (long long)ind[sl];
+#pragma unroll
+            for (int sl = 4; sl < kSlices; sl++) lo = lo * 256 + (long long)ind[sl];
+            out_hi[v * 16 + 15] = hi;
+            out_lo[v * 16 + 15] = lo;
+        }
+        tc_fence_before();
+    } else if (warp == 4) {
+        // ===================================================================== MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t kIdescMain = idesc_i8(kTcRows, 112), kIdescInd = idesc_i8(kTcRows, 8);
+            for (int64_t kb = 0; kb < n_kblocks; kb++) {
+                const int sa = (int)(kb % kStagesA), sb = (int)(kb % kStagesB);
+                bar_wait(&b_full[sb], (uint32_t)((kb / kStagesB) & 1));
+                bar_wait(&a_full[sa], (uint32_t)((kb / kStagesA) & 1));
+                tc_fence_after();
+                const uint32_t bbase = s_addr(sB + (size_t)sb * kChunkBytesB);
+                const uint32_t a1 = tmem + kColA + sa * 128, a2 = a1 + 64;
+#pragma unroll
+                for (int ks = 0; ks < 8; ks++) {
+                    const uint32_t accum = (kb > 0 || ks > 0) ? 1u : 0u;
+                    umma_i8_ts(tmem + kColD, a1 + 8 * ks, smem_desc(bbase + ks * (2 * 14 * 128), 14 * 128, 128), kIdescMain, accum);
+                    umma_i8_ts(tmem + kColD2, a2 + 8 * ks, smem_desc(bbase + kMainBytes + ks * 256, 128, 128), kIdescInd, accum);
+                }
+                tc_commit(&a_empty[sa]);                                    // frees the TMEM A stage when these MMAs retire
+                tc_commit(&b_empty[sb]);                                    // frees the shared-memory digit stage
+            }
+            tc_commit(d_full);
+        }
+        __syncwarp();
+    } else {
+        // ===================================================================== digit producer (one thread)
+        if (lane == 0) {
+            for (int64_t kb = 0; kb < n_kblocks; kb++) {
+                const int sb = (int)(kb % kStagesB);
+                bar_wait(&b_empty[sb], (uint32_t)(((kb / kStagesB) & 1) ^ 1));
+                bar_expect_tx(&b_full[sb], kChunkBytesB);
+                bulk_load(sB + (size_t)sb * kChunkBytesB, Ytc + (size_t)kb * kChunkBytesB, kChunkBytesB, &b_full[sb]);
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace
+
+int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, long long *d_hi,
+                       long long *d_lo)
+{
+    if (p == 0) return STAAR_OK;
+    const NullSparse &ns = ctx->ns;
+    if (!ns.sliced || !ns.Ytc) { set_error("packed contraction: sliced operand not built (q > 13?)"); return STAAR_ERR_STATE; }
+    const int64_t n_kblocks = (n + kChunkSamples - 1) / kChunkSamples;
+    const size_t smem = (size_t)kStagesB * kChunkBytesB + (size_t)kRing * kTcRows * kSlot + 32 * sizeof(uint64_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        STAAR_CUDA(cudaFuncSetAttribute(contract_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int64_t tiles = (p + kTcRows - 1) / kTcRows;
+    contract_tc_kernel<<<(unsigned)tiles, kTcThreads, smem, ctx->stream>>>(d_packed, stride, p, ns.Ytc, n_kblocks, d_hi, d_lo);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+// Digit operand in the canonical layout of the tcgen05 shared-memory descriptors used above.  One k-block:
+//   main: [k-step 8][k-chunk 2][row group 14][row 8][16 B]   row = 16 * slice + column   (N = 112)
+//   ind : [k-step 8][k-chunk 2][row 8][16 B]                 row = slice of diag(Sigma_i), row 7 = 0   (N = 8)
+// K index kk = 16 * k-chunk + byte of a k-step <-> sample 256 kb + 32 ks + 16 ((kk >> 2) >> 2) + 4 (kk & 3) + ((kk >> 2) & 3).
+int build_tc_operand(staar_ctx *ctx, const int8_t *digits /* n x kColsPerSlice x kSlices, position order */, int ncol)
+{
+    NullSparse &ns = ctx->ns;
+    const int64_t n = ns.n;
+    const int64_t n_kblocks = (n + kChunkSamples - 1) / kChunkSamples;
+    std::vector<int8_t> img((size_t)n_kblocks * kChunkBytesB, 0);
+    for (int64_t kb = 0; kb < n_kblocks; kb++)
+        for (int ks = 0; ks < 8; ks++)
+            for (int kk = 0; kk < 32; kk++) {
+                const int c = kk >> 2, y = kk & 3;
+                const int64_t smp = kb * 256 + 32 * ks + 16 * (c >> 2) + 4 * y + (c & 3);
+                if (smp >= n) continue;
+                const int8_t *dg = digits + (size_t)smp * kColsPerSlice * kSlices;
+                int8_t *base = img.data() + (size_t)kb * kChunkBytesB;
+                const size_t koff = (size_t)(kk >> 4) * (14 * 128) + (kk & 15);
+                for (int sl = 0; sl < kSlices; sl++)
+                    for (int col = 0; col < ncol; col++) {
+                        const int row = 16 * sl + col;
+                        base[(size_t)ks * (2 * 14 * 128) + koff + (size_t)(row >> 3) * 128 + (size_t)(row & 7) * 16] = dg[col * kSlices + sl];
+                    }
+                const size_t ioff = (size_t)kMainBytes + (size_t)ks * 256 + (size_t)(kk >> 4) * 128 + (kk & 15);
+                for (int sl = 0; sl < kSlices; sl++) base[ioff + (size_t)sl * 16] = dg[(ncol - 1) * kSlices + sl];
+            }
+    cudaFree(ns.Ytc);
+    ns.Ytc = nullptr;
+    STAAR_CUDA(cudaMalloc(&ns.Ytc, img.size()));
+    STAAR_CUDA(cudaMemcpyAsync(ns.Ytc, img.data(), img.size(), cudaMemcpyHostToDevice, ctx->stream));
+    STAAR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return STAAR_OK;
+}
+
+}  // namespace staar

@@ -58,7 +58,7 @@ void NullSparse::release()
     }
     if (permuted) cudaFree(Yp);
     cudaFree(diag); cudaFree(sinfo_p); cudaFree(off_ent_p); cudaFree(relmask); cudaFree(rel); cudaFree(up_ent); cudaFree(Y);
-    cudaFree(Yfrag); cudaFree(col_scale); cudaFree(col_total); cudaFree(perm); cudaFree(gdesc); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut);
+    cudaFree(Yfrag); cudaFree(Ytc); cudaFree(col_scale); cudaFree(col_total); cudaFree(perm); cudaFree(gdesc); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut);
     *this = NullSparse();
 }
 void NullDense::release()
@@ -497,6 +497,10 @@ int staar_ctx_create(int device, staar_ctx **out)
     staar_ctx *ctx = new staar_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    {
+        const char *sel = getenv("STAAR_B200_CONTRACT");
+        ctx->use_mma_sync = sel && strcmp(sel, "mma") == 0;
+    }
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; staar::set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return STAAR_ERR_CUDA; }
     *out = ctx;
