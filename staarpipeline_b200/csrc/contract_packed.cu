@@ -213,12 +213,13 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
                     imma16832(acc[mt][2 * jj + 1], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b.z, b.w);
                 }
             }
-            // indicator [code >= 2] against the digit slices of diag(Sigma_i): one more n-tile (g^2 - g = 2 [g == 2])
+            // low bit of the code against the digit slices of diag(Sigma_i): one more n-tile
+            // (g^2 - g = 2 [g == 2] and 2 [code >= 2] = code - (code & 1))
             const uint2 b14 = reinterpret_cast<const uint2 *>(sb + (size_t)s * kStepBytesB + (kNT / 2) * 512)[lane];
 #pragma unroll
             for (int mt = 0; mt < kMT; mt++)
-                imma16832(acc2[mt], (a[mt][0] >> 1) & 0x01010101u, (a[mt][1] >> 1) & 0x01010101u,
-                          (a[mt][2] >> 1) & 0x01010101u, (a[mt][3] >> 1) & 0x01010101u, b14.x, b14.y);
+                imma16832(acc2[mt], a[mt][0] & 0x01010101u, a[mt][1] & 0x01010101u, a[mt][2] & 0x01010101u,
+                          a[mt][3] & 0x01010101u, b14.x, b14.y);
         }
         // release the stage back to the producer
         __syncwarp();

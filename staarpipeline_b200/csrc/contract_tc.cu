@@ -2,25 +2,26 @@
 //
 // Same contract as contract_packed.cu (the mma.sync version): for every variant the EXACT integers
 //     R_c = sum_j code_j * X_jc   (c = residuals | Sigma_iX | diag(Sigma_i); raw 2-bit codes, missing = 3)
-//     I   = sum_j [code_j >= 2] * X_jd                                  (d = the diag(Sigma_i) column)
+//     B   = sum_j (code_j & 1) * X_jd                                   (d = the diag(Sigma_i) column;
+//                                                                        2 [code >= 2] = code - (code & 1))
 // with X the 54-bit fixed-point image of Y split into 7 balanced base-256 digits (see contract_packed.cu), i.e. the
 // first factor of every Cov in the reference (trans(residuals)*G, trans(Sigma_iX)*G; src/Individual_Score_Test.cpp:17,42).
 //
 // Mapping onto tcgen05.mma.cta_group::1.kind::i8 (int8 x int8 -> int32 accumulators in TMEM):
 //   M = 128 variants per CTA (TMEM lane = variant), K = samples (32 per instruction), N = 112 = 7 digit slices x 16
-//   columns for the main product and N = 8 for the [code >= 2] indicator against the 7 slices of diag(Sigma_i).
+//   columns for the main product and N = 8 for the low-bit indicator against the 7 slices of diag(Sigma_i).
 //   * B (digits) is pre-arranged at null-model set-up in the canonical K-major, non-swizzled core-matrix layout, so a
 //     256-sample k-block (30 KiB) is ONE cp.async.bulk from L2 into a 4-stage shared-memory ring (mbarrier tx-count).
-//   * A (genotypes) never exists as int8 in memory: each of 128 "expander" threads owns one variant row, streams its
-//     2-bit column HBM -> shared memory with cp.async (4 k-blocks ahead), expands 2-bit -> int8 with shift/mask in
+//   * A (genotypes) never exists as int8 in memory: two "expander" threads own each variant row (half a k-block
+//     each), stream the 2-bit column HBM -> shared memory with cp.async (3 k-blocks ahead), expand 2-bit -> int8 with shift/mask in
 //     registers (no flip, no missing fix-up: both are applied analytically by the finaliser) and writes the int8 tile
 //     straight into TMEM with tcgen05.st; the MMA reads A from TMEM (".ts" form), so shared-memory bandwidth is
 //     spent on B only.
 //   * One elected thread issues the MMAs; tcgen05.commit releases the A (TMEM) and B (smem) stages to the expanders and
 //     the bulk-copy producer through mbarriers; the expander warps read the accumulators back with tcgen05.ld and
 //     recombine the 7 digit sums per (variant, column) in 64-bit integers.
-// Roles: warps 0-3 expanders + epilogue (TMEM lane quarter = warp id), warp 4 MMA issuer + TMEM allocator, warp 5
-// bulk-copy producer.  Every genotype byte is read from HBM exactly once per launch.
+// Roles: warps 0-7 expanders + epilogue (TMEM lane quarter = warp id % 4, k-block half = warp id / 4), warp 8 MMA issuer
+// + TMEM allocator, warp 9 bulk-copy producer.  Every genotype byte is read from HBM exactly once per launch.
 #include "common.cuh"
 #include "packed.cuh"
 
@@ -29,7 +30,8 @@ namespace staar {
 namespace {
 
 constexpr int kTcRows = 128;                 // variants per CTA
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;
+constexpr int kExpThreads = 256;             // 8 expander warps
 constexpr int kStagesA = 3;                  // TMEM stages of the expanded A tiles
 constexpr int kStagesB = 4;                  // shared-memory stages of the digit operand
 constexpr int kMainBytes = 8 * 2 * 14 * 128; // per k-block: 8 k-steps x 2 k-chunks x 14 row groups x (8 rows x 16 B)
@@ -64,6 +66,21 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity)
         "bra TC_WAIT;\n"
         "TC_DONE:\n"
         "}\n" ::"r"(s_addr(bar)), "r"(parity) : "memory");
+}
+// same, for roles that are far ahead of the critical path (keeps their polling out of the expanders' issue slots)
+__device__ __forceinline__ void bar_wait_relaxed(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(s_addr(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(200);
+    }
 }
 __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
@@ -159,14 +176,15 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kMmaWarp = kExpThreads / 32, kProdWarp = kMmaWarp + 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStagesA; s++) { bar_init(&a_full[s], kTcRows); bar_init(&a_empty[s], 1); }
+        for (int s = 0; s < kStagesA; s++) { bar_init(&a_full[s], kExpThreads); bar_init(&a_empty[s], 1); }
         for (int s = 0; s < kStagesB; s++) { bar_init(&b_full[s], 1); bar_init(&b_empty[s], 1); }
         bar_init(d_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {                                                          // whole warp: allocate all 512 TMEM columns
+    if (warp == kMmaWarp) {                                                   // whole warp: allocate all 512 TMEM columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -175,19 +193,19 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 4) {
-        // ===================================================================== expanders (one variant row each)
-        const int row = threadIdx.x;                                         // TMEM lane
+    if (warp < kMmaWarp) {
+        // ===================================================================== expanders: (variant row, k-block half)
+        const int row = threadIdx.x & (kTcRows - 1), half = threadIdx.x >> 7;   // TMEM lane quarter = warp % 4
         const int64_t v = (int64_t)blockIdx.x * kTcRows + row;
         const bool rok = v < p;
-        const uint8_t *rowp = packed + (size_t)(rok ? v : 0) * stride;
-        uint8_t *slot0 = sG + (size_t)row * kSlot;
-        auto fetch = [&](int64_t kb) {                                       // raw 64 bytes of k-block kb -> ring slot
+        const uint8_t *rowp = packed + (size_t)(rok ? v : 0) * stride + 32 * half;
+        uint8_t *slot0 = sG + (size_t)row * kSlot + 32 * half;
+        auto fetch = [&](int64_t kb) {                                       // raw 32 bytes of k-block kb -> ring slot
             uint8_t *dst = slot0 + (size_t)(kb % kRing) * (kTcRows * kSlot);
             const size_t off = (size_t)kb * 64;
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const bool ok = rok && off + 16 * c + 16 <= stride;
+            for (int c = 0; c < 2; c++) {
+                const bool ok = rok && off + 32 * half + 16 * c + 16 <= stride;
                 cp_async16(dst + 16 * c, ok ? rowp + off + 16 * c : packed, ok ? 16u : 0u);   // zero fill outside the column
             }
         };
@@ -195,81 +213,89 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
             if (kb < n_kblocks) fetch(kb);
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         for (int64_t kb = 0; kb < n_kblocks; kb++) {
             if (kb + kRing - 1 < n_kblocks) fetch(kb + kRing - 1);
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group %0;" ::"n"(kRing - 1) : "memory");
             const uint4 *src = reinterpret_cast<const uint4 *>(slot0 + (size_t)(kb % kRing) * (kTcRows * kSlot));
-            uint32_t w[16];
+            uint32_t w[8];
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
+            for (int c = 0; c < 2; c++) {
                 const uint4 q = src[c];
                 w[4 * c] = q.x; w[4 * c + 1] = q.y; w[4 * c + 2] = q.z; w[4 * c + 3] = q.w;
             }
             const int sa = (int)(kb % kStagesA);
             bar_wait(&a_empty[sa], (uint32_t)(((kb / kStagesA) & 1) ^ 1));  // MMAs that read this TMEM stage are done
             tc_fence_after();
-            const uint32_t a1 = lane_base + kColA + sa * 128, a2 = a1 + 64;
+            const uint32_t a1 = lane_base + kColA + sa * 128 + 32 * half, a2 = a1 + 64;
             // K index 4c + y of k-step ks <-> sample 32 ks + 16 (c >> 2) + 4 y + (c & 3): column c of a k-step is field
             // (c & 3) of word 2 ks + (c >> 2); the digit operand is laid out with the same map (build_tc_operand)
+            uint32_t x[32];
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                uint32_t x[32];
+            for (int c = 0; c < 32; c++) x[c] = (w[c >> 2] >> (2 * (c & 3))) & 0x03030303u;
+            tmem_st32(a1, x);
 #pragma unroll
-                for (int c = 0; c < 32; c++) x[c] = (w[8 * h + (c >> 2)] >> (2 * (c & 3))) & 0x03030303u;
-                tmem_st32(a1 + 32 * h, x);
-#pragma unroll
-                for (int c = 0; c < 32; c++) x[c] = (w[8 * h + (c >> 2)] >> (2 * (c & 3) + 1)) & 0x01010101u;
-                tmem_st32(a2 + 32 * h, x);
-            }
+            for (int c = 0; c < 32; c++) x[c] &= 0x01010101u;               // low bit: 2 [code >= 2] = code - (code & 1)
+            tmem_st32(a2, x);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             bar_arrive(&a_full[sa]);
         }
         // ===================================================================== epilogue: TMEM -> 64-bit recombination
+        // half 0 reads the accumulators of digit slices 0-3 (the "hi" part), half 1 slices 4-6 and the indicator tile
         bar_wait(d_full, 0u);
         tc_fence_after();
-        int acc[112];
+        int acc[64];
         {
             int t32[32];
 #pragma unroll
-            for (int b = 0; b < 3; b++) {
-                tmem_ld32(lane_base + kColD + 32 * b, t32);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int b = 0; b < 2; b++) {
+                if (half == 0 || b == 0) {
+                    tmem_ld32(lane_base + kColD + 64 * half + 32 * b, t32);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int e = 0; e < 32; e++) acc[32 * b + e] = t32[e];
+                    for (int e = 0; e < 32; e++) acc[32 * b + e] = t32[e];
+                } else {
+                    int t16[16], t8[8];
+                    tmem_ld16(lane_base + kColD + 96, t16);
+                    tmem_ld8(lane_base + kColD2, t8);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int e = 0; e < 16; e++) acc[32 + e] = t16[e];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) acc[48 + e] = t8[e];
+                }
             }
-            int t16[16];
-            tmem_ld16(lane_base + kColD + 96, t16);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int e = 0; e < 16; e++) acc[96 + e] = t16[e];
         }
-        int ind[8];
-        tmem_ld8(lane_base + kColD2, ind);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (rok) {
+            if (half == 0) {
 #pragma unroll
-            for (int c = 0; c < 15; c++) {                                   // accumulator column = 16 * slice + c
-                long long hi = 0, lo = 0;
+                for (int c = 0; c < 15; c++) {                               // accumulator column = 16 * slice + c
+                    long long hi = 0;
 #pragma unroll
-                for (int sl = 0; sl < 4; sl++) hi = hi * 256 + (long long)acc[16 * sl + c];
+                    for (int sl = 0; sl < 4; sl++) hi = hi * 256 + (long long)acc[16 * sl + c];
+                    out_hi[v * 16 + c] = hi;
+                }
+            } else {
 #pragma unroll
-                for (int sl = 4; sl < kSlices; sl++) lo = lo * 256 + (long long)acc[16 * sl + c];
-                out_hi[v * 16 + c] = hi;
-                out_lo[v * 16 + c] = lo;
+                for (int c = 0; c < 15; c++) {
+                    long long lo = 0;
+#pragma unroll
+                    for (int sl = 4; sl < kSlices; sl++) lo = lo * 256 + (long long)acc[16 * (sl - 4) + c];
+                    out_lo[v * 16 + c] = lo;
+                }
+                long long hi = 0, lo = 0;                                    // indicator tile: column = digit slice
+#pragma unroll
+                for (int sl = 0; sl < 4; sl++) hi = hi * 256 + (long long)acc[48 + sl];
+#pragma unroll
+                for (int sl = 4; sl < kSlices; sl++) lo = lo * 256 + (long long)acc[48 + sl];
+                out_hi[v * 16 + 15] = hi;
+                out_lo[v * 16 + 15] = lo;
             }
-            long long hi = 0, lo = 0;
-#pragma unroll
-            for (int sl = 0; sl < 4; sl++) hi = hi * 256 + (long long)ind[sl];
-#pragma unroll
-            for (int sl = 4; sl < kSlices; sl++) lo = lo * 256 + (long long)ind[sl];
-            out_hi[v * 16 + 15] = hi;
-            out_lo[v * 16 + 15] = lo;
         }
         tc_fence_before();
-    } else if (warp == 4) {
+    } else if (warp == kMmaWarp) {
         // ===================================================================== MMA issuer (one thread)
         if (lane == 0) {
             constexpr uint32_t kIdescMain = idesc_i8(kTcRows, 112), kIdescInd = idesc_i8(kTcRows, 8);
@@ -297,7 +323,7 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
         if (lane == 0) {
             for (int64_t kb = 0; kb < n_kblocks; kb++) {
                 const int sb = (int)(kb % kStagesB);
-                bar_wait(&b_empty[sb], (uint32_t)(((kb / kStagesB) & 1) ^ 1));
+                bar_wait_relaxed(&b_empty[sb], (uint32_t)(((kb / kStagesB) & 1) ^ 1));
                 bar_expect_tx(&b_full[sb], kChunkBytesB);
                 bulk_load(sB + (size_t)sb * kChunkBytesB, Ytc + (size_t)kb * kChunkBytesB, kChunkBytesB, &b_full[sb]);
             }
@@ -305,7 +331,7 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
         __syncwarp();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }

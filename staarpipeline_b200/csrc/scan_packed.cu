@@ -517,7 +517,8 @@ struct FinParams {
 };
 
 // The contraction delivers, per variant and column c, the exact integers R_c = sum_j code_j X_jc over the RAW codes
-// (missing = 3) and I = sum_j [code_j >= 2] X_jd for the diag(Sigma_i) column d; the scan delivers the FP64 column
+// (missing = 3) and B = sum_j (code_j & 1) X_jd for the diag(Sigma_i) column d, so that I = sum_j [code_j >= 2] X_jd
+// satisfies 2 I = R_d - B; the scan delivers the FP64 column
 // sums Sm_c over missing samples, the flip decision, the imputation value mu and the kinship off-diagonal part.
 // With T_c = sum_j X_jc (exact, set-up time) the genotype the reference tests (flipped, imputed) gives
 //   no flip: G'y_c = R_c - 3 M_c + mu M_c                 g'diag g = R_d + 2 I - 5 M_d + mu^2 M_d
@@ -550,10 +551,11 @@ __global__ void __launch_bounds__(128) finalize_packed_kernel(FinParams P)
             tct += xb * L[1 + b];
         }
         const int d = P.q + 1;
-        const long long rhi = P.hi[i * 16 + d], rlo = P.lo[i * 16 + d], ihi = P.hi[i * 16 + 15], ilo = P.lo[i * 16 + 15];
+        const long long rhi = P.hi[i * 16 + d], rlo = P.lo[i * 16 + d];
+        const long long i2hi = rhi - P.hi[i * 16 + 15], i2lo = rlo - P.lo[i * 16 + 15];      // 2 I = R_d - B
         long long qhi, qlo;
-        if (flip) { qhi = 4 * P.tot[d] - 3 * rhi + 2 * ihi; qlo = 4 * P.tot[kColsPerSlice + d] - 3 * rlo + 2 * ilo; }
-        else { qhi = rhi + 2 * ihi; qlo = rlo + 2 * ilo; }
+        if (flip) { qhi = 4 * P.tot[d] - 3 * rhi + i2hi; qlo = 4 * P.tot[kColsPerSlice + d] - 3 * rlo + i2lo; }
+        else { qhi = rhi + i2hi; qlo = rlo + i2lo; }
         const double smd = P.Sm[i * kColsPerSlice + d];
         const double quad = ((double)qhi * 16777216.0 + (double)qlo) * P.scale[d] + ((flip ? 3.0 : -5.0) + mu * mu) * smd + P.quad[i];
         const double C = quad - tct;
