@@ -198,8 +198,8 @@ int staar_ctx_set_profiling(staar_ctx *ctx, int on);
 int staar_ctx_last_stage_ms(staar_ctx *ctx, float ms[3]);
 
 /* Test hook: intermediates of the LAST staar_packed_score_device call, copied to host arrays (any may be NULL):
- * hi/lo (p x 16 int64: exact integer contraction of the raw codes, X = hi*2^24 + lo in units of col_scale[c];
- * slot 15 = sum of (code & 1) against diag(Sigma_i)), Sm (p x 16 sums over missing samples), quad (kinship off-diagonal part), mu, flip,
+ * hi/lo (p x 16 int64: exact integer contraction of the raw codes, X = hi*2^24 + lo in units of col_scale[c]),
+ * Sm (p x 16 sums over missing samples; slot 15 = sum of Sigma_i[j,j] over hom-minor carriers), quad (kinship off-diagonal part), mu, flip,
  * col_scale (16). */
 int staar_packed_debug_dump(staar_ctx *ctx, int64_t p, long long *hi, long long *lo, double *Sm, double *quad,
                             double *mu, int32_t *flip, double *col_scale);

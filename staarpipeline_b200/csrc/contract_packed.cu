@@ -162,15 +162,13 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
             }
     };
 
-    int acc[kMT][kNT][4], acc2[kMT][4];      // acc2: [code == 2] x the 7 digit slices of diag(Sigma_i)
+    int acc[kMT][kNT][4];
 #pragma unroll
     for (int mt = 0; mt < kMT; mt++) {
 #pragma unroll
         for (int j = 0; j < kNT; j++)
 #pragma unroll
             for (int e = 0; e < 4; e++) acc[mt][j][e] = 0;
-#pragma unroll
-        for (int e = 0; e < 4; e++) acc2[mt][e] = 0;
     }
 
     auto adopt = [&](uint4 (&cur)[kMT][2], const uint4 (&nxt)[kMT][2]) {
@@ -213,13 +211,6 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
                     imma16832(acc[mt][2 * jj + 1], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b.z, b.w);
                 }
             }
-            // low bit of the code against the digit slices of diag(Sigma_i): one more n-tile
-            // (g^2 - g = 2 [g == 2] and 2 [code >= 2] = code - (code & 1))
-            const uint2 b14 = reinterpret_cast<const uint2 *>(sb + (size_t)s * kStepBytesB + (kNT / 2) * 512)[lane];
-#pragma unroll
-            for (int mt = 0; mt < kMT; mt++)
-                imma16832(acc2[mt], a[mt][0] & 0x01010101u, a[mt][1] & 0x01010101u, a[mt][2] & 0x01010101u,
-                          a[mt][3] & 0x01010101u, b14.x, b14.y);
         }
         // release the stage back to the producer
         __syncwarp();
@@ -232,25 +223,6 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
     for (int mt = 0; mt < kMT; mt++)
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            // hom-minor tile: lane t holds digit slices 2t, 2t+1 of row (h ? g+8 : g); gather the quad's partials
-            {
-                const long long part = (long long)acc2[mt][h * 2] * 256 + (long long)acc2[mt][h * 2 + 1];
-                const int q0 = lane & ~3;
-                const long long p0 = __shfl_sync(0xffffffffu, part, q0), p1 = __shfl_sync(0xffffffffu, part, q0 + 1);
-                const long long p2 = __shfl_sync(0xffffffffu, part, q0 + 2);
-                const long long d6 = __shfl_sync(0xffffffffu, (long long)acc2[mt][h * 2], q0 + 3);
-                if (t == 0 && rok[mt][h]) {
-                    const int64_t v = v0 + mt * 16 + h * 8 + g;
-                    const long long hi2 = p0 * 65536 + p1, lo2 = p2 * 256 + d6;
-                    if (use_atomics) {
-                        atomicAdd(reinterpret_cast<unsigned long long *>(out_hi + v * 16 + 15), (unsigned long long)hi2);
-                        atomicAdd(reinterpret_cast<unsigned long long *>(out_lo + v * 16 + 15), (unsigned long long)lo2);
-                    } else {
-                        out_hi[v * 16 + 15] = hi2;
-                        out_lo[v * 16 + 15] = lo2;
-                    }
-                }
-            }
             if (!rok[mt][h]) continue;
             const int64_t v = v0 + mt * 16 + h * 8 + g;
 #pragma unroll
@@ -258,7 +230,6 @@ contract_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int c = cg * 8 + 2 * t + e;
-                    if (c == 15) continue;                 // slot 15 carries the hom-minor sum written above
                     long long hi = 0, lo = 0;
 #pragma unroll
                     for (int sl = 0; sl < 4; sl++) hi = hi * 256 + (long long)acc[mt][2 * sl + cg][h * 2 + e];

@@ -2,14 +2,14 @@
 //
 // Same contract as contract_packed.cu (the mma.sync version): for every variant the EXACT integers
 //     R_c = sum_j code_j * X_jc   (c = residuals | Sigma_iX | diag(Sigma_i); raw 2-bit codes, missing = 3)
-//     B   = sum_j (code_j & 1) * X_jd                                   (d = the diag(Sigma_i) column;
-//                                                                        2 [code >= 2] = code - (code & 1))
 // with X the 54-bit fixed-point image of Y split into 7 balanced base-256 digits (see contract_packed.cu), i.e. the
 // first factor of every Cov in the reference (trans(residuals)*G, trans(Sigma_iX)*G; src/Individual_Score_Test.cpp:17,42).
 //
 // Mapping onto tcgen05.mma.cta_group::1.kind::i8 (int8 x int8 -> int32 accumulators in TMEM):
 //   M = 128 variants per CTA (TMEM lane = variant), K = samples (32 per instruction), N = 112 = 7 digit slices x 16
-//   columns for the main product and N = 8 for the low-bit indicator against the 7 slices of diag(Sigma_i).
+//   columns.  (Measured: one K = 32 instruction costs ~52 clk whatever N <= 112 is — the A tile is read from TMEM —
+//   so a separate narrow N = 8 tile for the hom-minor indicator doubled the tensor time; that term now comes from
+//   the scan kernel's sparse sweep instead.)
 //   * B (digits) is pre-arranged at null-model set-up in the canonical K-major, non-swizzled core-matrix layout, so a
 //     256-sample k-block (30 KiB) is ONE cp.async.bulk from L2 into a 4-stage shared-memory ring (mbarrier tx-count).
 //   * A (genotypes) never exists as int8 in memory: two "expander" threads own each variant row (half a k-block
@@ -32,14 +32,12 @@ namespace {
 constexpr int kTcRows = 128;                 // variants per CTA
 constexpr int kTcThreads = 320;
 constexpr int kExpThreads = 256;             // 8 expander warps
-constexpr int kStagesA = 3;                  // TMEM stages of the expanded A tiles
+constexpr int kStagesA = 4;                  // TMEM stages of the expanded A tiles (64 columns each)
 constexpr int kStagesB = 4;                  // shared-memory stages of the digit operand
-constexpr int kMainBytes = 8 * 2 * 14 * 128; // per k-block: 8 k-steps x 2 k-chunks x 14 row groups x (8 rows x 16 B)
-constexpr int kIndBytes = 8 * 2 * 128;       // per k-block: 8 k-steps x 2 k-chunks x (8 rows x 16 B)
-static_assert(kMainBytes + kIndBytes == kChunkBytesB, "tcgen05 and mma.sync digit layouts have the same size");
+constexpr int kTcBlockBytes = 8 * 2 * 14 * 128;   // per k-block: 8 k-steps x 2 k-chunks x 14 row groups x (8 rows x 16 B) = 28 KiB
 constexpr int kRing = 4;                     // per-thread ring of raw 64-byte genotype slices (cp.async)
 constexpr int kSlot = 80;                    // 64 B + 16 B pad: conflict-free 128-bit reads of one's own slot
-constexpr int kColD = 0, kColD2 = 112, kColA = 128;   // TMEM columns: accumulators, indicator accumulators, A stages
+constexpr int kColD = 0, kColA = 128;        // TMEM columns: accumulators [0,112), A stages from 128
 
 __device__ __forceinline__ uint32_t s_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -161,14 +159,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8])
                  : "memory");
 }
 
-// grid = ceil(p / 128); out_hi / out_lo: p x 16 int64 (slot 15 = indicator sum), X = hi * 2^24 + lo
+// grid = ceil(p / 128); out_hi / out_lo: p x 16 int64, X = hi * 2^24 + lo
 __global__ void __launch_bounds__(kTcThreads, 1)
 contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p, const int8_t *__restrict__ Ytc,
                    int64_t n_kblocks, long long *__restrict__ out_hi, long long *__restrict__ out_lo)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *sB = smem;                                                       // kStagesB x kChunkBytesB
-    uint8_t *sG = smem + (size_t)kStagesB * kChunkBytesB;                     // kRing x 128 x kSlot
+    uint8_t *sB = smem;                                                       // kStagesB x kTcBlockBytes
+    uint8_t *sG = smem + (size_t)kStagesB * kTcBlockBytes;                     // kRing x 128 x kSlot
     uint64_t *bars = reinterpret_cast<uint64_t *>(sG + (size_t)kRing * kTcRows * kSlot);
     uint64_t *a_full = bars, *a_empty = bars + kStagesA;
     uint64_t *b_full = bars + 2 * kStagesA, *b_empty = b_full + kStagesB;
@@ -214,7 +212,12 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        for (int64_t kb = 0; kb < n_kblocks; kb++) {
+        // Software pipeline: the int8 tile of k-block kb+1 is expanded into registers while the TMEM stores of k-block
+        // kb are still in flight; only then does the thread wait for them and publish stage kb to the MMA issuer.
+        // K index 4c + y of k-step ks <-> sample 32 ks + 16 (c >> 2) + 4 y + (c & 3): column c of a k-step is field
+        // (c & 3) of word 2 ks + (c >> 2); the digit operand is laid out with the same map (build_tc_operand).
+        uint32_t x[32];
+        auto expand = [&](int64_t kb) {
             if (kb + kRing - 1 < n_kblocks) fetch(kb + kRing - 1);
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group %0;" ::"n"(kRing - 1) : "memory");
@@ -225,25 +228,22 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
                 const uint4 q = src[c];
                 w[4 * c] = q.x; w[4 * c + 1] = q.y; w[4 * c + 2] = q.z; w[4 * c + 3] = q.w;
             }
+#pragma unroll
+            for (int c = 0; c < 32; c++) x[c] = (w[c >> 2] >> (2 * (c & 3))) & 0x03030303u;
+        };
+        if (n_kblocks > 0) expand(0);
+        for (int64_t kb = 0; kb < n_kblocks; kb++) {
             const int sa = (int)(kb % kStagesA);
             bar_wait(&a_empty[sa], (uint32_t)(((kb / kStagesA) & 1) ^ 1));  // MMAs that read this TMEM stage are done
             tc_fence_after();
-            const uint32_t a1 = lane_base + kColA + sa * 128 + 32 * half, a2 = a1 + 64;
-            // K index 4c + y of k-step ks <-> sample 32 ks + 16 (c >> 2) + 4 y + (c & 3): column c of a k-step is field
-            // (c & 3) of word 2 ks + (c >> 2); the digit operand is laid out with the same map (build_tc_operand)
-            uint32_t x[32];
-#pragma unroll
-            for (int c = 0; c < 32; c++) x[c] = (w[c >> 2] >> (2 * (c & 3))) & 0x03030303u;
-            tmem_st32(a1, x);
-#pragma unroll
-            for (int c = 0; c < 32; c++) x[c] &= 0x01010101u;               // low bit: 2 [code >= 2] = code - (code & 1)
-            tmem_st32(a2, x);
+            tmem_st32(lane_base + kColA + sa * 64 + 32 * half, x);
+            if (kb + 1 < n_kblocks) expand(kb + 1);                          // overlaps the store latency
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             bar_arrive(&a_full[sa]);
         }
         // ===================================================================== epilogue: TMEM -> 64-bit recombination
-        // half 0 reads the accumulators of digit slices 0-3 (the "hi" part), half 1 slices 4-6 and the indicator tile
+        // half 0 reads the accumulators of digit slices 0-3 (the "hi" part), half 1 those of slices 4-6
         bar_wait(d_full, 0u);
         tc_fence_after();
         int acc[64];
@@ -257,21 +257,18 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
 #pragma unroll
                     for (int e = 0; e < 32; e++) acc[32 * b + e] = t32[e];
                 } else {
-                    int t16[16], t8[8];
+                    int t16[16];
                     tmem_ld16(lane_base + kColD + 96, t16);
-                    tmem_ld8(lane_base + kColD2, t8);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int e = 0; e < 16; e++) acc[32 + e] = t16[e];
-#pragma unroll
-                    for (int e = 0; e < 8; e++) acc[48 + e] = t8[e];
                 }
             }
         }
         if (rok) {
             if (half == 0) {
 #pragma unroll
-                for (int c = 0; c < 15; c++) {                               // accumulator column = 16 * slice + c
+                for (int c = 0; c < 16; c++) {                               // accumulator column = 16 * slice + c
                     long long hi = 0;
 #pragma unroll
                     for (int sl = 0; sl < 4; sl++) hi = hi * 256 + (long long)acc[16 * sl + c];
@@ -279,39 +276,30 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
                 }
             } else {
 #pragma unroll
-                for (int c = 0; c < 15; c++) {
+                for (int c = 0; c < 16; c++) {
                     long long lo = 0;
 #pragma unroll
                     for (int sl = 4; sl < kSlices; sl++) lo = lo * 256 + (long long)acc[16 * (sl - 4) + c];
                     out_lo[v * 16 + c] = lo;
                 }
-                long long hi = 0, lo = 0;                                    // indicator tile: column = digit slice
-#pragma unroll
-                for (int sl = 0; sl < 4; sl++) hi = hi * 256 + (long long)acc[48 + sl];
-#pragma unroll
-                for (int sl = 4; sl < kSlices; sl++) lo = lo * 256 + (long long)acc[48 + sl];
-                out_hi[v * 16 + 15] = hi;
-                out_lo[v * 16 + 15] = lo;
             }
         }
         tc_fence_before();
     } else if (warp == kMmaWarp) {
         // ===================================================================== MMA issuer (one thread)
         if (lane == 0) {
-            constexpr uint32_t kIdescMain = idesc_i8(kTcRows, 112), kIdescInd = idesc_i8(kTcRows, 8);
+            constexpr uint32_t kIdescMain = idesc_i8(kTcRows, 112);
             for (int64_t kb = 0; kb < n_kblocks; kb++) {
                 const int sa = (int)(kb % kStagesA), sb = (int)(kb % kStagesB);
                 bar_wait(&b_full[sb], (uint32_t)((kb / kStagesB) & 1));
                 bar_wait(&a_full[sa], (uint32_t)((kb / kStagesA) & 1));
                 tc_fence_after();
-                const uint32_t bbase = s_addr(sB + (size_t)sb * kChunkBytesB);
-                const uint32_t a1 = tmem + kColA + sa * 128, a2 = a1 + 64;
+                const uint64_t bdesc = smem_desc(s_addr(sB + (size_t)sb * kTcBlockBytes), 14 * 128, 128);
+                const uint32_t a1 = tmem + kColA + sa * 64;
 #pragma unroll
-                for (int ks = 0; ks < 8; ks++) {
-                    const uint32_t accum = (kb > 0 || ks > 0) ? 1u : 0u;
-                    umma_i8_ts(tmem + kColD, a1 + 8 * ks, smem_desc(bbase + ks * (2 * 14 * 128), 14 * 128, 128), kIdescMain, accum);
-                    umma_i8_ts(tmem + kColD2, a2 + 8 * ks, smem_desc(bbase + kMainBytes + ks * 256, 128, 128), kIdescInd, accum);
-                }
+                for (int ks = 0; ks < 8; ks++)       // descriptor start address advances by one k-step (3584 B >> 4)
+                    umma_i8_ts(tmem + kColD, a1 + 8 * ks, bdesc + (uint64_t)(ks * ((2 * 14 * 128) >> 4)), kIdescMain,
+                               (kb > 0 || ks > 0) ? 1u : 0u);
                 tc_commit(&a_empty[sa]);                                    // frees the TMEM A stage when these MMAs retire
                 tc_commit(&b_empty[sb]);                                    // frees the shared-memory digit stage
             }
@@ -324,8 +312,8 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
             for (int64_t kb = 0; kb < n_kblocks; kb++) {
                 const int sb = (int)(kb % kStagesB);
                 bar_wait_relaxed(&b_empty[sb], (uint32_t)(((kb / kStagesB) & 1) ^ 1));
-                bar_expect_tx(&b_full[sb], kChunkBytesB);
-                bulk_load(sB + (size_t)sb * kChunkBytesB, Ytc + (size_t)kb * kChunkBytesB, kChunkBytesB, &b_full[sb]);
+                bar_expect_tx(&b_full[sb], kTcBlockBytes);
+                bulk_load(sB + (size_t)sb * kTcBlockBytes, Ytc + (size_t)kb * kTcBlockBytes, kTcBlockBytes, &b_full[sb]);
             }
         }
         __syncwarp();
@@ -346,7 +334,7 @@ int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     const NullSparse &ns = ctx->ns;
     if (!ns.sliced || !ns.Ytc) { set_error("packed contraction: sliced operand not built (q > 13?)"); return STAAR_ERR_STATE; }
     const int64_t n_kblocks = (n + kChunkSamples - 1) / kChunkSamples;
-    const size_t smem = (size_t)kStagesB * kChunkBytesB + (size_t)kRing * kTcRows * kSlot + 32 * sizeof(uint64_t);
+    const size_t smem = (size_t)kStagesB * kTcBlockBytes + (size_t)kRing * kTcRows * kSlot + 32 * sizeof(uint64_t);
     static bool attr_set = false;
     if (!attr_set) {
         STAAR_CUDA(cudaFuncSetAttribute(contract_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -360,15 +348,14 @@ int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
 }
 
 // Digit operand in the canonical layout of the tcgen05 shared-memory descriptors used above.  One k-block:
-//   main: [k-step 8][k-chunk 2][row group 14][row 8][16 B]   row = 16 * slice + column   (N = 112)
-//   ind : [k-step 8][k-chunk 2][row 8][16 B]                 row = slice of diag(Sigma_i), row 7 = 0   (N = 8)
+//   [k-step 8][k-chunk 2][row group 14][row 8][16 B]   row = 16 * slice + column   (N = 112); k-blocks are kTcBlockBytes apart
 // K index kk = 16 * k-chunk + byte of a k-step <-> sample 256 kb + 32 ks + 16 ((kk >> 2) >> 2) + 4 (kk & 3) + ((kk >> 2) & 3).
 int build_tc_operand(staar_ctx *ctx, const int8_t *digits /* n x kColsPerSlice x kSlices, position order */, int ncol)
 {
     NullSparse &ns = ctx->ns;
     const int64_t n = ns.n;
     const int64_t n_kblocks = (n + kChunkSamples - 1) / kChunkSamples;
-    std::vector<int8_t> img((size_t)n_kblocks * kChunkBytesB, 0);
+    std::vector<int8_t> img((size_t)n_kblocks * kTcBlockBytes, 0);
     for (int64_t kb = 0; kb < n_kblocks; kb++)
         for (int ks = 0; ks < 8; ks++)
             for (int kk = 0; kk < 32; kk++) {
@@ -376,15 +363,13 @@ int build_tc_operand(staar_ctx *ctx, const int8_t *digits /* n x kColsPerSlice x
                 const int64_t smp = kb * 256 + 32 * ks + 16 * (c >> 2) + 4 * y + (c & 3);
                 if (smp >= n) continue;
                 const int8_t *dg = digits + (size_t)smp * kColsPerSlice * kSlices;
-                int8_t *base = img.data() + (size_t)kb * kChunkBytesB;
+                int8_t *base = img.data() + (size_t)kb * kTcBlockBytes;
                 const size_t koff = (size_t)(kk >> 4) * (14 * 128) + (kk & 15);
                 for (int sl = 0; sl < kSlices; sl++)
                     for (int col = 0; col < ncol; col++) {
                         const int row = 16 * sl + col;
                         base[(size_t)ks * (2 * 14 * 128) + koff + (size_t)(row >> 3) * 128 + (size_t)(row & 7) * 16] = dg[col * kSlices + sl];
                     }
-                const size_t ioff = (size_t)kMainBytes + (size_t)ks * 256 + (size_t)(kk >> 4) * 128 + (kk & 15);
-                for (int sl = 0; sl < kSlices; sl++) base[ioff + (size_t)sl * 16] = dg[(ncol - 1) * kSlices + sl];
             }
     cudaFree(ns.Ytc);
     ns.Ytc = nullptr;

@@ -184,12 +184,26 @@ __global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams
             __syncwarp();
         }
         quad = warp_sum(quad);
+        double hom = 0.0;                        // hom-minor carriers: sum of Sigma_i[j,j] (see scan_block_kernel)
+        for (int k = lane; k < (int)((P.n + 15) >> 4); k += 32) {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(colp) + k);
+            uint32_t wf = flip ? flip_word(w) : w;
+            const int64_t valid = P.n - (int64_t)k * 16;
+            if (valid < 16) wf &= (1u << (2 * valid)) - 1u;
+            uint32_t h = (wf >> 1) & ~wf & 0x55555555u;
+            while (h) {
+                const int b = __ffs(h) - 1;
+                h &= h - 1u;
+                hom += P.sinfo[(int64_t)k * 16 + (b >> 1)].diag;
+            }
+        }
+        hom = warp_sum(hom);
         if (lane == 0) {
             const int c0 = (int)(P.n - pc.c1 - pc.c2 - pc.cm);
             const int mono = (pc.c1 == 0 && (pc.c2 == 0 || c0 == 0)) ? 2 : 0;
             P.AF[i] = vf.af; P.MAF[i] = vf.maf; P.flip[i] = vf.flip | mono; P.mu[i] = mu; P.quad[i] = quad;
         }
-        if (lane < kColsPerSlice) P.Sm[i * kColsPerSlice + lane] = (lane < P.ncol) ? sm : 0.0;
+        if (lane < kColsPerSlice) P.Sm[i * kColsPerSlice + lane] = (lane == kColsPerSlice - 1) ? hom : ((lane < P.ncol) ? sm : 0.0);
     }
 }
 
@@ -227,8 +241,8 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
     uint32_t *wq = reinterpret_cast<uint32_t *>(smem + (size_t)nstage * stride) + wib * (kQueueCap + kRelQueueCap);   // this warp's queues
     uint32_t *rq = wq + kQueueCap;
     double *s_sm = reinterpret_cast<double *>(smem + (size_t)nstage * stride + sizeof(uint32_t) * kBlkWarps * (kQueueCap + kRelQueueCap));
-    double *s_quad = s_sm + kBlkWarps * kColsPerSlice;                           // [kBlkWarps]
-    int *s_cnt = reinterpret_cast<int *>(s_quad + kBlkWarps);                    // [4][kBlkWarps]
+    double *s_quad = s_sm + kBlkWarps * kColsPerSlice;                           // [2][kBlkWarps]: kinship part, hom-minor diag part
+    int *s_cnt = reinterpret_cast<int *>(s_quad + 2 * kBlkWarps);                // [4][kBlkWarps]
     unsigned long long *s_work = reinterpret_cast<unsigned long long *>(s_cnt + 4 * kBlkWarps);   // [2]
     uint64_t *full = reinterpret_cast<uint64_t *>(s_work + 2);                   // [2]
 
@@ -274,6 +288,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
     const int kin_words = (int)P.kin_words, tab_words = (int)P.tab_words, x_words = (int)P.x_words;
     const int n32 = (int)P.n;
     const int tail_word = n32 >> 4;                              // first word with padding positions
+    const int nwords = (n32 + 15) >> 4;
     const uint32_t tail_mask = (1u << (2 * (n32 & 15))) - 1u;    // valid codes of that word
     const int ycol = lane & 15;
     const uint32_t tab_samples = (uint32_t)tab_words * 16u;
@@ -381,9 +396,19 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
 
         // ---- sweep 2: kinship off-diagonal part of g' Sigma_i g over the related prefix of the column, one
         //      16-sample word per thread.
-        double quad = 0.0;
+        double quad = 0.0, hom = 0.0;
         const uint32_t *col32 = reinterpret_cast<const uint32_t *>(col);
         const uint32_t flipmask = flip ? 0x55555555u : 0u;
+        // sum of Sigma_i[j,j] over the hom-minor carriers (post-flip code 2): g^2 - g = 2 [g == 2], the part of
+        // g' diag(Sigma_i) g that is not linear in the codes (the linear part rides in the tensor-core contraction)
+        auto hom_accum = [&](uint32_t wf, int k) {
+            uint32_t h = (wf >> 1) & ~wf & 0x55555555u;
+            while (h) {
+                const int b = __ffs(h) - 1;
+                h &= h - 1u;
+                hom += P.sinfo[(int64_t)k * 16 + (b >> 1)].diag;
+            }
+        };
         // correction for a missing related sample j of a table word (imputed to mu; the tables see it as 0)
         auto related_missing = [&](int64_t j, double mu) {
             const NullSparse::SampleInfo si = P.sinfo[j];
@@ -406,6 +431,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             const uint32_t lo = w & 0x55555555u;
             const uint32_t mis = lo & (w >> 1);
             const uint32_t wf = w ^ ((~lo & flipmask) << 1);         // g -> 2 - g on the codes 0 and 2
+            if (k < tab_words) hom_accum(wf, k);                     // idle lanes hold w = 0, which flips to 2
             const uint32_t km = __byte_perm(__byte_perm(gd.x, gd.y, 0x0040), __byte_perm(gd.z, gd.w, 0x0040), 0x5410);
             const uint32_t wz = wf & ~(mis * 3u) & km;               // related, non-missing codes (tables hold such pairs)
             const uint32_t hit = (wz | (wz >> 1)) & 0x55555555u;     // carriers: bits 0,2,4,6 of every group byte
@@ -447,6 +473,13 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             const double mu = mu_of();
             for (int e = lane; e < rn; e += 32) related_missing((int64_t)rq[e], mu);
         }
+        // (c) the rest of the column: hom-minor carriers only
+        for (int k = tab_words + tid; k < nwords; k += kBlkWarps * 32) {
+            const uint32_t w = col32[k];
+            uint32_t wf = w ^ ((~w & flipmask) << 1);
+            if (k >= tail_word) wf &= (k == tail_word) ? tail_mask : 0u;   // padding codes would flip to 2
+            hom_accum(wf, k);
+        }
         // (b) generic words [tab_words, kin_words): per-carrier records (families of more than 16 members)
         for (int k = tab_words + tid; k < kin_words; k += kBlkWarps * 32) {
             const uint32_t w = col32[k];
@@ -473,13 +506,21 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             }
         }
         quad = warp_sum(quad);
-        if (lane == 0) s_quad[wib] = quad;
+        hom = warp_sum(hom);
+        if (lane == 0) { s_quad[wib] = quad; s_quad[kBlkWarps + wib] = hom; }
         __syncthreads();                      // also: every read of this stage's column is complete
         if (tid < kColsPerSlice) {
             double t = 0.0;
 #pragma unroll
             for (int w = 0; w < kBlkWarps; w++) t += s_sm[w * kColsPerSlice + tid];
-            P.Sm[i * kColsPerSlice + tid] = (tid < P.ncol) ? t : 0.0;
+            if (tid == kColsPerSlice - 1) {                              // slot 15: hom-minor diag sum
+                t = 0.0;
+#pragma unroll
+                for (int w = 0; w < kBlkWarps; w++) t += s_quad[kBlkWarps + w];
+                P.Sm[i * kColsPerSlice + tid] = t;
+            } else {
+                P.Sm[i * kColsPerSlice + tid] = (tid < P.ncol) ? t : 0.0;
+            }
         } else if (tid == 32) {
             double t = 0.0;
 #pragma unroll
@@ -517,12 +558,11 @@ struct FinParams {
 };
 
 // The contraction delivers, per variant and column c, the exact integers R_c = sum_j code_j X_jc over the RAW codes
-// (missing = 3) and B = sum_j (code_j & 1) X_jd for the diag(Sigma_i) column d, so that I = sum_j [code_j >= 2] X_jd
-// satisfies 2 I = R_d - B; the scan delivers the FP64 column
+// (missing = 3); the scan delivers the FP64 column
 // sums Sm_c over missing samples, the flip decision, the imputation value mu and the kinship off-diagonal part.
 // With T_c = sum_j X_jc (exact, set-up time) the genotype the reference tests (flipped, imputed) gives
-//   no flip: G'y_c = R_c - 3 M_c + mu M_c                 g'diag g = R_d + 2 I - 5 M_d + mu^2 M_d
-//   flip   : G'y_c = 2 T_c - R_c + M_c + mu M_c           g'diag g = 4 T_d - 3 R_d + 2 I + 3 M_d + mu^2 M_d
+//   no flip: G'y_c = R_c - 3 M_c + mu M_c
+//   flip   : G'y_c = 2 T_c - R_c + M_c + mu M_c
 // (integer parts combined exactly in 64-bit, M_c = Sm_c).  A variant whose genotypes are all 0 after flip and
 // imputation takes the reference's exact Cov == 0 branch from the integer counts (bit 1 of flip[]).
 __global__ void __launch_bounds__(128) finalize_packed_kernel(FinParams P)
@@ -550,14 +590,15 @@ __global__ void __launch_bounds__(128) finalize_packed_kernel(FinParams P)
             for (int a = 0; a < P.q; a++) xb += L[1 + a] * P.cov[a + b * P.q];
             tct += xb * L[1 + b];
         }
+        // g' Sigma_i g = sum_j s_jj g_j (non-missing; the contraction's diag column, same algebra as L_c above)
+        //              + 2 sum over hom-minor carriers of s_jj   (g^2 - g = 2 [g == 2]; scan, slot 15 of Sm)
+        //              + mu^2 sum over missing of s_jj + kinship off-diagonal part (scan)
         const int d = P.q + 1;
-        const long long rhi = P.hi[i * 16 + d], rlo = P.lo[i * 16 + d];
-        const long long i2hi = rhi - P.hi[i * 16 + 15], i2lo = rlo - P.lo[i * 16 + 15];      // 2 I = R_d - B
-        long long qhi, qlo;
-        if (flip) { qhi = 4 * P.tot[d] - 3 * rhi + i2hi; qlo = 4 * P.tot[kColsPerSlice + d] - 3 * rlo + i2lo; }
-        else { qhi = rhi + i2hi; qlo = rlo + i2lo; }
+        long long dhi = P.hi[i * 16 + d], dlo = P.lo[i * 16 + d];
+        if (flip) { dhi = 2 * P.tot[d] - dhi; dlo = 2 * P.tot[kColsPerSlice + d] - dlo; }
         const double smd = P.Sm[i * kColsPerSlice + d];
-        const double quad = ((double)qhi * 16777216.0 + (double)qlo) * P.scale[d] + ((flip ? 3.0 : -5.0) + mu * mu) * smd + P.quad[i];
+        const double lin = ((double)dhi * 16777216.0 + (double)dlo) * P.scale[d] + (flip ? 1.0 : -3.0) * smd;
+        const double quad = lin + 2.0 * P.Sm[i * kColsPerSlice + 15] + mu * mu * smd + P.quad[i];
         const double C = quad - tct;
         P.Score[i] = U;
         single_trait_stats(U, C, P.Score_se[i], P.pl[i], P.Est[i], P.Est_se[i]);
@@ -581,7 +622,7 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     P.AF = dAF; P.MAF = dMAF; P.flip = dflip; P.mu = d_mu; P.quad = d_quad; P.Sm = d_Sm;
     // block-per-variant kernel: column(s) in shared memory, double-buffered when two fit
     const size_t extra = sizeof(uint32_t) * kBlkWarps * (kQueueCap + kRelQueueCap) +
-                         sizeof(double) * (kBlkWarps * kColsPerSlice + kBlkWarps) + sizeof(int) * 4 * kBlkWarps + 64;
+                         sizeof(double) * (kBlkWarps * kColsPerSlice + 2 * kBlkWarps) + sizeof(int) * 4 * kBlkWarps + 64;
     const size_t smem_max = 227 * 1024;
     const int nstage = (2 * stride + extra <= smem_max) ? 2 : (stride + extra <= smem_max) ? 1 : 0;
     if (nstage > 0) {
