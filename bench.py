@@ -270,27 +270,25 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = V * bytes_per_variant / (stage_ms[dominant] / 1e3) / 1e9
-    traffic = None
+    traffic = None                                      # DRAM bytes per launch of the dominant kernel (ncu --set full capture)
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dominant)
+        per_variant = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[dominant]["dram_bytes_per_variant"]
+        traffic = per_variant * V
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"bound": "hbm", "kernel": {"scan": "scan_packed_kernel", "contract": "contract_packed_kernel",
+    roofline = {"bound": "hbm", "kernel": {"scan": "scan_block_kernel", "contract": "contract_tc_kernel",
                                            "finalize": "finalize_packed_kernel"}[dominant],
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "stage_ms": stage_ms, "step_frac": stage_ms[dominant] / sum(stage_ms.values()),
                 "whole_step": {"achieved": V * bytes_per_variant / (ms_total / args.steps / 1e3) / 1e9,
                                "frac": V * bytes_per_variant / (ms_total / args.steps / 1e3) / 1e9 / hbm_peak}}
-    # secondary roof: the INT8 tensor pipe the contraction runs on (mma.sync s8, measured by tools/pipe_peaks.cu)
-    try:
-        pp = json.load(open(os.path.join(ROOT, "profiles", "r01_pipe_peaks.json")))
-        ops = 2.0 * V * n * 112                         # 7 digit slices x 16 columns per genotype
-        roofline["int8_mma"] = {"achieved_tops": ops / (stage_ms["contract"] / 1e3) / 1e12,
-                                "peak_tops": pp["int8_mma_m16n8k32_tops"],
-                                "frac": ops / (stage_ms["contract"] / 1e3) / 1e12 / pp["int8_mma_m16n8k32_tops"]}
-    except Exception:  # noqa: BLE001
-        pass
+    # secondary roof: the INT8 tensor pipe the contraction runs on (tcgen05.mma.kind::i8).  No measured tcgen05 int8
+    # peak exists for this pool; the denominator is the NOMINAL dense figure (4.5 POP/s, same as fp8), stated as such.
+    ops = 2.0 * V * n * 112                             # 7 digit slices x 16 columns per genotype
+    roofline["int8_tensor"] = {"kernel": "contract_tc_kernel", "achieved_tops": ops / (stage_ms["contract"] / 1e3) / 1e12,
+                               "peak_tops": 4500.0, "peak_source": "nominal dense int8/fp8 (B200_PROFILING.md)",
+                               "frac": ops / (stage_ms["contract"] / 1e3) / 1e12 / 4500.0}
 
     # ---- end to end: host FP64 dosage chunks (what the Rcpp boundary delivers) through the C-ABI chunk driver
     e2e = None
