@@ -80,6 +80,7 @@ struct NullSparse {
     double *lut = nullptr;
     int64_t lut_entries = 0;
     SampleInfo *sinfo_p = nullptr;    // full kinship rows in null-model positions (missing related samples)
+    double *diag_p = nullptr;         // Sigma_i[j,j] in null-model positions (n + 64 entries, zero padded)
     OffEntry *off_ent_p = nullptr;
     // generic path (families of more than 16 members, or every family when the column does not fit in shared memory):
     // 2-bit mask (11 = sample has kinship off-diagonals with a LARGER position), one 32-byte record per sample with

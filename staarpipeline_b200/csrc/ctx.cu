@@ -57,7 +57,7 @@ void NullSparse::release()
         cudaFree(row_ptr); cudaFree(col); cudaFree(val); cudaFree(SX); cudaFree(cov);
     }
     if (permuted) cudaFree(Yp);
-    cudaFree(diag); cudaFree(sinfo_p); cudaFree(off_ent_p); cudaFree(relmask); cudaFree(rel); cudaFree(up_ent); cudaFree(Y);
+    cudaFree(diag); cudaFree(diag_p); cudaFree(sinfo_p); cudaFree(off_ent_p); cudaFree(relmask); cudaFree(rel); cudaFree(up_ent); cudaFree(Y);
     cudaFree(Yfrag); cudaFree(Ytc); cudaFree(col_scale); cudaFree(col_total); cudaFree(perm); cudaFree(gdesc); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut);
     *this = NullSparse();
 }
@@ -414,6 +414,11 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
     STAAR_TRY(upload_vec(ctx, &ns.val, val));
     STAAR_TRY(upload_vec(ctx, &ns.diag, diag));
     STAAR_TRY(upload_vec(ctx, &ns.sinfo_p, sinfo));
+    {
+        std::vector<double> diag_p((size_t)n + 64, 0.0);
+        for (int64_t pz = 0; pz < n; pz++) diag_p[pz] = sinfo[pz].diag;
+        STAAR_TRY(upload_vec(ctx, &ns.diag_p, diag_p));
+    }
     STAAR_TRY(upload_vec(ctx, &ns.off_ent_p, off_ent));
     STAAR_TRY(upload_vec(ctx, &ns.gdesc, gdesc));
     STAAR_TRY(upload_vec(ctx, &ns.wdesc, wdesc));

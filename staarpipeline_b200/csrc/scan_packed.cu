@@ -34,6 +34,7 @@ struct ScanParams {
     const NullSparse::KinTerm *xterms;
     const double *lut;
     const NullSparse::SampleInfo *sinfo;   // full kinship rows per position (missing related samples)
+    const double *diag;                    // Sigma_i[j,j] by position
     const NullSparse::OffEntry *off_ent;
     const double *Y; int ldY, ncol;        // Y rows in null-model order
     double *AF, *MAF; int32_t *flip; double *mu, *quad, *Sm;
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
     const int kin_words = (int)P.kin_words, tab_words = (int)P.tab_words, x_words = (int)P.x_words;
     const int n32 = (int)P.n;
     const int tail_word = n32 >> 4;                              // first word with padding positions
-    const int nwords = (n32 + 15) >> 4;
+    const int tab_vec = (tab_words + 3) >> 2;                   // 64-sample vectors covering the table words
     const uint32_t tail_mask = (1u << (2 * (n32 & 15))) - 1u;    // valid codes of that word
     const int ycol = lane & 15;
     const uint32_t tab_samples = (uint32_t)tab_words * 16u;
@@ -304,14 +305,18 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         const uint8_t *col = cols + (size_t)stage * stride;
         const int64_t i = (int64_t)cur;
 
-        // ---- sweep 1: popcounts -> AF / MAF / flip / imputation value (bit-exact integer counts), and the column
-        //      sums of Y over missing samples (independent of the flip).  Missing positions go to the warp's queue;
-        //      a flush reads two rows of Y per warp instruction (half-warp h: entries h, h+2, ...; lane c: column c)
-        //      and keeps the positions inside the table region in a second queue for the kinship correction.
+        // ---- sweep 1 (whole column, 64 samples per lane and step): popcounts -> AF / MAF / flip / imputation value
+        //      (bit-exact integer counts); column sums of Y over missing samples (independent of the flip): missing
+        //      positions go to the warp's queue, a flush reads two rows of Y per warp instruction (half-warp h:
+        //      entries h, h+2, ...; lane c: column c) and keeps the positions inside the table region in a second
+        //      queue for the kinship correction; and the sum of Sigma_i[j,j] over hom-minor carriers (g^2 - g =
+        //      2 [g == 2], the part of g' diag(Sigma_i) g that is not linear in the codes) under a per-warp GUESS of the
+        //      flip taken from the warp's first step — redone below for the warps that guessed wrong.
         int clo = 0, chi = 0, cm = 0;                            // popcounts of low bits, high bits, both (missing)
-        double sm = 0.0;
+        double sm = 0.0, hom = 0.0;
         int qn = 0, rn = 0;
         bool rq_over = false;
+        const uint4 *v4 = reinterpret_cast<const uint4 *>(col);
         auto flush_missing = [&]() {
             __syncwarp();
             if (ycol < P.ncol) {
@@ -329,8 +334,39 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             __syncwarp();
             qn = 0;
         };
+        // hom-minor carriers of one 64-sample vector under orientation `fl`: raw code 0 (flip) or raw code 2 (no flip);
+        // the four words are walked together so that four independent gathers of Sigma_i[j,j] are in flight
+        auto hom_vec = [&](const uint4 &q4, int k, bool fl, double &acc) {
+            const uint32_t gm = fl ? 0xffffffffu : 0u;
+            uint32_t h0 = ((q4.x >> 1) ^ gm) & ~q4.x & 0x55555555u, h1 = ((q4.y >> 1) ^ gm) & ~q4.y & 0x55555555u;
+            uint32_t h2 = ((q4.z >> 1) ^ gm) & ~q4.z & 0x55555555u, h3 = ((q4.w >> 1) ^ gm) & ~q4.w & 0x55555555u;
+            const int kw = 4 * k;
+            if (kw + 3 >= tail_word) {                               // padding positions hold code 0
+                h0 &= kw > tail_word ? 0u : (kw == tail_word ? tail_mask : 0xffffffffu);
+                h1 &= kw + 1 > tail_word ? 0u : (kw + 1 == tail_word ? tail_mask : 0xffffffffu);
+                h2 &= kw + 2 > tail_word ? 0u : (kw + 2 == tail_word ? tail_mask : 0xffffffffu);
+                h3 &= kw + 3 > tail_word ? 0u : (kw + 3 == tail_word ? tail_mask : 0xffffffffu);
+            }
+            const double *dg = P.diag + (int64_t)kw * 16;
+            while (h0 | h1 | h2 | h3) {
+                double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+                if (h0) { v0 = __ldg(dg + ((__ffs(h0) - 1) >> 1)); h0 &= h0 - 1u; }
+                if (h1) { v1 = __ldg(dg + 16 + ((__ffs(h1) - 1) >> 1)); h1 &= h1 - 1u; }
+                if (h2) { v2 = __ldg(dg + 32 + ((__ffs(h2) - 1) >> 1)); h2 &= h2 - 1u; }
+                if (h3) { v3 = __ldg(dg + 48 + ((__ffs(h3) - 1) >> 1)); h3 &= h3 - 1u; }
+                acc += (v0 + v1) + (v2 + v3);
+            }
+        };
+        bool guess;
         {
-            const uint4 *v4 = reinterpret_cast<const uint4 *>(col);
+            const int k = wib * 32 + lane;
+            uint4 q4 = make_uint4(0u, 0u, 0u, 0u);
+            if (k < nvec16) q4 = v4[k];
+            const int s = __popc(q4.x) + __popc(q4.y) + __popc(q4.z) + __popc(q4.w) + __popc(q4.x & 0xaaaaaaaau) +
+                          __popc(q4.y & 0xaaaaaaaau) + __popc(q4.z & 0xaaaaaaaau) + __popc(q4.w & 0xaaaaaaaau);   // sum of codes
+            guess = __reduce_add_sync(0xffffffffu, s) > 2048;    // mean dosage of the warp's first 2048 samples > 1
+        }
+        {
             for (int k0 = wib * 32; k0 < nvec16; k0 += kBlkWarps * 32) {
                 const int k = k0 + lane;
                 uint4 q4 = make_uint4(0u, 0u, 0u, 0u);
@@ -339,6 +375,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
                 const uint32_t m2 = q4.z & (q4.z >> 1) & 0x55555555u, m3 = q4.w & (q4.w >> 1) & 0x55555555u;
                 clo += __popc(q4.x & 0x55555555u) + __popc(q4.y & 0x55555555u) + __popc(q4.z & 0x55555555u) + __popc(q4.w & 0x55555555u);
                 chi += __popc(q4.x & 0xaaaaaaaau) + __popc(q4.y & 0xaaaaaaaau) + __popc(q4.z & 0xaaaaaaaau) + __popc(q4.w & 0xaaaaaaaau);
+                if (k < nvec16) hom_vec(q4, k, guess, hom);
                 // bit 2f + w of a half = sample f of word w (low half: words 0,1; high half: words 2,3)
                 uint32_t blo = m0 | (m1 << 1), bhi = m2 | (m3 << 1);
                 uint32_t bal = __ballot_sync(0xffffffffu, (blo | bhi) != 0u);
@@ -360,12 +397,9 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             }
             if (qn > 0) flush_missing();
             sm += __shfl_xor_sync(0xffffffffu, sm, 16);            // the two half-warps' partial sums (fixed order)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                clo += __shfl_xor_sync(0xffffffffu, clo, o);
-                chi += __shfl_xor_sync(0xffffffffu, chi, o);
-                cm += __shfl_xor_sync(0xffffffffu, cm, o);
-            }
+            clo = __reduce_add_sync(0xffffffffu, clo);
+            chi = __reduce_add_sync(0xffffffffu, chi);
+            cm = __reduce_add_sync(0xffffffffu, cm);
             if (lane == 0) { s_cnt[wib] = clo; s_cnt[kBlkWarps + wib] = chi; s_cnt[2 * kBlkWarps + wib] = cm; s_cnt[3 * kBlkWarps + wib] = rq_over; }
             if (lane < kColsPerSlice) s_sm[wib * kColsPerSlice + lane] = sm;
             __syncthreads();
@@ -393,22 +427,16 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             mu_zero = flip ? (fill == 2) : (fill == 0);            // mu = fill or 2 - fill
         }
         auto mu_of = [&]() { return flip_from_counts(pc, P.n, P.impute).mu; };   // rare paths only
+        if (guess != flip) {                                       // warp-uniform: this warp's steps again, right orientation
+            hom = 0.0;
+            for (int k0 = wib * 32; k0 < nvec16; k0 += kBlkWarps * 32)
+                if (k0 + lane < nvec16) hom_vec(v4[k0 + lane], k0 + lane, flip, hom);
+        }
 
-        // ---- sweep 2: kinship off-diagonal part of g' Sigma_i g over the related prefix of the column, one
-        //      16-sample word per thread.
-        double quad = 0.0, hom = 0.0;
+        // ---- sweep 2: kinship off-diagonal part of g' Sigma_i g over the related prefix of the column.
+        double quad = 0.0;
         const uint32_t *col32 = reinterpret_cast<const uint32_t *>(col);
         const uint32_t flipmask = flip ? 0x55555555u : 0u;
-        // sum of Sigma_i[j,j] over the hom-minor carriers (post-flip code 2): g^2 - g = 2 [g == 2], the part of
-        // g' diag(Sigma_i) g that is not linear in the codes (the linear part rides in the tensor-core contraction)
-        auto hom_accum = [&](uint32_t wf, int k) {
-            uint32_t h = (wf >> 1) & ~wf & 0x55555555u;
-            while (h) {
-                const int b = __ffs(h) - 1;
-                h &= h - 1u;
-                hom += P.sinfo[(int64_t)k * 16 + (b >> 1)].diag;
-            }
-        };
         // correction for a missing related sample j of a table word (imputed to mu; the tables see it as 0)
         auto related_missing = [&](int64_t j, double mu) {
             const NullSparse::SampleInfo si = P.sinfo[j];
@@ -422,49 +450,57 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             }
             quad += 2.0 * mu * sacc;
         };
-        // (a) table words [0, tab_words): full words of real samples; a 4-sample group's codes index that group's table
-        for (int k0 = wib * 32; k0 < tab_words; k0 += kBlkWarps * 32) {
+        // (a) table words [0, tab_words): full words of real samples, four words per lane and step.  A lane only
+        //     works on the words in which a group holds two related carriers (or, in a cross word, two anywhere):
+        //     the codes of a 4-sample group index that group's table.
+        for (int k0 = wib * 32; k0 < tab_vec; k0 += kBlkWarps * 32) {
             const int k = k0 + lane;
-            uint32_t w = 0u;
-            uint4 gd = make_uint4(0u, 0u, 0u, 0u);
-            if (k < tab_words) { w = col32[k]; gd = __ldg(reinterpret_cast<const uint4 *>(P.gdesc) + k); }
-            const uint32_t lo = w & 0x55555555u;
-            const uint32_t mis = lo & (w >> 1);
-            const uint32_t wf = w ^ ((~lo & flipmask) << 1);         // g -> 2 - g on the codes 0 and 2
-            if (k < tab_words) hom_accum(wf, k);                     // idle lanes hold w = 0, which flips to 2
-            const uint32_t km = __byte_perm(__byte_perm(gd.x, gd.y, 0x0040), __byte_perm(gd.z, gd.w, 0x0040), 0x5410);
-            const uint32_t wz = wf & ~(mis * 3u) & km;               // related, non-missing codes (tables hold such pairs)
-            const uint32_t hit = (wz | (wz >> 1)) & 0x55555555u;     // carriers: bits 0,2,4,6 of every group byte
-            // per byte: clear the lowest carrier bit (bit 7 guards the borrow): non-zero byte <=> >= 2 carriers in the group
-            const uint32_t two = hit & ((hit | 0x80808080u) - 0x01010101u);
-            const bool cross = k < x_words && (hit & (hit - 1u)) != 0u;   // >= 2 carriers anywhere in a cross word
-            if (__any_sync(0xffffffffu, two != 0u || cross)) {
-                const uint32_t g4[4] = {gd.x, gd.y, gd.z, gd.w};
+            uint4 q4 = make_uint4(0u, 0u, 0u, 0u);
+            if (k < tab_vec) q4 = v4[k];
+            const uint32_t wv[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
-                for (int g = 0; g < 4; g++) {                        // entry 0 of the table at offset 0 is 0.0
-                    const uint32_t idx = (wz >> (8 * g)) & 0xffu;
-                    const uint32_t off = (two & (0xffu << (8 * g))) ? (g4[g] >> 8) * 16u + idx : 0u;
-                    quad += __ldg(P.lut + off);
-                }
-                if (cross) {                                         // families of 5..16 members: member x other chunk
-                    const uint2 wd = __ldg(reinterpret_cast<const uint2 *>(P.wdesc) + k);
-                    const uint2 *tp = reinterpret_cast<const uint2 *>(P.xterms) + wd.x;
-                    for (uint32_t t = 0; t < wd.y; t++) {
-                        const uint2 tr = __ldg(tp + t);
-                        const uint32_t idx = (wz >> (tr.y & 0xffu)) & ((tr.y >> 8) & 0xffu);
-                        const uint32_t gj = (wz >> ((tr.y >> 16) & 0xffu)) & 3u;
-                        if (gj != 0u && idx != 0u) quad += (double)gj * __ldg(P.lut + tr.x + idx);
+            for (int wi = 0; wi < 4; wi++) {
+                const int kw = 4 * k + wi;
+                if (kw >= tab_words) continue;
+                const uint32_t w = wv[wi];
+                const uint4 gd = __ldg(reinterpret_cast<const uint4 *>(P.gdesc) + kw);
+                const uint32_t lo = w & 0x55555555u;
+                const uint32_t mis = lo & (w >> 1);
+                const uint32_t wf = w ^ ((~lo & flipmask) << 1);     // g -> 2 - g on the codes 0 and 2
+                const uint32_t km = __byte_perm(__byte_perm(gd.x, gd.y, 0x0040), __byte_perm(gd.z, gd.w, 0x0040), 0x5410);
+                const uint32_t wz = wf & ~(mis * 3u) & km;           // related, non-missing codes (tables hold such pairs)
+                const uint32_t hit = (wz | (wz >> 1)) & 0x55555555u; // carriers: bits 0,2,4,6 of every group byte
+                // per byte: clear the lowest carrier bit (bit 7 guards the borrow): non-zero byte <=> >= 2 carriers in the group
+                const uint32_t two = hit & ((hit | 0x80808080u) - 0x01010101u);
+                const bool cross = kw < x_words && (hit & (hit - 1u)) != 0u;   // >= 2 carriers anywhere in a cross word
+                if (two != 0u || cross) {
+                    const uint32_t g4[4] = {gd.x, gd.y, gd.z, gd.w};
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {                    // entry 0 of the table at offset 0 is 0.0
+                        const uint32_t idx = (wz >> (8 * g)) & 0xffu;
+                        const uint32_t off = (two & (0xffu << (8 * g))) ? (g4[g] >> 8) * 16u + idx : 0u;
+                        quad += __ldg(P.lut + off);
+                    }
+                    if (cross) {                                     // families of 5..16 members: member x other chunk
+                        const uint2 wd = __ldg(reinterpret_cast<const uint2 *>(P.wdesc) + kw);
+                        const uint2 *tp = reinterpret_cast<const uint2 *>(P.xterms) + wd.x;
+                        for (uint32_t t = 0; t < wd.y; t++) {
+                            const uint2 tr = __ldg(tp + t);
+                            const uint32_t idx = (wz >> (tr.y & 0xffu)) & ((tr.y >> 8) & 0xffu);
+                            const uint32_t gj = (wz >> ((tr.y >> 16) & 0xffu)) & 3u;
+                            if (gj != 0u && idx != 0u) quad += (double)gj * __ldg(P.lut + tr.x + idx);
+                        }
                     }
                 }
-            }
-            if (rq_over && !mu_zero) {                               // slow path: the position queues overflowed
-                uint32_t mk = mis & km;
-                if (mk) {
-                    const double mu = mu_of();
-                    while (mk) {
-                        const int b = __ffs(mk) - 1;
-                        mk &= mk - 1u;
-                        related_missing((int64_t)k * 16 + (b >> 1), mu);
+                if (rq_over && !mu_zero) {                           // slow path: the position queues overflowed
+                    uint32_t mk = mis & km;
+                    if (mk) {
+                        const double mu = mu_of();
+                        while (mk) {
+                            const int b = __ffs(mk) - 1;
+                            mk &= mk - 1u;
+                            related_missing((int64_t)kw * 16 + (b >> 1), mu);
+                        }
                     }
                 }
             }
@@ -472,13 +508,6 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         if (!rq_over && !mu_zero && rn > 0) {                        // missing samples queued in sweep 1 (this warp's)
             const double mu = mu_of();
             for (int e = lane; e < rn; e += 32) related_missing((int64_t)rq[e], mu);
-        }
-        // (c) the rest of the column: hom-minor carriers only
-        for (int k = tab_words + tid; k < nwords; k += kBlkWarps * 32) {
-            const uint32_t w = col32[k];
-            uint32_t wf = w ^ ((~w & flipmask) << 1);
-            if (k >= tail_word) wf &= (k == tail_word) ? tail_mask : 0u;   // padding codes would flip to 2
-            hom_accum(wf, k);
         }
         // (b) generic words [tab_words, kin_words): per-carrier records (families of more than 16 members)
         for (int k = tab_words + tid; k < kin_words; k += kBlkWarps * 32) {
@@ -617,14 +646,18 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     P.packed = d_packed; P.stride = stride; P.n = n; P.p = p; P.impute = impute;
     P.relmask = ns.relmask; P.rel = ns.rel; P.up_ent = ns.up_ent;
     P.tab_words = ns.tab_words; P.kin_words = ns.kin_words; P.x_words = ns.x_words; P.gdesc = ns.gdesc; P.wdesc = ns.wdesc;
-    P.xterms = ns.xterms; P.lut = ns.lut; P.sinfo = ns.sinfo_p; P.off_ent = ns.off_ent_p;
+    P.xterms = ns.xterms; P.lut = ns.lut; P.sinfo = ns.sinfo_p; P.off_ent = ns.off_ent_p; P.diag = ns.diag_p;
     P.Y = ns.Yp; P.ldY = ns.ldY; P.ncol = (int)ns.q + 2;
     P.AF = dAF; P.MAF = dMAF; P.flip = dflip; P.mu = d_mu; P.quad = d_quad; P.Sm = d_Sm;
     // block-per-variant kernel: column(s) in shared memory, double-buffered when two fit
     const size_t extra = sizeof(uint32_t) * kBlkWarps * (kQueueCap + kRelQueueCap) +
                          sizeof(double) * (kBlkWarps * kColsPerSlice + 2 * kBlkWarps) + sizeof(int) * 4 * kBlkWarps + 64;
     const size_t smem_max = 227 * 1024;
-    const int nstage = (2 * stride + extra <= smem_max) ? 2 : (stride + extra <= smem_max) ? 1 : 0;
+    // The kernel is latency-bound (dependent gathers between block barriers), so resident warps matter more than
+    // overlapping the column copy: two stages only when they still leave >= 6 CTAs per SM (measured: 9.8 -> 7.9 ms).
+    static const int force = getenv("STAAR_B200_SCAN_STAGES") ? atoi(getenv("STAAR_B200_SCAN_STAGES")) : 0;   // tuning experiments
+    int nstage = (stride + extra <= smem_max) ? 1 : 0;
+    if (nstage == 1 && (force == 2 || (force == 0 && 6 * (2 * stride + extra + 1024) <= 228 * 1024)) && 2 * stride + extra <= smem_max) nstage = 2;
     if (nstage > 0) {
         const size_t smem = (size_t)nstage * stride + extra;
         STAAR_CUDA(cudaFuncSetAttribute(scan_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
