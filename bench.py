@@ -315,6 +315,19 @@ def run_ours(args):
         # parity of the device-resident step against the host-buffer path on the same variants (bit-identical)
         same = all(np.array_equal(outs[i, :p].cpu().numpy(), out7[i], equal_nan=True) for i in range(7))
         e2e["matches_resident_path"] = bool(same)
+        # the same chunk as SeqArray's raw dosage bytes (1 B/genotype on the host instead of the 8 B Rcpp widens it to)
+        Gu8 = np.where(np.isnan(G), 255, G).astype(np.uint8, order="F")
+        out7b = [np.zeros(p) for _ in range(7)]
+        ctx.individual_analysis_chunk(Gu8, api.IMPUTE_MEAN, 0, out7b)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.individual_analysis_chunk(Gu8, api.IMPUTE_MEAN, 0, out7b)
+        barrier()
+        dtb = time.perf_counter() - t0
+        e2e["raw_u8_input"] = {"value": world * p * args.steps / dtb, "unit": "variants/s", "ms_per_chunk": 1e3 * dtb / args.steps,
+                               "host_bytes_read_per_step": int(p * n),
+                               "matches_fp64_input": bool(all(np.array_equal(out7[i], out7b[i], equal_nan=True) for i in range(7)))}
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None

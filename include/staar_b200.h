@@ -159,6 +159,11 @@ size_t staar_packed_stride(int64_t n);
 /* host FP64 dosage (n x p, NaN / <= -1 missing) -> packed host buffer (p x stride).  Returns
  * STAAR_ERR_ARG if a non-missing value is not exactly 0, 1 or 2 (such matrices take the FP64 path). */
 int staar_pack_dosage_host(const double *G, int64_t n, int64_t p, uint8_t *packed, size_t stride_bytes, int threads);
+/* same for an R integer matrix (NA_integer_ = INT_MIN, or any value <= -1, is missing) and for SeqArray's raw
+ * dosage bytes (0xFF missing): what seqGetData("$dosage") holds BEFORE Rcpp widens it to FP64
+ * (R/Individual_Analysis.R:186; the conversion happens at src/RcppExports.cpp:23). */
+int staar_pack_dosage_host_i32(const int32_t *G, int64_t n, int64_t p, uint8_t *packed, size_t stride_bytes, int threads);
+int staar_pack_dosage_host_u8(const uint8_t *G, int64_t n, int64_t p, uint8_t *packed, size_t stride_bytes, int threads);
 
 /* Null model, uploaded once (host pointers) ... */
 int staar_nullmodel_set_sparse(staar_ctx *ctx, int64_t n, int64_t q,
@@ -217,6 +222,13 @@ int staar_packed_score_host(staar_ctx *ctx, const uint8_t *packed, size_t stride
 int staar_individual_analysis_chunk(staar_ctx *ctx, const double *G, int64_t n, int64_t p, int impute, int threads,
                                     double *AF, double *MAF, double *Score, double *Score_se, double *pvalue_log,
                                     double *Est, double *Est_se);
+/* the same chunk from the R integer matrix / raw bytes SeqArray returns (4 or 1 bytes per genotype on the host) */
+int staar_individual_analysis_chunk_i32(staar_ctx *ctx, const int32_t *G, int64_t n, int64_t p, int impute, int threads,
+                                        double *AF, double *MAF, double *Score, double *Score_se, double *pvalue_log,
+                                        double *Est, double *Est_se);
+int staar_individual_analysis_chunk_u8(staar_ctx *ctx, const uint8_t *G, int64_t n, int64_t p, int impute, int threads,
+                                       double *AF, double *MAF, double *Score, double *Score_se, double *pvalue_log,
+                                       double *Est, double *Est_se);
 
 /* Synthetic packed dosage columns generated on the device (bench / parity subsets); per-variant
  * thresholds as in staarpipeline_b200/synth.py (device pointers, uint64 / uint8).  d_sample_order (device int32[n],

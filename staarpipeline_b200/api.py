@@ -295,12 +295,20 @@ class Context:
         return dict(zip(("AF", "MAF", "Score", "Score_se", "pvalue_log", "Est", "Est_se"), o))
 
     def individual_analysis_chunk(self, G, impute: int = IMPUTE_MEAN, threads: int = 0, out=None):
-        """FP64 `$dosage` host block (n x p, F-order; a raw pointer to pinned memory also works via `out`-style reuse)
-        -> dict of the 7 per-variant arrays.  One call per chunk of the R driver (flip + score test)."""
-        G = _f(G); n, p = G.shape
+        """`$dosage` host block (n x p, F-order) -> dict of the 7 per-variant arrays.  One call per chunk of the R driver
+        (flip + score test).  dtype float64 (NaN missing; what the Rcpp boundary delivers), int32 (R integer matrix,
+        NA_integer_ missing) or uint8 (SeqArray raw dosage, 0xFF missing)."""
+        G = np.asarray(G)
+        if G.dtype == np.int32 or G.dtype == np.uint8:
+            G = np.asfortranarray(G)
+            fn = "staar_individual_analysis_chunk_i32" if G.dtype == np.int32 else "staar_individual_analysis_chunk_u8"
+            gp = G.ctypes.data_as(C.c_void_p)
+        else:
+            G = _f(G)
+            fn, gp = "staar_individual_analysis_chunk", _p(G)
+        n, p = G.shape
         o = out if out is not None else [np.zeros(p) for _ in range(7)]
-        self._call("staar_individual_analysis_chunk", _p(G), C.c_int64(n), C.c_int64(p), C.c_int(impute), C.c_int(threads),
-                   *[_p(a) for a in o])
+        self._call(fn, gp, C.c_int64(n), C.c_int64(p), C.c_int(impute), C.c_int(threads), *[_p(a) for a in o])
         return dict(zip(("AF", "MAF", "Score", "Score_se", "pvalue_log", "Est", "Est_se"), o))
 
     def packed_debug_dump(self, p: int):
@@ -347,13 +355,21 @@ def packed_stride(n: int) -> int:
 
 
 def pack_dosage_host(G, threads: int = 0) -> np.ndarray:
-    """FP64 `$dosage` matrix (n x p, NaN / <= -1 missing) -> (p, stride) uint8 packed columns (host, threaded)."""
+    """`$dosage` matrix (n x p; float64 with NaN / <= -1 missing, int32 with negative missing, or uint8 with 0xFF
+    missing) -> (p, stride) uint8 packed columns (host, threaded, AVX-512 where available)."""
     lib = load_library()
-    G = _f(G); n, p = G.shape
+    G = np.asarray(G)
+    if G.dtype == np.int32 or G.dtype == np.uint8:
+        G = np.asfortranarray(G)
+        fn = lib.staar_pack_dosage_host_i32 if G.dtype == np.int32 else lib.staar_pack_dosage_host_u8
+        gp = G.ctypes.data_as(C.c_void_p)
+    else:
+        G = _f(G)
+        fn, gp = lib.staar_pack_dosage_host, _p(G)
+    n, p = G.shape
     stride = packed_stride(n)
-    out = np.zeros((p, stride), dtype=np.uint8)
-    rc = lib.staar_pack_dosage_host(_p(G), C.c_int64(n), C.c_int64(p), out.ctypes.data_as(_u8p), C.c_size_t(stride),
-                                    C.c_int(threads))
+    out = np.full((p, stride), 0xCC, dtype=np.uint8)        # poison: the packer must write every byte of the stride
+    rc = fn(gp, C.c_int64(n), C.c_int64(p), out.ctypes.data_as(_u8p), C.c_size_t(stride), C.c_int(threads))
     if rc != 0:
         raise StaarError(rc, lib.staar_last_error().decode())
     return out

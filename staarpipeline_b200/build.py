@@ -17,7 +17,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    """CUDA sources (nvcc, sm_100a) and host-only sources (g++: AVX-512 intrinsics / target attributes)"""
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu"))) + sorted(glob.glob(os.path.join(CSRC, "*.cpp")))
 
 
 def needs_build() -> bool:
@@ -37,7 +38,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
+        if src.endswith(".cpp"):
+            cmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-pthread", "-c", src, "-o", obj]
+        else:
+            cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False

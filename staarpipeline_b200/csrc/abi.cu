@@ -469,43 +469,6 @@ int staar_individual_score_test_SPA(staar_ctx *ctx, const double *G, int64_t n, 
 // ============================================================================================ packed fast path
 size_t staar_packed_stride(int64_t n) { return (size_t)(((n + 3) / 4 + 15) / 16 * 16); }
 
-int staar_pack_dosage_host(const double *G, int64_t n, int64_t p, uint8_t *packed, size_t stride, int threads)
-{
-    if (!G || !packed || stride < (size_t)((n + 3) / 4) || stride % 16 != 0) { set_error("pack_dosage: bad arguments"); return STAAR_ERR_ARG; }
-    if (threads < 1) threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    threads = (int)std::min<int64_t>(threads, std::max<int64_t>(p, 1));
-    std::vector<int> bad(threads, 0);
-    auto work = [&](int tid) {
-        for (int64_t i = tid; i < p; i += threads) {
-            const double *g = G + i * n;
-            uint8_t *dst = packed + (size_t)i * stride;
-            // branch-free: code = [v==1] + 2[v==2] + 3[!(v>-1)]; anything else (incl. 0 < v < 1) is flagged
-            auto enc = [](double v, unsigned &okacc) -> unsigned {
-                const unsigned is1 = v == 1.0, is2 = v == 2.0, is0 = v == 0.0, miss = !(v > -1.0);
-                okacc &= (is0 | is1 | is2 | miss);
-                return is1 + 2u * is2 + 3u * miss;
-            };
-            unsigned ok = 1;
-            const int64_t n4 = n / 4;
-            for (int64_t b = 0; b < n4; b++) {
-                const double *s = g + 4 * b;
-                dst[b] = (uint8_t)(enc(s[0], ok) | (enc(s[1], ok) << 2) | (enc(s[2], ok) << 4) | (enc(s[3], ok) << 6));
-            }
-            unsigned last = 0;
-            for (int64_t j = 4 * n4; j < n; j++) last |= enc(g[j], ok) << (2 * (j & 3));
-            memset(dst + n4, 0, stride - n4);
-            if (n & 3) dst[n4] = (uint8_t)last;
-            if (!ok) bad[tid] = 1;
-        }
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < threads; t++) th.emplace_back(work, t);
-    work(0);
-    for (auto &t : th) t.join();
-    for (int b : bad) if (b) { set_error("pack_dosage: a non-missing genotype is not 0, 1 or 2"); return STAAR_ERR_ARG; }
-    return STAAR_OK;
-}
-
 int staar_nullmodel_set_sparse(staar_ctx *ctx, int64_t n, int64_t q, const double *Sv, const uint64_t *Sr,
                                const uint64_t *Sc, const double *SX, const double *cov, const double *res)
 {
@@ -670,14 +633,16 @@ int staar_packed_reorder_device(staar_ctx *ctx, const uint8_t *d_in, uint8_t *d_
     return sync(ctx);
 }
 
-// One chunk of the single-variant driver (R/Individual_Analysis.R:186-196,264): FP64 `$dosage` block in host memory
+// One chunk of the single-variant driver (R/Individual_Analysis.R:186-196,264): a `$dosage` block in host memory
 // -> flip/impute + Individual_Score_Test statistics, without materialising Geno on the host.  0/1/2/NA dosages are
-// packed to 2 bits on the host (threaded) so 1/32 of the bytes cross PCIe; anything else takes the FP64 kernels.
-int staar_individual_analysis_chunk(staar_ctx *ctx, const double *G, int64_t n, int64_t p, int impute, int threads,
-                                    double *AF, double *MAF, double *Score, double *Score_se, double *pl, double *Est,
-                                    double *Est_se)
+// packed to 2 bits on the host (threaded, AVX-512 when the CPU has it) so 1/32 of the FP64 bytes cross PCIe; real-valued
+// FP64 blocks take the FP64 kernels.  elem: 8 = FP64 (NaN / <= -1 missing), 4 = int32 (R integer matrix, NA_integer_
+// or any value <= -1 missing), 1 = uint8 (SeqArray raw dosage, 0xFF missing).
+namespace staar {
+namespace {
+int chunk_impl(staar_ctx *ctx, const void *G, int elem, int64_t n, int64_t p, int impute, int threads, double *AF,
+               double *MAF, double *Score, double *Score_se, double *pl, double *Est, double *Est_se)
 {
-    CHECK_CTX(ctx);
     STAAR_TRY(check_dims(n, p));
     NullSparse &ns = ctx->ns;
     if (!ns.set || ns.n != n) { set_error("individual_analysis_chunk: null model not set for n = %lld", (long long)n); return STAAR_ERR_STATE; }
@@ -686,13 +651,19 @@ int staar_individual_analysis_chunk(staar_ctx *ctx, const double *G, int64_t n, 
     bool packed_ok = false;
     if (ns.q + 2 <= kColsPerSlice - 1) {
         STAAR_TRY(pinned_reserve(ctx, stride * (size_t)p));
-        packed_ok = staar_pack_dosage_host(G, n, p, static_cast<uint8_t *>(ctx->pinned), stride, threads) == STAAR_OK;
+        uint8_t *dst = static_cast<uint8_t *>(ctx->pinned);
+        int rc = elem == 8   ? staar_pack_dosage_host(static_cast<const double *>(G), n, p, dst, stride, threads)
+                 : elem == 4 ? staar_pack_dosage_host_i32(static_cast<const int32_t *>(G), n, p, dst, stride, threads)
+                             : staar_pack_dosage_host_u8(static_cast<const uint8_t *>(G), n, p, dst, stride, threads);
+        packed_ok = rc == STAAR_OK;
+        if (!packed_ok && elem != 8) return rc;        // integer dosages other than 0/1/2/NA are an error
     }
     if (packed_ok)
         return staar_packed_score_host(ctx, static_cast<const uint8_t *>(ctx->pinned), stride, n, p, impute, AF, MAF,
                                        Score, Score_se, pl, Est, Est_se);
+    if (elem != 8) { set_error("individual_analysis_chunk: integer dosages need q <= %d covariates", kColsPerSlice - 3); return STAAR_ERR_ARG; }
     // real-valued genotypes: FP64 flip kernel in place on the device copy, then the FP64 score kernels
-    STAAR_TRY(upload_dense_G(ctx, G, n, p));
+    STAAR_TRY(upload_dense_G(ctx, static_cast<const double *>(G), n, p));
     STAAR_TRY(ctx->out.reserve(sizeof(double) * 5 * (size_t)p));
     double *o = ctx->out.as<double>();
     STAAR_TRY(launch_flip_dense(ctx, ctx->G.as<double>(), n, p, impute == STAAR_IMPUTE_MINOR, true, o, o + p));
@@ -700,6 +671,30 @@ int staar_individual_analysis_chunk(staar_ctx *ctx, const double *G, int64_t n, 
     STAAR_TRY(d2h(ctx, MAF, o + p, sizeof(double) * p));
     STAAR_TRY(sync(ctx));
     return run_sparse_family(ctx, n, p, 0, nullptr, Score, Score_se, pl, Est, Est_se);
+}
+}  // namespace
+}  // namespace staar
+
+int staar_individual_analysis_chunk(staar_ctx *ctx, const double *G, int64_t n, int64_t p, int impute, int threads,
+                                    double *AF, double *MAF, double *Score, double *Score_se, double *pl, double *Est,
+                                    double *Est_se)
+{
+    CHECK_CTX(ctx);
+    return chunk_impl(ctx, G, 8, n, p, impute, threads, AF, MAF, Score, Score_se, pl, Est, Est_se);
+}
+int staar_individual_analysis_chunk_i32(staar_ctx *ctx, const int32_t *G, int64_t n, int64_t p, int impute, int threads,
+                                        double *AF, double *MAF, double *Score, double *Score_se, double *pl,
+                                        double *Est, double *Est_se)
+{
+    CHECK_CTX(ctx);
+    return chunk_impl(ctx, G, 4, n, p, impute, threads, AF, MAF, Score, Score_se, pl, Est, Est_se);
+}
+int staar_individual_analysis_chunk_u8(staar_ctx *ctx, const uint8_t *G, int64_t n, int64_t p, int impute, int threads,
+                                       double *AF, double *MAF, double *Score, double *Score_se, double *pl,
+                                       double *Est, double *Est_se)
+{
+    CHECK_CTX(ctx);
+    return chunk_impl(ctx, G, 1, n, p, impute, threads, AF, MAF, Score, Score_se, pl, Est, Est_se);
 }
 
 int staar_synth_packed_device(staar_ctx *ctx, uint8_t *d_packed, size_t stride, int64_t n, int64_t first_variant,

@@ -188,6 +188,29 @@ def test_packed_kinship_paths(gpu_ctx, oracle):
         assert_stats_close({k: got[k] for k in want}, want, score_floor(fl["Geno"], res))
 
 
+def test_full_size_chunk_vs_oracle(gpu_ctx, oracle):
+    """BASELINE configs[1] sample size (n = 100,000, sparse GRM, q = 13): one chunk through the chunk-driver entry
+    point (host FP64 block -> pack -> re-order -> scan / tcgen05 contraction / finaliser) against the oracle, and the
+    int32 / raw-byte ingest paths against the FP64 one (bit-identical)."""
+    from staarpipeline_b200 import synth
+    from staarpipeline_b200.api import IMPUTE_MEAN
+    n, p = 100_000, 48
+    nm = synth.nullmodel_sparse_grm(n, seed=synth.BASE_SEED, q=13, shuffle=True)
+    codes = synth.dosage_codes(n, 1000, p)
+    G0 = synth.codes_to_dosage(codes)
+    fl = oracle.matrix_flip_mean(G0)
+    want = oracle.Individual_Score_Test(fl["Geno"], nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+    gpu_ctx.set_nullmodel_sparse(nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+    got = gpu_ctx.individual_analysis_chunk(G0, IMPUTE_MEAN)
+    assert np.array_equal(got["AF"], fl["AF"]) and np.array_equal(got["MAF"], fl["MAF"])
+    assert_stats_close({k: got[k] for k in want}, want, score_floor(fl["Geno"], nm.residuals))
+    ci = codes.astype(np.int32)
+    for G in (np.where(ci == 3, np.int32(-2147483648), ci).astype(np.int32), np.where(codes == 3, np.uint8(255), codes).astype(np.uint8)):
+        alt = gpu_ctx.individual_analysis_chunk(np.asfortranarray(G), IMPUTE_MEAN)
+        for k in got:
+            assert np.array_equal(alt[k], got[k], equal_nan=True), (G.dtype, k)
+
+
 def test_host_packer_matches_numpy(oracle):
     from staarpipeline_b200 import api, synth
     G0 = cases.raw_dosage(333, 21)
