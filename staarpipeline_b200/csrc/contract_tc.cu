@@ -11,7 +11,7 @@
 //   so a separate narrow N = 8 tile for the hom-minor indicator doubled the tensor time; that term now comes from
 //   the scan kernel's sparse sweep instead.)
 //   * B (digits) is pre-arranged at null-model set-up in the canonical K-major, non-swizzled core-matrix layout, so a
-//     256-sample k-block (30 KiB) is ONE cp.async.bulk from L2 into a 4-stage shared-memory ring (mbarrier tx-count).
+//     512-sample k-block (56 KiB) is ONE cp.async.bulk from L2 into a 2-stage shared-memory ring (mbarrier tx-count).
 //   * A (genotypes) never exists as int8 in memory: two "expander" threads own each variant row (half a k-block
 //     each), stream the 2-bit column HBM -> shared memory with cp.async (3 k-blocks ahead), expand 2-bit -> int8 with shift/mask in
 //     registers (no flip, no missing fix-up: both are applied analytically by the finaliser) and writes the int8 tile
@@ -32,11 +32,20 @@ namespace {
 constexpr int kTcRows = 128;                 // variants per CTA
 constexpr int kTcThreads = 320;
 constexpr int kExpThreads = 256;             // 8 expander warps
-constexpr int kStagesA = 4;                  // TMEM stages of the expanded A tiles (64 columns each)
-constexpr int kStagesB = 4;                  // shared-memory stages of the digit operand
-constexpr int kTcBlockBytes = 8 * 2 * 14 * 128;   // per k-block: 8 k-steps x 2 k-chunks x 14 row groups x (8 rows x 16 B) = 28 KiB
-constexpr int kRing = 4;                     // per-thread ring of raw 64-byte genotype slices (cp.async)
-constexpr int kSlot = 80;                    // 64 B + 16 B pad: conflict-free 128-bit reads of one's own slot
+// A k-block is the unit of every hand-off (expanders -> MMA issuer -> expanders, producer -> MMA issuer): its fixed
+// cost (two mbarrier waits of ~90 clk each in the single issuing thread, fences, commits) is amortised over kKS
+// instructions, so k-blocks are 16 k-steps = 512 samples.
+constexpr int kKS = 16;                      // k-steps (K = 32 samples each) per k-block
+constexpr int kTcSamples = 32 * kKS;         // samples per k-block
+constexpr int kHalfCols = 4 * kKS;           // TMEM columns (= registers) one expander thread writes per k-block
+constexpr int kHalfBytes = kTcSamples / 8;   // raw 2-bit bytes one expander thread consumes per k-block
+constexpr int kStagesA = 3;                  // TMEM stages of the expanded A tiles (8 kKS columns each)
+constexpr int kStagesB = 2;                  // shared-memory stages of the digit operand
+constexpr int kStepBytes = 2 * 14 * 128;     // one k-step: 2 k-chunks x 14 row groups x (8 rows x 16 B)
+constexpr int kTcBlockBytes = kKS * kStepBytes;
+constexpr int kRing = 5;                     // ring of raw genotype slices per row (cp.async), kRing - 1 k-blocks ahead
+constexpr int kSlot = 2 * kHalfBytes + 16;   // + 16 B pad: conflict-free 128-bit reads of one's own slot
+static_assert(kColsPerSlice * kSlices == 112 && 112 + kStagesA * 8 * kKS <= 512, "TMEM budget");
 constexpr int kColD = 0, kColA = 128;        // TMEM columns: accumulators [0,112), A stages from 128
 
 __device__ __forceinline__ uint32_t s_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -196,14 +205,16 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
         const int row = threadIdx.x & (kTcRows - 1), half = threadIdx.x >> 7;   // TMEM lane quarter = warp % 4
         const int64_t v = (int64_t)blockIdx.x * kTcRows + row;
         const bool rok = v < p;
-        const uint8_t *rowp = packed + (size_t)(rok ? v : 0) * stride + 32 * half;
-        uint8_t *slot0 = sG + (size_t)row * kSlot + 32 * half;
-        auto fetch = [&](int64_t kb) {                                       // raw 32 bytes of k-block kb -> ring slot
-            uint8_t *dst = slot0 + (size_t)(kb % kRing) * (kTcRows * kSlot);
-            const size_t off = (size_t)kb * 64;
+        const uint8_t *rowp = packed + (size_t)(rok ? v : 0) * stride + kHalfBytes * half;
+        uint8_t *slot0 = sG + (size_t)row * kSlot + kHalfBytes * half;
+        int fetch_slot = 0;                                                  // ring slot of the next k-block to fetch
+        auto fetch = [&](int64_t kb) {                                       // raw bytes of k-block kb -> ring slot
+            uint8_t *dst = slot0 + (size_t)fetch_slot * (kTcRows * kSlot);
+            fetch_slot = fetch_slot + 1 == kRing ? 0 : fetch_slot + 1;
+            const size_t off = (size_t)kb * (2 * kHalfBytes);
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const bool ok = rok && off + 32 * half + 16 * c + 16 <= stride;
+            for (int c = 0; c < kHalfBytes / 16; c++) {
+                const bool ok = rok && off + kHalfBytes * half + 16 * c + 16 <= stride;
                 cp_async16(dst + 16 * c, ok ? rowp + off + 16 * c : packed, ok ? 16u : 0u);   // zero fill outside the column
             }
         };
@@ -216,31 +227,37 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
         // kb are still in flight; only then does the thread wait for them and publish stage kb to the MMA issuer.
         // K index 4c + y of k-step ks <-> sample 32 ks + 16 (c >> 2) + 4 y + (c & 3): column c of a k-step is field
         // (c & 3) of word 2 ks + (c >> 2); the digit operand is laid out with the same map (build_tc_operand).
-        uint32_t x[32];
+        uint32_t x[kHalfCols];
+        int ring_slot = 0;                                                   // kb % kRing, kept incrementally (no 64-bit %)
         auto expand = [&](int64_t kb) {
             if (kb + kRing - 1 < n_kblocks) fetch(kb + kRing - 1);
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group %0;" ::"n"(kRing - 1) : "memory");
-            const uint4 *src = reinterpret_cast<const uint4 *>(slot0 + (size_t)(kb % kRing) * (kTcRows * kSlot));
-            uint32_t w[8];
+            const uint4 *src = reinterpret_cast<const uint4 *>(slot0 + (size_t)ring_slot * (kTcRows * kSlot));
+            ring_slot = ring_slot + 1 == kRing ? 0 : ring_slot + 1;
+            uint32_t w[kHalfBytes / 4];
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
+            for (int c = 0; c < kHalfBytes / 16; c++) {
                 const uint4 q = src[c];
                 w[4 * c] = q.x; w[4 * c + 1] = q.y; w[4 * c + 2] = q.z; w[4 * c + 3] = q.w;
             }
 #pragma unroll
-            for (int c = 0; c < 32; c++) x[c] = (w[c >> 2] >> (2 * (c & 3))) & 0x03030303u;
+            for (int c = 0; c < kHalfCols; c++) x[c] = (w[c >> 2] >> (2 * (c & 3))) & 0x03030303u;
         };
         if (n_kblocks > 0) expand(0);
+        int sa = 0;
+        uint32_t a_par = 1u;                                                 // parity to wait for on a_empty[sa]
         for (int64_t kb = 0; kb < n_kblocks; kb++) {
-            const int sa = (int)(kb % kStagesA);
-            bar_wait(&a_empty[sa], (uint32_t)(((kb / kStagesA) & 1) ^ 1));  // MMAs that read this TMEM stage are done
+            bar_wait(&a_empty[sa], a_par);                                   // MMAs that read this TMEM stage are done
             tc_fence_after();
-            tmem_st32(lane_base + kColA + sa * 64 + 32 * half, x);
+#pragma unroll
+            for (int b = 0; b < kHalfCols / 32; b++)
+                tmem_st32(lane_base + kColA + sa * (8 * kKS) + kHalfCols * half + 32 * b, *reinterpret_cast<const uint32_t (*)[32]>(&x[32 * b]));
             if (kb + 1 < n_kblocks) expand(kb + 1);                          // overlaps the store latency
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             bar_arrive(&a_full[sa]);
+            if (++sa == kStagesA) { sa = 0; a_par ^= 1u; }
         }
         // ===================================================================== epilogue: TMEM -> 64-bit recombination
         // half 0 reads the accumulators of digit slices 0-3 (the "hi" part), half 1 those of slices 4-6
@@ -289,19 +306,22 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
         // ===================================================================== MMA issuer (one thread)
         if (lane == 0) {
             constexpr uint32_t kIdescMain = idesc_i8(kTcRows, 112);
+            int sa = 0, sb = 0;
+            uint32_t a_par = 0u, b_par = 0u;
             for (int64_t kb = 0; kb < n_kblocks; kb++) {
-                const int sa = (int)(kb % kStagesA), sb = (int)(kb % kStagesB);
-                bar_wait(&b_full[sb], (uint32_t)((kb / kStagesB) & 1));
-                bar_wait(&a_full[sa], (uint32_t)((kb / kStagesA) & 1));
+                bar_wait(&b_full[sb], b_par);
+                bar_wait(&a_full[sa], a_par);
                 tc_fence_after();
                 const uint64_t bdesc = smem_desc(s_addr(sB + (size_t)sb * kTcBlockBytes), 14 * 128, 128);
-                const uint32_t a1 = tmem + kColA + sa * 64;
+                const uint32_t a1 = tmem + kColA + sa * (8 * kKS);
 #pragma unroll
-                for (int ks = 0; ks < 8; ks++)       // descriptor start address advances by one k-step (3584 B >> 4)
-                    umma_i8_ts(tmem + kColD, a1 + 8 * ks, bdesc + (uint64_t)(ks * ((2 * 14 * 128) >> 4)), kIdescMain,
+                for (int ks = 0; ks < kKS; ks++)     // descriptor start address advances by one k-step (3584 B >> 4)
+                    umma_i8_ts(tmem + kColD, a1 + 8 * ks, bdesc + (uint64_t)(ks * (kStepBytes >> 4)), kIdescMain,
                                (kb > 0 || ks > 0) ? 1u : 0u);
                 tc_commit(&a_empty[sa]);                                    // frees the TMEM A stage when these MMAs retire
                 tc_commit(&b_empty[sb]);                                    // frees the shared-memory digit stage
+                if (++sa == kStagesA) { sa = 0; a_par ^= 1u; }
+                if (++sb == kStagesB) { sb = 0; b_par ^= 1u; }
             }
             tc_commit(d_full);
         }
@@ -309,11 +329,13 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
     } else {
         // ===================================================================== digit producer (one thread)
         if (lane == 0) {
+            int sb = 0;
+            uint32_t b_par = 1u;
             for (int64_t kb = 0; kb < n_kblocks; kb++) {
-                const int sb = (int)(kb % kStagesB);
-                bar_wait_relaxed(&b_empty[sb], (uint32_t)(((kb / kStagesB) & 1) ^ 1));
+                bar_wait_relaxed(&b_empty[sb], b_par);
                 bar_expect_tx(&b_full[sb], kTcBlockBytes);
                 bulk_load(sB + (size_t)sb * kTcBlockBytes, Ytc + (size_t)kb * kTcBlockBytes, kTcBlockBytes, &b_full[sb]);
+                if (++sb == kStagesB) { sb = 0; b_par ^= 1u; }
             }
         }
         __syncwarp();
@@ -333,7 +355,7 @@ int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     if (p == 0) return STAAR_OK;
     const NullSparse &ns = ctx->ns;
     if (!ns.sliced || !ns.Ytc) { set_error("packed contraction: sliced operand not built (q > 13?)"); return STAAR_ERR_STATE; }
-    const int64_t n_kblocks = (n + kChunkSamples - 1) / kChunkSamples;
+    const int64_t n_kblocks = (n + kTcSamples - 1) / kTcSamples;
     const size_t smem = (size_t)kStagesB * kTcBlockBytes + (size_t)kRing * kTcRows * kSlot + 32 * sizeof(uint64_t);
     static bool attr_set = false;
     if (!attr_set) {
@@ -348,19 +370,19 @@ int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
 }
 
 // Digit operand in the canonical layout of the tcgen05 shared-memory descriptors used above.  One k-block:
-//   [k-step 8][k-chunk 2][row group 14][row 8][16 B]   row = 16 * slice + column   (N = 112); k-blocks are kTcBlockBytes apart
-// K index kk = 16 * k-chunk + byte of a k-step <-> sample 256 kb + 32 ks + 16 ((kk >> 2) >> 2) + 4 (kk & 3) + ((kk >> 2) & 3).
+//   [k-step kKS][k-chunk 2][row group 14][row 8][16 B]   row = 16 * slice + column   (N = 112); k-blocks are kTcBlockBytes apart
+// K index kk = 16 * k-chunk + byte of a k-step <-> sample kTcSamples kb + 32 ks + 16 ((kk >> 2) >> 2) + 4 (kk & 3) + ((kk >> 2) & 3).
 int build_tc_operand(staar_ctx *ctx, const int8_t *digits /* n x kColsPerSlice x kSlices, position order */, int ncol)
 {
     NullSparse &ns = ctx->ns;
     const int64_t n = ns.n;
-    const int64_t n_kblocks = (n + kChunkSamples - 1) / kChunkSamples;
+    const int64_t n_kblocks = (n + kTcSamples - 1) / kTcSamples;
     std::vector<int8_t> img((size_t)n_kblocks * kTcBlockBytes, 0);
     for (int64_t kb = 0; kb < n_kblocks; kb++)
-        for (int ks = 0; ks < 8; ks++)
+        for (int ks = 0; ks < kKS; ks++)
             for (int kk = 0; kk < 32; kk++) {
                 const int c = kk >> 2, y = kk & 3;
-                const int64_t smp = kb * 256 + 32 * ks + 16 * (c >> 2) + 4 * y + (c & 3);
+                const int64_t smp = kb * kTcSamples + 32 * ks + 16 * (c >> 2) + 4 * y + (c & 3);
                 if (smp >= n) continue;
                 const int8_t *dg = digits + (size_t)smp * kColsPerSlice * kSlices;
                 int8_t *base = img.data() + (size_t)kb * kTcBlockBytes;
@@ -368,7 +390,7 @@ int build_tc_operand(staar_ctx *ctx, const int8_t *digits /* n x kColsPerSlice x
                 for (int sl = 0; sl < kSlices; sl++)
                     for (int col = 0; col < ncol; col++) {
                         const int row = 16 * sl + col;
-                        base[(size_t)ks * (2 * 14 * 128) + koff + (size_t)(row >> 3) * 128 + (size_t)(row & 7) * 16] = dg[col * kSlices + sl];
+                        base[(size_t)ks * kStepBytes + koff + (size_t)(row >> 3) * 128 + (size_t)(row & 7) * 16] = dg[col * kSlices + sl];
                     }
             }
     cudaFree(ns.Ytc);
