@@ -463,14 +463,21 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
                 const int kw = 4 * k + wi;
                 if (kw >= tab_words) continue;
                 const uint32_t w = wv[wi];
-                const uint4 gd = __ldg(reinterpret_cast<const uint4 *>(P.gdesc) + kw);
                 const uint32_t lo = w & 0x55555555u;
                 const uint32_t mis = lo & (w >> 1);
                 const uint32_t wf = w ^ ((~lo & flipmask) << 1);     // g -> 2 - g on the codes 0 and 2
+                // cheap pre-test before touching the descriptors: a table look-up needs two carriers in one 4-sample
+                // group (bit 7 of every byte guards the borrow: non-zero byte <=> >= 2 carriers), a cross term two carriers
+                // anywhere in the word, the slow path a missing sample — most words of a rare variant have none of these
+                const uint32_t nm = wf & ~(mis * 3u);
+                const uint32_t car = (nm | (nm >> 1)) & 0x55555555u;
+                const bool maybe = (car & ((car | 0x80808080u) - 0x01010101u)) != 0u ||
+                                   (kw < x_words && (car & (car - 1u)) != 0u) || (rq_over && mis != 0u);
+                if (!maybe) continue;
+                const uint4 gd = __ldg(reinterpret_cast<const uint4 *>(P.gdesc) + kw);
                 const uint32_t km = __byte_perm(__byte_perm(gd.x, gd.y, 0x0040), __byte_perm(gd.z, gd.w, 0x0040), 0x5410);
-                const uint32_t wz = wf & ~(mis * 3u) & km;           // related, non-missing codes (tables hold such pairs)
-                const uint32_t hit = (wz | (wz >> 1)) & 0x55555555u; // carriers: bits 0,2,4,6 of every group byte
-                // per byte: clear the lowest carrier bit (bit 7 guards the borrow): non-zero byte <=> >= 2 carriers in the group
+                const uint32_t wz = nm & km;                         // related, non-missing codes (tables hold such pairs)
+                const uint32_t hit = car & km;                       // carriers: bits 0,2,4,6 of every group byte
                 const uint32_t two = hit & ((hit | 0x80808080u) - 0x01010101u);
                 const bool cross = kw < x_words && (hit & (hit - 1u)) != 0u;   // >= 2 carriers anywhere in a cross word
                 if (two != 0u || cross) {
