@@ -531,12 +531,14 @@ int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t st
     int32_t *dflip = ctx->tmp.as<int32_t>();
     double *dmu = reinterpret_cast<double *>(dflip + pi), *dquad = dmu + p, *dSm = dquad + p;
     long long *dhi = reinterpret_cast<long long *>(dSm + 16 * p), *dlo = dhi + 16 * p;
+    // order: contraction (raw codes; also yields the exact sum of codes per variant) -> scan (flip decision from
+    // that sum and its own missing count, sparse terms) -> finaliser.  ev[0..3] bracket the three kernels.
     const bool prof = ctx->profiling;
     if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-    STAAR_TRY(launch_scan_packed(ctx, d_packed, stride, n, p, impute, d_AF, d_MAF, dflip, dmu, dquad, dSm));
-    if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     if (ctx->use_mma_sync) STAAR_TRY(launch_contract_packed(ctx, d_packed, stride, n, p, dhi, dlo));
     else STAAR_TRY(launch_contract_tc(ctx, d_packed, stride, n, p, dhi, dlo));
+    if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    STAAR_TRY(launch_scan_packed(ctx, d_packed, stride, n, p, impute, dlo, d_AF, d_MAF, dflip, dmu, dquad, dSm));
     if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
     STAAR_TRY(launch_finalize_packed(ctx, p, dflip, dmu, dquad, dSm, dhi, dlo, d_Score, d_Score_se, d_pl, d_Est, d_Est_se));
     if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -578,7 +580,10 @@ int staar_ctx_last_stage_ms(staar_ctx *ctx, float ms[3])
     CHECK_CTX(ctx);
     if (!ctx->ev[0]) { set_error("profiling was never enabled on this context"); return STAAR_ERR_STATE; }
     STAAR_CUDA(cudaEventSynchronize(ctx->ev[3]));
-    for (int i = 0; i < 3; i++) STAAR_CUDA(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    // kernels run contraction, scan, finaliser; ms[] is reported as scan, contraction, finaliser
+    STAAR_CUDA(cudaEventElapsedTime(&ms[0], ctx->ev[1], ctx->ev[2]));
+    STAAR_CUDA(cudaEventElapsedTime(&ms[1], ctx->ev[0], ctx->ev[1]));
+    STAAR_CUDA(cudaEventElapsedTime(&ms[2], ctx->ev[2], ctx->ev[3]));
     return STAAR_OK;
 }
 

@@ -169,7 +169,8 @@ int launch_spa(staar_ctx *ctx, const double *dG, int64_t n, int64_t p, const dou
                double *d_pvalue, long long *d_trace);
 // packed path — scan_packed.cu / contract_packed.cu / finalize
 int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
-                       double *dAF, double *dMAF, int32_t *dflip, double *d_mu, double *d_quad, double *d_Sm);
+                       const long long *d_lo /* contraction output: slot 15 = sum of codes */, double *dAF, double *dMAF,
+                       int32_t *dflip, double *d_mu, double *d_quad, double *d_Sm);
 int launch_contract_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p,
                            long long *d_hi, long long *d_lo);
 int launch_finalize_packed(staar_ctx *ctx, int64_t p, const int32_t *d_flip, const double *d_mu, const double *d_quad,

@@ -312,18 +312,22 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
     std::vector<int8_t> digits((size_t)n * kSlices);
     std::vector<int8_t> alldigits((size_t)n * kColsPerSlice * kSlices, 0);   // [position][column][slice] for the tcgen05 image
     std::vector<long long> tot(2 * kColsPerSlice, 0);          // exact column totals of the fixed-point operand: hi | lo
-    for (int c = 0; c < ncol; c++) {
+    // column kColsPerSlice - 1 is the constant 1 with X = 1 exactly (digits 0,...,0,1): its contraction is the exact
+    // sum of a variant's codes, from which the scan gets allele counts without popcounting the column again
+    for (int cc = 0; cc <= ncol; cc++) {
+        const bool ones = cc == ncol;
+        const int c = ones ? kColsPerSlice - 1 : cc;
         double mx = 0.0;
-        for (int64_t j = 0; j < n; j++) {
+        for (int64_t j = 0; j < n && !ones; j++) {
             const double a = fabs(hY[j * ldY + c]);
             if (!(a <= 1.79e308)) { set_error("null-model operand column %d holds a non-finite value", c); return STAAR_ERR_ARG; }
             if (a > mx) mx = a;
         }
         int e = 0;
         if (mx > 0.0) frexp(mx, &e);                 // mx = f * 2^e, f in [0.5, 1)  =>  |Y| < 2^e
-        scale[c] = ldexp(1.0, e - 54);
+        scale[c] = ones ? 1.0 : ldexp(1.0, e - 54);
         for (int64_t j = 0; j < n; j++) {
-            long long X = llrint(ldexp(hY[row_of(j) * ldY + c], 54 - e));     // |X| <= 2^54; digits[] is in position order
+            long long X = ones ? 1 : llrint(ldexp(hY[row_of(j) * ldY + c], 54 - e));     // |X| <= 2^54; digits[] is in position order
             int8_t d[kSlices];
             for (int s = kSlices - 1; s >= 1; s--) {
                 const long long dd = ((X + 128) & 255) - 128;
@@ -355,21 +359,6 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
                             }
                     }
                 }
-        if (c == ncol - 1) {
-            // extra n-tile: column g (0..6) = digit slice g of diag(Sigma_i), column 7 = 0; same sample map
-            for (int64_t kc = 0; kc < n_chunks; kc++)
-                for (int s = 0; s < 8; s++)
-                    for (int sl = 0; sl < kSlices; sl++)
-                        for (int t = 0; t < 4; t++) {
-                            int8_t *dst = frag.data() + (size_t)kc * kChunkBytesB + (size_t)s * kStepBytesB +
-                                          (size_t)(kNT / 2) * 512 + (size_t)(4 * sl + t) * 8;
-                            for (int half = 0; half < 2; half++)
-                                for (int y = 0; y < 4; y++) {
-                                    const int64_t smp = kc * 256 + 64 * t + 16 * (s / 2) + 4 * y + 2 * (s % 2) + half;
-                                    dst[half * 4 + y] = smp < n ? digits[(size_t)smp * kSlices + sl] : (int8_t)0;
-                                }
-                        }
-        }
     }
     STAAR_CUDA(cudaMalloc(&ns.Yfrag, frag.size()));
     STAAR_CUDA(cudaMalloc(&ns.col_scale, sizeof(double) * kColsPerSlice));
@@ -378,7 +367,7 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
     STAAR_CUDA(cudaMemcpyAsync(ns.Yfrag, frag.data(), frag.size(), cudaMemcpyHostToDevice, ctx->stream));
     STAAR_CUDA(cudaMemcpyAsync(ns.col_scale, scale.data(), sizeof(double) * kColsPerSlice, cudaMemcpyHostToDevice, ctx->stream));
     STAAR_CUDA(cudaStreamSynchronize(ctx->stream));
-    STAAR_TRY(build_tc_operand(ctx, alldigits.data(), ncol));
+    STAAR_TRY(build_tc_operand(ctx, alldigits.data(), kColsPerSlice));
     ns.n_chunks = n_chunks;
     ns.sliced = true;
     return STAAR_OK;

@@ -37,6 +37,7 @@ struct ScanParams {
     const double *diag;                    // Sigma_i[j,j] by position
     const NullSparse::OffEntry *off_ent;
     const double *Y; int ldY, ncol;        // Y rows in null-model order
+    const long long *codesum;              // contraction output `lo` (p x 16): slot 15 = exact sum of the codes
     double *AF, *MAF; int32_t *flip; double *mu, *quad, *Sm;
 };
 
@@ -305,14 +306,16 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         const uint8_t *col = cols + (size_t)stage * stride;
         const int64_t i = (int64_t)cur;
 
-        // ---- sweep 1 (whole column, 64 samples per lane and step): popcounts -> AF / MAF / flip / imputation value
-        //      (bit-exact integer counts); column sums of Y over missing samples (independent of the flip): missing
-        //      positions go to the warp's queue, a flush reads two rows of Y per warp instruction (half-warp h:
-        //      entries h, h+2, ...; lane c: column c) and keeps the positions inside the table region in a second
-        //      queue for the kinship correction; and the sum of Sigma_i[j,j] over hom-minor carriers (g^2 - g =
-        //      2 [g == 2], the part of g' diag(Sigma_i) g that is not linear in the codes) under a per-warp GUESS of the
-        //      flip taken from the warp's first step — redone below for the warps that guessed wrong.
-        int clo = 0, chi = 0, cm = 0;                            // popcounts of low bits, high bits, both (missing)
+        // ---- sweep 1 (whole column, 64 samples per lane and step).  The sum of the variant's codes S = c1 + 2 c2 + 3 cm
+        //      comes EXACTLY from the tensor-core contraction (its constant-1 column), so no genotype popcounts are
+        //      needed here: the sweep finds the missing samples (cm; column sums of Y over them — positions go to the
+        //      warp's queue, a flush reads two rows of Y per warp instruction (half-warp h: entries h, h+2, ...; lane c:
+        //      column c) and keeps the positions inside the table region in a second queue for the kinship
+        //      correction) and the sum of Sigma_i[j,j] over hom-minor carriers (g^2 - g = 2 [g == 2], the part of
+        //      g' diag(Sigma_i) g that is not linear in the codes).  The latter needs the flip, which needs cm: it is
+        //      computed under the guess cm = 0 and redone in the rare case that the missing count changes the decision.
+        const long long S = P.codesum[i * 16 + 15];
+        int cm = 0;
         double sm = 0.0, hom = 0.0;
         int qn = 0, rn = 0;
         bool rq_over = false;
@@ -357,25 +360,15 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
                 acc += (v0 + v1) + (v2 + v3);
             }
         };
-        bool guess;
-        {
-            const int k = wib * 32 + lane;
-            uint4 q4 = make_uint4(0u, 0u, 0u, 0u);
-            if (k < nvec16) q4 = v4[k];
-            const int s = __popc(q4.x) + __popc(q4.y) + __popc(q4.z) + __popc(q4.w) + __popc(q4.x & 0xaaaaaaaau) +
-                          __popc(q4.y & 0xaaaaaaaau) + __popc(q4.z & 0xaaaaaaaau) + __popc(q4.w & 0xaaaaaaaau);   // sum of codes
-            guess = __reduce_add_sync(0xffffffffu, s) > 2048;    // mean dosage of the warp's first 2048 samples > 1
-        }
+        // both imputation modes flip iff the mean dosage exceeds 1 when nothing is missing
+        const bool guess = S > (long long)P.n;
         {
             for (int k0 = wib * 32; k0 < nvec16; k0 += kBlkWarps * 32) {
                 const int k = k0 + lane;
                 uint4 q4 = make_uint4(0u, 0u, 0u, 0u);
-                if (k < nvec16) q4 = v4[k];
+                if (k < nvec16) { q4 = v4[k]; hom_vec(q4, k, guess, hom); }
                 const uint32_t m0 = q4.x & (q4.x >> 1) & 0x55555555u, m1 = q4.y & (q4.y >> 1) & 0x55555555u;
                 const uint32_t m2 = q4.z & (q4.z >> 1) & 0x55555555u, m3 = q4.w & (q4.w >> 1) & 0x55555555u;
-                clo += __popc(q4.x & 0x55555555u) + __popc(q4.y & 0x55555555u) + __popc(q4.z & 0x55555555u) + __popc(q4.w & 0x55555555u);
-                chi += __popc(q4.x & 0xaaaaaaaau) + __popc(q4.y & 0xaaaaaaaau) + __popc(q4.z & 0xaaaaaaaau) + __popc(q4.w & 0xaaaaaaaau);
-                if (k < nvec16) hom_vec(q4, k, guess, hom);
                 // bit 2f + w of a half = sample f of word w (low half: words 0,1; high half: words 2,3)
                 uint32_t blo = m0 | (m1 << 1), bhi = m2 | (m3 << 1);
                 uint32_t bal = __ballot_sync(0xffffffffu, (blo | bhi) != 0u);
@@ -397,26 +390,22 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             }
             if (qn > 0) flush_missing();
             sm += __shfl_xor_sync(0xffffffffu, sm, 16);            // the two half-warps' partial sums (fixed order)
-            clo = __reduce_add_sync(0xffffffffu, clo);
-            chi = __reduce_add_sync(0xffffffffu, chi);
             cm = __reduce_add_sync(0xffffffffu, cm);
-            if (lane == 0) { s_cnt[wib] = clo; s_cnt[kBlkWarps + wib] = chi; s_cnt[2 * kBlkWarps + wib] = cm; s_cnt[3 * kBlkWarps + wib] = rq_over; }
+            if (lane == 0) { s_cnt[wib] = cm; s_cnt[kBlkWarps + wib] = rq_over; }
             if (lane < kColsPerSlice) s_sm[wib * kColsPerSlice + lane] = sm;
             __syncthreads();
-            clo = chi = cm = 0;
+            cm = 0;
             int over = 0;
 #pragma unroll
-            for (int w = 0; w < kBlkWarps; w++) {
-                clo += s_cnt[w]; chi += s_cnt[kBlkWarps + w]; cm += s_cnt[2 * kBlkWarps + w]; over |= s_cnt[3 * kBlkWarps + w];
-            }
+            for (int w = 0; w < kBlkWarps; w++) { cm += s_cnt[w]; over |= s_cnt[kBlkWarps + w]; }
             rq_over = over != 0;                                  // block-wide: some warp could not keep its positions
         }
-        const int c1 = clo - cm, c2 = chi - cm;
         // flip decision in exact integers (every thread; the FP64 divisions stay off the critical path):
+        //   sum = c1 + 2 c2 = S - 3 cm,  num = n - cm
         //   mean : AF = sum/2/num > 0.5  <=>  sum > num          (|AF - 0.5| >= 1/(4 num) >> ulp, division is monotone)
         //   minor: fill = AF > 0.5 ? 2 : 0;  AF' = (sum + fill cm)/2/n > 0.5  <=>  sum + fill cm > n
-        const PackedCounts pc{c1, c2, cm};
-        const long long gsum = (long long)c1 + 2ll * c2, gnum = (long long)P.n - cm;
+        const long long gsum = S - 3ll * cm, gnum = (long long)P.n - cm;
+        const PackedCounts pc{(int)gsum, 0, cm};                   // flip_from_counts only uses c1 + 2 c2 and cm
         bool flip, mu_zero;
         if (P.impute == STAAR_IMPUTE_MEAN) {
             flip = gsum > gnum;
@@ -427,7 +416,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             mu_zero = flip ? (fill == 2) : (fill == 0);            // mu = fill or 2 - fill
         }
         auto mu_of = [&]() { return flip_from_counts(pc, P.n, P.impute).mu; };   // rare paths only
-        if (guess != flip) {                                       // warp-uniform: this warp's steps again, right orientation
+        if (guess != flip) {                                       // block-uniform and rare: the missing count decided
             hom = 0.0;
             for (int k0 = wib * 32; k0 < nvec16; k0 += kBlkWarps * 32)
                 if (k0 + lane < nvec16) hom_vec(v4[k0 + lane], k0 + lane, flip, hom);
@@ -562,9 +551,9 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
 #pragma unroll
             for (int w = 0; w < kBlkWarps; w++) t += s_quad[w];
             const VariantFlip vf = flip_from_counts(pc, P.n, P.impute);
-            // bit 1: every genotype is 0 after flip and imputation (the reference's exact Cov == 0 branch)
-            const int c0 = (int)(P.n - c1 - c2 - cm);
-            const int mono = (c1 == 0 && (c2 == 0 || c0 == 0)) ? 2 : 0;
+            // bit 1: every genotype is 0 after flip and imputation (the reference's exact Cov == 0 branch):
+            // all non-missing codes are 0 (sum == 0) or all are 2 (sum == 2 num)
+            const int mono = (gsum == 0 || gsum == 2 * gnum) ? 2 : 0;
             P.AF[i] = vf.af; P.MAF[i] = vf.maf; P.flip[i] = (flip ? 1 : 0) | mono; P.mu[i] = vf.mu; P.quad[i] = t;
         }
         if (nstage == 2) {
@@ -644,7 +633,8 @@ __global__ void __launch_bounds__(128) finalize_packed_kernel(FinParams P)
 }  // namespace
 
 int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
-                       double *dAF, double *dMAF, int32_t *dflip, double *d_mu, double *d_quad, double *d_Sm)
+                       const long long *d_lo, double *dAF, double *dMAF, int32_t *dflip, double *d_mu, double *d_quad,
+                       double *d_Sm)
 {
     if (p == 0) return STAAR_OK;
     const NullSparse &ns = ctx->ns;
@@ -655,6 +645,7 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     P.tab_words = ns.tab_words; P.kin_words = ns.kin_words; P.x_words = ns.x_words; P.gdesc = ns.gdesc; P.wdesc = ns.wdesc;
     P.xterms = ns.xterms; P.lut = ns.lut; P.sinfo = ns.sinfo_p; P.off_ent = ns.off_ent_p; P.diag = ns.diag_p;
     P.Y = ns.Yp; P.ldY = ns.ldY; P.ncol = (int)ns.q + 2;
+    P.codesum = d_lo;
     P.AF = dAF; P.MAF = dMAF; P.flip = dflip; P.mu = d_mu; P.quad = d_quad; P.Sm = d_Sm;
     // block-per-variant kernel: column(s) in shared memory, double-buffered when two fit
     const size_t extra = sizeof(uint32_t) * kBlkWarps * (kQueueCap + kRelQueueCap) +

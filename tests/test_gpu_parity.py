@@ -298,4 +298,6 @@ def test_packed_contraction_is_exact_integer(gpu_ctx, oracle):
             assert d["col_scale"][c] == math.ldexp(1.0, e - 54)
             X = np.array([int(np.rint(math.ldexp(float(y), 54 - e))) for y in Y[:, c]], dtype=object)
             assert list(got[:, c]) == list((codes.astype(object) * X[:, None]).sum(axis=0)), f"column {c}"
+        # slot 15: the constant-1 column (scale 1) = exact sum of the raw codes
+        assert d["col_scale"][15] == 1.0 and list(got[:, 15]) == list(codes.astype(object).sum(axis=0))
         assert np.array_equal((d["flip"] & 1) != 0, oracle.matrix_flip_mean(G0)["AF"] > 0.5)
