@@ -42,9 +42,8 @@ constexpr int kSlices = 7;          // 7 balanced base-256 digits = 54-bit fixed
 constexpr int kColsPerSlice = 16;   // 1 + q <= 16 columns per slice group (r | Sigma_iX), padded
 constexpr int kNT = kSlices * kColsPerSlice / 8;   // n-tiles of 8 columns (14)
 constexpr int kChunkSamples = 256;  // samples per k-chunk (8 IMMA k32 steps)
-constexpr int kStepBytesB = (kNT + 1) * 32 * 8;       // per IMMA k32 step: 14 column tiles + 1 tile with the 7 digit
-                                                       // slices of diag(Sigma_i) for the hom-minor indicator (3840)
-constexpr int kChunkBytesB = 8 * kStepBytesB;         // bytes of fragment-major B per k-chunk (30720)
+constexpr int kStepBytesB = kNT * 32 * 8;             // mma.sync version, per IMMA k32 step: 14 column tiles (3584)
+constexpr int kChunkBytesB = 8 * kStepBytesB;         // bytes of fragment-major B per k-chunk (28672)
 
 struct NullSparse {
     bool set = false, owned = true;

@@ -8,21 +8,21 @@
 // Genotypes are exact small integers, so instead the FP64 operand Y = [r | Sigma_iX] is split ONCE, at null-model
 // set-up, into 7 balanced base-256 digits per entry (54-bit fixed point per column, Ozaki-style slicing):
 //     Y[j,c] ~= 2^(e_c-54) * sum_s d_s[j,c] * 256^(6-s),   d_s in [-128,127]
-// and G' * d_s is an INT8 x INT8 -> INT32 tensor-core GEMM whose result is exact (|acc| <= 2*128*n < 2^31).
+// and G' * d_s is an INT8 x INT8 -> INT32 tensor-core GEMM whose result is exact (|acc| <= 3*128*n < 2^31).
 // The 7 partial results are recombined in 64-bit integer arithmetic, so the contraction is bit-reproducible for any
-// tiling / split / GPU count, a monomorphic column gives an exact 0 (the reference's Cov_ii == 0 branch), and the
-// only rounding left is the 2^-54 truncation of Y (relative to the column maximum) — far inside the 1e-10 budget.
+// tiling / split / GPU count, and the only rounding left is the 2^-54 truncation of Y (relative to the column
+// maximum) — far inside the 1e-10 budget.
 // The kernel contracts the RAW 2-bit codes (0, 1, 2 and 3 = missing, taken as the value 3): the flip to the minor
 // allele g -> 2 - g and the imputation of missing entries are linear in these exact integer sums and are applied
 // analytically by finalize_packed_kernel (scan_packed.cu), so the contraction does not depend on the scan.
 //
-// Kernel: M = variants (2 m16 tiles per warp, 8 warps per CTA), N = 7 slices x 16 columns = 14 n8 tiles (+1 tile:
-// the hom-minor indicator [g == 2] against the 7 digit slices of diag(Sigma_i), for sum_j s_jj g_j^2),
-// K = samples, mma.sync.m16n8k32.s8 (measured 1.14 POP/s on B200).  The digit operand is pre-arranged in
-// fragment-major order so a k-chunk (256 samples, 28 KiB) is ONE contiguous bulk copy: it is streamed from L2 into
-// a 4-stage shared-memory ring by cp.async.bulk (TMA 1-D) completing on mbarriers, and read back with conflict-free
-// 128-bit LDS.  Genotype words go HBM -> registers (128-bit, L1::no_allocate) and are expanded 2-bit -> int8 with
-// shift/mask only; every genotype byte is read exactly once per launch.
+// This file is the LEGACY tensor path (mma.sync.m16n8k32.s8; measured 1.14 POP/s on B200), kept as a cross-check of
+// the tcgen05 kernel (STAAR_B200_CONTRACT=mma) and because the host-side slicing of Y lives here.
+// Kernel: M = variants (2 m16 tiles per warp, 8 warps per CTA), N = 7 slices x 16 columns = 14 n8 tiles, K = samples.
+// The digit operand is pre-arranged in fragment-major order so a k-chunk (256 samples, 28 KiB) is ONE contiguous
+// bulk copy: it is streamed from L2 into a 4-stage shared-memory ring by cp.async.bulk (TMA 1-D) completing on
+// mbarriers, and read back with conflict-free 128-bit LDS.  Genotype words go HBM -> registers (128-bit,
+// L1::no_allocate) and are expanded 2-bit -> int8 with shift/mask only; every genotype byte is read once per launch.
 #include "common.cuh"
 #include "packed.cuh"
 

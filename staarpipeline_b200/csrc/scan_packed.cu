@@ -1,19 +1,19 @@
-// scan_packed.cu — K1 + K3 for packed dosages, and the per-variant finalisation (K5) of the packed path.
+// scan_packed.cu — the sparse, per-variant terms of the packed path (K1 + K3) and its finaliser (K5).
 //
-// scan_packed_kernel (one warp per variant, two sweeps over the 2-bit column):
-//   sweep 1: popcount the codes -> AF, MAF, flip decision, imputation value — bit-exact with
-//            matrix_flip_mean / matrix_flip_minor (src/matrix_flip_mean.cpp:23-70, src/matrix_flip_minor.cpp:23-95);
-//   sweep 2 (the column is L1/L2-hot): flip the codes in the bit domain and visit only the NON-ZERO genotypes
-//            (carriers and imputed entries, a few % of a rare variant's column) to accumulate the sparse quadratic
-//            form g' Sigma_i g (the (trans(G)*Sigma_i)*G factor of src/Individual_Score_Test.cpp:43, diagonal entry
-//            only): hom-minor corrections and the kinship off-diagonal rows of related carriers — the linear part
-//            sum_j s_jj g_j rides in the tensor-core contraction — plus the column sums over missing entries that
-//            the integer contraction (contract_packed.cu) leaves out.
-// finalize_packed_kernel (one thread per variant): integer contraction -> FP64, imputation correction mu * Sm,
-//   Cov_ii = quad - t' cov t, and the statistics loop of src/Individual_Score_Test.cpp:45-64.
+// What the exact tensor-core contraction (contract_tc.cu) cannot deliver are the terms that are not linear in the raw
+// 2-bit codes; scan_block_kernel computes them, one CTA per variant with the column staged in shared memory:
+//   * flip / impute decisions, AF and MAF — bit-exact with matrix_flip_mean / matrix_flip_minor
+//     (src/matrix_flip_mean.cpp:23-70, src/matrix_flip_minor.cpp:23-95) from exact integers: the sum of codes comes from
+//     the contraction's constant-1 column, the missing count from this kernel;
+//   * column sums of Y over the missing samples (imputation correction of G'[r | Sigma_iX]);
+//   * g' Sigma_i g beyond its linear part (the (trans(G)*Sigma_i)*G factor of src/Individual_Score_Test.cpp:43, diagonal
+//     entry only): the sum of Sigma_i[j,j] over hom-minor carriers (g^2 - g = 2 [g == 2]) and the kinship off-diagonal
+//     part, which thanks to the null-model sample order (common.cuh) is a table look-up per 4-sample group.
+// finalize_packed_kernel (one thread per variant): flip and imputation applied analytically to the exact integer sums,
+//   Cov_ii = g' Sigma_i g - t' cov t, and the statistics loop of src/Individual_Score_Test.cpp:45-64.
 //
-// Integer/byte work, HBM/L2-bound: 128-bit coalesced loads, popc/ffs bit tricks, warp-shuffle reductions with a
-// fixed tree (no atomics => 1/2/4/8-GPU runs are bit-identical).
+// Integer/byte work: 128-bit shared-memory reads, popc/ffs bit tricks, warp-shuffle reductions with fixed trees and
+// per-warp queues filled in a fixed order (no floating-point atomics => 1/2/4/8-GPU runs are bit-identical).
 #include "common.cuh"
 #include "packed.cuh"
 
@@ -41,184 +41,19 @@ struct ScanParams {
     double *AF, *MAF; int32_t *flip; double *mu, *quad, *Sm;
 };
 
-constexpr int kScanWarps = 8;
-constexpr int kCarrierCap = 1024 + 32;  // related carriers found in one iteration (<= 1024) + a carried remainder (< 32)
-
 __device__ __forceinline__ double code_value(uint32_t code, double mu)
 {
     return code == 3u ? mu : (double)code;
 }
 
-// decoded (post-flip) genotype of sample k in a packed column
-__device__ __forceinline__ double lookup_value(const uint8_t *colp, int64_t k, bool flip, double mu)
-{
-    uint32_t code = (__ldg(colp + (k >> 2)) >> (2 * (k & 3))) & 3u;
-    if (flip && !(code & 1u)) code ^= 2u;
-    return code_value(code, mu);
-}
-
-// One warp per variant, two sweeps over the 2-bit column.
-//  sweep 1: popcounts -> AF / MAF / flip / imputation value.
-//  sweep 2: only what the integer contraction cannot account for is visited:
-//            code 3 (missing): column sums of Y for the imputation correction;
-//            carriers with a kinship off-diagonal towards a larger sample index (relmask):
-//            2 * g_j * sum_{k > j} s_jk g_k   (each related pair once, from its smaller index).
-//           Those carriers are compacted (bit tricks only) into a per-warp shared-memory list and handled in full
-//           rounds of 32, so the latency-bound gathers (32-byte record -> relatives' genotype bytes) always have
-//           every lane busy; the remainder (< 32) is carried over and flushed at the end of the column.
-// The diagonal of g' Sigma_i g rides in the tensor-core contraction (column q+1 of Y and the hom-minor tile).
-template <bool HAS_OFF>
-__global__ void __launch_bounds__(kScanWarps * 32) scan_packed_kernel(ScanParams P)
-{
-    __shared__ uint32_t s_car[HAS_OFF ? kScanWarps : 1][kCarrierCap];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int nvec8 = (int)(P.stride >> 3);
-    uint32_t *car = s_car[HAS_OFF ? wib : 0];
-    const uint2 *rmask = reinterpret_cast<const uint2 *>(P.relmask);
-    for (int64_t i = warp; i < P.p; i += nwarps) {
-        const uint8_t *colp = P.packed + (size_t)i * P.stride;
-        const PackedCounts pc = count_packed_column(colp, P.stride, lane);
-        const VariantFlip vf = flip_from_counts(pc, P.n, P.impute);
-        const bool flip = vf.flip != 0;
-        const double mu = vf.mu;
-        double quad = 0.0, sm = 0.0;           // sm: lane c (< ncol) accumulates sum over missing j of Y[j][c]
-        int ncar = 0;                          // warp-uniform fill level of the carrier list
-
-        auto carrier_round = [&](int first, int count) {
-            if (lane < count) {
-                const uint32_t ce = car[first + lane];
-                const NullSparse::CarrierRec rr = P.rel[ce >> 2];
-                double s = rr.val[0] * lookup_value(colp, rr.col[0], flip, mu);
-                if (rr.count > 1) s += rr.val[1] * lookup_value(colp, rr.col[1], flip, mu);
-                for (uint32_t t = 2; t < rr.count; t++) {
-                    const NullSparse::OffEntry oe = P.up_ent[rr.start + t];
-                    s += oe.val * lookup_value(colp, oe.col, flip, mu);
-                }
-                quad += 2.0 * code_value(ce & 3u, mu) * s;
-            }
-        };
-
-        const uint2 *vecs = reinterpret_cast<const uint2 *>(colp);
-        for (int k0 = 0; k0 < nvec8; k0 += 32) {
-            const int k = k0 + lane;
-            uint2 q2 = make_uint2(0u, 0u), r2 = make_uint2(0u, 0u);
-            if (k < nvec8) {
-                q2 = __ldg(vecs + k);
-                if (HAS_OFF) r2 = __ldg(rmask + k);
-            }
-            uint32_t w[2] = {q2.x, q2.y}, sel[2], mis[2];
-            const uint32_t rm[2] = {r2.x, r2.y};
-            const int64_t base = (int64_t)k * 32;                   // first sample of this lane's 8 bytes
-            int cnt = 0;
-            bool any_missing = false;
-#pragma unroll
-            for (int wi = 0; wi < 2; wi++) {
-                if (flip) {
-                    w[wi] = flip_word(w[wi]);
-                    const int64_t valid = P.n - (base + wi * 16);  // padding codes would flip to 2
-                    if (valid < 16) w[wi] &= (valid <= 0) ? 0u : ((1u << (2 * valid)) - 1u);
-                }
-                const uint32_t lo = w[wi] & 0x55555555u, hi = (w[wi] >> 1) & 0x55555555u;
-                mis[wi] = lo & hi;                                                    // code 3
-                // related carriers; a missing sample counts only if its imputed value is non-zero
-                sel[wi] = HAS_OFF ? ((lo | hi) & rm[wi] & ~(mu == 0.0 ? mis[wi] : 0u)) : 0u;
-                cnt += __popc(sel[wi]);
-                any_missing |= mis[wi] != 0u;
-            }
-            // ---- missing entries (rare): all lanes cooperate on the Y row (lane c adds column c)
-            if (__any_sync(0xffffffffu, any_missing)) {
-#pragma unroll
-                for (int wi = 0; wi < 2; wi++) {
-                    uint32_t mine = mis[wi];
-                    uint32_t who = __ballot_sync(0xffffffffu, mine != 0u);
-                    while (who) {
-                        const int src = __ffs(who) - 1;
-                        who &= who - 1;
-                        uint32_t mw = __shfl_sync(0xffffffffu, mine, src);
-                        const int64_t b0 = __shfl_sync(0xffffffffu, base, src) + wi * 16;
-                        while (mw) {
-                            const int b = __ffs(mw) - 1;
-                            mw &= mw - 1;
-                            if (lane < P.ncol) sm += P.Y[(b0 + (b >> 1)) * P.ldY + lane];
-                        }
-                    }
-                }
-            }
-            if (!HAS_OFF) continue;
-            // ---- related carriers: append to the list, then run full rounds
-            if (__any_sync(0xffffffffu, cnt != 0)) {
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                int pos = ncar + incl - cnt;
-#pragma unroll
-                for (int wi = 0; wi < 2; wi++) {
-                    uint32_t ss = sel[wi];
-                    while (ss) {
-                        const int b = __ffs(ss) - 1;                 // even bit position = 2 * field
-                        ss &= ss - 1;
-                        car[pos++] = ((uint32_t)(base + wi * 16 + (b >> 1)) << 2) | ((w[wi] >> b) & 3u);
-                    }
-                }
-                ncar += total;
-                if (ncar >= 32) {
-                    __syncwarp();
-                    int done = 0;
-                    while (ncar - done >= 32) { carrier_round(done, 32); done += 32; }
-                    const int rem = ncar - done;                   // move the remainder (< 32) to the front
-                    const uint32_t keep = lane < rem ? car[done + lane] : 0u;
-                    __syncwarp();
-                    if (lane < rem) car[lane] = keep;
-                    ncar = rem;
-                    __syncwarp();
-                }
-            }
-        }
-        if (HAS_OFF) {
-            __syncwarp();
-            if (ncar > 0) carrier_round(0, ncar);
-            __syncwarp();
-        }
-        quad = warp_sum(quad);
-        double hom = 0.0;                        // hom-minor carriers: sum of Sigma_i[j,j] (see scan_block_kernel)
-        for (int k = lane; k < (int)((P.n + 15) >> 4); k += 32) {
-            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(colp) + k);
-            uint32_t wf = flip ? flip_word(w) : w;
-            const int64_t valid = P.n - (int64_t)k * 16;
-            if (valid < 16) wf &= (1u << (2 * valid)) - 1u;
-            uint32_t h = (wf >> 1) & ~wf & 0x55555555u;
-            while (h) {
-                const int b = __ffs(h) - 1;
-                h &= h - 1u;
-                hom += P.sinfo[(int64_t)k * 16 + (b >> 1)].diag;
-            }
-        }
-        hom = warp_sum(hom);
-        if (lane == 0) {
-            const int c0 = (int)(P.n - pc.c1 - pc.c2 - pc.cm);
-            const int mono = (pc.c1 == 0 && (pc.c2 == 0 || c0 == 0)) ? 2 : 0;
-            P.AF[i] = vf.af; P.MAF[i] = vf.maf; P.flip[i] = vf.flip | mono; P.mu[i] = mu; P.quad[i] = quad;
-        }
-        if (lane < kColsPerSlice) P.Sm[i * kColsPerSlice + lane] = (lane == kColsPerSlice - 1) ? hom : ((lane < P.ncol) ? sm : 0.0);
-    }
-}
-
-
 // ---------------------------------------------------------------------------------------------------------
-// Block-per-variant scan (the production kernel).  The warp-per-variant kernel above keeps ~10^4 columns in
-// flight at once (240 MB at n = 1e5), so its second sweep and the relatives' genotype look-ups miss L2 and the
-// column is fetched from HBM ~5x (ncu: 134 KB/variant).  Here a CTA owns one variant at a time: its 2-bit column is
-// brought into shared memory ONCE by a 1-D bulk copy (cp.async.bulk completing on an mbarrier), the next column is
-// prefetched into the second stage while this one is processed, both sweeps and every relative's genotype look-up
-// read shared memory, and only the per-sample kinship records / rows of Y (L2-resident, a few MB) are gathered
-// from global memory.  Variants are handed out by an atomic work counter (their cost varies >20x with allele
-// frequency); each variant's arithmetic is independent of which CTA runs it, so results stay bit-reproducible.
+// Block-per-variant scan.  (A warp-per-variant kernel reading global memory kept ~10^4 columns in flight, 240 MB at
+// n = 1e5, so every second sweep missed L2: ncu showed 134 KB/variant of DRAM traffic.)  A CTA owns one variant at a
+// time: its 2-bit column is brought into shared memory ONCE by a 1-D bulk copy (cp.async.bulk completing on an
+// mbarrier; optionally the next column is prefetched into a second stage), both sweeps and every relative's genotype
+// look-up read shared memory, and only kinship tables / rows of Y (L2-resident, a few MB) are gathered from global
+// memory.  Variants are handed out by an atomic work counter (their cost varies >20x with allele frequency); each
+// variant's arithmetic is independent of which CTA runs it, so results stay bit-reproducible.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kBlkWarps = 8;
 constexpr int kQueueCap = 96;            // per-warp queue of missing-sample positions; flushed when nearly full
@@ -667,12 +502,8 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
         const int64_t blocks = std::min<int64_t>(p, (int64_t)ctx->sm_count * per_sm);
         scan_block_kernel<<<(int)blocks, kBlkWarps * 32, smem, ctx->stream>>>(P, nstage, ctx->ctr.as<unsigned long long>());
     } else {
-        // columns too long for shared memory (n > ~9e5): warp-per-variant kernel reading global memory; the null
-        // model was then set up with every family on the generic path and the identity sample order
-        if (ns.tab_words > 0) { set_error("packed scan: stride %zu does not fit in shared memory", stride); return STAAR_ERR_ARG; }
-        int64_t blocks = std::min<int64_t>((p + kScanWarps - 1) / kScanWarps, (int64_t)ctx->sm_count * 8);
-        if (ns.nnz_offdiag > 0) scan_packed_kernel<true><<<(int)blocks, kScanWarps * 32, 0, ctx->stream>>>(P);
-        else scan_packed_kernel<false><<<(int)blocks, kScanWarps * 32, 0, ctx->stream>>>(P);
+        set_error("packed scan: a column of %zu bytes does not fit in shared memory (n > ~9e5): use the FP64 entry points", stride);
+        return STAAR_ERR_ARG;
     }
     ctx->launches++;
     STAAR_CUDA(cudaGetLastError());
