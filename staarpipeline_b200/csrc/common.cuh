@@ -70,13 +70,13 @@ struct NullSparse {
     int64_t kin_words = 0;            // 16-sample words [0, kin_words) hold every sample with kinship off-diagonals
     int64_t tab_words = 0;            // words [0, tab_words): table words; [tab_words, kin_words): generic families
     int64_t x_words = 0;              // words [0, x_words) additionally carry cross terms (families of 5..16 members)
-    uint32_t *gdesc = nullptr;        // 4 per table word: (table offset / 16) << 8 | code mask of the group's related slots
+    uint32_t *kmask = nullptr;        // per table word (padded to a multiple of 4 words): both bits of every related slot
     // cross term: value = code(word >> jshift2) * lut[off + ((word >> shift2) & mask)]
     struct KinTerm { uint32_t off; uint8_t shift2, mask, jshift2, pad; };
     struct WordDesc { uint32_t start, count; };
     WordDesc *wdesc = nullptr;        // x_words descriptors
     KinTerm *xterms = nullptr;
-    double *lut = nullptr;
+    double *lut = nullptr;            // group tables at stride 256: lut[((4 word + group) << 8) + codes]; then cross-term tables
     int64_t lut_entries = 0;
     SampleInfo *sinfo_p = nullptr;    // full kinship rows in null-model positions (missing related samples)
     double *diag_p = nullptr;         // Sigma_i[j,j] in null-model positions (n + 64 entries, zero padded)

@@ -58,7 +58,7 @@ void NullSparse::release()
     }
     if (permuted) cudaFree(Yp);
     cudaFree(diag); cudaFree(diag_p); cudaFree(sinfo_p); cudaFree(off_ent_p); cudaFree(relmask); cudaFree(rel); cudaFree(up_ent); cudaFree(Y);
-    cudaFree(Yfrag); cudaFree(Ytc); cudaFree(col_scale); cudaFree(col_total); cudaFree(perm); cudaFree(gdesc); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut);
+    cudaFree(Yfrag); cudaFree(Ytc); cudaFree(col_scale); cudaFree(col_total); cudaFree(perm); cudaFree(kmask); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut);
     *this = NullSparse();
 }
 void NullDense::release()
@@ -299,11 +299,13 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
     }
     // ---- table words: one look-up table per 4-sample group (all related pairs inside the group), and for words
     //      holding a family of more than 4 members the member x later-chunk terms ----------------------------
-    std::vector<uint32_t> gdesc((size_t)std::max<int64_t>(ns.tab_words, 1) * 4, 0u);   // (lut offset / 16) << 8 | code mask
+    std::vector<uint32_t> kmask((size_t)(ns.tab_words + 7) / 4 * 4, 0u);   // per table word: both bits of every related slot
     std::vector<NullSparse::WordDesc> wdesc((size_t)std::max<int64_t>(ns.x_words, 1));
     memset(wdesc.data(), 0, sizeof(NullSparse::WordDesc) * wdesc.size());
     std::vector<NullSparse::KinTerm> xterms;
-    std::vector<double> lut(256, 0.0);            // offset 0 = an all-zero table (groups without related pairs)
+    // group tables at a fixed stride: entry idx of group g (= 4 * word + group-in-word) lives at lut[(g << 8) + idx], so a
+    // look-up needs no descriptor; the member x chunk tables of the cross words follow
+    std::vector<double> lut((size_t)std::max<int64_t>(ns.tab_words, 1) * 4 * 256, 0.0);
     {
         auto codeval = [](int idx, int m) { const int c = (idx >> (2 * m)) & 3; return c == 3 ? 0.0 : (double)c; };
         // kinship entry between two positions (0 when unrelated)
@@ -327,19 +329,17 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
                 }
             }
             if (hi < 0) continue;                                    // only unrelated samples in this group
-            gdesc[g] = mask;                                         // table offset 0: the all-zero table
+            kmask[g >> 2] |= mask << (8 * (g & 3));
             if (!any_pair) continue;                                 // e.g. the lone last member of a 5-member family
             const int entries = 1 << (2 * (hi + 1));
-            if (lut.size() / 16 >= (1u << 24)) { set_error("kinship tables exceed 2^28 entries"); return STAAR_ERR_ARG; }
-            gdesc[g] |= (uint32_t)((lut.size() / 16) << 8);
             for (int idx = 0; idx < entries; idx++) {
                 double v = 0.0;
                 for (int m = 0; m <= hi; m++)
                     for (int m2 = m + 1; m2 <= hi; m2++) v += 2.0 * S[m][m2] * codeval(idx, m) * codeval(idx, m2);
-                lut.push_back(v);
+                lut[((size_t)g << 8) + idx] = v;
             }
-            while (lut.size() % 16) lut.push_back(0.0);
         }
+        if (lut.size() >= (1ull << 32) - (1u << 20)) { set_error("kinship tables exceed 2^32 entries"); return STAAR_ERR_ARG; }
         // cross terms of a family of 5..16 members: for every pair of chunks the LARGER chunk indexes a table
         // (<= 256 entries) per member of the smaller one:  sum_j code_j * T_j[codes of the other chunk]
         std::vector<std::vector<NullSparse::KinTerm>> word_terms((size_t)ns.x_words);
@@ -420,7 +420,7 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
         STAAR_TRY(upload_vec(ctx, &ns.diag_p, diag_p));
     }
     STAAR_TRY(upload_vec(ctx, &ns.off_ent_p, off_ent));
-    STAAR_TRY(upload_vec(ctx, &ns.gdesc, gdesc));
+    STAAR_TRY(upload_vec(ctx, &ns.kmask, kmask));
     STAAR_TRY(upload_vec(ctx, &ns.wdesc, wdesc));
     STAAR_TRY(upload_vec(ctx, &ns.xterms, xterms));
     STAAR_TRY(upload_vec(ctx, &ns.lut, lut));

@@ -29,7 +29,7 @@ struct ScanParams {
     const NullSparse::OffEntry *up_ent;    // all upper-triangle entries (rows with more than two)
     // table kinship path: families inside one 16-sample word
     int64_t tab_words, kin_words, x_words;
-    const uint32_t *gdesc;                 // 4 per table word: (table offset / 16) << 8 | code mask of related slots
+    const uint32_t *kmask;                 // per table word: both bits of every related slot
     const NullSparse::WordDesc *wdesc;
     const NullSparse::KinTerm *xterms;
     const double *lut;
@@ -277,52 +277,29 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         // (a) table words [0, tab_words): full words of real samples, four words per lane and step.  A lane only
         //     works on the words in which a group holds two related carriers (or, in a cross word, two anywhere):
         //     the codes of a 4-sample group index that group's table.
+        //     The kernel is latency-bound, so the look-ups of two words (8 groups) are issued together: the table of a
+        //     group sits at a fixed stride (no descriptor fetch in front of it) and the related-slot masks of a lane's four
+        //     words are one 128-bit load issued before anything else.
         for (int k0 = wib * 32; k0 < tab_vec; k0 += kBlkWarps * 32) {
             const int k = k0 + lane;
-            uint4 q4 = make_uint4(0u, 0u, 0u, 0u);
-            if (k < tab_vec) q4 = v4[k];
-            const uint32_t wv[4] = {q4.x, q4.y, q4.z, q4.w};
+            uint4 q4 = make_uint4(0u, 0u, 0u, 0u), km4 = make_uint4(0u, 0u, 0u, 0u);
+            if (k < tab_vec) { km4 = __ldg(reinterpret_cast<const uint4 *>(P.kmask) + k); q4 = v4[k]; }
+            const uint32_t wv[4] = {q4.x, q4.y, q4.z, q4.w}, kmv[4] = {km4.x, km4.y, km4.z, km4.w};
+            uint32_t wzv[4], twov[4];
+            bool crossv[4];
 #pragma unroll
             for (int wi = 0; wi < 4; wi++) {
                 const int kw = 4 * k + wi;
-                if (kw >= tab_words) continue;
-                const uint32_t w = wv[wi];
+                const uint32_t w = wv[wi], km = kmv[wi];             // km == 0 beyond the table words
                 const uint32_t lo = w & 0x55555555u;
                 const uint32_t mis = lo & (w >> 1);
                 const uint32_t wf = w ^ ((~lo & flipmask) << 1);     // g -> 2 - g on the codes 0 and 2
-                // cheap pre-test before touching the descriptors: a table look-up needs two carriers in one 4-sample
-                // group (bit 7 of every byte guards the borrow: non-zero byte <=> >= 2 carriers), a cross term two carriers
-                // anywhere in the word, the slow path a missing sample — most words of a rare variant have none of these
-                const uint32_t nm = wf & ~(mis * 3u);
-                const uint32_t car = (nm | (nm >> 1)) & 0x55555555u;
-                const bool maybe = (car & ((car | 0x80808080u) - 0x01010101u)) != 0u ||
-                                   (kw < x_words && (car & (car - 1u)) != 0u) || (rq_over && mis != 0u);
-                if (!maybe) continue;
-                const uint4 gd = __ldg(reinterpret_cast<const uint4 *>(P.gdesc) + kw);
-                const uint32_t km = __byte_perm(__byte_perm(gd.x, gd.y, 0x0040), __byte_perm(gd.z, gd.w, 0x0040), 0x5410);
-                const uint32_t wz = nm & km;                         // related, non-missing codes (tables hold such pairs)
-                const uint32_t hit = car & km;                       // carriers: bits 0,2,4,6 of every group byte
-                const uint32_t two = hit & ((hit | 0x80808080u) - 0x01010101u);
-                const bool cross = kw < x_words && (hit & (hit - 1u)) != 0u;   // >= 2 carriers anywhere in a cross word
-                if (two != 0u || cross) {
-                    const uint32_t g4[4] = {gd.x, gd.y, gd.z, gd.w};
-#pragma unroll
-                    for (int g = 0; g < 4; g++) {                    // entry 0 of the table at offset 0 is 0.0
-                        const uint32_t idx = (wz >> (8 * g)) & 0xffu;
-                        const uint32_t off = (two & (0xffu << (8 * g))) ? (g4[g] >> 8) * 16u + idx : 0u;
-                        quad += __ldg(P.lut + off);
-                    }
-                    if (cross) {                                     // families of 5..16 members: member x other chunk
-                        const uint2 wd = __ldg(reinterpret_cast<const uint2 *>(P.wdesc) + kw);
-                        const uint2 *tp = reinterpret_cast<const uint2 *>(P.xterms) + wd.x;
-                        for (uint32_t t = 0; t < wd.y; t++) {
-                            const uint2 tr = __ldg(tp + t);
-                            const uint32_t idx = (wz >> (tr.y & 0xffu)) & ((tr.y >> 8) & 0xffu);
-                            const uint32_t gj = (wz >> ((tr.y >> 16) & 0xffu)) & 3u;
-                            if (gj != 0u && idx != 0u) quad += (double)gj * __ldg(P.lut + tr.x + idx);
-                        }
-                    }
-                }
+                const uint32_t wz = wf & ~(mis * 3u) & km;           // related, non-missing codes (tables hold such pairs)
+                const uint32_t hit = (wz | (wz >> 1)) & 0x55555555u; // carriers: bits 0,2,4,6 of every group byte
+                // per byte: clear the lowest carrier bit (bit 7 guards the borrow): non-zero byte <=> >= 2 carriers in the group
+                twov[wi] = hit & ((hit | 0x80808080u) - 0x01010101u);
+                crossv[wi] = kw < x_words && (hit & (hit - 1u)) != 0u;   // >= 2 carriers anywhere in a cross word
+                wzv[wi] = wz;
                 if (rq_over && !mu_zero) {                           // slow path: the position queues overflowed
                     uint32_t mk = mis & km;
                     if (mk) {
@@ -335,6 +312,36 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
                     }
                 }
             }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (!__any_sync(0xffffffffu, (twov[2 * h] | twov[2 * h + 1]) != 0u)) continue;
+                double v[2][4];
+#pragma unroll
+                for (int wj = 0; wj < 2; wj++) {
+                    const int wi = 2 * h + wj;
+                    const uint32_t gbase = (uint32_t)(4 * (4 * k + wi)) << 8;
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        v[wj][g] = 0.0;
+                        if (twov[wi] & (0xffu << (8 * g))) v[wj][g] = __ldg(P.lut + gbase + (g << 8) + ((wzv[wi] >> (8 * g)) & 0xffu));
+                    }
+                }
+                quad += ((v[0][0] + v[0][1]) + (v[0][2] + v[0][3])) + ((v[1][0] + v[1][1]) + (v[1][2] + v[1][3]));
+            }
+#pragma unroll
+            for (int wi = 0; wi < 4; wi++)
+                if (crossv[wi]) {                                    // families of 5..16 members: member x other chunk
+                    const int kw = 4 * k + wi;
+                    const uint32_t wz = wzv[wi];
+                    const uint2 wd = __ldg(reinterpret_cast<const uint2 *>(P.wdesc) + kw);
+                    const uint2 *tp = reinterpret_cast<const uint2 *>(P.xterms) + wd.x;
+                    for (uint32_t t = 0; t < wd.y; t++) {
+                        const uint2 tr = __ldg(tp + t);
+                        const uint32_t idx = (wz >> (tr.y & 0xffu)) & ((tr.y >> 8) & 0xffu);
+                        const uint32_t gj = (wz >> ((tr.y >> 16) & 0xffu)) & 3u;
+                        if (gj != 0u && idx != 0u) quad += (double)gj * __ldg(P.lut + tr.x + idx);
+                    }
+                }
         }
         if (!rq_over && !mu_zero && rn > 0) {                        // missing samples queued in sweep 1 (this warp's)
             const double mu = mu_of();
@@ -477,7 +484,7 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     ScanParams P;
     P.packed = d_packed; P.stride = stride; P.n = n; P.p = p; P.impute = impute;
     P.relmask = ns.relmask; P.rel = ns.rel; P.up_ent = ns.up_ent;
-    P.tab_words = ns.tab_words; P.kin_words = ns.kin_words; P.x_words = ns.x_words; P.gdesc = ns.gdesc; P.wdesc = ns.wdesc;
+    P.tab_words = ns.tab_words; P.kin_words = ns.kin_words; P.x_words = ns.x_words; P.kmask = ns.kmask; P.wdesc = ns.wdesc;
     P.xterms = ns.xterms; P.lut = ns.lut; P.sinfo = ns.sinfo_p; P.off_ent = ns.off_ent_p; P.diag = ns.diag_p;
     P.Y = ns.Yp; P.ldY = ns.ldY; P.ncol = (int)ns.q + 2;
     P.codesum = d_lo;
