@@ -494,10 +494,11 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
                          sizeof(double) * (kBlkWarps * kColsPerSlice + 2 * kBlkWarps) + sizeof(int) * 4 * kBlkWarps + 64;
     const size_t smem_max = 227 * 1024;
     // The kernel is latency-bound (dependent gathers between block barriers), so resident warps matter more than
-    // overlapping the column copy: two stages only when they still leave >= 6 CTAs per SM (measured: 9.8 -> 7.9 ms).
-    static const int force = getenv("STAAR_B200_SCAN_STAGES") ? atoi(getenv("STAAR_B200_SCAN_STAGES")) : 0;   // tuning experiments
+    // overlapping the column copy: one column stage (measured at n = 1e5: 6.76 ms vs 7.13 ms with two stages per
+    // 250 k variants); STAAR_B200_SCAN_STAGES=2 forces the double-buffered variant for experiments.
+    static const int force = getenv("STAAR_B200_SCAN_STAGES") ? atoi(getenv("STAAR_B200_SCAN_STAGES")) : 0;
     int nstage = (stride + extra <= smem_max) ? 1 : 0;
-    if (nstage == 1 && (force == 2 || (force == 0 && 6 * (2 * stride + extra + 1024) <= 228 * 1024)) && 2 * stride + extra <= smem_max) nstage = 2;
+    if (nstage == 1 && force == 2 && 2 * stride + extra <= smem_max) nstage = 2;
     if (nstage > 0) {
         const size_t smem = (size_t)nstage * stride + extra;
         STAAR_CUDA(cudaFuncSetAttribute(scan_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
