@@ -208,15 +208,25 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
         const uint8_t *rowp = packed + (size_t)(rok ? v : 0) * stride + kHalfBytes * half;
         uint8_t *slot0 = sG + (size_t)row * kSlot + kHalfBytes * half;
         int fetch_slot = 0;                                                  // ring slot of the next k-block to fetch
+        const uint8_t *gsrc = rowp;                                          // this thread's bytes of the next k-block
+        // k-blocks whose kHalfBytes of this thread lie entirely inside the column: plain copies, no predicates
+        const int64_t full_blocks = rok ? (int64_t)((stride - (size_t)kHalfBytes * half) / (2 * kHalfBytes)) : 0;
         auto fetch = [&](int64_t kb) {                                       // raw bytes of k-block kb -> ring slot
             uint8_t *dst = slot0 + (size_t)fetch_slot * (kTcRows * kSlot);
             fetch_slot = fetch_slot + 1 == kRing ? 0 : fetch_slot + 1;
-            const size_t off = (size_t)kb * (2 * kHalfBytes);
+            if (kb < full_blocks) {
 #pragma unroll
-            for (int c = 0; c < kHalfBytes / 16; c++) {
-                const bool ok = rok && off + kHalfBytes * half + 16 * c + 16 <= stride;
-                cp_async16(dst + 16 * c, ok ? rowp + off + 16 * c : packed, ok ? 16u : 0u);   // zero fill outside the column
+                for (int c = 0; c < kHalfBytes / 16; c++)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_addr(dst + 16 * c)), "l"(gsrc + 16 * c) : "memory");
+            } else {
+                const size_t off = (size_t)kb * (2 * kHalfBytes);
+#pragma unroll
+                for (int c = 0; c < kHalfBytes / 16; c++) {
+                    const bool ok = rok && off + kHalfBytes * half + 16 * c + 16 <= stride;
+                    cp_async16(dst + 16 * c, ok ? gsrc + 16 * c : packed, ok ? 16u : 0u);   // zero fill outside the column
+                }
             }
+            gsrc += 2 * kHalfBytes;
         };
         for (int64_t kb = 0; kb < kRing - 1; kb++) {
             if (kb < n_kblocks) fetch(kb);
@@ -242,7 +252,9 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
                 w[4 * c] = q.x; w[4 * c + 1] = q.y; w[4 * c + 2] = q.z; w[4 * c + 3] = q.w;
             }
 #pragma unroll
-            for (int c = 0; c < kHalfCols; c++) x[c] = (w[c >> 2] >> (2 * (c & 3))) & 0x03030303u;
+            // right shifts as IMAD.HI (w * 2^(32-s) >> 32) run on the FMA pipe, leaving the ALU pipe the masks only
+            for (int c = 0; c < kHalfCols; c++)
+                x[c] = ((c & 3) == 0 ? w[c >> 2] : __umulhi(w[c >> 2], 1u << (32 - 2 * (c & 3)))) & 0x03030303u;
         };
         if (n_kblocks > 0) expand(0);
         int sa = 0;
