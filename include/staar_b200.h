@@ -196,6 +196,18 @@ int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t st
                               int impute, double *d_AF, double *d_MAF, double *d_Score, double *d_Score_se,
                               double *d_pvalue_log, double *d_Est, double *d_Est_se);
 
+/* One region of the single-variant driver on resident columns (R/Individual_Analysis.R:164-450 without the GDS I/O):
+ * flip/impute + score test for all p variants, then the driver's filter on the device — a variant is kept when
+ * MAF > (mac_cutoff - 0.5)/n/2 (:242, :324; mac_cutoff = 20 by default, :45) — and the kept rows are compacted in
+ * variant order into the caller's DEVICE arrays (capacity p each): d_index (variant number within the block) and the
+ * seven statistics.  If d_spa_index is not NULL it receives, for binary traits analysed with SPA, the rows OF THE
+ * COMPACTED TABLE with exp(-pvalue_log) < spa_p_cutoff (:290-297; 0.05 in the reference).  Synchronous; the counts
+ * come back in *n_tested / *n_spa. */
+int staar_packed_analysis_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride_bytes, int64_t n, int64_t p,
+                                 int impute, double mac_cutoff, double spa_p_cutoff, int64_t *d_index, double *d_AF,
+                                 double *d_MAF, double *d_Score, double *d_Score_se, double *d_pvalue_log, double *d_Est,
+                                 double *d_Est_se, int64_t *d_spa_index, int64_t *n_tested, int64_t *n_spa);
+
 /* Per-kernel device times of the LAST staar_packed_score_device call, measured with CUDA events on the context
  * stream when profiling is on: ms[0] = scan (K1+K3), ms[1] = contraction (K2), ms[2] = finalize (K5).
  * Used by bench.py for the live roofline figure; off by default (no events recorded). */

@@ -326,6 +326,15 @@ class Context:
         self._call("staar_packed_score_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n), C.c_int64(p),
                    C.c_int(impute), *[C.c_void_p(x) for x in d_out7])
 
+    def packed_analysis_device(self, d_packed: int, stride: int, n: int, p: int, impute: int, mac_cutoff: float,
+                               spa_p_cutoff: float, d_index: int, d_out7, d_spa_index: int = 0):
+        """resident columns -> compacted table of the tested variants (device pointers); returns (n_tested, n_spa)"""
+        nt, ns = C.c_int64(0), C.c_int64(0)
+        self._call("staar_packed_analysis_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n), C.c_int64(p),
+                   C.c_int(impute), C.c_double(mac_cutoff), C.c_double(spa_p_cutoff), C.c_void_p(d_index),
+                   *[C.c_void_p(x) for x in d_out7], C.c_void_p(d_spa_index or None), C.byref(nt), C.byref(ns))
+        return nt.value, ns.value
+
     def packed_flip_stats_device(self, d_packed: int, stride: int, n: int, p: int, impute: int, d_AF: int, d_MAF: int,
                                  d_flip: int, d_nmiss: int):
         self._call("staar_packed_flip_stats_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n),

@@ -612,6 +612,37 @@ int staar_packed_score_host(staar_ctx *ctx, const uint8_t *packed, size_t stride
     return sync(ctx);
 }
 
+int staar_packed_analysis_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
+                                 double mac_cutoff, double spa_p_cutoff, int64_t *d_index, double *d_AF, double *d_MAF,
+                                 double *d_Score, double *d_Score_se, double *d_pl, double *d_Est, double *d_Est_se,
+                                 int64_t *d_spa_index, int64_t *n_tested, int64_t *n_spa)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    if (!n_tested) { set_error("packed_analysis: n_tested is NULL"); return STAAR_ERR_ARG; }
+    // all variants first (scratch), then the driver's filter: MAF > (mac_cutoff - 0.5)/n/2  (R/Individual_Analysis.R:242,324)
+    STAAR_TRY(ctx->out.reserve(sizeof(double) * 7 * (size_t)std::max<int64_t>(p, 1) + 4 * sizeof(long long)));
+    double *o = ctx->out.as<double>();
+    long long *d_tot = reinterpret_cast<long long *>(o + 7 * (size_t)std::max<int64_t>(p, 1));
+    STAAR_TRY(staar_packed_score_device(ctx, d_packed, stride, n, p, impute, o, o + p, o + 2 * p, o + 3 * p, o + 4 * p,
+                                        o + 5 * p, o + 6 * p));
+    const double *in7[7] = {o, o + p, o + 2 * p, o + 3 * p, o + 4 * p, o + 5 * p, o + 6 * p};
+    double *out7[7] = {d_AF, d_MAF, d_Score, d_Score_se, d_pl, d_Est, d_Est_se};
+    long long *sel = reinterpret_cast<long long *>(d_spa_index);
+    if (!sel) {                                  // no SPA stage requested: selection goes to scratch and is ignored
+        STAAR_TRY(ctx->tmp2.reserve(sizeof(long long) * (size_t)std::max<int64_t>(p, 1)));
+        sel = ctx->tmp2.as<long long>();
+    }
+    STAAR_TRY(launch_compact_results(ctx, p, in7, (mac_cutoff - 0.5) / (double)n / 2.0, d_spa_index ? spa_p_cutoff : 0.0,
+                                     reinterpret_cast<long long *>(d_index), out7, sel, d_tot));
+    long long tot[2] = {0, 0};
+    STAAR_TRY(d2h(ctx, tot, d_tot, sizeof tot));
+    STAAR_TRY(sync(ctx));
+    *n_tested = tot[0];
+    if (n_spa) *n_spa = tot[1];
+    return STAAR_OK;
+}
+
 int staar_nullmodel_sample_order(staar_ctx *ctx, int64_t n, int32_t *order)
 {
     CHECK_CTX(ctx);

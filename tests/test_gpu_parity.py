@@ -152,6 +152,39 @@ def test_packed_score_vs_oracle(gpu_ctx, oracle, n, p, q, related, impute):
     assert zero.any() and np.array_equal(got["Score_se"] == 0, zero)
 
 
+def test_packed_analysis_filter_and_compaction(gpu_ctx, oracle):
+    """The driver's MAF/MAC filter and SPA pre-filter on the device == the same filter applied on the host to the
+    unfiltered results (R/Individual_Analysis.R:242,324,290-297); stable order, exact copies."""
+    import torch
+    from staarpipeline_b200 import api
+    from staarpipeline_b200 import synth
+    n, p, q = 2000, 3000, 5
+    nm = synth.nullmodel_sparse_grm(n, seed=9, q=q, shuffle=True)
+    G0 = cases.raw_dosage(n, p, 9)
+    packed = synth.pack_codes(np.asfortranarray(np.where(np.isnan(G0) | (G0 <= -1), 3, G0).astype(np.uint8)))
+    gpu_ctx.set_nullmodel_sparse(nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+    full = gpu_ctx.packed_score_host(packed, n, api.IMPUTE_MEAN)
+    dev = torch.device("cuda:0")
+    P, stride = packed.shape
+    d_in = torch.from_numpy(packed).to(dev); d_cols = torch.zeros_like(d_in)
+    torch.cuda.synchronize()
+    gpu_ctx.packed_reorder_device(d_in.data_ptr(), d_cols.data_ptr(), stride, n, P)
+    idx = torch.full((P,), -1, dtype=torch.int64, device=dev); sel = torch.full((P,), -1, dtype=torch.int64, device=dev)
+    outs = torch.zeros((7, P), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    mac_cutoff, pcut = 20.0, 0.05
+    nt, nsel = gpu_ctx.packed_analysis_device(d_cols.data_ptr(), stride, n, P, api.IMPUTE_MEAN, mac_cutoff, pcut,
+                                              idx.data_ptr(), [outs[i].data_ptr() for i in range(7)], sel.data_ptr())
+    keep = full["MAF"] > (mac_cutoff - 0.5) / n / 2
+    assert 0 < keep.sum() < P and nt == keep.sum()
+    assert np.array_equal(idx.cpu().numpy()[:nt], np.flatnonzero(keep))
+    res = outs.cpu().numpy()
+    for i, k in enumerate(("AF", "MAF", "Score", "Score_se", "pvalue_log", "Est", "Est_se")):
+        assert np.array_equal(res[i, :nt], full[k][keep], equal_nan=True), k
+    want_sel = np.flatnonzero(np.exp(-full["pvalue_log"][keep]) < pcut)
+    assert nsel == want_sel.size and np.array_equal(sel.cpu().numpy()[:nsel], want_sel)
+
+
 def test_packed_kinship_paths(gpu_ctx, oracle):
     """Kinship term of the packed path on every route: table families (sizes 2-16, chunked above 4), a family of more
     than 16 members (generic record path), heavy missingness among relatives, mean and minor imputation."""
