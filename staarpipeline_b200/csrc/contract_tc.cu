@@ -12,25 +12,28 @@
 //   the scan kernel's sparse sweep instead.)
 //   * B (digits) is pre-arranged at null-model set-up in the canonical K-major, non-swizzled core-matrix layout, so a
 //     512-sample k-block (56 KiB) is ONE cp.async.bulk from L2 into a 2-stage shared-memory ring (mbarrier tx-count).
-//   * A (genotypes) never exists as int8 in memory: two "expander" threads own each variant row (half a k-block
-//     each), stream the 2-bit column HBM -> shared memory with cp.async (3 k-blocks ahead), expand 2-bit -> int8 with shift/mask in
-//     registers (no flip, no missing fix-up: both are applied analytically by the finaliser) and writes the int8 tile
-//     straight into TMEM with tcgen05.st; the MMA reads A from TMEM (".ts" form), so shared-memory bandwidth is
-//     spent on B only.
+//   * A (genotypes) never exists as int8 in memory.  The raw 2-bit tile of a k-block (128 variant rows x 128 bytes) is
+//     one TMA tensor load (cp.async.bulk.tensor.2d, 128-byte swizzle, zero fill outside the matrix) into a 4-stage
+//     ring — a per-thread copy of row-strided 16-byte pieces costs one L1 wavefront per lane and was the measured
+//     bottleneck.  Two "expander" threads own each variant row (half a k-block each): they read their row from the
+//     swizzled tile (conflict-free 128-bit LDS), expand 2-bit -> int8 with shift/mask in registers (no flip, no
+//     missing fix-up: both are applied analytically by the finaliser) and write the int8 tile straight into TMEM with
+//     tcgen05.st; the MMA reads A from TMEM (".ts" form), so shared-memory bandwidth is spent on B only.
 //   * One elected thread issues the MMAs; tcgen05.commit releases the A (TMEM) and B (smem) stages to the expanders and
 //     the bulk-copy producer through mbarriers; the expander warps read the accumulators back with tcgen05.ld and
 //     recombine the 7 digit sums per (variant, column) in 64-bit integers.
 // Roles: warps 0-7 expanders + epilogue (TMEM lane quarter = warp id % 4, k-block half = warp id / 4), warp 8 MMA issuer
-// + TMEM allocator, warp 9 bulk-copy producer.  Every genotype byte is read from HBM exactly once per launch.
+// + TMEM allocator, warp 9 digit producer (bulk copies), warp 10 genotype producer (tensor loads).  Every genotype byte is read from HBM exactly once per launch.
 #include "common.cuh"
 #include "packed.cuh"
+#include <cuda.h>            // CUtensorMap and the cuTensorMapEncodeTiled prototype (resolved at run time, no -lcuda)
 
 namespace staar {
 
 namespace {
 
 constexpr int kTcRows = 128;                 // variants per CTA
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 352;              // 8 expander warps + MMA issuer + digit producer + genotype producer
 constexpr int kExpThreads = 256;             // 8 expander warps
 // A k-block is the unit of every hand-off (expanders -> MMA issuer -> expanders, producer -> MMA issuer): its fixed
 // cost (two mbarrier waits of ~90 clk each in the single issuing thread, fences, commits) is amortised over kKS
@@ -43,8 +46,10 @@ constexpr int kStagesA = 3;                  // TMEM stages of the expanded A ti
 constexpr int kStagesB = 2;                  // shared-memory stages of the digit operand
 constexpr int kStepBytes = 2 * 14 * 128;     // one k-step: 2 k-chunks x 14 row groups x (8 rows x 16 B)
 constexpr int kTcBlockBytes = kKS * kStepBytes;
-constexpr int kRing = 5;                     // ring of raw genotype slices per row (cp.async), kRing - 1 k-blocks ahead
-constexpr int kSlot = 2 * kHalfBytes + 16;   // + 16 B pad: conflict-free 128-bit reads of one's own slot
+constexpr int kRing = 4;                     // stages of raw genotype tiles (TMA)
+constexpr int kRowBytes = kTcSamples / 4;    // raw bytes of one variant row per k-block: the TMA box is kRowBytes x 128 rows
+constexpr int kTileBytes = kRowBytes * 128;
+static_assert(kRowBytes == 128, "the 128-byte swizzle of the tensor load assumes 128-byte rows");
 static_assert(kColsPerSlice * kSlices == 112 && 112 + kStagesA * 8 * kKS <= 512, "TMEM budget");
 constexpr int kColD = 0, kColA = 128;        // TMEM columns: accumulators [0,112), A stages from 128
 
@@ -93,10 +98,6 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_addr(dst)),
                  "l"(src), "r"(bytes), "r"(s_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void *dst, const void *src, uint32_t src_bytes)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s_addr(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -170,16 +171,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8])
 
 // grid = ceil(p / 128); out_hi / out_lo: p x 16 int64, X = hi * 2^24 + lo
 __global__ void __launch_bounds__(kTcThreads, 1)
-contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p, const int8_t *__restrict__ Ytc,
+contract_tc_kernel(const __grid_constant__ CUtensorMap gmap, int64_t p, const int8_t *__restrict__ Ytc,
                    int64_t n_kblocks, long long *__restrict__ out_hi, long long *__restrict__ out_lo)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *sB = smem;                                                       // kStagesB x kTcBlockBytes
-    uint8_t *sG = smem + (size_t)kStagesB * kTcBlockBytes;                     // kRing x 128 x kSlot
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sG + (size_t)kRing * kTcRows * kSlot);
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *sG = smem;                                                       // kRing x kTileBytes (1024-byte aligned: swizzle)
+    uint8_t *sB = smem + (size_t)kRing * kTileBytes;                           // kStagesB x kTcBlockBytes
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)kStagesB * kTcBlockBytes);
     uint64_t *a_full = bars, *a_empty = bars + kStagesA;
     uint64_t *b_full = bars + 2 * kStagesA, *b_empty = b_full + kStagesB;
-    uint64_t *d_full = b_empty + kStagesB;
+    uint64_t *g_full = b_empty + kStagesB, *g_empty = g_full + kRing;
+    uint64_t *d_full = g_empty + kRing;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -188,6 +190,7 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStagesA; s++) { bar_init(&a_full[s], kExpThreads); bar_init(&a_empty[s], 1); }
         for (int s = 0; s < kStagesB; s++) { bar_init(&b_full[s], 1); bar_init(&b_empty[s], 1); }
+        for (int s = 0; s < kRing; s++) { bar_init(&g_full[s], 1); bar_init(&g_empty[s], kExpThreads); }
         bar_init(d_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -205,33 +208,6 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
         const int row = threadIdx.x & (kTcRows - 1), half = threadIdx.x >> 7;   // TMEM lane quarter = warp % 4
         const int64_t v = (int64_t)blockIdx.x * kTcRows + row;
         const bool rok = v < p;
-        const uint8_t *rowp = packed + (size_t)(rok ? v : 0) * stride + kHalfBytes * half;
-        uint8_t *slot0 = sG + (size_t)row * kSlot + kHalfBytes * half;
-        int fetch_slot = 0;                                                  // ring slot of the next k-block to fetch
-        const uint8_t *gsrc = rowp;                                          // this thread's bytes of the next k-block
-        // k-blocks whose kHalfBytes of this thread lie entirely inside the column: plain copies, no predicates
-        const int64_t full_blocks = rok ? (int64_t)((stride - (size_t)kHalfBytes * half) / (2 * kHalfBytes)) : 0;
-        auto fetch = [&](int64_t kb) {                                       // raw bytes of k-block kb -> ring slot
-            uint8_t *dst = slot0 + (size_t)fetch_slot * (kTcRows * kSlot);
-            fetch_slot = fetch_slot + 1 == kRing ? 0 : fetch_slot + 1;
-            if (kb < full_blocks) {
-#pragma unroll
-                for (int c = 0; c < kHalfBytes / 16; c++)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_addr(dst + 16 * c)), "l"(gsrc + 16 * c) : "memory");
-            } else {
-                const size_t off = (size_t)kb * (2 * kHalfBytes);
-#pragma unroll
-                for (int c = 0; c < kHalfBytes / 16; c++) {
-                    const bool ok = rok && off + kHalfBytes * half + 16 * c + 16 <= stride;
-                    cp_async16(dst + 16 * c, ok ? gsrc + 16 * c : packed, ok ? 16u : 0u);   // zero fill outside the column
-                }
-            }
-            gsrc += 2 * kHalfBytes;
-        };
-        for (int64_t kb = 0; kb < kRing - 1; kb++) {
-            if (kb < n_kblocks) fetch(kb);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         // Software pipeline: the int8 tile of k-block kb+1 is expanded into registers while the TMEM stores of k-block
         // kb are still in flight; only then does the thread wait for them and publish stage kb to the MMA issuer.
@@ -239,18 +215,21 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
         // (c & 3) of word 2 ks + (c >> 2); the digit operand is laid out with the same map (build_tc_operand).
         uint32_t x[kHalfCols];
         int ring_slot = 0;                                                   // kb % kRing, kept incrementally (no 64-bit %)
-        auto expand = [&](int64_t kb) {
-            if (kb + kRing - 1 < n_kblocks) fetch(kb + kRing - 1);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group %0;" ::"n"(kRing - 1) : "memory");
-            const uint4 *src = reinterpret_cast<const uint4 *>(slot0 + (size_t)ring_slot * (kTcRows * kSlot));
-            ring_slot = ring_slot + 1 == kRing ? 0 : ring_slot + 1;
+        uint32_t g_par = 0u;                                                 // parity to wait for on g_full[ring_slot]
+        // this thread's row of the swizzled tile: logical 16-byte chunk c sits at physical chunk c ^ (row & 7)
+        const uint8_t *my_row = sG + (size_t)row * kRowBytes;
+        auto expand = [&](int64_t) {
+            bar_wait(&g_full[ring_slot], g_par);                             // the tensor load of this k-block has landed
+            const uint8_t *rowp = my_row + (size_t)ring_slot * kTileBytes;
             uint32_t w[kHalfBytes / 4];
 #pragma unroll
             for (int c = 0; c < kHalfBytes / 16; c++) {
-                const uint4 q = src[c];
+                const int chunk = (half * (kHalfBytes / 16) + c) ^ (row & 7);
+                const uint4 q = *reinterpret_cast<const uint4 *>(rowp + 16 * chunk);
                 w[4 * c] = q.x; w[4 * c + 1] = q.y; w[4 * c + 2] = q.z; w[4 * c + 3] = q.w;
             }
+            bar_arrive(&g_empty[ring_slot]);                                 // words are in registers: the stage may be refilled
+            if (++ring_slot == kRing) { ring_slot = 0; g_par ^= 1u; }
 #pragma unroll
             // right shifts as IMAD.HI (w * 2^(32-s) >> 32) run on the FMA pipe, leaving the ALU pipe the masks only
             for (int c = 0; c < kHalfCols; c++)
@@ -338,7 +317,7 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
             tc_commit(d_full);
         }
         __syncwarp();
-    } else {
+    } else if (warp == kProdWarp) {
         // ===================================================================== digit producer (one thread)
         if (lane == 0) {
             int sb = 0;
@@ -348,6 +327,22 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
                 bar_expect_tx(&b_full[sb], kTcBlockBytes);
                 bulk_load(sB + (size_t)sb * kTcBlockBytes, Ytc + (size_t)kb * kTcBlockBytes, kTcBlockBytes, &b_full[sb]);
                 if (++sb == kStagesB) { sb = 0; b_par ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================================================================== genotype producer (one thread)
+        if (lane == 0) {
+            int sg = 0;
+            uint32_t g_par = 1u;
+            const int32_t row0 = (int32_t)(blockIdx.x * kTcRows);
+            for (int64_t kb = 0; kb < n_kblocks; kb++) {
+                bar_wait(&g_empty[sg], g_par);                               // raw genotype tile: rows row0.., bytes kb * 128..
+                bar_expect_tx(&g_full[sg], kTileBytes);
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(s_addr(sG + (size_t)sg * kTileBytes)), "l"(&gmap), "r"((int32_t)(kb * kRowBytes)), "r"(row0),
+                               "r"(s_addr(&g_full[sg])) : "memory");
+                if (++sg == kRing) { sg = 0; g_par ^= 1u; }
             }
         }
         __syncwarp();
@@ -361,6 +356,33 @@ contract_tc_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t p,
 
 }  // namespace
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+static int encode_genotype_map(CUtensorMap *map, const uint8_t *d_packed, size_t stride, int64_t p)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        STAAR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return STAAR_ERR_CUDA; }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    // rank-2 byte tensor: dim 0 = bytes of a column (stride), dim 1 = variants; box = 128 bytes x 128 variants;
+    // reads beyond either extent are zero-filled (missing rows of the last tile, the tail of the last k-block)
+    const cuuint64_t dims[2] = {(cuuint64_t)stride, (cuuint64_t)p};
+    const cuuint64_t strides[1] = {(cuuint64_t)stride};
+    const cuuint32_t box[2] = {(cuuint32_t)kRowBytes, (cuuint32_t)kTcRows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(d_packed), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d): packed base must be 16-byte aligned", (int)r); return STAAR_ERR_CUDA; }
+    return STAAR_OK;
+}
+
 int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, long long *d_hi,
                        long long *d_lo)
 {
@@ -368,14 +390,16 @@ int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     const NullSparse &ns = ctx->ns;
     if (!ns.sliced || !ns.Ytc) { set_error("packed contraction: sliced operand not built (q > 13?)"); return STAAR_ERR_STATE; }
     const int64_t n_kblocks = (n + kTcSamples - 1) / kTcSamples;
-    const size_t smem = (size_t)kStagesB * kTcBlockBytes + (size_t)kRing * kTcRows * kSlot + 32 * sizeof(uint64_t);
+    const size_t smem = (size_t)kRing * kTileBytes + (size_t)kStagesB * kTcBlockBytes + 32 * sizeof(uint64_t);
     static bool attr_set = false;
     if (!attr_set) {
         STAAR_CUDA(cudaFuncSetAttribute(contract_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
+    CUtensorMap gmap;
+    STAAR_TRY(encode_genotype_map(&gmap, d_packed, stride, p));
     const int64_t tiles = (p + kTcRows - 1) / kTcRows;
-    contract_tc_kernel<<<(unsigned)tiles, kTcThreads, smem, ctx->stream>>>(d_packed, stride, p, ns.Ytc, n_kblocks, d_hi, d_lo);
+    contract_tc_kernel<<<(unsigned)tiles, kTcThreads, smem, ctx->stream>>>(gmap, p, ns.Ytc, n_kblocks, d_hi, d_lo);
     ctx->launches++;
     STAAR_CUDA(cudaGetLastError());
     return STAAR_OK;
