@@ -587,16 +587,13 @@ int staar_ctx_last_stage_ms(staar_ctx *ctx, float ms[3])
     return STAAR_OK;
 }
 
-int staar_packed_score_host(staar_ctx *ctx, const uint8_t *packed, size_t stride, int64_t n, int64_t p, int impute,
-                            double *AF, double *MAF, double *Score, double *Score_se, double *pl, double *Est,
-                            double *Est_se)
+namespace staar {
+namespace {
+// caller-order packed columns already in ctx->pk: re-order into the resident layout, score, copy the 7 arrays out
+int score_from_pk(staar_ctx *ctx, size_t stride, int64_t n, int64_t p, int impute, double *AF, double *MAF, double *Score,
+                  double *Score_se, double *pl, double *Est, double *Est_se)
 {
-    CHECK_CTX(ctx);
-    STAAR_TRY(check_dims(n, p));
     NullSparse &ns = ctx->ns;
-    if (!ns.set) { set_error("packed score: call staar_nullmodel_set_sparse first"); return STAAR_ERR_STATE; }
-    STAAR_TRY(ctx->pk.reserve(stride * (size_t)std::max<int64_t>(p, 1)));
-    STAAR_TRY(h2d(ctx, ctx->pk.p, packed, stride * (size_t)p));
     const uint8_t *d_cols = ctx->pk.as<uint8_t>();
     if (ns.permuted) {      // host columns are in the caller's sample order: re-order into the resident layout
         STAAR_TRY(ctx->pk2.reserve(stride * (size_t)std::max<int64_t>(p, 1)));
@@ -610,6 +607,21 @@ int staar_packed_score_host(staar_ctx *ctx, const uint8_t *packed, size_t stride
     double *dst[7] = {AF, MAF, Score, Score_se, pl, Est, Est_se};
     for (int a = 0; a < 7; a++) STAAR_TRY(d2h(ctx, dst[a], o + (size_t)a * p, sizeof(double) * p));
     return sync(ctx);
+}
+}  // namespace
+}  // namespace staar
+
+int staar_packed_score_host(staar_ctx *ctx, const uint8_t *packed, size_t stride, int64_t n, int64_t p, int impute,
+                            double *AF, double *MAF, double *Score, double *Score_se, double *pl, double *Est,
+                            double *Est_se)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    NullSparse &ns = ctx->ns;
+    if (!ns.set) { set_error("packed score: call staar_nullmodel_set_sparse first"); return STAAR_ERR_STATE; }
+    STAAR_TRY(ctx->pk.reserve(stride * (size_t)std::max<int64_t>(p, 1)));
+    STAAR_TRY(h2d(ctx, ctx->pk.p, packed, stride * (size_t)p));
+    return score_from_pk(ctx, stride, n, p, impute, AF, MAF, Score, Score_se, pl, Est, Est_se);
 }
 
 int staar_packed_analysis_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
@@ -669,6 +681,14 @@ int staar_packed_reorder_device(staar_ctx *ctx, const uint8_t *d_in, uint8_t *d_
     return sync(ctx);
 }
 
+// share of a pinned FP64 chunk's variants that the GPU packs itself over PCIe (measured optimum on the 16-vCPU B200
+// box: 0.25-0.35; 0.45 makes the PCIe side the bottleneck).  STAAR_B200_GPU_PACK_SHARE overrides, 0 disables.
+double staar_chunk_gpu_pack_share(void)
+{
+    static const double share = getenv("STAAR_B200_GPU_PACK_SHARE") ? atof(getenv("STAAR_B200_GPU_PACK_SHARE")) : 0.3;
+    return share < 0.0 ? 0.0 : (share > 1.0 ? 1.0 : share);
+}
+
 // One chunk of the single-variant driver (R/Individual_Analysis.R:186-196,264): a `$dosage` block in host memory
 // -> flip/impute + Individual_Score_Test statistics, without materialising Geno on the host.  0/1/2/NA dosages are
 // packed to 2 bits on the host (threaded, AVX-512 when the CPU has it) so 1/32 of the FP64 bytes cross PCIe; real-valued
@@ -687,16 +707,46 @@ int chunk_impl(staar_ctx *ctx, const void *G, int elem, int64_t n, int64_t p, in
     bool packed_ok = false;
     if (ns.q + 2 <= kColsPerSlice - 1) {
         STAAR_TRY(pinned_reserve(ctx, stride * (size_t)p));
+        STAAR_TRY(ctx->pk.reserve(stride * (size_t)p + 16));
         uint8_t *dst = static_cast<uint8_t *>(ctx->pinned);
-        int rc = elem == 8   ? staar_pack_dosage_host(static_cast<const double *>(G), n, p, dst, stride, threads)
+        // FP64 blocks in pinned (device-visible) host memory: the GPU packs the LAST share of the variants itself,
+        // reading the host matrix over PCIe, while the host threads pack the rest -- the two bandwidths add up
+        int64_t p_gpu = 0;
+        int *d_bad = reinterpret_cast<int *>(ctx->pk.as<uint8_t>() + stride * (size_t)p);
+        const double *G_dev = nullptr;
+        if (elem == 8) {
+            const double share = staar_chunk_gpu_pack_share();
+            cudaPointerAttributes at;
+            if (share > 0.0 && cudaPointerGetAttributes(&at, G) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+                G_dev = static_cast<const double *>(at.devicePointer);
+                p_gpu = std::min<int64_t>(p, (int64_t)(share * (double)p));
+            } else {
+                cudaGetLastError();               // pageable memory: not an error, the host packs everything
+            }
+        }
+        const int64_t p_cpu = p - p_gpu;
+        if (p_gpu > 0) {
+            STAAR_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+            STAAR_TRY(launch_pack_f64(ctx, G_dev + (size_t)p_cpu * n, n, p_gpu, ctx->pk.as<uint8_t>() + stride * (size_t)p_cpu, stride, d_bad));
+        }
+        int rc = elem == 8   ? staar_pack_dosage_host(static_cast<const double *>(G), n, p_cpu, dst, stride, threads)
                  : elem == 4 ? staar_pack_dosage_host_i32(static_cast<const int32_t *>(G), n, p, dst, stride, threads)
                              : staar_pack_dosage_host_u8(static_cast<const uint8_t *>(G), n, p, dst, stride, threads);
         packed_ok = rc == STAAR_OK;
         if (!packed_ok && elem != 8) return rc;        // integer dosages other than 0/1/2/NA are an error
+        if (packed_ok) {
+            STAAR_TRY(h2d(ctx, ctx->pk.p, dst, stride * (size_t)p_cpu));
+            if (p_gpu > 0) {
+                int bad = 0;
+                STAAR_TRY(d2h(ctx, &bad, d_bad, sizeof(int)));
+                STAAR_TRY(sync(ctx));
+                packed_ok = bad == 0;
+            }
+        } else {
+            STAAR_TRY(sync(ctx));
+        }
     }
-    if (packed_ok)
-        return staar_packed_score_host(ctx, static_cast<const uint8_t *>(ctx->pinned), stride, n, p, impute, AF, MAF,
-                                       Score, Score_se, pl, Est, Est_se);
+    if (packed_ok) return score_from_pk(ctx, stride, n, p, impute, AF, MAF, Score, Score_se, pl, Est, Est_se);
     if (elem != 8) { set_error("individual_analysis_chunk: integer dosages need q <= %d covariates", kColsPerSlice - 3); return STAAR_ERR_ARG; }
     // real-valued genotypes: FP64 flip kernel in place on the device copy, then the FP64 score kernels
     STAAR_TRY(upload_dense_G(ctx, static_cast<const double *>(G), n, p));

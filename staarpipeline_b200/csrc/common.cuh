@@ -196,6 +196,8 @@ int launch_set_Y_col0(staar_ctx *ctx, int64_t n, int ldY, const double *d_res, d
 int launch_px_adj(staar_ctx *ctx, int64_t n, const int64_t *row_ptr, const int32_t *col, const double *val,
                   const double *dA, int m, const double *dSX, int q, const double *dT1, double *dOut);
 int launch_fill_pairs(staar_ctx *ctx, int64_t pp, int k, int32_t *d_colA, int32_t *d_colB);
+int launch_pack_f64(staar_ctx *ctx, const double *G_dev_visible, int64_t n, int64_t pcount, uint8_t *d_packed, size_t stride,
+                    int *d_bad);
 int launch_permute_packed(staar_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, size_t stride, int64_t n, int64_t p,
                           const int32_t *d_perm);
 int spa_scratch_slots(staar_ctx *ctx, int64_t p);

@@ -111,6 +111,42 @@ __global__ void __launch_bounds__(256) permute_packed_kernel(const uint8_t *__re
     }
 }
 
+// FP64 `$dosage` block in PINNED (device-visible) host memory -> packed 2-bit columns written straight to HBM: the
+// kernel reads the host matrix over PCIe (zero copy), 32 samples = 256 contiguous bytes per warp instruction, and
+// builds the two code bit planes with warp ballots.  Used for a share of a chunk's variants while the host threads
+// pack the rest (abi.cu: chunk driver), so that PCIe and host-memory bandwidth add up.
+__device__ __forceinline__ uint32_t spread16(uint32_t x)      // bit f of the low half -> bit 2f
+{
+    x &= 0xffffu;
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+__global__ void __launch_bounds__(256) pack_f64_kernel(const double *__restrict__ G, int64_t n, int64_t pcount,
+                                                       uint8_t *__restrict__ packed, size_t stride, int *__restrict__ bad)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nseg = (int64_t)(stride >> 3), total = pcount * nseg;
+    for (int64_t item = warp; item < total; item += nwarps) {
+        const int64_t i = item / nseg, sgm = item - i * nseg, j = sgm * 32 + lane;
+        const double v = j < n ? __ldg(G + i * n + j) : 0.0;
+        const bool is1 = v == 1.0, is2 = v == 2.0, is0 = v == 0.0, miss = !(v > -1.0);   // NaN or <= -1 (matrix_flip_mean.cpp:26)
+        const uint32_t lo = __ballot_sync(0xffffffffu, is1 || miss), hi = __ballot_sync(0xffffffffu, is2 || miss);
+        const uint32_t okb = __ballot_sync(0xffffffffu, is0 || is1 || is2 || miss);
+        if (lane == 0) {
+            if (okb != 0xffffffffu) atomicOr(bad, 1);
+            uint2 w;
+            w.x = spread16(lo) | (spread16(hi) << 1);
+            w.y = spread16(lo >> 16) | (spread16(hi >> 16) << 1);
+            *reinterpret_cast<uint2 *>(packed + (size_t)i * stride + (size_t)sgm * 8) = w;
+        }
+    }
+}
+
 inline int grid_for(staar_ctx *ctx, int64_t work, int threads)
 {
     return (int)std::max<int64_t>(1, std::min<int64_t>((work + threads - 1) / threads, (int64_t)ctx->sm_count * 16));
@@ -167,6 +203,16 @@ int launch_permute_packed(staar_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, s
     }
     const int grid = (int)std::min<int64_t>(p, (int64_t)ctx->sm_count * 4);
     permute_packed_kernel<<<grid, 256, stride, ctx->stream>>>(d_in, d_out, stride, n, p, d_perm);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+int launch_pack_f64(staar_ctx *ctx, const double *G_dev_visible, int64_t n, int64_t pcount, uint8_t *d_packed, size_t stride,
+                    int *d_bad)
+{
+    if (pcount == 0) return STAAR_OK;
+    pack_f64_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(G_dev_visible, n, pcount, d_packed, stride, d_bad);
     ctx->launches++;
     STAAR_CUDA(cudaGetLastError());
     return STAAR_OK;

@@ -237,6 +237,12 @@ def test_full_size_chunk_vs_oracle(gpu_ctx, oracle):
     got = gpu_ctx.individual_analysis_chunk(G0, IMPUTE_MEAN)
     assert np.array_equal(got["AF"], fl["AF"]) and np.array_equal(got["MAF"], fl["MAF"])
     assert_stats_close({k: got[k] for k in want}, want, score_floor(fl["Geno"], nm.residuals))
+    # pinned host memory: a share of the variants is packed by the GPU itself, reading the host matrix over PCIe
+    import torch
+    pinned = torch.from_numpy(np.ascontiguousarray(G0.T)).pin_memory()          # (p, n) C-order == n x p F-order
+    alt = gpu_ctx.individual_analysis_chunk(pinned.numpy().T, IMPUTE_MEAN)
+    for k in got:
+        assert np.array_equal(alt[k], got[k], equal_nan=True), ("pinned", k)
     ci = codes.astype(np.int32)
     for G in (np.where(ci == 3, np.int32(-2147483648), ci).astype(np.int32), np.where(codes == 3, np.uint8(255), codes).astype(np.uint8)):
         alt = gpu_ctx.individual_analysis_chunk(np.asfortranarray(G), IMPUTE_MEAN)
