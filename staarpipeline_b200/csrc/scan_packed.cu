@@ -55,7 +55,7 @@ __device__ __forceinline__ double code_value(uint32_t code, double mu)
 // memory.  Variants are handed out by an atomic work counter (their cost varies >20x with allele frequency); each
 // variant's arithmetic is independent of which CTA runs it, so results stay bit-reproducible.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kBlkWarps = 8;
+constexpr int kBlkWarps = 4;
 constexpr int kQueueCap = 96;            // per-warp queue of missing-sample positions; flushed when nearly full
 constexpr int kRelQueueCap = 64;         // per-warp queue of missing positions inside the table region (kept per variant)
 
