@@ -55,7 +55,6 @@ __device__ __forceinline__ double code_value(uint32_t code, double mu)
 // memory.  Variants are handed out by an atomic work counter (their cost varies >20x with allele frequency); each
 // variant's arithmetic is independent of which CTA runs it, so results stay bit-reproducible.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kBlkWarps = 4;
 constexpr int kQueueCap = 96;            // per-warp queue of missing-sample positions; flushed when nearly full
 constexpr int kRelQueueCap = 64;         // per-warp queue of missing positions inside the table region (kept per variant)
 
@@ -69,6 +68,7 @@ __device__ __forceinline__ uint32_t code_smem(const uint8_t *col, int64_t k, boo
     return code;
 }
 
+template <int kBlkWarps>
 __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P, int nstage, unsigned long long *work)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -489,10 +489,16 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     P.Y = ns.Yp; P.ldY = ns.ldY; P.ncol = (int)ns.q + 2;
     P.codesum = d_lo;
     P.AF = dAF; P.MAF = dMAF; P.flip = dflip; P.mu = d_mu; P.quad = d_quad; P.Sm = d_Sm;
-    // block-per-variant kernel: column(s) in shared memory, double-buffered when two fit
-    const size_t extra = sizeof(uint32_t) * kBlkWarps * (kQueueCap + kRelQueueCap) +
-                         sizeof(double) * (kBlkWarps * kColsPerSlice + 2 * kBlkWarps) + sizeof(int) * 4 * kBlkWarps + 64;
+    // block-per-variant kernel, column in shared memory.  CTA width: 4 warps put more variants in flight per SM (7 vs 4 at
+    // n = 1e5: 6.75 -> 6.63 ms per 250 k variants); when long columns leave room for few CTAs (n = 4e5: 2 per SM), 8 warps
+    // per CTA keep more warps resident (6.1 M -> 8.5 M variants/s).
+    auto extra_for = [](int warps) {
+        return sizeof(uint32_t) * warps * (kQueueCap + kRelQueueCap) + sizeof(double) * (warps * kColsPerSlice + 2 * warps) +
+               sizeof(int) * 4 * warps + 64;
+    };
     const size_t smem_max = 227 * 1024;
+    const int warps = (6 * (stride + extra_for(4) + 1024) <= 228 * 1024) ? 4 : 8;
+    const size_t extra = extra_for(warps);
     // The kernel is latency-bound (dependent gathers between block barriers), so resident warps matter more than
     // overlapping the column copy: one column stage (measured at n = 1e5: 6.76 ms vs 7.13 ms with two stages per
     // 250 k variants); STAAR_B200_SCAN_STAGES=2 forces the double-buffered variant for experiments.
@@ -501,14 +507,15 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     if (nstage == 1 && force == 2 && 2 * stride + extra <= smem_max) nstage = 2;
     if (nstage > 0) {
         const size_t smem = (size_t)nstage * stride + extra;
-        STAAR_CUDA(cudaFuncSetAttribute(scan_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        auto kern = warps == 4 ? scan_block_kernel<4> : scan_block_kernel<8>;
+        STAAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        STAAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_block_kernel, kBlkWarps * 32, smem));
+        STAAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
         if (per_sm < 1) { set_error("packed scan: kernel does not fit on an SM (smem %zu B)", smem); return STAAR_ERR_CUDA; }
         STAAR_TRY(ctx->ctr.reserve(sizeof(unsigned long long)));
         STAAR_CUDA(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(unsigned long long), ctx->stream));
         const int64_t blocks = std::min<int64_t>(p, (int64_t)ctx->sm_count * per_sm);
-        scan_block_kernel<<<(int)blocks, kBlkWarps * 32, smem, ctx->stream>>>(P, nstage, ctx->ctr.as<unsigned long long>());
+        kern<<<(int)blocks, warps * 32, smem, ctx->stream>>>(P, nstage, ctx->ctr.as<unsigned long long>());
     } else {
         set_error("packed scan: a column of %zu bytes does not fit in shared memory (n > ~9e5): use the FP64 entry points", stride);
         return STAAR_ERR_ARG;
