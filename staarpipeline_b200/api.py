@@ -335,6 +335,19 @@ class Context:
                    *[C.c_void_p(x) for x in d_out7], C.c_void_p(d_spa_index or None), C.byref(nt), C.byref(ns))
         return nt.value, ns.value
 
+    def set_nullmodel_spa(self, XW, XXWX_inv, residuals, muhat):
+        XWm, XXi = _f(XW), _f(XXWX_inv)
+        q, n = XWm.shape
+        if XXi.shape != (n, q):
+            raise StaarError(1, "matrix multiplication: incompatible matrix dimensions (XW / XXWX_inv)")
+        r, mu = _f(residuals).ravel(), _f(muhat).ravel()
+        self._call("staar_nullmodel_set_spa", C.c_int64(n), C.c_int64(q), _p(XWm), _p(XXi), _p(r), _p(mu))
+
+    def packed_spa_device(self, d_packed: int, stride: int, n: int, d_variant: int, n_sel: int, impute: int, tol: float,
+                          max_iter: int, d_pvalue: int):
+        self._call("staar_packed_spa_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n), C.c_void_p(d_variant),
+                   C.c_int64(n_sel), C.c_int(impute), C.c_double(tol), C.c_int(max_iter), C.c_void_p(d_pvalue))
+
     def packed_flip_stats_device(self, d_packed: int, stride: int, n: int, p: int, impute: int, d_AF: int, d_MAF: int,
                                  d_flip: int, d_nmiss: int):
         self._call("staar_packed_flip_stats_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n),

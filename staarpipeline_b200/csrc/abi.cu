@@ -655,6 +655,52 @@ int staar_packed_analysis_device(staar_ctx *ctx, const uint8_t *d_packed, size_t
     return STAAR_OK;
 }
 
+int staar_nullmodel_set_spa(staar_ctx *ctx, int64_t n, int64_t q, const double *XW, const double *XXWX_inv,
+                            const double *residuals, const double *muhat)
+{
+    CHECK_CTX(ctx);
+    if (n <= 0 || q <= 0 || !XW || !XXWX_inv || !residuals || !muhat) { set_error("nullmodel_set_spa: bad arguments"); return STAAR_ERR_ARG; }
+    NullSpa &sp = ctx->nspa;
+    sp.release();
+    STAAR_CUDA(cudaMalloc(&sp.XW, sizeof(double) * n * q));
+    STAAR_CUDA(cudaMalloc(&sp.XXWX_inv, sizeof(double) * n * q));
+    STAAR_CUDA(cudaMalloc(&sp.residuals, sizeof(double) * n));
+    STAAR_CUDA(cudaMalloc(&sp.muhat, sizeof(double) * n));
+    STAAR_TRY(h2d(ctx, sp.XW, XW, sizeof(double) * n * q));
+    STAAR_TRY(h2d(ctx, sp.XXWX_inv, XXWX_inv, sizeof(double) * n * q));
+    STAAR_TRY(h2d(ctx, sp.residuals, residuals, sizeof(double) * n));
+    STAAR_TRY(h2d(ctx, sp.muhat, muhat, sizeof(double) * n));
+    STAAR_TRY(sync(ctx));
+    sp.n = n; sp.q = q; sp.set = true;
+    return STAAR_OK;
+}
+
+int staar_packed_spa_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, const int64_t *d_variant,
+                            int64_t n_sel, int impute, double tol, int max_iter, double *d_pvalue)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, n_sel));
+    const NullSpa &sp = ctx->nspa;
+    if (!sp.set || sp.n != n) { set_error("packed SPA: call staar_nullmodel_set_spa for n = %lld first", (long long)n); return STAAR_ERR_STATE; }
+    if (stride % 16 != 0 || stride < (size_t)((n + 3) / 4)) { set_error("packed stride must be a multiple of 16 and >= ceil(n/4)"); return STAAR_ERR_ARG; }
+    if (n_sel == 0) return STAAR_OK;
+    // resident columns are in the sparse null model's sample order (identity when none is set or it is unrelated)
+    const int32_t *d_perm = (ctx->ns.set && ctx->ns.n == n && ctx->ns.permuted) ? ctx->ns.perm : nullptr;
+    // batches of decoded FP64 columns (<= 1 GiB): decode -> saddle-point kernel of the frozen-signature entry point
+    const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(n_sel, (1ll << 30) / (8 * n)));
+    STAAR_TRY(ctx->G.reserve(sizeof(double) * (size_t)n * batch));
+    const int slots = spa_scratch_slots(ctx, batch);
+    STAAR_TRY(ctx->aux.reserve(sizeof(double) * (size_t)slots * n));
+    for (int64_t first = 0; first < n_sel; first += batch) {
+        const int64_t count = std::min(batch, n_sel - first);
+        STAAR_TRY(launch_decode_packed(ctx, d_packed, stride, n, reinterpret_cast<const long long *>(d_variant), first, count,
+                                       impute, d_perm, ctx->G.as<double>()));
+        STAAR_TRY(launch_spa(ctx, ctx->G.as<double>(), n, count, sp.XW, sp.XXWX_inv, (int)sp.q, sp.residuals, sp.muhat, tol,
+                             max_iter, ctx->aux.as<double>(), d_pvalue + first, nullptr));
+    }
+    return sync(ctx);
+}
+
 int staar_nullmodel_sample_order(staar_ctx *ctx, int64_t n, int32_t *order)
 {
     CHECK_CTX(ctx);

@@ -107,6 +107,16 @@ struct NullSparse {
     void release();
 };
 
+// SPA operands of a binary-trait null model (R/fit_nullmodel.R:153-162), resident for the packed path
+struct NullSpa {
+    bool set = false;
+    int64_t n = 0, q = 0;
+    double *XW = nullptr;         // q x n column-major
+    double *XXWX_inv = nullptr;   // n x q column-major
+    double *residuals = nullptr, *muhat = nullptr;
+    void release();
+};
+
 struct NullDense {
     bool set = false;
     int64_t n = 0;
@@ -125,6 +135,7 @@ struct staar_ctx {
     uint64_t launches = 0;
     staar::NullSparse ns;
     staar::NullDense nd;
+    staar::NullSpa nspa;
     // scratch
     staar::DevBuf G, L, aux, out, tmp, tmp2, pk, pk2, ctr;
     bool use_mma_sync = false;       // STAAR_B200_CONTRACT=mma: legacy mma.sync contraction instead of tcgen05
@@ -180,6 +191,9 @@ int build_tc_operand(staar_ctx *ctx, const int8_t *digits, int ncol);
 int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, long long *d_hi,
                        long long *d_lo);
 int refresh_permuted_Y(staar_ctx *ctx, const double *hY);
+// driver.cu — selected packed columns -> flipped, imputed FP64 columns in the caller's sample order (input of K6)
+int launch_decode_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, const long long *d_variant,
+                         int64_t first, int64_t count, int impute, const int32_t *d_perm, double *dG);
 // driver.cu — MAF/MAC filter + SPA pre-filter: stable compaction of the per-variant arrays
 int launch_compact_results(staar_ctx *ctx, int64_t p, const double *const d_in[7], double maf_cut, double p_cut,
                            long long *d_index, double *const d_out[7], long long *d_sel_index, long long *d_totals);

@@ -61,6 +61,11 @@ void NullSparse::release()
     cudaFree(Yfrag); cudaFree(Ytc); cudaFree(col_scale); cudaFree(col_total); cudaFree(perm); cudaFree(kmask); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut);
     *this = NullSparse();
 }
+void NullSpa::release()
+{
+    cudaFree(XW); cudaFree(XXWX_inv); cudaFree(residuals); cudaFree(muhat);
+    *this = NullSpa();
+}
 void NullDense::release()
 {
     cudaFree(P); cudaFree(residuals);
@@ -517,7 +522,7 @@ void staar_ctx_destroy(staar_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->ns.release(); ctx->nd.release();
+    ctx->ns.release(); ctx->nd.release(); ctx->nspa.release();
     ctx->G.release(); ctx->L.release(); ctx->aux.release(); ctx->out.release(); ctx->tmp.release();
     ctx->tmp2.release(); ctx->pk.release(); ctx->pk2.release(); ctx->ctr.release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -340,3 +340,46 @@ def test_packed_contraction_is_exact_integer(gpu_ctx, oracle):
         # slot 15: the constant-1 column (scale 1) = exact sum of the raw codes
         assert d["col_scale"][15] == 1.0 and list(got[:, 15]) == list(codes.astype(object).sum(axis=0))
         assert np.array_equal((d["flip"] & 1) != 0, oracle.matrix_flip_mean(G0)["AF"] > 0.5)
+
+
+@pytest.mark.parametrize("impute", ["mean", "minor"])
+def test_packed_spa_stage_vs_oracle(gpu_ctx, oracle, impute):
+    """SPA stage on resident 2-bit columns (cfg5's second stage) == Individual_Score_Test_SPA of the reference on the
+    flipped / imputed FP64 columns of the same variants (R/Individual_Analysis.R:290-297), with the resident block in
+    the sparse null model's sample order and missing genotypes present."""
+    import torch
+    from staarpipeline_b200 import api, synth
+    n, p, q = 5000, 64, 5
+    nb = synth.nullmodel_binary(n, seed=31, q=q, intercept=-3.5)
+    ns = synth.nullmodel_sparse_grm(n, seed=31, q=q, shuffle=True)
+    G0 = cases.raw_dosage(n, p, 31)
+    rng = np.random.default_rng(31)
+    case_idx = np.flatnonzero(nb.extra["y"] == 1)
+    for c in range(6):                                                      # planted signals: Newton-Raphson branch
+        take = rng.choice(case_idx, size=max(2, int(len(case_idx) * (0.15 + 0.1 * c))), replace=False)
+        G0[take, c] = np.where(np.isnan(G0[take, c]) | (G0[take, c] <= -1), G0[take, c], np.minimum(G0[take, c] + 1.0, 2.0))
+    codes = np.where(np.isnan(G0) | (G0 <= -1), 3, G0).astype(np.uint8)
+    packed = synth.pack_codes(np.asfortranarray(codes))
+    P, stride = packed.shape
+    gpu_ctx.set_nullmodel_sparse(ns.Sigma_i, ns.Sigma_iX, ns.cov, ns.residuals)     # fixes the resident sample order
+    gpu_ctx.set_nullmodel_spa(nb.XW, nb.XXWX_inv, nb.residuals, nb.muhat)
+    dev = torch.device("cuda:0")
+    d_in = torch.from_numpy(packed).to(dev); d_cols = torch.zeros_like(d_in)
+    torch.cuda.synchronize()
+    gpu_ctx.packed_reorder_device(d_in.data_ptr(), d_cols.data_ptr(), stride, n, P)
+    sel = np.array([0, 1, 2, 3, 4, 5, 9, 17, 18, 40, P - 1, 7], dtype=np.int64)      # any order, as a gather list
+    d_sel = torch.from_numpy(sel).to(dev)
+    d_p = torch.full((sel.size,), -1.0, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    flag = api.IMPUTE_MEAN if impute == "mean" else api.IMPUTE_MINOR
+    gpu_ctx.packed_spa_device(d_cols.data_ptr(), stride, n, d_sel.data_ptr(), sel.size, flag, cases.TOL_SPA,
+                              cases.MAX_ITER, d_p.data_ptr())
+    fl = getattr(oracle, f"matrix_flip_{impute}")(G0)
+    want = oracle.Individual_Score_Test_SPA(np.asfortranarray(fl["Geno"][:, sel]), nb.XW, nb.XXWX_inv, nb.residuals,
+                                            nb.muhat, cases.TOL_SPA, cases.MAX_ITER)
+    got = d_p.cpu().numpy()
+    assert rel_err(got, want, 1e-300) < 1e-8
+    # and identical to the frozen-signature entry point on the same FP64 columns
+    same = gpu_ctx.Individual_Score_Test_SPA(np.asfortranarray(fl["Geno"][:, sel]), nb.XW, nb.XXWX_inv, nb.residuals,
+                                             nb.muhat, cases.TOL_SPA, cases.MAX_ITER)
+    assert np.array_equal(got, same)
