@@ -213,12 +213,13 @@ int staar_packed_analysis_device(staar_ctx *ctx, const uint8_t *d_packed, size_t
  * then runs Individual_Score_Test_SPA (src/Individual_Score_Test_SPA.cpp:38-533) on the n_sel variants listed in
  * d_variant (device int64: column numbers of d_packed, e.g. d_index gathered at d_spa_index of
  * staar_packed_analysis_device): each column is flipped / imputed exactly as matrix_flip_mean|minor and decoded to the
- * FP64 column the reference would pass, on the device.  d_pvalue: n_sel p-values (device).  Synchronous. */
+ * FP64 column the reference would pass, inside the saddle-point kernel (no FP64 matrix is materialised).  d_pvalue: n_sel
+ * p-values (device).  Synchronous. */
 int staar_nullmodel_set_spa(staar_ctx *ctx, int64_t n, int64_t q, const double *XW, const double *XXWX_inv,
                             const double *residuals, const double *muhat);
 int staar_packed_spa_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride_bytes, int64_t n,
                             const int64_t *d_variant, int64_t n_sel, int impute, double tol, int max_iter,
-                            double *d_pvalue);
+                            double *d_pvalue, int64_t *d_trace /* 4 per variant as staar_individual_score_test_SPA, or NULL */);
 
 /* Per-kernel device times of the LAST staar_packed_score_device call, measured with CUDA events on the context
  * stream when profiling is on: ms[0] = scan (K1+K3), ms[1] = contraction (K2), ms[2] = finalize (K5).

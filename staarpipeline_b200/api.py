@@ -344,9 +344,10 @@ class Context:
         self._call("staar_nullmodel_set_spa", C.c_int64(n), C.c_int64(q), _p(XWm), _p(XXi), _p(r), _p(mu))
 
     def packed_spa_device(self, d_packed: int, stride: int, n: int, d_variant: int, n_sel: int, impute: int, tol: float,
-                          max_iter: int, d_pvalue: int):
+                          max_iter: int, d_pvalue: int, d_trace: int = 0):
         self._call("staar_packed_spa_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n), C.c_void_p(d_variant),
-                   C.c_int64(n_sel), C.c_int(impute), C.c_double(tol), C.c_int(max_iter), C.c_void_p(d_pvalue))
+                   C.c_int64(n_sel), C.c_int(impute), C.c_double(tol), C.c_int(max_iter), C.c_void_p(d_pvalue),
+                   C.c_void_p(d_trace or None))
 
     def packed_flip_stats_device(self, d_packed: int, stride: int, n: int, p: int, impute: int, d_AF: int, d_MAF: int,
                                  d_flip: int, d_nmiss: int):

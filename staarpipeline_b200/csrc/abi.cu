@@ -448,7 +448,8 @@ int staar_individual_score_test_SPA(staar_ctx *ctx, const double *G, int64_t n, 
     STAAR_TRY(check_dims(n, p));
     if (!G || !XW || !XXWX_inv || !res || !muhat || !pvalue) { set_error("SPA: NULL pointer"); return STAAR_ERR_ARG; }
     STAAR_TRY(upload_dense_G(ctx, G, n, p));
-    const int slots = spa_scratch_slots(ctx, std::max<int64_t>(p, 1));
+    const int slots = spa_scratch_slots(ctx, n, p);
+    if (slots < 1) return STAAR_ERR_CUDA;
     // aux: XW (q*n) | XXWX_inv (n*q) | res (n) | mu (n) | gt scratch (slots*n)
     STAAR_TRY(ctx->aux.reserve(sizeof(double) * ((size_t)2 * n * q + 2 * (size_t)n + (size_t)slots * n)));
     double *dXW = ctx->aux.as<double>(), *dXX = dXW + n * q, *dres = dXX + n * q, *dmu = dres + n, *dgt = dmu + n;
@@ -676,7 +677,7 @@ int staar_nullmodel_set_spa(staar_ctx *ctx, int64_t n, int64_t q, const double *
 }
 
 int staar_packed_spa_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, const int64_t *d_variant,
-                            int64_t n_sel, int impute, double tol, int max_iter, double *d_pvalue)
+                            int64_t n_sel, int impute, double tol, int max_iter, double *d_pvalue, int64_t *d_trace)
 {
     CHECK_CTX(ctx);
     STAAR_TRY(check_dims(n, n_sel));
@@ -685,19 +686,13 @@ int staar_packed_spa_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stri
     if (stride % 16 != 0 || stride < (size_t)((n + 3) / 4)) { set_error("packed stride must be a multiple of 16 and >= ceil(n/4)"); return STAAR_ERR_ARG; }
     if (n_sel == 0) return STAAR_OK;
     // resident columns are in the sparse null model's sample order (identity when none is set or it is unrelated)
-    const int32_t *d_perm = (ctx->ns.set && ctx->ns.n == n && ctx->ns.permuted) ? ctx->ns.perm : nullptr;
-    // batches of decoded FP64 columns (<= 1 GiB): decode -> saddle-point kernel of the frozen-signature entry point
-    const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(n_sel, (1ll << 30) / (8 * n)));
-    STAAR_TRY(ctx->G.reserve(sizeof(double) * (size_t)n * batch));
-    const int slots = spa_scratch_slots(ctx, batch);
+    const int32_t *d_inv = (ctx->ns.set && ctx->ns.n == n && ctx->ns.permuted) ? ctx->ns.inv_perm : nullptr;
+    const int slots = spa_scratch_slots(ctx, n, n_sel);
+    if (slots < 1) return STAAR_ERR_CUDA;
     STAAR_TRY(ctx->aux.reserve(sizeof(double) * (size_t)slots * n));
-    for (int64_t first = 0; first < n_sel; first += batch) {
-        const int64_t count = std::min(batch, n_sel - first);
-        STAAR_TRY(launch_decode_packed(ctx, d_packed, stride, n, reinterpret_cast<const long long *>(d_variant), first, count,
-                                       impute, d_perm, ctx->G.as<double>()));
-        STAAR_TRY(launch_spa(ctx, ctx->G.as<double>(), n, count, sp.XW, sp.XXWX_inv, (int)sp.q, sp.residuals, sp.muhat, tol,
-                             max_iter, ctx->aux.as<double>(), d_pvalue + first, nullptr));
-    }
+    STAAR_TRY(launch_spa_packed(ctx, d_packed, stride, reinterpret_cast<const long long *>(d_variant), d_inv, impute, n, n_sel,
+                                sp.XW, sp.XXWX_inv, (int)sp.q, sp.residuals, sp.muhat, tol, max_iter, ctx->aux.as<double>(),
+                                d_pvalue, reinterpret_cast<long long *>(d_trace)));
     return sync(ctx);
 }
 

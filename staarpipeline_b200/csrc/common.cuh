@@ -66,6 +66,7 @@ struct NullSparse {
     bool permuted = false;            // false: perm is the identity
     std::vector<int32_t> h_perm;      // position -> original sample (empty when identity)
     int32_t *perm = nullptr;          // device copy (nullptr when identity)
+    int32_t *inv_perm = nullptr;      // original sample -> position (nullptr when identity)
     double *Yp = nullptr;             // Y rows in null-model order (== Y when !permuted; then not owned)
     int64_t kin_words = 0;            // 16-sample words [0, kin_words) hold every sample with kinship off-diagonals
     int64_t tab_words = 0;            // words [0, tab_words): table words; [tab_words, kin_words): generic families
@@ -177,6 +178,10 @@ int launch_epilogue_general(staar_ctx *ctx, int64_t p_total, int k, const double
 int launch_spa(staar_ctx *ctx, const double *dG, int64_t n, int64_t p, const double *dXW, const double *dXXWX_inv,
                int q, const double *d_res, const double *d_mu, double tol, int max_iter, double *d_gt,
                double *d_pvalue, long long *d_trace);
+int launch_spa_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, const long long *d_variant,
+                      const int32_t *d_inv_perm, int impute, int64_t n, int64_t p, const double *dXW,
+                      const double *dXXWX_inv, int q, const double *d_res, const double *d_mu, double tol, int max_iter,
+                      double *d_gt, double *d_pvalue, long long *d_trace);
 // packed path — scan_packed.cu / contract_packed.cu / finalize
 int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
                        const long long *d_lo /* contraction output: slot 15 = sum of codes */, double *dAF, double *dMAF,
@@ -191,9 +196,6 @@ int build_tc_operand(staar_ctx *ctx, const int8_t *digits, int ncol);
 int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, long long *d_hi,
                        long long *d_lo);
 int refresh_permuted_Y(staar_ctx *ctx, const double *hY);
-// driver.cu — selected packed columns -> flipped, imputed FP64 columns in the caller's sample order (input of K6)
-int launch_decode_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, const long long *d_variant,
-                         int64_t first, int64_t count, int impute, const int32_t *d_perm, double *dG);
 // driver.cu — MAF/MAC filter + SPA pre-filter: stable compaction of the per-variant arrays
 int launch_compact_results(staar_ctx *ctx, int64_t p, const double *const d_in[7], double maf_cut, double p_cut,
                            long long *d_index, double *const d_out[7], long long *d_sel_index, long long *d_totals);
@@ -214,7 +216,7 @@ int launch_pack_f64(staar_ctx *ctx, const double *G_dev_visible, int64_t n, int6
                     int *d_bad);
 int launch_permute_packed(staar_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, size_t stride, int64_t n, int64_t p,
                           const int32_t *d_perm);
-int spa_scratch_slots(staar_ctx *ctx, int64_t p);
+int spa_scratch_slots(staar_ctx *ctx, int64_t n, int64_t p);
 
 // ------------------------------------------------------------------ device math shared by kernels
 #ifdef __CUDACC__

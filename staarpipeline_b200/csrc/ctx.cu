@@ -58,7 +58,7 @@ void NullSparse::release()
     }
     if (permuted) cudaFree(Yp);
     cudaFree(diag); cudaFree(diag_p); cudaFree(sinfo_p); cudaFree(off_ent_p); cudaFree(relmask); cudaFree(rel); cudaFree(up_ent); cudaFree(Y);
-    cudaFree(Yfrag); cudaFree(Ytc); cudaFree(col_scale); cudaFree(col_total); cudaFree(perm); cudaFree(kmask); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut);
+    cudaFree(Yfrag); cudaFree(Ytc); cudaFree(col_scale); cudaFree(col_total); cudaFree(perm); cudaFree(inv_perm); cudaFree(kmask); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut);
     *this = NullSparse();
 }
 void NullSpa::release()
@@ -434,7 +434,12 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
         STAAR_TRY(upload_vec(ctx, &ns.rel, rel));
         STAAR_TRY(upload_vec(ctx, &ns.up_ent, up_ent));
     }
-    if (permute) STAAR_TRY(upload_vec(ctx, &ns.perm, perm));
+    if (permute) {
+        STAAR_TRY(upload_vec(ctx, &ns.perm, perm));
+        std::vector<int32_t> inv((size_t)n);
+        for (int64_t pz = 0; pz < n; pz++) inv[perm[pz]] = (int32_t)pz;
+        STAAR_TRY(upload_vec(ctx, &ns.inv_perm, inv));
+    }
     STAAR_TRY(upload_vec(ctx, &ns.Y, Y));
     STAAR_CUDA(cudaMalloc(&ns.SX, sizeof(double) * std::max<int64_t>(n * q, 1)));
     STAAR_CUDA(cudaMalloc(&ns.cov, sizeof(double) * std::max<int64_t>(q * q, 1)));

@@ -120,52 +120,7 @@ __global__ void __launch_bounds__(kCompactThreads) compact_scatter_kernel(Compac
     }
 }
 
-// Selected variants of a resident packed block -> the matrix Individual_Score_Test_SPA receives in the reference
-// (R/Individual_Analysis.R:290-297: the flipped, imputed Geno columns with score-test p < 0.05): FP64, column-major,
-// caller's sample order.  One CTA per variant: popcounts -> flip / imputation value exactly as matrix_flip_mean /
-// matrix_flip_minor (packed.cuh), then every code is written as a double at the sample's original index.
-__global__ void __launch_bounds__(256) decode_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t n,
-                                                            const long long *__restrict__ variant, int64_t first, int64_t count,
-                                                            int impute, const int32_t *__restrict__ perm, double *__restrict__ G)
-{
-    __shared__ int s_cnt[3][8];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int64_t c = blockIdx.x; c < count; c += gridDim.x) {
-        const uint8_t *col = packed + (size_t)variant[first + c] * stride;
-        int c1 = 0, c2 = 0, cm = 0;
-        const uint4 *v4 = reinterpret_cast<const uint4 *>(col);
-        for (int k = threadIdx.x; k < (int)(stride >> 4); k += blockDim.x) {
-            const uint4 q = __ldg(v4 + k);
-            count_word(q.x, c1, c2, cm); count_word(q.y, c1, c2, cm); count_word(q.z, c1, c2, cm); count_word(q.w, c1, c2, cm);
-        }
-        c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2); cm = __reduce_add_sync(0xffffffffu, cm);
-        __syncthreads();
-        if (lane == 0) { s_cnt[0][w] = c1; s_cnt[1][w] = c2; s_cnt[2][w] = cm; }
-        __syncthreads();
-        c1 = c2 = cm = 0;
-        for (int ww = 0; ww < 8; ww++) { c1 += s_cnt[0][ww]; c2 += s_cnt[1][ww]; cm += s_cnt[2][ww]; }
-        const VariantFlip vf = flip_from_counts(PackedCounts{c1, c2, cm}, n, impute);
-        double *g = G + (size_t)c * n;
-        for (int64_t pos = threadIdx.x; pos < n; pos += blockDim.x) {
-            uint32_t code = ((uint32_t)__ldg(col + (pos >> 2)) >> (2 * (pos & 3))) & 3u;
-            if (vf.flip && !(code & 1u)) code ^= 2u;
-            g[perm ? perm[pos] : pos] = code == 3u ? vf.mu : (double)code;
-        }
-    }
-}
-
 }  // namespace
-
-int launch_decode_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, const long long *d_variant,
-                         int64_t first, int64_t count, int impute, const int32_t *d_perm, double *dG)
-{
-    if (count == 0) return STAAR_OK;
-    const int grid = (int)std::min<int64_t>(count, (int64_t)ctx->sm_count * 8);
-    decode_packed_kernel<<<grid, 256, 0, ctx->stream>>>(d_packed, stride, n, d_variant, first, count, impute, d_perm, dG);
-    ctx->launches++;
-    STAAR_CUDA(cudaGetLastError());
-    return STAAR_OK;
-}
 
 int launch_compact_results(staar_ctx *ctx, int64_t p, const double *const d_in[7], double maf_cut, double p_cut,
                            long long *d_index, double *const d_out[7], long long *d_sel_index, long long *d_totals)

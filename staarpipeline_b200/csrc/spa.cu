@@ -1,114 +1,226 @@
 // spa.cu — K6: saddle-point approximation p-values for imbalanced binary traits.
 //
 // Replaces Individual_Score_Test_SPA and its 13 helpers (reference src/Individual_Score_Test_SPA.cpp:38-533).
-// One CTA per variant; the control flow of the reference (Newton-Raphson, its max_iter quirk, golden-section
-// bracket + bisection fallback, every "_alt if not finite" retry, the ==1.0 / NaN fallbacks and the final clamp)
-// runs uniformly in all threads, and every O(n) CGF sum is a block-parallel pass with a fixed reduction tree.
-// What changes versus the reference is only work the reference repeats: K1 and K2 at the same point share one
-// pass (one exp per sample), and G_tilde = G - XXWX_inv*(XW*G) (:61) is formed per column into an L2/HBM
-// scratch slot instead of as a second n x p matrix.  FP64-ALU bound (exp/div per sample per pass).
+// One thread-block CLUSTER per variant: the control flow of the reference (Newton-Raphson, its max_iter quirk,
+// golden-section bracket + bisection fallback, every "_alt if not finite" retry, the ==1.0 / NaN fallbacks and the
+// final clamp) runs uniformly in every thread of every CTA of the cluster, and each O(n) CGF sum is a pass in which
+// CTA r of the cluster covers samples [r*len, (r+1)*len); partial sums are exchanged through distributed shared
+// memory and added in rank order, so all CTAs continue with bit-identical values.  Why a cluster: the number of
+// passes per variant ranges from ~15 to several thousand (a Newton-Raphson run that exhausts max_iter = 1000 and
+// falls back to the bracket search), a pass is FP64-pipe bound on the SM it runs on (exp + divisions per sample), so
+// the long variants set the makespan unless each one is spread over several SMs.  Variants are handed out through an
+// atomic counter.  What changes versus the reference is only work the reference repeats: K1 and K2 at the same point
+// share one pass (one exp per sample), and G_tilde = G - XXWX_inv*(XW*G) (:61) is formed per column into an L2-resident
+// scratch slot instead of as a second n x p matrix.  The column comes either from the FP64 matrix of the frozen
+// signature or straight from resident 2-bit columns (flip / imputation as matrix_flip_mean|minor, packed.cuh).
+#include <cooperative_groups.h>
 #include "common.cuh"
+#include "packed.cuh"
 
 namespace staar {
 
 namespace {
 
-constexpr int kThreads = 256;
+namespace cg = cooperative_groups;
+
+constexpr int kThreads = 512;
 constexpr int kMaxQ = 64;
+constexpr int kMaxCluster = 16;     // 16 needs the non-portable cluster size attribute (B200: supported)
 
 struct SpaCol {
     const double *mu;   // muhat, length n
     const double *g;    // G_tilde column, length n
-    int64_t n;
-    double *red;        // shared double[32]
+    int64_t lo, hi;     // this CTA's samples
+    double *red;        // shared double[3][32]: warp partials of up to three sums
+    double *slots;      // shared double[2][3][kMaxCluster]: [parity][value][rank], written by every CTA of the cluster
+    unsigned csize, crank;
+    int parity;
     long long passes;
 };
 
+// Up to three cluster-wide sums with a fixed tree: warp shuffles -> CTA partial -> one DSMEM store per peer -> cluster
+// barrier -> rank-ordered add.  Every thread of every CTA returns the same bits.  The slot buffers alternate so that a
+// CTA that runs ahead writes the buffer its peers are not reading (a buffer is reused only after the next barrier).
+constexpr int kMaxSums = 3;
+template <int K> __device__ __forceinline__ void cluster_sums(SpaCol &c, double (&v)[K])
+{
+    static_assert(K <= kMaxSums, "slot layout");
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        v[k] = warp_sum(v[k]);
+        if (lane == 0) c.red[32 * k + w] = v[k];
+    }
+    __syncthreads();
+    cg::cluster_group cluster = cg::this_cluster();
+    double *slot = c.slots + c.parity * kMaxSums * kMaxCluster;
+    if (w == 0) {
+        double t[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) t[k] = warp_sum(lane < kThreads / 32 ? c.red[32 * k + lane] : 0.0);
+        if (lane < (int)c.csize) {
+            double *peer = cluster.map_shared_rank(slot, lane);
+#pragma unroll
+            for (int k = 0; k < K; k++) peer[k * kMaxCluster + c.crank] = t[k];
+        }
+    }
+    cluster.sync();
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double t = 0.0;
+        for (unsigned r = 0; r < c.csize; r++) t += slot[k * kMaxCluster + r];
+        v[k] = t;
+    }
+    c.parity ^= 1;
+}
+__device__ __forceinline__ void cluster_sum2(SpaCol &c, double a, double b, double &A, double &B)
+{
+    double v[2] = {a, b};
+    cluster_sums(c, v);
+    A = v[0]; B = v[1];
+}
+__device__ __forceinline__ double cluster_sum(SpaCol &c, double a)
+{
+    double v[1] = {a};
+    cluster_sums(c, v);
+    return v[0];
+}
+
 __device__ __forceinline__ bool is_bad(double v) { return !isfinite(v); }   // (R_finite(v)==0)||check_is_na(v)
 __device__ __forceinline__ bool same_sign(double a, double b) { return (a >= 0) == (b >= 0); }   // :531-533
+
+// One pass over this CTA's samples, kUnroll samples per thread in flight: the loads of the next batch are issued
+// before the arithmetic of the current one (the loop is otherwise latency-bound: ~120 dependent instructions per sample
+// behind two L2 loads at 4 warps per scheduler).
+constexpr int kUnroll = 4;
+template <class Body> __device__ __forceinline__ void sweep(const SpaCol &c, Body body)
+{
+    double m[kUnroll], g[kUnroll];
+    int64_t i = c.lo + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < kUnroll; k++) {
+        const int64_t j = i + (int64_t)k * kThreads;
+        const bool ok = j < c.hi;
+        m[k] = ok ? c.mu[j] : 0.5;
+        g[k] = ok ? c.g[j] : 0.0;
+    }
+    while (i < c.hi) {
+        double mc[kUnroll], gc[kUnroll];
+#pragma unroll
+        for (int k = 0; k < kUnroll; k++) { mc[k] = m[k]; gc[k] = g[k]; }
+        const int64_t i0 = i;
+        i += (int64_t)kUnroll * kThreads;
+#pragma unroll
+        for (int k = 0; k < kUnroll; k++) {
+            const int64_t j = i + (int64_t)k * kThreads;
+            const bool ok = j < c.hi;
+            m[k] = ok ? c.mu[j] : 0.5;
+            g[k] = ok ? c.g[j] : 0.0;
+        }
+        if (i0 + (int64_t)(kUnroll - 1) * kThreads < c.hi) {
+#pragma unroll
+            for (int k = 0; k < kUnroll; k++) body(mc[k], gc[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kUnroll; k++)
+                if (i0 + (int64_t)k * kThreads < c.hi) body(mc[k], gc[k]);
+        }
+    }
+}
 
 // K1 (:453-467) and K2 (:488-505) at the same x in one pass
 __device__ void pass_K1K2(SpaCol &c, double x, double q, double &k1, double &k2)
 {
     double s1 = 0.0, s2 = 0.0;
-    for (int64_t i = threadIdx.x; i < c.n; i += kThreads) {
-        const double mu = c.mu[i], g = c.g[i];
+    sweep(c, [&](double mu, double g) {
         const double e = exp(-x * g);
-        const double den = mu + (1 - mu) * e;
-        s1 += -mu * g + mu * g / den;
-        s2 += (mu * (1 - mu) * (g * g) * e) / (den * den);
-    }
-    k1 = block_sum(s1, c.red) - q;
-    k2 = block_sum(s2, c.red);
+        const double r = 1.0 / (mu + (1 - mu) * e);            // one reciprocal serves both quotients
+        s1 += -mu * g + mu * g * r;
+        s2 += (mu * (1 - mu) * (g * g) * e) * r * r;
+    });
+    cluster_sum2(c, s1, s2, k1, k2);
+    k1 -= q;
+    c.passes++;
+}
+// The Newton-Raphson pass: K1, K2 and, from the same exponential, K2_alt (:508-525).  With e = exp(-x g) and
+// r = 1/(mu + (1-mu) e):  mu exp(x g) + (1-mu) = (mu + (1-mu) e)/e, so the summand of K2_alt,
+// mu(1-mu)g^2 / (mu exp(x g) + 1-mu)^2, equals mu(1-mu)g^2 (e r)^2 — no second exponential, no second pass.  Where e
+// overflowed (the case that makes K2 NaN and sends the reference to K2_alt) e r is taken at its limit 1/(1-mu), which
+// is what the reference's expression evaluates to there (exp(x g) = 0).  Matters because a run that leaves the range of
+// exp() keeps stepping with K2_alt until max_iter: one pass per step instead of two.
+__device__ void pass_K1K2_nr(SpaCol &c, double x, double q, double &k1, double &k2, double &k2_alt)
+{
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    sweep(c, [&](double mu, double g) {
+        const double e = exp(-x * g);
+        const double r = 1.0 / (mu + (1 - mu) * e);
+        const double a = mu * (1 - mu) * (g * g);
+        s1 += -mu * g + mu * g * r;
+        s2 += a * e * r * r;
+        const double t = isinf(e) ? 1.0 / (1 - mu) : e * r;
+        s3 += a * t * t;
+    });
+    double v[3] = {s1, s2, s3};
+    cluster_sums(c, v);
+    k1 = v[0] - q; k2 = v[1]; k2_alt = v[2];
     c.passes++;
 }
 __device__ double pass_K1_alt(SpaCol &c, double x, double q)   // :471-485
 {
     double s = 0.0;
-    for (int64_t i = threadIdx.x; i < c.n; i += kThreads) {
-        const double mu = c.mu[i], g = c.g[i];
+    sweep(c, [&](double mu, double g) {
         const double e = exp(x * g);
         s += -mu * g + mu * g * e / (mu * e + (1 - mu));
-    }
+    });
     c.passes++;
-    return block_sum(s, c.red) - q;
+    return cluster_sum(c, s) - q;
 }
 __device__ double pass_K2(SpaCol &c, double x)                  // :488-505
 {
     double s = 0.0;
-    for (int64_t i = threadIdx.x; i < c.n; i += kThreads) {
-        const double mu = c.mu[i], g = c.g[i];
+    sweep(c, [&](double mu, double g) {
         const double e = exp(-x * g);
         const double den = mu + (1 - mu) * e;
         s += (mu * (1 - mu) * (g * g) * e) / (den * den);
-    }
+    });
     c.passes++;
-    return block_sum(s, c.red);
+    return cluster_sum(c, s);
 }
 __device__ double pass_K2_alt(SpaCol &c, double x)              // :508-525
 {
     double s = 0.0;
-    for (int64_t i = threadIdx.x; i < c.n; i += kThreads) {
-        const double mu = c.mu[i], g = c.g[i];
+    sweep(c, [&](double mu, double g) {
         const double den = mu * exp(x * g) + (1 - mu);
         s += (mu * (1 - mu) * (g * g)) / (den * den);
-    }
+    });
     c.passes++;
-    return block_sum(s, c.red);
+    return cluster_sum(c, s);
 }
 __device__ double pass_K(SpaCol &c, double x)                   // :421-433
 {
     double s = 0.0;
-    for (int64_t i = threadIdx.x; i < c.n; i += kThreads) {
-        const double mu = c.mu[i], g = c.g[i];
-        s += -x * mu * g + log(1 - mu + mu * exp(x * g));
-    }
+    sweep(c, [&](double mu, double g) { s += -x * mu * g + log(1 - mu + mu * exp(x * g)); });
     c.passes++;
-    return block_sum(s, c.red);
+    return cluster_sum(c, s);
 }
 __device__ double pass_K_alt(SpaCol &c, double x)               // :437-450
 {
     double s = 0.0;
-    for (int64_t i = threadIdx.x; i < c.n; i += kThreads) {
-        const double mu = c.mu[i], g = c.g[i];
-        s += log((1 - mu) * exp(-x * g) + mu);
-    }
+    sweep(c, [&](double mu, double g) { s += log((1 - mu) * exp(-x * g) + mu); });
     c.passes++;
-    return block_sum(s, c.red);
+    return cluster_sum(c, s);
 }
 // K(x) and K2(x) of the tail formula in one pass (:129,:140)
 __device__ void pass_K_K2(SpaCol &c, double x, double &k, double &k2)
 {
     double s = 0.0, s2 = 0.0;
-    for (int64_t i = threadIdx.x; i < c.n; i += kThreads) {
-        const double mu = c.mu[i], g = c.g[i];
+    sweep(c, [&](double mu, double g) {
         s += -x * mu * g + log(1 - mu + mu * exp(x * g));
         const double e = exp(-x * g);
-        const double den = mu + (1 - mu) * e;
-        s2 += (mu * (1 - mu) * (g * g) * e) / (den * den);
-    }
-    k = block_sum(s, c.red);
-    k2 = block_sum(s2, c.red);
+        const double r = 1.0 / (mu + (1 - mu) * e);
+        s2 += (mu * (1 - mu) * (g * g) * e) * r * r;
+    });
+    cluster_sum2(c, s, s2, k, k2);
     c.passes++;
 }
 __device__ double K1_fb(SpaCol &c, double x, double q)          // K1, "_alt if not finite"
@@ -122,14 +234,14 @@ __device__ double K1_fb(SpaCol &c, double x, double q)          // K1, "_alt if 
 // NR_Binary_SPA (:158-233)
 __device__ double NR_spa(SpaCol &c, double q, double tol, int max_iter, long long &nr_iter)
 {
-    double xi = 0.0, xi_update = 0.0, k1, k2;
+    double xi = 0.0, xi_update = 0.0, k1, k2, k2_alt;
     pass_K1K2(c, xi, q, k1, k2);
     if (fabs(k1) > tol) xi_update = xi - k1 / k2;                  // :167-170 (no _alt retry here)
     int no_iter = 0;
     while (true) {                                                 // :177
         if (isnan(xi_update) || !isfinite(xi_update)) break;
         if (!(fabs(xi_update - xi) > tol)) break;
-        pass_K1K2(c, xi_update, q, k1, k2);
+        pass_K1K2_nr(c, xi_update, q, k1, k2, k2_alt);
         if (!(fabs(k1) > tol)) break;
         if (!(no_iter < max_iter)) break;
         no_iter = no_iter + 1;
@@ -137,7 +249,7 @@ __device__ double NR_spa(SpaCol &c, double q, double tol, int max_iter, long lon
         double numerator = k1;                                     // K1(xi), same point as the loop test
         if (is_bad(numerator)) numerator = pass_K1_alt(c, xi, q);
         double denominator = k2;
-        if (is_bad(denominator)) denominator = pass_K2_alt(c, xi);
+        if (is_bad(denominator)) denominator = k2_alt;             // K2_alt(xi), from the same pass
         xi_update = xi - numerator / denominator;
     }
     nr_iter += no_iter;
@@ -217,42 +329,87 @@ __device__ double saddle_bisect(SpaCol &c, double q, double tol, int max_iter, b
     return tail_from_xhat(c, xhat, q, lower);
 }
 
-// grid-stride over variants; CTA `blockIdx.x` owns scratch slot blockIdx.x (n doubles) for G_tilde.
-__global__ void __launch_bounds__(kThreads) spa_kernel(const double *__restrict__ G, int64_t n, int64_t p,
+// Where a variant's column comes from: the FP64 matrix of the frozen signature, or resident 2-bit columns.
+struct SpaInput {
+    const double *G;                // n x p column-major (dense mode) or nullptr
+    const uint8_t *packed;          // packed mode: resident block, `stride` bytes per column, null-model sample order
+    size_t stride;
+    const long long *variant;       // packed mode: column number of entry v
+    const int32_t *inv_perm;        // packed mode: original sample -> position (nullptr: identity)
+    int impute;
+};
+
+// Persistent clusters; cluster k owns scratch slot k (n doubles) for G_tilde; variants come from the counter `work`.
+__global__ void __launch_bounds__(kThreads) spa_kernel(SpaInput in, int64_t n, int64_t p,
                                                        const double *__restrict__ XW,          // q x n
                                                        const double *__restrict__ XXWX_inv,    // n x q
                                                        int q, const double *__restrict__ residuals,
                                                        const double *__restrict__ muhat, double tol, int max_iter,
                                                        double *__restrict__ gt_scratch, double *__restrict__ pvalue,
-                                                       long long *__restrict__ trace)
+                                                       long long *__restrict__ trace, unsigned long long *work)
 {
-    __shared__ double red[32];
+    __shared__ double red[32 * kMaxSums];
+    __shared__ double slots[2 * kMaxSums * kMaxCluster];
     __shared__ double sb[kMaxQ];
-    double *gt = gt_scratch + (size_t)blockIdx.x * n;
-    for (int64_t v = blockIdx.x; v < p; v += gridDim.x) {
-        const double *g = G + v * n;
-        // b = XW * g (:61 inner product), sum0 = residuals' g (:64, raw G)
-        double s0 = 0.0;
-        for (int64_t j = threadIdx.x; j < n; j += kThreads) s0 += residuals[j] * g[j];
-        const double sum0 = block_sum(s0, red);
-        for (int c0 = 0; c0 < q; c0++) {
-            double s = 0.0;
-            for (int64_t j = threadIdx.x; j < n; j += kThreads) {
-                const double gj = g[j];
-                if (gj != 0.0) s += XW[c0 + j * q] * gj;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned csize = cluster.num_blocks(), crank = cluster.block_rank();
+    const int64_t len = ((n + csize - 1) / csize + 3) & ~(int64_t)3;
+    const int64_t lo = min((long long)n, (long long)crank * len), hi = min((long long)n, (long long)(lo + len));
+    double *gt = gt_scratch + (size_t)(blockIdx.x / csize) * n;
+    SpaCol col{muhat, gt, lo, hi, red, slots, csize, crank, 0, 0};
+    while (true) {
+        // next variant: rank 0 draws, the cluster sum broadcasts (exact: integers below 2^53)
+        double draw = 0.0;
+        if (crank == 0 && threadIdx.x == 0) draw = (double)atomicAdd(work, 1ull);
+        const int64_t v = (int64_t)cluster_sum(col, draw);
+        if (v >= p) break;
+        col.passes = 0;
+        // the column in FP64, caller's sample order, into this CTA's part of the scratch slot
+        if (in.G) {
+            const double *g = in.G + v * n;
+            for (int64_t j = lo + threadIdx.x; j < hi; j += kThreads) gt[j] = g[j];
+        } else {
+            const uint8_t *pc = in.packed + (size_t)in.variant[v] * in.stride;
+            int c1 = 0, c2 = 0, cm = 0;
+            const uint4 *v4 = reinterpret_cast<const uint4 *>(pc);
+            for (int64_t k = (int64_t)crank * kThreads + threadIdx.x; k < (int64_t)(in.stride >> 4); k += (int64_t)csize * kThreads) {
+                const uint4 w = __ldg(v4 + k);
+                count_word(w.x, c1, c2, cm); count_word(w.y, c1, c2, cm); count_word(w.z, c1, c2, cm); count_word(w.w, c1, c2, cm);
             }
-            s = block_sum(s, red);
-            if (threadIdx.x == 0) sb[c0] = s;
+            double t1, t2;
+            cluster_sum2(col, (double)c1, (double)c2, t1, t2);
+            const double tm = cluster_sum(col, (double)cm);
+            const VariantFlip vf = flip_from_counts(PackedCounts{(int)t1, (int)t2, (int)tm}, n, in.impute);
+            for (int64_t j = lo + threadIdx.x; j < hi; j += kThreads) {
+                const int64_t pos = in.inv_perm ? in.inv_perm[j] : j;
+                uint32_t code = ((uint32_t)__ldg(pc + (pos >> 2)) >> (2 * (pos & 3))) & 3u;
+                if (vf.flip && !(code & 1u)) code ^= 2u;
+                gt[j] = code == 3u ? vf.mu : (double)code;
+            }
         }
         __syncthreads();
-        for (int64_t j = threadIdx.x; j < n; j += kThreads) {
+        // b = XW * g (:61 inner product), sum0 = residuals' g (:64, raw G)
+        double s0 = 0.0;
+        for (int64_t j = lo + threadIdx.x; j < hi; j += kThreads) s0 += residuals[j] * gt[j];
+        const double sum0 = cluster_sum(col, s0);
+        for (int c0 = 0; c0 < q; c0 += 2) {
+            double sa = 0.0, sc = 0.0;
+            const bool two = c0 + 1 < q;
+            for (int64_t j = lo + threadIdx.x; j < hi; j += kThreads) {
+                const double gj = gt[j];
+                if (gj != 0.0) { sa += XW[c0 + j * q] * gj; if (two) sc += XW[c0 + 1 + j * q] * gj; }
+            }
+            cluster_sum2(col, sa, sc, sa, sc);
+            if (threadIdx.x == 0) { sb[c0] = sa; if (two) sb[c0 + 1] = sc; }
+        }
+        __syncthreads();
+        for (int64_t j = lo + threadIdx.x; j < hi; j += kThreads) {
             double s = 0.0;
             for (int c0 = 0; c0 < q; c0++) s += XXWX_inv[j + (int64_t)c0 * n] * sb[c0];
-            gt[j] = g[j] - s;
+            gt[j] -= s;
         }
         __syncthreads();
 
-        SpaCol col{muhat, gt, n, red, 0};
         long long nr_iter = 0, bits = 0;
         const double aq = fabs(sum0);
         double res = 1.0;
@@ -276,32 +433,98 @@ __global__ void __launch_bounds__(kThreads) spa_kernel(const double *__restrict_
             else res = respart1 + respart2;
         }
         if (res > 1) { bits |= 16; res = 1.0; }                                // :107-110
-        if (threadIdx.x == 0) {
+        if (crank == 0 && threadIdx.x == 0) {
             pvalue[v] = res;
             if (trace) {
                 trace[4 * v + 0] = col.passes; trace[4 * v + 1] = nr_iter; trace[4 * v + 2] = 0;
                 trace[4 * v + 3] = bits | (nr_iter << 8);
             }
         }
-        __syncthreads();
     }
+    cluster.sync();      // no CTA exits while a peer may still address its shared memory
+}
+
+// samples per variant decide the cluster width (a function of n only, so a variant's result does not depend on
+// which other variants share the call)
+int cluster_width(int64_t n)
+{
+    static const int cap = getenv("STAAR_B200_SPA_CLUSTER") ? atoi(getenv("STAAR_B200_SPA_CLUSTER")) : 8;
+    const int w = n >= (1 << 18) ? 16 : n >= (1 << 17) ? 8 : n >= (1 << 15) ? 4 : n >= (1 << 13) ? 2 : 1;
+    return std::min(w, std::max(cap, 1));
+}
+
+int resident_clusters(staar_ctx *ctx, int width)
+{
+    static int cached[kMaxCluster + 1] = {0};
+    if (cached[width] > 0) return cached[width];
+    if (width > 8 && cudaFuncSetAttribute(spa_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("SPA: cluster width %d is not available on this device", width);
+        return -1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ctx->sm_count * 4 / width * width));
+    cfg.blockDim = dim3(kThreads);
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)width; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int k = 0;
+    if (cudaOccupancyMaxActiveClusters(&k, spa_kernel, &cfg) != cudaSuccess || k <= 0) {
+        cudaGetLastError();
+        k = std::max(1, ctx->sm_count / width);
+    }
+    cached[width] = k;
+    return k;
 }
 
 }  // namespace
 
-int spa_scratch_slots(staar_ctx *ctx, int64_t p) { return (int)std::min<int64_t>(p, (int64_t)ctx->sm_count * 2); }
+int spa_scratch_slots(staar_ctx *ctx, int64_t n, int64_t p)
+{
+    return (int)std::min<int64_t>(std::max<int64_t>(p, 1), resident_clusters(ctx, cluster_width(n)));
+}
+
+static int launch_spa_input(staar_ctx *ctx, const SpaInput &in, int64_t n, int64_t p, const double *dXW,
+                            const double *dXXWX_inv, int q, const double *d_res, const double *d_mu, double tol,
+                            int max_iter, double *d_gt, double *d_pvalue, long long *d_trace)
+{
+    if (p == 0) return STAAR_OK;
+    if (q > kMaxQ) { set_error("SPA: q = %d exceeds the supported maximum of %d", q, kMaxQ); return STAAR_ERR_ARG; }
+    const int width = cluster_width(n), clusters = spa_scratch_slots(ctx, n, p);
+    if (clusters < 1) return STAAR_ERR_CUDA;
+    STAAR_TRY(ctx->ctr.reserve(sizeof(unsigned long long)));
+    unsigned long long *work = ctx->ctr.as<unsigned long long>();
+    STAAR_CUDA(cudaMemsetAsync(work, 0, sizeof(unsigned long long), ctx->stream));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * width));
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)width; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    STAAR_CUDA(cudaLaunchKernelEx(&cfg, spa_kernel, in, n, p, dXW, dXXWX_inv, q, d_res, d_mu, tol, max_iter, d_gt, d_pvalue,
+                                  d_trace, work));
+    ctx->launches++;
+    return STAAR_OK;
+}
 
 int launch_spa(staar_ctx *ctx, const double *dG, int64_t n, int64_t p, const double *dXW, const double *dXXWX_inv,
                int q, const double *d_res, const double *d_mu, double tol, int max_iter, double *d_gt,
                double *d_pvalue, long long *d_trace)
 {
-    if (p == 0) return STAAR_OK;
-    if (q > kMaxQ) { set_error("SPA: q = %d exceeds the supported maximum of %d", q, kMaxQ); return STAAR_ERR_ARG; }
-    spa_kernel<<<spa_scratch_slots(ctx, p), kThreads, 0, ctx->stream>>>(dG, n, p, dXW, dXXWX_inv, q, d_res, d_mu, tol,
-                                                                        max_iter, d_gt, d_pvalue, d_trace);
-    ctx->launches++;
-    STAAR_CUDA(cudaGetLastError());
-    return STAAR_OK;
+    SpaInput in{dG, nullptr, 0, nullptr, nullptr, 0};
+    return launch_spa_input(ctx, in, n, p, dXW, dXXWX_inv, q, d_res, d_mu, tol, max_iter, d_gt, d_pvalue, d_trace);
+}
+
+int launch_spa_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, const long long *d_variant,
+                      const int32_t *d_inv_perm, int impute, int64_t n, int64_t p, const double *dXW,
+                      const double *dXXWX_inv, int q, const double *d_res, const double *d_mu, double tol, int max_iter,
+                      double *d_gt, double *d_pvalue, long long *d_trace)
+{
+    SpaInput in{nullptr, d_packed, stride, d_variant, d_inv_perm, impute};
+    return launch_spa_input(ctx, in, n, p, dXW, dXXWX_inv, q, d_res, d_mu, tol, max_iter, d_gt, d_pvalue, d_trace);
 }
 
 }  // namespace staar

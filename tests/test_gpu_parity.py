@@ -370,15 +370,17 @@ def test_packed_spa_stage_vs_oracle(gpu_ctx, oracle, impute):
     sel = np.array([0, 1, 2, 3, 4, 5, 9, 17, 18, 40, P - 1, 7], dtype=np.int64)      # any order, as a gather list
     d_sel = torch.from_numpy(sel).to(dev)
     d_p = torch.full((sel.size,), -1.0, dtype=torch.float64, device=dev)
+    d_tr = torch.zeros((sel.size, 4), dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
     flag = api.IMPUTE_MEAN if impute == "mean" else api.IMPUTE_MINOR
     gpu_ctx.packed_spa_device(d_cols.data_ptr(), stride, n, d_sel.data_ptr(), sel.size, flag, cases.TOL_SPA,
-                              cases.MAX_ITER, d_p.data_ptr())
+                              cases.MAX_ITER, d_p.data_ptr(), d_tr.data_ptr())
     fl = getattr(oracle, f"matrix_flip_{impute}")(G0)
-    want = oracle.Individual_Score_Test_SPA(np.asfortranarray(fl["Geno"][:, sel]), nb.XW, nb.XXWX_inv, nb.residuals,
-                                            nb.muhat, cases.TOL_SPA, cases.MAX_ITER)
+    want, otr = oracle.Individual_Score_Test_SPA(np.asfortranarray(fl["Geno"][:, sel]), nb.XW, nb.XXWX_inv, nb.residuals,
+                                                 nb.muhat, cases.TOL_SPA, cases.MAX_ITER, return_trace=True)
     got = d_p.cpu().numpy()
     assert rel_err(got, want, 1e-300) < 1e-8
+    assert np.array_equal(d_tr.cpu().numpy()[:, 3], otr[:, 3])             # same branches, same Newton iteration counts
     # and identical to the frozen-signature entry point on the same FP64 columns
     same = gpu_ctx.Individual_Score_Test_SPA(np.asfortranarray(fl["Geno"][:, sel]), nb.XW, nb.XXWX_inv, nb.residuals,
                                              nb.muhat, cases.TOL_SPA, cases.MAX_ITER)

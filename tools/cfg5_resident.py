@@ -32,12 +32,20 @@ for rep in range(2):
     nt, nsel = ctx.packed_analysis_device(packed.data_ptr(), stride, n, V, api.IMPUTE_MEAN, 20.0, 0.05, idx.data_ptr(), ptrs, sel.data_ptr())
     t1 = time.perf_counter()
     cols = idx[sel[:nsel]].contiguous()
-    pv = torch.zeros(nsel, dtype=torch.float64, device=dev)
+    pv = torch.zeros(nsel, dtype=torch.float64, device=dev); tr = torch.zeros((nsel, 4), dtype=torch.int64, device=dev)
     torch.cuda.synchronize(); t2 = time.perf_counter()
-    ctx.packed_spa_device(packed.data_ptr(), stride, n, cols.data_ptr(), nsel, api.IMPUTE_MEAN, tol, 1000, pv.data_ptr())
+    ctx.packed_spa_device(packed.data_ptr(), stride, n, cols.data_ptr(), nsel, api.IMPUTE_MEAN, tol, 1000, pv.data_ptr(), tr.data_ptr())
     t3 = time.perf_counter()
 print(json.dumps({"what": "cfg5 resident flow (n=4e5): stage 1 + SPA stage on the device", "n": n, "variants": V, "tested": nt,
                   "spa_variants": nsel, "stage1_s": t1 - t0, "spa_s": t3 - t2, "spa_variants_per_s": nsel / (t3 - t2),
                   "variants_per_s_overall": V / ((t1 - t0) + (t3 - t2)),
-                  "p_min": float(pv.min().item()) if nsel else None}), flush=True)
+                  "p_min": float(pv.min().item()) if nsel else None,
+                  "passes": {k: float(np.percentile(tr[:, 0].cpu().numpy(), k)) for k in (50, 90, 99, 100)},
+                  "passes_total": int(tr[:, 0].sum().item()), "fallback_variants": int((tr[:, 3] & 5 != 0).sum().item())}), flush=True)
+trh = tr.cpu().numpy(); o = outs.cpu().numpy(); s_ = sel[:nsel].cpu().numpy(); ix = idx.cpu().numpy()
+slow = np.flatnonzero(trh[:, 0] > 1000)[:12]
+for k in slow:
+    r = s_[k]
+    print(json.dumps({"variant": int(ix[r]), "AF": o[0, r], "MAF": o[1, r], "mac": o[1, r] * 2 * n, "score": o[2, r], "se": o[3, r],
+                      "p_score": float(np.exp(-o[4, r])), "p_spa": float(pv[k].item()), "passes": int(trh[k, 0]), "nr_iter": int(trh[k, 1]), "bits": int(trh[k, 3] & 255)}))
 ctx.close()
