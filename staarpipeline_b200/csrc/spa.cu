@@ -350,8 +350,11 @@ __global__ void __launch_bounds__(kThreads) spa_kernel(SpaInput in, int64_t n, i
 {
     __shared__ double red[32 * kMaxSums];
     __shared__ double slots[2 * kMaxSums * kMaxCluster];
-    __shared__ double sb[kMaxQ];
+    __shared__ double sb[kMaxQ + 1];                          // b = XW g; slot kMaxQ = residuals'g
+    __shared__ double wacc[kThreads / 32][kMaxQ + 1];         // per-warp partials of the same
+    __shared__ double xch[kMaxCluster][kMaxQ + 1];            // per-CTA partials, written by every CTA of the cluster
     cg::cluster_group cluster = cg::this_cluster();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned csize = cluster.num_blocks(), crank = cluster.block_rank();
     const int64_t len = ((n + csize - 1) / csize + 3) & ~(int64_t)3;
     const int64_t lo = min((long long)n, (long long)crank * len), hi = min((long long)n, (long long)(lo + len));
@@ -364,49 +367,79 @@ __global__ void __launch_bounds__(kThreads) spa_kernel(SpaInput in, int64_t n, i
         const int64_t v = (int64_t)cluster_sum(col, draw);
         if (v >= p) break;
         col.passes = 0;
-        // the column in FP64, caller's sample order, into this CTA's part of the scratch slot
-        if (in.G) {
-            const double *g = in.G + v * n;
-            for (int64_t j = lo + threadIdx.x; j < hi; j += kThreads) gt[j] = g[j];
-        } else {
-            const uint8_t *pc = in.packed + (size_t)in.variant[v] * in.stride;
+        // flip / imputation value of a resident column from its code counts (matrix_flip_mean|minor on integers)
+        const double *gd = in.G ? in.G + v * n : nullptr;
+        const uint8_t *pc = in.G ? nullptr : in.packed + (size_t)in.variant[v] * in.stride;
+        VariantFlip vf{0.0, 0.0, 0.0, 0};
+        if (!in.G) {
             int c1 = 0, c2 = 0, cm = 0;
             const uint4 *v4 = reinterpret_cast<const uint4 *>(pc);
             for (int64_t k = (int64_t)crank * kThreads + threadIdx.x; k < (int64_t)(in.stride >> 4); k += (int64_t)csize * kThreads) {
-                const uint4 w = __ldg(v4 + k);
-                count_word(w.x, c1, c2, cm); count_word(w.y, c1, c2, cm); count_word(w.z, c1, c2, cm); count_word(w.w, c1, c2, cm);
+                const uint4 wd = __ldg(v4 + k);
+                count_word(wd.x, c1, c2, cm); count_word(wd.y, c1, c2, cm); count_word(wd.z, c1, c2, cm); count_word(wd.w, c1, c2, cm);
             }
-            double t1, t2;
-            cluster_sum2(col, (double)c1, (double)c2, t1, t2);
-            const double tm = cluster_sum(col, (double)cm);
-            const VariantFlip vf = flip_from_counts(PackedCounts{(int)t1, (int)t2, (int)tm}, n, in.impute);
-            for (int64_t j = lo + threadIdx.x; j < hi; j += kThreads) {
-                const int64_t pos = in.inv_perm ? in.inv_perm[j] : j;
-                uint32_t code = ((uint32_t)__ldg(pc + (pos >> 2)) >> (2 * (pos & 3))) & 3u;
-                if (vf.flip && !(code & 1u)) code ^= 2u;
-                gt[j] = code == 3u ? vf.mu : (double)code;
+            double cnt[3] = {(double)c1, (double)c2, (double)cm};
+            cluster_sums(col, cnt);
+            vf = flip_from_counts(PackedCounts{(int)cnt[0], (int)cnt[1], (int)cnt[2]}, n, in.impute);
+        }
+        // One sweep over this CTA's samples, a warp per 32 consecutive samples: the column in FP64 (caller's sample order)
+        // goes to the scratch slot, sum0 = residuals'g (:64, raw G), and b = XW g (:61) is accumulated over the carriers
+        // only — lane c holds covariate c (and c + 32), so a carrier costs one coalesced read of its q-vector of XW.
+        double s0 = 0.0, b0 = 0.0, b1 = 0.0;
+        for (int64_t j0 = lo + 32 * warp; j0 < hi; j0 += kThreads) {
+            const int64_t j = j0 + lane;
+            double gj = 0.0;
+            if (j < hi) {
+                if (gd) gj = gd[j];
+                else {
+                    const int64_t pos = in.inv_perm ? in.inv_perm[j] : j;
+                    uint32_t code = ((uint32_t)__ldg(pc + (pos >> 2)) >> (2 * (pos & 3))) & 3u;
+                    if (vf.flip && !(code & 1u)) code ^= 2u;
+                    gj = code == 3u ? vf.mu : (double)code;
+                }
+                gt[j] = gj;
+                s0 += residuals[j] * gj;
+            }
+            unsigned carriers = __ballot_sync(0xffffffffu, gj != 0.0);
+            while (carriers) {
+                const int src = __ffs(carriers) - 1;
+                carriers &= carriers - 1;
+                const double gs = __shfl_sync(0xffffffffu, gj, src);
+                const double *xw = XW + (j0 + src) * q;
+                if (lane < q) b0 += xw[lane] * gs;
+                if (lane + 32 < q) b1 += xw[lane + 32] * gs;
             }
         }
+        s0 = warp_sum(s0);
+        wacc[warp][lane] = b0; wacc[warp][lane + 32] = b1;
+        if (lane == 0) wacc[warp][kMaxQ] = s0;
         __syncthreads();
-        // b = XW * g (:61 inner product), sum0 = residuals' g (:64, raw G)
-        double s0 = 0.0;
-        for (int64_t j = lo + threadIdx.x; j < hi; j += kThreads) s0 += residuals[j] * gt[j];
-        const double sum0 = cluster_sum(col, s0);
-        for (int c0 = 0; c0 < q; c0 += 2) {
+        if (threadIdx.x <= kMaxQ) {                     // warps in order, then CTAs in rank order: fixed summation tree
+            double t = 0.0;
+            for (int ww = 0; ww < kThreads / 32; ww++) t += wacc[ww][threadIdx.x];
+            for (unsigned r = 0; r < csize; r++) cluster.map_shared_rank(&xch[0][0], r)[crank * (kMaxQ + 1) + threadIdx.x] = t;
+        }
+        cluster.sync();
+        if (threadIdx.x <= kMaxQ) {
+            double t = 0.0;
+            for (unsigned r = 0; r < csize; r++) t += xch[r][threadIdx.x];
+            sb[threadIdx.x] = t;
+        }
+        __syncthreads();
+        const double sum0 = sb[kMaxQ];
+        // G_tilde = g - XXWX_inv b (:61), two samples per thread in flight
+        for (int64_t j = lo + threadIdx.x; j < hi; j += 2 * kThreads) {
+            const int64_t j2 = j + kThreads;
+            const bool ok2 = j2 < hi;
             double sa = 0.0, sc = 0.0;
-            const bool two = c0 + 1 < q;
-            for (int64_t j = lo + threadIdx.x; j < hi; j += kThreads) {
-                const double gj = gt[j];
-                if (gj != 0.0) { sa += XW[c0 + j * q] * gj; if (two) sc += XW[c0 + 1 + j * q] * gj; }
+#pragma unroll 4
+            for (int c0 = 0; c0 < q; c0++) {
+                const double bc = sb[c0];
+                sa += XXWX_inv[j + (int64_t)c0 * n] * bc;
+                if (ok2) sc += XXWX_inv[j2 + (int64_t)c0 * n] * bc;
             }
-            cluster_sum2(col, sa, sc, sa, sc);
-            if (threadIdx.x == 0) { sb[c0] = sa; if (two) sb[c0 + 1] = sc; }
-        }
-        __syncthreads();
-        for (int64_t j = lo + threadIdx.x; j < hi; j += kThreads) {
-            double s = 0.0;
-            for (int c0 = 0; c0 < q; c0++) s += XXWX_inv[j + (int64_t)c0 * n] * sb[c0];
-            gt[j] -= s;
+            gt[j] -= sa;
+            if (ok2) gt[j2] -= sc;
         }
         __syncthreads();
 

@@ -385,3 +385,14 @@ def test_packed_spa_stage_vs_oracle(gpu_ctx, oracle, impute):
     same = gpu_ctx.Individual_Score_Test_SPA(np.asfortranarray(fl["Geno"][:, sel]), nb.XW, nb.XXWX_inv, nb.residuals,
                                              nb.muhat, cases.TOL_SPA, cases.MAX_ITER)
     assert np.array_equal(got, same)
+
+
+@pytest.mark.parametrize("n,q,p,planted", [(9000, 5, 10, 3), (40000, 34, 8, 3), (140000, 13, 6, 1)])
+def test_spa_cluster_widths_vs_oracle(gpu_ctx, oracle, n, q, p, planted):
+    """The SPA kernel splits a variant over a thread-block cluster whose width grows with n (2, 4, 8 CTAs here;
+    1 in the small cases above); q = 34 exercises the second covariate slot per lane of the XW·g sweep."""
+    c, _ = cases.case_spa(oracle, n=n, p=p, q=q, seed=n % 97, planted=planted)
+    got, tr = gpu_ctx.Individual_Score_Test_SPA(**c, return_trace=True)
+    want, otr = oracle.Individual_Score_Test_SPA(**c, return_trace=True)
+    assert rel_err(got, want, 1e-300) < 1e-8
+    assert np.array_equal(tr[:, 3], otr[:, 3])
