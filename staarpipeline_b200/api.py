@@ -20,7 +20,7 @@ import numpy as np
 import scipy.sparse as sp
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstaar_b200.so")
+LIB_PATH = os.environ.get("STAAR_B200_LIB") or os.path.join(_HERE, "libstaar_b200.so")   # override: experiment builds
 _dp = C.POINTER(C.c_double)
 _u64p = C.POINTER(C.c_uint64)
 _u8p = C.POINTER(C.c_uint8)

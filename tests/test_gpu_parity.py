@@ -9,7 +9,7 @@ import pytest
 import scipy.sparse as sp
 
 import cases
-from util import assert_stats_close, rel_err
+from util import assert_spa_pvalues_close, assert_stats_close, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -119,7 +119,7 @@ def test_spa_trace_and_parity(gpu_ctx, oracle):
     c, _ = cases.case_spa(oracle, n=6000, p=48, seed=41)
     got, tr = gpu_ctx.Individual_Score_Test_SPA(**c, return_trace=True)
     want, otr = oracle.Individual_Score_Test_SPA(**c, return_trace=True)
-    assert rel_err(got, want, 1e-300) < 1e-8
+    assert_spa_pvalues_close(got, want)
     # same branches taken and same number of Newton iterations as the reference's control flow
     assert np.array_equal(tr[:, 3], otr[:, 3])
 
@@ -379,7 +379,7 @@ def test_packed_spa_stage_vs_oracle(gpu_ctx, oracle, impute):
     want, otr = oracle.Individual_Score_Test_SPA(np.asfortranarray(fl["Geno"][:, sel]), nb.XW, nb.XXWX_inv, nb.residuals,
                                                  nb.muhat, cases.TOL_SPA, cases.MAX_ITER, return_trace=True)
     got = d_p.cpu().numpy()
-    assert rel_err(got, want, 1e-300) < 1e-8
+    assert_spa_pvalues_close(got, want)
     assert np.array_equal(d_tr.cpu().numpy()[:, 3], otr[:, 3])             # same branches, same Newton iteration counts
     # and identical to the frozen-signature entry point on the same FP64 columns
     same = gpu_ctx.Individual_Score_Test_SPA(np.asfortranarray(fl["Geno"][:, sel]), nb.XW, nb.XXWX_inv, nb.residuals,
@@ -394,5 +394,5 @@ def test_spa_cluster_widths_vs_oracle(gpu_ctx, oracle, n, q, p, planted):
     c, _ = cases.case_spa(oracle, n=n, p=p, q=q, seed=n % 97, planted=planted)
     got, tr = gpu_ctx.Individual_Score_Test_SPA(**c, return_trace=True)
     want, otr = oracle.Individual_Score_Test_SPA(**c, return_trace=True)
-    assert rel_err(got, want, 1e-300) < 1e-8
+    assert_spa_pvalues_close(got, want)
     assert np.array_equal(tr[:, 3], otr[:, 3])
