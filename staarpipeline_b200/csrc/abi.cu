@@ -278,6 +278,60 @@ int run_dense_family(staar_ctx *ctx, int64_t n, int64_t p, int k, const double *
     return sync(ctx);
 }
 
+// Sparse genotype columns against the dense P: carriers only (quadform.cu).  Taken when no column has more than n/8
+// stored entries — the R driver sends MAF < 0.05 here, i.e. <= 0.0975 n carriers; denser input goes through P*G.
+bool csc_is_sparse_enough(const uint64_t *Gc, int64_t n, int64_t p)
+{
+    uint64_t worst = 0;
+    for (int64_t j = 0; j < p; j++) worst = std::max<uint64_t>(worst, Gc[j + 1] - Gc[j]);
+    return worst <= (uint64_t)(n / 8);
+}
+
+int run_dense_family_carriers(staar_ctx *ctx, const double *Gv, const uint64_t *Gr, const uint64_t *Gc, int64_t n, int64_t p,
+                              int k, const double *residuals, double *Score, double *Score_se, double *pl, double *Est,
+                              double *Est_se)
+{
+    const int kk = k > 0 ? k : 1;
+    if (k > 0 && p % k != 0) { set_error("number of columns of G (%lld) is not a multiple of n_pheno (%d)", (long long)p, k); return STAAR_ERR_ARG; }
+    if (!Gv || !Gr || !Gc) { set_error("sparse G pointer is NULL"); return STAAR_ERR_ARG; }
+    const int64_t pp = p / kk, npairs = pp * kk * kk;
+    const uint64_t nnz = Gc[p];
+    for (uint64_t e = 0; e < nnz; e++)
+        if (Gr[e] >= (uint64_t)n) { set_error("sparse G: row index out of range"); return STAAR_ERR_ARG; }
+    STAAR_TRY(ctx->pk.reserve(nnz * 16 + (size_t)(p + 1) * 8 + 64));
+    double *dval = ctx->pk.as<double>();
+    int64_t *drow = reinterpret_cast<int64_t *>(dval + nnz), *dcp = drow + nnz;
+    STAAR_TRY(h2d(ctx, dval, Gv, nnz * 8));
+    STAAR_TRY(h2d(ctx, drow, Gr, nnz * 8));
+    STAAR_TRY(h2d(ctx, dcp, Gc, (size_t)(p + 1) * 8));
+    const int ldY = 8;
+    STAAR_TRY(ctx->aux.reserve(sizeof(double) * (size_t)n));
+    double *dres = ctx->aux.as<double>();
+    STAAR_TRY(h2d(ctx, dres, residuals, sizeof(double) * n));
+    STAAR_TRY(ctx->L.reserve(sizeof(double) * (size_t)std::max<int64_t>(p, 1) * ldY));
+    STAAR_CUDA(cudaMemsetAsync(ctx->L.p, 0, sizeof(double) * (size_t)std::max<int64_t>(p, 1) * ldY, ctx->stream));
+    STAAR_TRY(launch_score_carriers(ctx, dval, drow, dcp, p, dres, ctx->L.as<double>(), ldY));
+    STAAR_TRY(ctx->tmp.reserve(sizeof(int32_t) * 2 * (size_t)npairs + sizeof(double) * (size_t)npairs + 64));
+    double *dquad = ctx->tmp.as<double>();
+    int32_t *dcolA = reinterpret_cast<int32_t *>(dquad + npairs), *dcolB = dcolA + npairs;
+    STAAR_TRY(launch_fill_pairs(ctx, pp, kk, dcolA, dcolB));
+    STAAR_TRY(launch_quad_pairs_carriers_P(ctx, dval, drow, dcp, n, ctx->nd.P, dcolA, dcolB, npairs, dquad));
+    STAAR_TRY(ctx->out.reserve(sizeof(double) * 5 * (size_t)std::max<int64_t>(p, 1)));
+    double *o = ctx->out.as<double>();
+    STAAR_TRY(launch_epilogue_general(ctx, p, k, ctx->L.as<double>(), ldY, 0, nullptr, dquad, 0, nullptr, nullptr, 0, 0,
+                                      o, o + p, o + 2 * p, o + 3 * p, o + 4 * p));
+    STAAR_TRY(d2h(ctx, Score, o, sizeof(double) * p));
+    if (k == 0) {
+        STAAR_TRY(d2h(ctx, Score_se, o + p, sizeof(double) * p));
+        STAAR_TRY(d2h(ctx, pl, o + 2 * p, sizeof(double) * p));
+        STAAR_TRY(d2h(ctx, Est, o + 3 * p, sizeof(double) * p));
+        STAAR_TRY(d2h(ctx, Est_se, o + 4 * p, sizeof(double) * p));
+    } else {
+        STAAR_TRY(d2h(ctx, pl, o + 2 * p, sizeof(double) * pp));
+    }
+    return sync(ctx);
+}
+
 int check_dims(int64_t n, int64_t p)
 {
     if (n <= 0 || p < 0) { set_error("bad dimensions n=%lld p=%lld", (long long)n, (long long)p); return STAAR_ERR_ARG; }
@@ -357,6 +411,8 @@ int staar_individual_score_test_sp_denseGRM(staar_ctx *ctx, const double *Gv, co
     CHECK_CTX(ctx);
     STAAR_TRY(check_dims(n, p));
     STAAR_TRY(ensure_dense(ctx, n, P));
+    if (Gc && csc_is_sparse_enough(Gc, n, p))
+        return run_dense_family_carriers(ctx, Gv, Gr, Gc, n, p, 0, res, Score, Score_se, pl, Est, Est_se);
     STAAR_TRY(upload_csc_G(ctx, Gv, Gr, Gc, n, p));
     return run_dense_family(ctx, n, p, 0, res, Score, Score_se, pl, Est, Est_se);
 }
@@ -405,6 +461,8 @@ int staar_individual_score_test_sp_denseGRM_multi(staar_ctx *ctx, const double *
     STAAR_TRY(check_dims(n, p));
     if (n_pheno < 1) { set_error("n_pheno must be >= 1"); return STAAR_ERR_ARG; }
     STAAR_TRY(ensure_dense(ctx, n, P));
+    if (Gc && csc_is_sparse_enough(Gc, n, p))
+        return run_dense_family_carriers(ctx, Gv, Gr, Gc, n, p, n_pheno, res, Score, nullptr, pl, nullptr, nullptr);
     STAAR_TRY(upload_csc_G(ctx, Gv, Gr, Gc, n, p));
     return run_dense_family(ctx, n, p, n_pheno, res, Score, nullptr, pl, nullptr, nullptr);
 }

@@ -166,6 +166,10 @@ int launch_quad_pairs_csr(staar_ctx *ctx, const double *dG, int64_t n, const int
                           const double *val, const int32_t *d_colA, const int32_t *d_colB, int64_t npairs, double *d_out);
 // W = P * G (n x p), then out[pair] = g_a' * W[:, b]
 int launch_dense_P_times_G(staar_ctx *ctx, const double *dP, const double *dG, int64_t n, int64_t p, double *dW);
+int launch_quad_pairs_carriers_P(staar_ctx *ctx, const double *d_val, const int64_t *d_row, const int64_t *d_colptr, int64_t n,
+                                 const double *dP, const int32_t *d_colA, const int32_t *d_colB, int64_t npairs, double *d_out);
+int launch_score_carriers(staar_ctx *ctx, const double *d_val, const int64_t *d_row, const int64_t *d_colptr, int64_t p,
+                          const double *d_res, double *dL, int ldL);
 int launch_dot_pairs(staar_ctx *ctx, const double *dG, const double *dW, int64_t n, const int32_t *d_colA,
                      const int32_t *d_colB, int64_t npairs, double *d_out);
 // epilogue.cu — K5/K7.  k == 0: single-trait outputs; k >= 1: k-trait block test (pl has p_total/k entries).

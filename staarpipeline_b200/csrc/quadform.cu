@@ -7,6 +7,11 @@
 //  * dense_P_times_G : W = P*G for the dense-GRM family (src/Individual_Score_Test_denseGRM.cpp:37) as an
 //                      FP64 tensor-core GEMM (mma.sync m8n8k4 DMMA, 128x64 CTA tile, next tiles
 //                      prefetched into registers under the MMAs); dot_pairs then takes g_a' * W[:,b].
+//  * quad_pairs_carriers_P / score_carriers : the same dense-GRM quantities for SPARSE genotype columns
+//                      (src/Individual_Score_Test_sp_denseGRM.cpp:17,37 — the route of rare variants, MAF < 0.05,
+//                      R/Individual_Analysis.R:372) taken over the carriers only: g_a' P g_b = sum_{i in a} sum_{j in b}
+//                      v_i v_j P[i,j], c_a*c_b gathers from P instead of 2 n^2 flop of P*G (a singleton with 40
+//                      carriers at n = 20 000: 820 loads against 8e8 flop).
 // FP64 throughout (1e-10 parity); deterministic tree reductions, no atomics.
 #include "common.cuh"
 
@@ -54,6 +59,78 @@ __global__ void __launch_bounds__(256) dot_pairs_kernel(const double *__restrict
         for (int64_t j = threadIdx.x; j < n; j += blockDim.x) acc += ga[j] * wb[j];
         acc = block_sum(acc, red);
         if (threadIdx.x == 0) out[pr] = acc;
+    }
+}
+
+
+// One CTA per (a, b) pair of sparse columns; the b list sits in shared memory in tiles, the a list is walked serially
+// with the threads spread over b.  For a == b only j >= i is visited (P is symmetric: Sigma^-1 - Sigma^-1 X cov X' Sigma^-1).
+constexpr int kCarrierTile = 1024;
+__global__ void __launch_bounds__(256) quad_pairs_carriers_P_kernel(const double *__restrict__ val, const int64_t *__restrict__ row,
+                                                                    const int64_t *__restrict__ colptr, int64_t n,
+                                                                    const double *__restrict__ P,
+                                                                    const int32_t *__restrict__ colA,
+                                                                    const int32_t *__restrict__ colB, int64_t npairs,
+                                                                    double *__restrict__ out)
+{
+    __shared__ double red[32];
+    __shared__ double bv[kCarrierTile];
+    __shared__ int32_t bi[kCarrierTile];
+    for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+        const int ca = colA[pr], cb = colB[pr];
+        const int64_t a0 = colptr[ca], a1 = colptr[ca + 1], b0 = colptr[cb], b1 = colptr[cb + 1];
+        const bool same = ca == cb;
+        double acc = 0.0;
+        for (int64_t t0 = b0; t0 < b1; t0 += kCarrierTile) {
+            const int tn = (int)min((long long)kCarrierTile, (long long)(b1 - t0));
+            __syncthreads();
+            for (int t = threadIdx.x; t < tn; t += blockDim.x) { bv[t] = val[t0 + t]; bi[t] = (int32_t)row[t0 + t]; }
+            __syncthreads();
+            // same column: entry e of the a list pairs with entries >= e of the b list (off-diagonal terms twice)
+            const int64_t e_end = same ? min((long long)a1, (long long)(t0 + tn)) : a1;
+            for (int64_t e = a0; e < e_end; e += 4) {                  // four rows of P in flight per thread
+                double va[4], s[4];
+                const double *Pi[4];
+                int first[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int64_t ek = e + k;
+                    const bool live = ek < e_end;
+                    va[k] = live ? val[ek] : 0.0;
+                    Pi[k] = P + (size_t)row[live ? ek : e] * n;        // column i of P (= row i)
+                    first[k] = !live ? tn : (same ? (int)max(0ll, (long long)(ek - t0)) : 0);
+                    s[k] = 0.0;
+                }
+                for (int t = first[0] + threadIdx.x; t < tn; t += blockDim.x) {
+                    const double b = bv[t];
+                    const int32_t j = bi[t];
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (t >= first[k]) {
+                            const double term = b * Pi[k][j];
+                            s[k] += (same && t0 + t != e + k) ? 2.0 * term : term;
+                        }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) acc += va[k] * s[k];
+            }
+        }
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) out[pr] = acc;
+    }
+}
+
+// Uscore of sparse columns: L[j*ldL] = sum_e val[e] * residuals[row[e]]   (a warp per column)
+__global__ void __launch_bounds__(256) score_carriers_kernel(const double *__restrict__ val, const int64_t *__restrict__ row,
+                                                             const int64_t *__restrict__ colptr, int64_t p,
+                                                             const double *__restrict__ residuals, double *__restrict__ L, int ldL)
+{
+    const int lane = threadIdx.x & 31;
+    for (int64_t j = blockIdx.x * 8ll + (threadIdx.x >> 5); j < p; j += gridDim.x * 8ll) {
+        double s = 0.0;
+        for (int64_t e = colptr[j] + lane; e < colptr[j + 1]; e += 32) s += val[e] * residuals[row[e]];
+        s = warp_sum(s);
+        if (lane == 0) L[j * ldL] = s;
     }
 }
 
@@ -167,6 +244,28 @@ int launch_dot_pairs(staar_ctx *ctx, const double *dG, const double *dW, int64_t
     if (npairs == 0) return STAAR_OK;
     int grid = (int)std::min<int64_t>(npairs, (int64_t)ctx->sm_count * 16);
     dot_pairs_kernel<<<grid, 256, 0, ctx->stream>>>(dG, dW, n, d_colA, d_colB, npairs, d_out);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+int launch_quad_pairs_carriers_P(staar_ctx *ctx, const double *d_val, const int64_t *d_row, const int64_t *d_colptr, int64_t n,
+                                 const double *dP, const int32_t *d_colA, const int32_t *d_colB, int64_t npairs, double *d_out)
+{
+    if (npairs == 0) return STAAR_OK;
+    const int grid = (int)std::min<int64_t>(npairs, (int64_t)ctx->sm_count * 8);
+    quad_pairs_carriers_P_kernel<<<grid, 256, 0, ctx->stream>>>(d_val, d_row, d_colptr, n, dP, d_colA, d_colB, npairs, d_out);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+int launch_score_carriers(staar_ctx *ctx, const double *d_val, const int64_t *d_row, const int64_t *d_colptr, int64_t p,
+                          const double *d_res, double *dL, int ldL)
+{
+    if (p == 0) return STAAR_OK;
+    const int grid = (int)std::min<int64_t>((p + 7) / 8, (int64_t)ctx->sm_count * 8);
+    score_carriers_kernel<<<grid, 256, 0, ctx->stream>>>(d_val, d_row, d_colptr, p, d_res, dL, ldL);
     ctx->launches++;
     STAAR_CUDA(cudaGetLastError());
     return STAAR_OK;

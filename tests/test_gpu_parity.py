@@ -396,3 +396,43 @@ def test_spa_cluster_widths_vs_oracle(gpu_ctx, oracle, n, q, p, planted):
     want, otr = oracle.Individual_Score_Test_SPA(**c, return_trace=True)
     assert_spa_pvalues_close(got, want)
     assert np.array_equal(tr[:, 3], otr[:, 3])
+
+
+def _rare_columns(rng, n, p, max_carriers):
+    """sparse genotype columns as the rare-variant route sees them: 0/1/2 carriers plus a few mean-imputed values"""
+    G = np.zeros((n, p))
+    for j in range(p):
+        c = int(rng.integers(0, max_carriers + 1)) if j > 2 else (0, 1, max_carriers)[j]
+        idx = rng.choice(n, size=c, replace=False)
+        G[idx, j] = rng.choice([1.0, 2.0, 0.0123], size=c, p=[0.8, 0.15, 0.05])
+    return G
+
+
+@pytest.mark.parametrize("n,p", [(1500, 24), (9000, 12)])
+def test_sp_dense_grm_carrier_route_vs_oracle(gpu_ctx, oracle, n, p):
+    """Individual_Score_Test_sp_denseGRM on columns with <= n/8 stored entries takes the carrier form of g'Pg
+    (no P*G product); n = 9000 makes the longest carrier list (1125) span two shared-memory tiles.  Compared with the
+    oracle and with the dense-G entry point (P*G route) on the same columns."""
+    from staarpipeline_b200 import synth
+    nd = synth.nullmodel_dense_grm(n, seed=n, q=5, markers=300)
+    G = _rare_columns(np.random.default_rng(n), n, p, n // 8)
+    Gs = sp.csc_matrix(G)
+    got = gpu_ctx.Individual_Score_Test_sp_denseGRM(Gs, nd.P, nd.residuals)
+    want = oracle.Individual_Score_Test_sp_denseGRM(Gs, nd.P, nd.residuals)
+    assert_stats_close(got, want, score_floor(G, nd.residuals))
+    dense = gpu_ctx.Individual_Score_Test_denseGRM(np.asfortranarray(G), nd.P, nd.residuals)
+    assert_stats_close(got, dense, score_floor(G, nd.residuals))
+    assert got["Score_se"][0] == 0.0 and got["pvalue_log"][0] == 0.0          # empty column: the Cov == 0 branch
+
+
+def test_sp_dense_grm_multi_carrier_route_vs_oracle(gpu_ctx, oracle):
+    """two traits: the k x k blocks need g_a' P g_b between DIFFERENT Kronecker columns (disjoint carrier rows)"""
+    c, _ = cases.case_dense_multi(oracle, n=400, p=12, k=2)
+    n = 400
+    G0 = _rare_columns(np.random.default_rng(3), n, 12, n // 8)
+    GK = sp.kron(sp.identity(2, format="csc"), sp.csc_matrix(G0), format="csc")
+    kw = dict(c, G=GK)
+    got = gpu_ctx.Individual_Score_Test_sp_denseGRM_multi(**kw)
+    want = oracle.Individual_Score_Test_sp_denseGRM_multi(**kw)
+    assert rel_err(got["Score"], want["Score"], score_floor(GK, kw["residuals"])) < 1e-10
+    assert np.all(np.abs(got["pvalue_log"] - want["pvalue_log"]) <= 1e-8 * np.maximum(1.0, np.abs(want["pvalue_log"])))
