@@ -141,9 +141,18 @@ int prepare_cond(staar_ctx *ctx, const double *X_adj, int64_t m, const double *c
     const int ldc = (int)((1 + q + 2 * m + 7) / 8 * 8), ld2 = (int)((1 + 2 * m + 7) / 8 * 8);
     // aux layout: A (n*m) | PA (n*m) | Ycond (n*ldc) | Y2 (n*ld2) | T1 (q*m) | M (m*m) | MQM (m*m)
     const size_t need = sizeof(double) * ((size_t)2 * n * m + (size_t)n * ldc + (size_t)n * ld2 + q * m + 2 * m * m);
-    STAAR_TRY(ctx->aux.reserve(need));
-    double *dA = ctx->aux.as<double>(), *dPA = dA + n * m, *dYc = dPA + n * m, *dY2 = dYc + (size_t)n * ldc;
+    // same X_adj, same null model, same residual vector as the previous call: everything below is still on the device
+    const uint64_t key = hash_bytes(X_adj, sizeof(double) * (size_t)n * m, 31) ^ ns.fingerprint ^ (ns.res_fingerprint * 3) ^ (uint64_t)m;
+    const void *before = ctx->cond.p;
+    STAAR_TRY(ctx->cond.reserve(need));
+    if (ctx->cond.p != before) ctx->cond_key = 0;                     // buffer grew: contents are gone
+    double *dA = ctx->cond.as<double>(), *dPA = dA + n * m, *dYc = dPA + n * m, *dY2 = dYc + (size_t)n * ldc;
     double *dT1 = dY2 + (size_t)n * ld2, *dM = dT1 + q * m, *dMQM = dM + m * m;
+    if (ctx->cond_key == key && ctx->cond_m == (int)m && ctx->cond_ld == ldc && key != 0) {
+        co.m = (int)m; co.dM = dM; co.dMQM = dMQM; co.dY = dYc; co.ldY = ldc; co.colA0 = (int)(1 + q); co.colPA0 = (int)(1 + q + m);
+        return STAAR_OK;
+    }
+    ctx->cond_key = 0;
     STAAR_TRY(h2d(ctx, dA, X_adj, sizeof(double) * n * m));
     // trans(Sigma_iX) * X_adj  (q x m): contraction of the m columns of A against Y = [res | SX]
     STAAR_TRY(ctx->L.reserve(sizeof(double) * (size_t)m * std::max(ns.ldY, ld2)));
@@ -196,6 +205,7 @@ int prepare_cond(staar_ctx *ctx, const double *X_adj, int64_t m, const double *c
                                  cudaMemcpyDeviceToDevice, ctx->stream));
     STAAR_TRY(launch_build_Y(ctx, n, ldc, ctx->tmp.as<double>(), ns.SX, (int)q, dA, dPA, (int)m, dYc));
     STAAR_TRY(sync(ctx));       // host vectors above go out of scope
+    ctx->cond_key = key; ctx->cond_m = (int)m; ctx->cond_ld = ldc;
     co.m = (int)m; co.dM = dM; co.dMQM = dMQM; co.dY = dYc; co.ldY = ldc; co.colA0 = (int)(1 + q); co.colPA0 = (int)(1 + q + m);
     return STAAR_OK;
 }
@@ -280,11 +290,69 @@ int run_dense_family(staar_ctx *ctx, int64_t n, int64_t p, int k, const double *
 
 // Sparse genotype columns against the dense P: carriers only (quadform.cu).  Taken when no column has more than n/8
 // stored entries — the R driver sends MAF < 0.05 here, i.e. <= 0.0975 n carriers; denser input goes through P*G.
-bool csc_is_sparse_enough(const uint64_t *Gc, int64_t n, int64_t p)
+bool csc_is_sparse_enough(const uint64_t *Gr, const uint64_t *Gc, int64_t n, int64_t p)
 {
+    if (!Gr || !Gc) return false;
     uint64_t worst = 0;
-    for (int64_t j = 0; j < p; j++) worst = std::max<uint64_t>(worst, Gc[j + 1] - Gc[j]);
+    for (int64_t j = 0; j < p; j++) {
+        worst = std::max<uint64_t>(worst, Gc[j + 1] - Gc[j]);
+        for (uint64_t e = Gc[j] + 1; e < Gc[j + 1]; e++)
+            if (Gr[e] <= Gr[e - 1]) return false;          // unsorted / duplicate rows (not an arma::sp_mat): dense route
+    }
     return worst <= (uint64_t)(n / 8);
+}
+
+// upload of a sparse genotype block as it is (values | int64 rows | int64 column pointers) into ctx->pk
+int upload_csc_carriers(staar_ctx *ctx, const double *Gv, const uint64_t *Gr, const uint64_t *Gc, int64_t n, int64_t p,
+                        double **dval, int64_t **drow, int64_t **dcp)
+{
+    if (!Gv || !Gr || !Gc) { set_error("sparse G pointer is NULL"); return STAAR_ERR_ARG; }
+    const uint64_t nnz = Gc[p];
+    for (uint64_t e = 0; e < nnz; e++)
+        if (Gr[e] >= (uint64_t)n) { set_error("sparse G: row index out of range"); return STAAR_ERR_ARG; }
+    STAAR_TRY(ctx->pk.reserve(nnz * 16 + (size_t)(p + 1) * 8 + 64));
+    *dval = ctx->pk.as<double>();
+    *drow = reinterpret_cast<int64_t *>(*dval + nnz);
+    *dcp = *drow + nnz;
+    STAAR_TRY(h2d(ctx, *dval, Gv, nnz * 8));
+    STAAR_TRY(h2d(ctx, *drow, Gr, nnz * 8));            // uint64 indices < 2^63: same bits as int64
+    STAAR_TRY(h2d(ctx, *dcp, Gc, (size_t)(p + 1) * 8));
+    return STAAR_OK;
+}
+
+// Individual_Score_Test_sp / _sp_multi on sparse columns: contraction and quadratic forms over the stored entries
+int run_sparse_family_carriers(staar_ctx *ctx, const double *Gv, const uint64_t *Gr, const uint64_t *Gc, int64_t n, int64_t p,
+                               int k, double *Score, double *Score_se, double *pl, double *Est, double *Est_se)
+{
+    NullSparse &ns = ctx->ns;
+    const int kk = k > 0 ? k : 1;
+    if (k > 0 && p % k != 0) { set_error("number of columns of G (%lld) is not a multiple of n_pheno (%d)", (long long)p, k); return STAAR_ERR_ARG; }
+    const int64_t pp = p / kk, npairs = pp * kk * kk;
+    double *dval; int64_t *drow, *dcp;
+    STAAR_TRY(upload_csc_carriers(ctx, Gv, Gr, Gc, n, p, &dval, &drow, &dcp));
+    const int ldY = ns.ldY, ncols = (int)(1 + ns.q);
+    STAAR_TRY(ctx->L.reserve(sizeof(double) * (size_t)std::max<int64_t>(p, 1) * ldY));
+    STAAR_CUDA(cudaMemsetAsync(ctx->L.p, 0, sizeof(double) * (size_t)std::max<int64_t>(p, 1) * ldY, ctx->stream));
+    STAAR_TRY(launch_contract_carriers(ctx, dval, drow, dcp, p, ns.Y, ldY, ncols, ctx->L.as<double>(), ldY));
+    STAAR_TRY(ctx->tmp.reserve(sizeof(int32_t) * 2 * (size_t)npairs + sizeof(double) * (size_t)npairs + 64));
+    double *dquad = ctx->tmp.as<double>();
+    int32_t *dcolA = reinterpret_cast<int32_t *>(dquad + npairs), *dcolB = dcolA + npairs;
+    STAAR_TRY(launch_fill_pairs(ctx, pp, kk, dcolA, dcolB));
+    STAAR_TRY(launch_quad_pairs_carriers_csr(ctx, dval, drow, dcp, ns.row_ptr, ns.col, ns.val, dcolA, dcolB, npairs, dquad));
+    STAAR_TRY(ctx->out.reserve(sizeof(double) * 5 * (size_t)std::max<int64_t>(p, 1)));
+    double *o = ctx->out.as<double>();
+    STAAR_TRY(launch_epilogue_general(ctx, p, k, ctx->L.as<double>(), ldY, (int)ns.q, ns.cov, dquad, 0, nullptr, nullptr, 0, 0,
+                                      o, o + p, o + 2 * p, o + 3 * p, o + 4 * p));
+    STAAR_TRY(d2h(ctx, Score, o, sizeof(double) * p));
+    if (k == 0) {
+        STAAR_TRY(d2h(ctx, Score_se, o + p, sizeof(double) * p));
+        STAAR_TRY(d2h(ctx, pl, o + 2 * p, sizeof(double) * p));
+        STAAR_TRY(d2h(ctx, Est, o + 3 * p, sizeof(double) * p));
+        STAAR_TRY(d2h(ctx, Est_se, o + 4 * p, sizeof(double) * p));
+    } else {
+        STAAR_TRY(d2h(ctx, pl, o + 2 * p, sizeof(double) * pp));
+    }
+    return sync(ctx);
 }
 
 int run_dense_family_carriers(staar_ctx *ctx, const double *Gv, const uint64_t *Gr, const uint64_t *Gc, int64_t n, int64_t p,
@@ -293,17 +361,9 @@ int run_dense_family_carriers(staar_ctx *ctx, const double *Gv, const uint64_t *
 {
     const int kk = k > 0 ? k : 1;
     if (k > 0 && p % k != 0) { set_error("number of columns of G (%lld) is not a multiple of n_pheno (%d)", (long long)p, k); return STAAR_ERR_ARG; }
-    if (!Gv || !Gr || !Gc) { set_error("sparse G pointer is NULL"); return STAAR_ERR_ARG; }
     const int64_t pp = p / kk, npairs = pp * kk * kk;
-    const uint64_t nnz = Gc[p];
-    for (uint64_t e = 0; e < nnz; e++)
-        if (Gr[e] >= (uint64_t)n) { set_error("sparse G: row index out of range"); return STAAR_ERR_ARG; }
-    STAAR_TRY(ctx->pk.reserve(nnz * 16 + (size_t)(p + 1) * 8 + 64));
-    double *dval = ctx->pk.as<double>();
-    int64_t *drow = reinterpret_cast<int64_t *>(dval + nnz), *dcp = drow + nnz;
-    STAAR_TRY(h2d(ctx, dval, Gv, nnz * 8));
-    STAAR_TRY(h2d(ctx, drow, Gr, nnz * 8));
-    STAAR_TRY(h2d(ctx, dcp, Gc, (size_t)(p + 1) * 8));
+    double *dval; int64_t *drow, *dcp;
+    STAAR_TRY(upload_csc_carriers(ctx, Gv, Gr, Gc, n, p, &dval, &drow, &dcp));
     const int ldY = 8;
     STAAR_TRY(ctx->aux.reserve(sizeof(double) * (size_t)n));
     double *dres = ctx->aux.as<double>();
@@ -389,6 +449,8 @@ int staar_individual_score_test_sp(staar_ctx *ctx, const double *Gv, const uint6
     CHECK_CTX(ctx);
     STAAR_TRY(check_dims(n, p));
     STAAR_TRY(ensure_sparse(ctx, n, q, Sv, Sr, Sc, SX, cov, res));
+    if (csc_is_sparse_enough(Gr, Gc, n, p))
+        return run_sparse_family_carriers(ctx, Gv, Gr, Gc, n, p, 0, Score, Score_se, pl, Est, Est_se);
     STAAR_TRY(upload_csc_G(ctx, Gv, Gr, Gc, n, p));
     return run_sparse_family(ctx, n, p, 0, nullptr, Score, Score_se, pl, Est, Est_se);
 }
@@ -411,7 +473,7 @@ int staar_individual_score_test_sp_denseGRM(staar_ctx *ctx, const double *Gv, co
     CHECK_CTX(ctx);
     STAAR_TRY(check_dims(n, p));
     STAAR_TRY(ensure_dense(ctx, n, P));
-    if (Gc && csc_is_sparse_enough(Gc, n, p))
+    if (csc_is_sparse_enough(Gr, Gc, n, p))
         return run_dense_family_carriers(ctx, Gv, Gr, Gc, n, p, 0, res, Score, Score_se, pl, Est, Est_se);
     STAAR_TRY(upload_csc_G(ctx, Gv, Gr, Gc, n, p));
     return run_dense_family(ctx, n, p, 0, res, Score, Score_se, pl, Est, Est_se);
@@ -438,6 +500,8 @@ int staar_individual_score_test_sp_multi(staar_ctx *ctx, const double *Gv, const
     STAAR_TRY(check_dims(n, p));
     if (n_pheno < 1) { set_error("n_pheno must be >= 1"); return STAAR_ERR_ARG; }
     STAAR_TRY(ensure_sparse(ctx, n, q, Sv, Sr, Sc, SX, cov, res));
+    if (csc_is_sparse_enough(Gr, Gc, n, p))
+        return run_sparse_family_carriers(ctx, Gv, Gr, Gc, n, p, n_pheno, Score, nullptr, pl, nullptr, nullptr);
     STAAR_TRY(upload_csc_G(ctx, Gv, Gr, Gc, n, p));
     return run_sparse_family(ctx, n, p, n_pheno, nullptr, Score, nullptr, pl, nullptr, nullptr);
 }
@@ -461,7 +525,7 @@ int staar_individual_score_test_sp_denseGRM_multi(staar_ctx *ctx, const double *
     STAAR_TRY(check_dims(n, p));
     if (n_pheno < 1) { set_error("n_pheno must be >= 1"); return STAAR_ERR_ARG; }
     STAAR_TRY(ensure_dense(ctx, n, P));
-    if (Gc && csc_is_sparse_enough(Gc, n, p))
+    if (csc_is_sparse_enough(Gr, Gc, n, p))
         return run_dense_family_carriers(ctx, Gv, Gr, Gc, n, p, n_pheno, res, Score, nullptr, pl, nullptr, nullptr);
     STAAR_TRY(upload_csc_G(ctx, Gv, Gr, Gc, n, p));
     return run_dense_family(ctx, n, p, n_pheno, res, Score, nullptr, pl, nullptr, nullptr);

@@ -139,6 +139,11 @@ struct staar_ctx {
     staar::NullSpa nspa;
     // scratch
     staar::DevBuf G, L, aux, out, tmp, tmp2, pk, pk2, ctr;
+    // operands of the conditional test derived from X_adj (PA, M, M Q M, Ycond), kept while X_adj and the null model
+    // stay the same: the reference calls Individual_Score_Test_cond once per tested variant with the same X_adj
+    staar::DevBuf cond;
+    uint64_t cond_key = 0;
+    int cond_m = 0, cond_ld = 0;
     bool use_mma_sync = false;       // STAAR_B200_CONTRACT=mma: legacy mma.sync contraction instead of tcgen05
     void *pinned = nullptr;
     size_t pinned_cap = 0;
@@ -168,6 +173,11 @@ int launch_quad_pairs_csr(staar_ctx *ctx, const double *dG, int64_t n, const int
 int launch_dense_P_times_G(staar_ctx *ctx, const double *dP, const double *dG, int64_t n, int64_t p, double *dW);
 int launch_quad_pairs_carriers_P(staar_ctx *ctx, const double *d_val, const int64_t *d_row, const int64_t *d_colptr, int64_t n,
                                  const double *dP, const int32_t *d_colA, const int32_t *d_colB, int64_t npairs, double *d_out);
+int launch_contract_carriers(staar_ctx *ctx, const double *d_val, const int64_t *d_row, const int64_t *d_colptr, int64_t p,
+                            const double *dY, int ldY, int ncols, double *dL, int ldL);
+int launch_quad_pairs_carriers_csr(staar_ctx *ctx, const double *d_val, const int64_t *d_row, const int64_t *d_colptr,
+                                   const int64_t *S_row_ptr, const int32_t *S_col, const double *S_val, const int32_t *d_colA,
+                                   const int32_t *d_colB, int64_t npairs, double *d_out);
 int launch_score_carriers(staar_ctx *ctx, const double *d_val, const int64_t *d_row, const int64_t *d_colptr, int64_t p,
                           const double *d_res, double *dL, int ldL);
 int launch_dot_pairs(staar_ctx *ctx, const double *dG, const double *dW, int64_t n, const int32_t *d_colA,

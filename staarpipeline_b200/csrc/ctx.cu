@@ -3,6 +3,7 @@
 // The Rcpp boundary passes Sigma_i, Sigma_iX, cov and residuals (or a 3.2 GB P) on EVERY chunk call
 // (reference src/RcppExports.cpp:19-31; R/Individual_Analysis.R:264).  They are uploaded once and kept in HBM,
 // keyed on a content hash, so that only genotypes cross PCIe per call (SURVEY.md §7 "null-model residency").
+#include <thread>
 #include "common.cuh"
 #include <cstring>
 #include <algorithm>
@@ -73,7 +74,7 @@ void NullDense::release()
 }
 
 // 4-lane multiplicative hash over 8-byte words (content key of host operands; ~8 GB/s)
-uint64_t hash_bytes(const void *data, size_t bytes, uint64_t seed)
+static uint64_t hash_bytes_serial(const void *data, size_t bytes, uint64_t seed)
 {
     const uint64_t *w = static_cast<const uint64_t *>(data);
     const size_t nw = bytes / 8;
@@ -88,6 +89,30 @@ uint64_t hash_bytes(const void *data, size_t bytes, uint64_t seed)
     uint64_t r = h[0];
     for (int l = 1; l < 4; l++) r = (r ^ h[l]) * 0x9E3779B97F4A7C15ull + (r >> 31);
     return r ^ bytes;
+}
+
+// Fingerprint of a host operand (the Rcpp signatures pass the null model on every call; the device copy is reused when
+// the fingerprint matches).  Every byte is hashed; operands of several MB are split into fixed 4 MB pieces hashed by
+// host threads and combined in order, so the value does not depend on the thread count.
+uint64_t hash_bytes(const void *data, size_t bytes, uint64_t seed)
+{
+    constexpr size_t kPiece = 4u << 20;
+    if (bytes < 2 * kPiece) return hash_bytes_serial(data, bytes, seed);
+    const size_t pieces = (bytes + kPiece - 1) / kPiece;
+    std::vector<uint64_t> part(pieces);
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nthreads = (unsigned)std::min<size_t>(std::min(hw, 8u), pieces);
+    auto work = [&](unsigned tid) {
+        for (size_t k = tid; k < pieces; k += nthreads) {
+            const size_t off = k * kPiece, len = std::min(kPiece, bytes - off);
+            part[k] = hash_bytes_serial(static_cast<const uint8_t *>(data) + off, len, seed + 0x51ull * (k + 1));
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &t : th) t.join();
+    return hash_bytes_serial(part.data(), pieces * 8, seed) ^ bytes;
 }
 
 // strided sample of a large dense matrix (P is 3.2 GB at n = 20k): every `step`-th word plus head and tail
@@ -529,7 +554,7 @@ void staar_ctx_destroy(staar_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->ns.release(); ctx->nd.release(); ctx->nspa.release();
     ctx->G.release(); ctx->L.release(); ctx->aux.release(); ctx->out.release(); ctx->tmp.release();
-    ctx->tmp2.release(); ctx->pk.release(); ctx->pk2.release(); ctx->ctr.release();
+    ctx->tmp2.release(); ctx->pk.release(); ctx->pk2.release(); ctx->ctr.release(); ctx->cond.release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);

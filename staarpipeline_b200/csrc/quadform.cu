@@ -134,6 +134,80 @@ __global__ void __launch_bounds__(256) score_carriers_kernel(const double *__res
     }
 }
 
+
+// ---------------------------------------------------------------- sparse genotype columns, sparse Sigma_i
+// The rare-variant route of the reference (Individual_Score_Test_sp / _sp_multi, src/Individual_Score_Test_sp.cpp:17,42-43;
+// _sp_multi.cpp:18,39-40) keeps G sparse.  Here too: everything is taken over the stored entries of a column.
+//   contract_carriers : L[j, c] = sum_e val[e] * Y[row[e], c]          (a warp per column, lanes = columns of Y)
+//   quad_pairs_carriers_csr : g_a' Sigma_i g_b = sum_{e in a} val[e] * sum_{f in row(row[e]) of Sigma_i} S_f * g_b[col_f],
+//                             g_b looked up by binary search in b's sorted row list (a warp per pair)
+__global__ void __launch_bounds__(256) contract_carriers_kernel(const double *__restrict__ val, const int64_t *__restrict__ row,
+                                                                const int64_t *__restrict__ colptr, int64_t p,
+                                                                const double *__restrict__ Y, int ldY, int ncols,
+                                                                double *__restrict__ L, int ldL)
+{
+    const int lane = threadIdx.x & 31;
+    for (int64_t j = blockIdx.x * 8ll + (threadIdx.x >> 5); j < p; j += gridDim.x * 8ll) {
+        const int64_t e0 = colptr[j], e1 = colptr[j + 1];
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+            const int c = c0 + lane;
+            const bool on = c < ncols;
+            double acc = 0.0;
+            int64_t e = e0;
+            for (; e + 4 <= e1; e += 4) {                              // four rows of Y in flight
+                double v[4], y[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { v[k] = val[e + k]; y[k] = on ? Y[(size_t)row[e + k] * ldY + c] : 0.0; }
+#pragma unroll
+                for (int k = 0; k < 4; k++) acc += v[k] * y[k];
+            }
+            for (; e < e1; e++) acc += val[e] * (on ? Y[(size_t)row[e] * ldY + c] : 0.0);
+            if (on) L[j * ldL + c] = acc;
+        }
+    }
+}
+
+__device__ __forceinline__ double carrier_lookup(const double *__restrict__ val, const int64_t *__restrict__ row, int64_t b0,
+                                                 int64_t b1, int64_t want)
+{
+    while (b0 < b1) {
+        const int64_t mid = (b0 + b1) >> 1;
+        const int64_t r = row[mid];
+        if (r == want) return val[mid];
+        if (r < want) b0 = mid + 1; else b1 = mid;
+    }
+    return 0.0;
+}
+
+__global__ void __launch_bounds__(256) quad_pairs_carriers_csr_kernel(const double *__restrict__ val, const int64_t *__restrict__ row,
+                                                                      const int64_t *__restrict__ colptr,
+                                                                      const int64_t *__restrict__ S_row_ptr,
+                                                                      const int32_t *__restrict__ S_col,
+                                                                      const double *__restrict__ S_val,
+                                                                      const int32_t *__restrict__ colA,
+                                                                      const int32_t *__restrict__ colB, int64_t npairs,
+                                                                      double *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    for (int64_t pr = blockIdx.x * 8ll + (threadIdx.x >> 5); pr < npairs; pr += gridDim.x * 8ll) {
+        const int ca = colA[pr], cb = colB[pr];
+        const int64_t a0 = colptr[ca], a1 = colptr[ca + 1], b0 = colptr[cb], b1 = colptr[cb + 1];
+        double acc = 0.0;
+        if (b1 > b0)
+            for (int64_t e = a0 + lane; e < a1; e += 32) {
+                const int64_t i = row[e];
+                double s = 0.0;
+                for (int64_t f = S_row_ptr[i]; f < S_row_ptr[i + 1]; f++) {
+                    const double gb = carrier_lookup(val, row, b0, b1, S_col[f]);
+                    if (gb != 0.0) s += S_val[f] * gb;
+                }
+                acc += val[e] * s;
+            }
+        acc = warp_sum(acc);
+        if (lane == 0) out[pr] = acc;
+    }
+}
+
 // ---------------------------------------------------------------- W = P * G  (FP64 DMMA GEMM)
 constexpr int BM = 128, BN = 64, BK = 16;
 constexpr int RSA = BM + 4;      // sP[k][i], stride = 4 mod 16 doubles -> conflict-free A fragments
@@ -266,6 +340,30 @@ int launch_score_carriers(staar_ctx *ctx, const double *d_val, const int64_t *d_
     if (p == 0) return STAAR_OK;
     const int grid = (int)std::min<int64_t>((p + 7) / 8, (int64_t)ctx->sm_count * 8);
     score_carriers_kernel<<<grid, 256, 0, ctx->stream>>>(d_val, d_row, d_colptr, p, d_res, dL, ldL);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+int launch_contract_carriers(staar_ctx *ctx, const double *d_val, const int64_t *d_row, const int64_t *d_colptr, int64_t p,
+                            const double *dY, int ldY, int ncols, double *dL, int ldL)
+{
+    if (p == 0) return STAAR_OK;
+    const int grid = (int)std::min<int64_t>((p + 7) / 8, (int64_t)ctx->sm_count * 8);
+    contract_carriers_kernel<<<grid, 256, 0, ctx->stream>>>(d_val, d_row, d_colptr, p, dY, ldY, ncols, dL, ldL);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+int launch_quad_pairs_carriers_csr(staar_ctx *ctx, const double *d_val, const int64_t *d_row, const int64_t *d_colptr,
+                                   const int64_t *S_row_ptr, const int32_t *S_col, const double *S_val, const int32_t *d_colA,
+                                   const int32_t *d_colB, int64_t npairs, double *d_out)
+{
+    if (npairs == 0) return STAAR_OK;
+    const int grid = (int)std::min<int64_t>((npairs + 7) / 8, (int64_t)ctx->sm_count * 8);
+    quad_pairs_carriers_csr_kernel<<<grid, 256, 0, ctx->stream>>>(d_val, d_row, d_colptr, S_row_ptr, S_col, S_val, d_colA, d_colB,
+                                                                 npairs, d_out);
     ctx->launches++;
     STAAR_CUDA(cudaGetLastError());
     return STAAR_OK;

@@ -436,3 +436,54 @@ def test_sp_dense_grm_multi_carrier_route_vs_oracle(gpu_ctx, oracle):
     want = oracle.Individual_Score_Test_sp_denseGRM_multi(**kw)
     assert rel_err(got["Score"], want["Score"], score_floor(GK, kw["residuals"])) < 1e-10
     assert np.all(np.abs(got["pvalue_log"] - want["pvalue_log"]) <= 1e-8 * np.maximum(1.0, np.abs(want["pvalue_log"])))
+
+
+@pytest.mark.parametrize("related", [True, False])
+def test_sp_carrier_route_vs_oracle(gpu_ctx, oracle, related):
+    """Individual_Score_Test_sp on columns with <= n/8 stored entries: contraction and g'Sigma_i g over the stored
+    entries only (no dense copy of G).  Against the oracle and against the dense-G entry point."""
+    from staarpipeline_b200 import synth
+    n, p, q = 3000, 40, 7
+    nm = synth.nullmodel_sparse_grm(n, seed=77, q=q, shuffle=True) if related else synth.nullmodel_unrelated(n, seed=77, q=q)
+    G = _rare_columns(np.random.default_rng(77), n, p, n // 8)
+    Gs = sp.csc_matrix(G)
+    got = gpu_ctx.Individual_Score_Test_sp(Gs, nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+    want = oracle.Individual_Score_Test_sp(Gs, nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+    assert_stats_close(got, want, score_floor(G, nm.residuals))
+    dense = gpu_ctx.Individual_Score_Test(np.asfortranarray(G), nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+    assert_stats_close(got, dense, score_floor(G, nm.residuals))
+    assert got["Score_se"][0] == 0.0 and got["pvalue_log"][0] == 0.0
+
+
+def test_sp_multi_carrier_route_vs_oracle(gpu_ctx, oracle):
+    """three traits, Kronecker-expanded sparse G as R/Individual_Analysis.R:267 builds it: k x k blocks from
+    g_a' Sigma_i g_b between columns of different trait blocks"""
+    from staarpipeline_b200 import synth
+    n, k, pp = 900, 3, 18
+    nm = synth.nullmodel_multi(n, k=k, seed=5, q=4)
+    G0 = _rare_columns(np.random.default_rng(5), n, pp, n * k // 8 // 2)
+    GK = sp.kron(sp.identity(k, format="csc"), sp.csc_matrix(G0), format="csc")
+    got = gpu_ctx.Individual_Score_Test_sp_multi(GK, nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals, k)
+    want = oracle.Individual_Score_Test_sp_multi(GK, nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals, k)
+    assert rel_err(got["Score"], want["Score"], score_floor(GK, nm.residuals)) < 1e-10
+    assert np.all(np.abs(got["pvalue_log"] - want["pvalue_log"]) <= 1e-8 * np.maximum(1.0, np.abs(want["pvalue_log"])))
+
+
+def test_cond_repeated_calls_reuse_and_invalidate(gpu_ctx, oracle):
+    """R/Individual_Analysis_cond.R:183-208 calls Individual_Score_Test_cond once per tested variant (p = 1) with the
+    same X_adj: the operands derived from X_adj stay on the device between such calls.  Same results as one batched
+    call and as the oracle; a different X_adj or residual vector must not see stale operands."""
+    c, _ = cases.case_cond(oracle, n=700, p=9, q=5, n_known=3, seed=21)
+    want = oracle.Individual_Score_Test_cond(**c)
+    batched = gpu_ctx.Individual_Score_Test_cond(**c)
+    floor = score_floor(c["G"], c["residuals"])
+    assert_stats_close(batched, want, floor)
+    for i in range(c["G"].shape[1]):
+        one = gpu_ctx.Individual_Score_Test_cond(**dict(c, G=np.asfortranarray(c["G"][:, i:i + 1])))
+        for k in want:
+            assert np.array_equal(one[k].ravel(), batched[k].ravel()[i:i + 1]), (k, i)
+    c2 = dict(c, X_adj=np.asfortranarray(c["X_adj"][:, 1:]))                   # drop one known variant
+    assert_stats_close(gpu_ctx.Individual_Score_Test_cond(**c2), oracle.Individual_Score_Test_cond(**c2), floor)
+    c3 = dict(c, residuals=c["residuals"] * 1.5)
+    assert_stats_close(gpu_ctx.Individual_Score_Test_cond(**c3), oracle.Individual_Score_Test_cond(**c3), 1.5 * floor)
+    assert_stats_close(gpu_ctx.Individual_Score_Test_cond(**c), want, floor)
