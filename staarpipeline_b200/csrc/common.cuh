@@ -81,6 +81,8 @@ struct NullSparse {
     int64_t lut_entries = 0;
     SampleInfo *sinfo_p = nullptr;    // full kinship rows in null-model positions (missing related samples)
     double *diag_p = nullptr;         // Sigma_i[j,j] in null-model positions (n + 64 entries, zero padded)
+    int64_t diag_uniform_vec = -1;  // from this 64-sample vector on every sample has the same Sigma_i[j,j] (-1: none)
+    double diag_uniform_val = 0.0;
     OffEntry *off_ent_p = nullptr;
     // generic path (families of more than 16 members, or every family when the column does not fit in shared memory):
     // 2-bit mask (11 = sample has kinship off-diagonals with a LARGER position), one 32-byte record per sample with

@@ -448,6 +448,13 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
         std::vector<double> diag_p((size_t)n + 64, 0.0);
         for (int64_t pz = 0; pz < n; pz++) diag_p[pz] = sinfo[pz].diag;
         STAAR_TRY(upload_vec(ctx, &ns.diag_p, diag_p));
+        // Unrelated samples of a linear mixed model all carry the same diagonal entry: find the longest suffix of
+        // positions with one value (the scan multiplies a count by it instead of gathering, scan_packed.cu:hom_vec).
+        int64_t first = n;
+        while (first > 0 && memcmp(&diag_p[first - 1], &diag_p[n - 1], sizeof(double)) == 0) first--;
+        const int64_t vec = (first + 63) / 64;
+        ns.diag_uniform_vec = (n > 0 && vec * 64 < n) ? vec : -1;
+        ns.diag_uniform_val = n > 0 ? diag_p[n - 1] : 0.0;
     }
     STAAR_TRY(upload_vec(ctx, &ns.off_ent_p, off_ent));
     STAAR_TRY(upload_vec(ctx, &ns.kmask, kmask));

@@ -14,6 +14,7 @@
 //
 // Integer/byte work: 128-bit shared-memory reads, popc/ffs bit tricks, warp-shuffle reductions with fixed trees and
 // per-warp queues filled in a fixed order (no floating-point atomics => 1/2/4/8-GPU runs are bit-identical).
+#include <climits>
 #include "common.cuh"
 #include "packed.cuh"
 
@@ -35,6 +36,7 @@ struct ScanParams {
     const double *lut;
     const NullSparse::SampleInfo *sinfo;   // full kinship rows per position (missing related samples)
     const double *diag;                    // Sigma_i[j,j] by position
+    int uvec; double dval;                 // vectors >= uvec: every sample has Sigma_i[j,j] == dval (uvec = INT_MAX: none)
     const NullSparse::OffEntry *off_ent;
     const double *Y; int ldY, ncol;        // Y rows in null-model order
     const long long *codesum;              // contraction output `lo` (p x 16): slot 15 = exact sum of the codes
@@ -174,6 +176,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         };
         // hom-minor carriers of one 64-sample vector under orientation `fl`: raw code 0 (flip) or raw code 2 (no flip);
         // the four words are walked together so that four independent gathers of Sigma_i[j,j] are in flight
+        int hom_cnt = 0;                                             // hom-minor carriers in the uniform-diagonal region
         auto hom_vec = [&](const uint4 &q4, int k, bool fl, double &acc) {
             const uint32_t gm = fl ? 0xffffffffu : 0u;
             uint32_t h0 = ((q4.x >> 1) ^ gm) & ~q4.x & 0x55555555u, h1 = ((q4.y >> 1) ^ gm) & ~q4.y & 0x55555555u;
@@ -184,6 +187,10 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
                 h1 &= kw + 1 > tail_word ? 0u : (kw + 1 == tail_word ? tail_mask : 0xffffffffu);
                 h2 &= kw + 2 > tail_word ? 0u : (kw + 2 == tail_word ? tail_mask : 0xffffffffu);
                 h3 &= kw + 3 > tail_word ? 0u : (kw + 3 == tail_word ? tail_mask : 0xffffffffu);
+            }
+            if (k >= P.uvec) {                                       // one diagonal value from here on: count, do not gather
+                hom_cnt += (__popc(h0) + __popc(h1)) + (__popc(h2) + __popc(h3));
+                return;
             }
             const double *dg = P.diag + (int64_t)kw * 16;
             while (h0 | h1 | h2 | h3) {
@@ -253,6 +260,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         auto mu_of = [&]() { return flip_from_counts(pc, P.n, P.impute).mu; };   // rare paths only
         if (guess != flip) {                                       // block-uniform and rare: the missing count decided
             hom = 0.0;
+            hom_cnt = 0;
             for (int k0 = wib * 32; k0 < nvec16; k0 += kBlkWarps * 32)
                 if (k0 + lane < nvec16) hom_vec(v4[k0 + lane], k0 + lane, flip, hom);
         }
@@ -372,6 +380,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
                 quad += 2.0 * code_value((wf >> b) & 3u, mu) * sacc;
             }
         }
+        hom += P.dval * (double)hom_cnt;
         quad = warp_sum(quad);
         hom = warp_sum(hom);
         if (lane == 0) { s_quad[wib] = quad; s_quad[kBlkWarps + wib] = hom; }
@@ -486,6 +495,7 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     P.relmask = ns.relmask; P.rel = ns.rel; P.up_ent = ns.up_ent;
     P.tab_words = ns.tab_words; P.kin_words = ns.kin_words; P.x_words = ns.x_words; P.kmask = ns.kmask; P.wdesc = ns.wdesc;
     P.xterms = ns.xterms; P.lut = ns.lut; P.sinfo = ns.sinfo_p; P.off_ent = ns.off_ent_p; P.diag = ns.diag_p;
+    P.uvec = ns.diag_uniform_vec >= 0 ? (int)ns.diag_uniform_vec : INT_MAX; P.dval = ns.diag_uniform_val;
     P.Y = ns.Yp; P.ldY = ns.ldY; P.ncol = (int)ns.q + 2;
     P.codesum = d_lo;
     P.AF = dAF; P.MAF = dMAF; P.flip = dflip; P.mu = d_mu; P.quad = d_quad; P.Sm = d_Sm;
