@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             } else {
                 P.Sm[i * kColsPerSlice + tid] = (tid < P.ncol) ? t : 0.0;
             }
-        } else if (tid == 32) {
+        } else if (tid == (kBlkWarps > 1 ? 32 : kColsPerSlice)) {
             double t = 0.0;
 #pragma unroll
             for (int w = 0; w < kBlkWarps; w++) t += s_quad[w];
@@ -507,7 +507,14 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
                sizeof(int) * 4 * warps + 64;
     };
     const size_t smem_max = 227 * 1024;
-    const int warps = (6 * (stride + extra_for(4) + 1024) <= 228 * 1024) ? 4 : 8;
+    // Short columns (e.g. BASELINE config 1, n = 1e4): per-variant block overheads dominate, so the block shrinks to one
+    // or two warps and up to 32 blocks share an SM (measured per 400 k variants, sparse GRM: n = 2e4: 2.37 / 3.15 / 3.78 ms
+    // with 1 / 2 / 4 warps; n = 4e4: 5.09 / 4.60 / 5.22 ms; n = 1e5: 27.9 / 13.8 / 10.5 ms).
+    static const int force_warps = getenv("STAAR_B200_SCAN_WARPS") ? atoi(getenv("STAAR_B200_SCAN_WARPS")) : 0;
+    int warps = (6 * (stride + extra_for(4) + 1024) <= 228 * 1024) ? 4 : 8;
+    if (stride <= 6144) warps = 1;
+    else if (stride <= 14336) warps = 2;
+    if (force_warps == 1 || force_warps == 2 || force_warps == 4 || force_warps == 8) warps = force_warps;
     const size_t extra = extra_for(warps);
     // The kernel is latency-bound (dependent gathers between block barriers), so resident warps matter more than
     // overlapping the column copy: one column stage (measured at n = 1e5: 6.76 ms vs 7.13 ms with two stages per
@@ -517,7 +524,7 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     if (nstage == 1 && force == 2 && 2 * stride + extra <= smem_max) nstage = 2;
     if (nstage > 0) {
         const size_t smem = (size_t)nstage * stride + extra;
-        auto kern = warps == 4 ? scan_block_kernel<4> : scan_block_kernel<8>;
+        auto kern = warps == 1 ? scan_block_kernel<1> : warps == 2 ? scan_block_kernel<2> : warps == 4 ? scan_block_kernel<4> : scan_block_kernel<8>;
         STAAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         STAAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));

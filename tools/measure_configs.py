@@ -37,8 +37,14 @@ def packed_resident(n, V, nm, label):
                       "hbm_frac": V * (stride + 56) / (ms / 1e3) / 1e9 / 6542.1, "stage_ms": st}), flush=True)
     del packed, outs
 
+if len(sys.argv) > 2 and sys.argv[1] == "n":          # python tools/measure_configs.py n <samples> [variants]: one size, sparse GRM
+    nn = int(sys.argv[2]); vv = int(sys.argv[3]) if len(sys.argv) > 3 else 400_000
+    packed_resident(nn, vv, synth.nullmodel_sparse_grm(nn), "packed resident, sparse GRM, n=%d, STAAR_B200_SCAN_WARPS=%s" % (nn, os.environ.get("STAAR_B200_SCAN_WARPS", "auto")))
+    ctx.close(); sys.exit(0)
 # cfg1: unrelated, n = 10,000
 packed_resident(10_000, 2_000_000, synth.nullmodel_unrelated(10_000), "cfg1 packed resident (unrelated, n=1e4)")
+if len(sys.argv) > 1 and sys.argv[1] == "cfg1":
+    ctx.close(); sys.exit(0)
 # cfg5 stage 1 sample size: n = 400,000 (unrelated: Sigma_i diagonal, as fit_nullmodel gives for a binary trait without GRM)
 nb = synth.nullmodel_binary(400_000)
 packed_resident(400_000, 100_000, nb, "cfg5 stage-1 packed resident (binary trait weights, n=4e5)")
