@@ -250,6 +250,9 @@ int staar_individual_analysis_chunk(staar_ctx *ctx, const double *G, int64_t n, 
 /* When the FP64 block lies in pinned (device-visible) host memory, this share of its variants is packed by the GPU,
  * which reads the host matrix over PCIe, while the host threads pack the rest (the two bandwidths add up). */
 double staar_chunk_gpu_pack_share(void);
+/* the share the next FP64 chunk call on this context will use (re-balanced after every chunk unless fixed by the
+ * environment variable) */
+double staar_ctx_gpu_pack_share(staar_ctx *ctx);
 /* the same chunk from the R integer matrix / raw bytes SeqArray returns (4 or 1 bytes per genotype on the host) */
 int staar_individual_analysis_chunk_i32(staar_ctx *ctx, const int32_t *G, int64_t n, int64_t p, int impute, int threads,
                                         double *AF, double *MAF, double *Score, double *Score_se, double *pvalue_log,

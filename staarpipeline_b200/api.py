@@ -335,6 +335,10 @@ class Context:
                    *[C.c_void_p(x) for x in d_out7], C.c_void_p(d_spa_index or None), C.byref(nt), C.byref(ns))
         return nt.value, ns.value
 
+    def gpu_pack_share(self) -> float:
+        self._lib.staar_ctx_gpu_pack_share.restype = C.c_double
+        return float(self._lib.staar_ctx_gpu_pack_share(self._h))
+
     def set_nullmodel_spa(self, XW, XXWX_inv, residuals, muhat):
         XWm, XXi = _f(XW), _f(XXWX_inv)
         q, n = XWm.shape

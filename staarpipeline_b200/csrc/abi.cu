@@ -5,6 +5,7 @@
 // tests happens on the host except the m x m (X_adj'X_adj)^-1 algebra of the conditional test, which the
 // reference recomputes per call on n x m operands (src/Individual_Score_Test_cond.cpp:48-49) and which here
 // acts on m x m matrices already reduced on the device.
+#include <chrono>
 #include "common.cuh"
 #include <algorithm>
 #include <cstring>
@@ -844,12 +845,20 @@ int staar_packed_reorder_device(staar_ctx *ctx, const uint8_t *d_in, uint8_t *d_
     return sync(ctx);
 }
 
-// share of a pinned FP64 chunk's variants that the GPU packs itself over PCIe (measured optimum on the 16-vCPU B200
-// box: 0.25-0.35; 0.45 makes the PCIe side the bottleneck).  STAAR_B200_GPU_PACK_SHARE overrides, 0 disables.
+// Share of a pinned FP64 chunk's variants that the GPU packs itself over PCIe.  Starts at 0.3 (measured optimum on the
+// 16-vCPU B200 box: 0.25-0.35; 0.45 makes the PCIe side the bottleneck) and is re-balanced per context after every
+// chunk from the two measured packing rates, so a box with slower host memory shifts work to the GPU and vice versa.
+// STAAR_B200_GPU_PACK_SHARE fixes it (0 disables GPU packing).
 double staar_chunk_gpu_pack_share(void)
 {
     static const double share = getenv("STAAR_B200_GPU_PACK_SHARE") ? atof(getenv("STAAR_B200_GPU_PACK_SHARE")) : 0.3;
     return share < 0.0 ? 0.0 : (share > 1.0 ? 1.0 : share);
+}
+
+double staar_ctx_gpu_pack_share(staar_ctx *ctx)
+{
+    if (!ctx) return staar_chunk_gpu_pack_share();
+    return ctx->pack_share < 0.0 ? staar_chunk_gpu_pack_share() : ctx->pack_share;
 }
 
 // One chunk of the single-variant driver (R/Individual_Analysis.R:186-196,264): a `$dosage` block in host memory
@@ -878,7 +887,8 @@ int chunk_impl(staar_ctx *ctx, const void *G, int elem, int64_t n, int64_t p, in
         int *d_bad = reinterpret_cast<int *>(ctx->pk.as<uint8_t>() + stride * (size_t)p);
         const double *G_dev = nullptr;
         if (elem == 8) {
-            const double share = staar_chunk_gpu_pack_share();
+            if (ctx->pack_share < 0.0) ctx->pack_share = staar_chunk_gpu_pack_share();
+            const double share = ctx->pack_share;
             cudaPointerAttributes at;
             if (share > 0.0 && cudaPointerGetAttributes(&at, G) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
                 G_dev = static_cast<const double *>(at.devicePointer);
@@ -889,12 +899,17 @@ int chunk_impl(staar_ctx *ctx, const void *G, int elem, int64_t n, int64_t p, in
         }
         const int64_t p_cpu = p - p_gpu;
         if (p_gpu > 0) {
+            if (!ctx->ev_pack[0]) { STAAR_CUDA(cudaEventCreate(&ctx->ev_pack[0])); STAAR_CUDA(cudaEventCreate(&ctx->ev_pack[1])); }
             STAAR_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+            STAAR_CUDA(cudaEventRecord(ctx->ev_pack[0], ctx->stream));
             STAAR_TRY(launch_pack_f64(ctx, G_dev + (size_t)p_cpu * n, n, p_gpu, ctx->pk.as<uint8_t>() + stride * (size_t)p_cpu, stride, d_bad));
+            STAAR_CUDA(cudaEventRecord(ctx->ev_pack[1], ctx->stream));
         }
+        const auto t_host0 = std::chrono::steady_clock::now();
         int rc = elem == 8   ? staar_pack_dosage_host(static_cast<const double *>(G), n, p_cpu, dst, stride, threads)
                  : elem == 4 ? staar_pack_dosage_host_i32(static_cast<const int32_t *>(G), n, p, dst, stride, threads)
                              : staar_pack_dosage_host_u8(static_cast<const uint8_t *>(G), n, p, dst, stride, threads);
+        const double t_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
         packed_ok = rc == STAAR_OK;
         if (!packed_ok && elem != 8) return rc;        // integer dosages other than 0/1/2/NA are an error
         if (packed_ok) {
@@ -904,6 +919,15 @@ int chunk_impl(staar_ctx *ctx, const void *G, int elem, int64_t n, int64_t p, in
                 STAAR_TRY(d2h(ctx, &bad, d_bad, sizeof(int)));
                 STAAR_TRY(sync(ctx));
                 packed_ok = bad == 0;
+                // re-balance for the next chunk: both sides ran concurrently, so the rates include their contention
+                static const bool fixed = getenv("STAAR_B200_GPU_PACK_SHARE") != nullptr;
+                float t_gpu = 0.f;
+                if (!fixed && p_cpu > 0 && cudaEventElapsedTime(&t_gpu, ctx->ev_pack[0], ctx->ev_pack[1]) == cudaSuccess &&
+                    t_gpu > 0.f && t_host > 0.0) {
+                    const double r_cpu = (double)p_cpu / t_host, r_gpu = (double)p_gpu / (double)t_gpu;
+                    const double target = r_gpu / (r_cpu + r_gpu);
+                    ctx->pack_share = std::min(0.6, std::max(0.05, 0.75 * ctx->pack_share + 0.25 * target));
+                }
             }
         } else {
             STAAR_TRY(sync(ctx));

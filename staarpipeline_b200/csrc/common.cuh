@@ -149,6 +149,10 @@ struct staar_ctx {
     bool use_mma_sync = false;       // STAAR_B200_CONTRACT=mma: legacy mma.sync contraction instead of tcgen05
     void *pinned = nullptr;
     size_t pinned_cap = 0;
+    // hybrid host/GPU packing of pinned FP64 chunks: share of the variants the GPU packs, re-balanced after every chunk
+    // from the two measured packing rates (negative: not initialised; fixed when STAAR_B200_GPU_PACK_SHARE is set)
+    double pack_share = -1.0;
+    cudaEvent_t ev_pack[2] = {nullptr, nullptr};
     // optional per-kernel timing of the packed path (bench.py roofline)
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

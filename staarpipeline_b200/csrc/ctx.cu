@@ -562,6 +562,7 @@ void staar_ctx_destroy(staar_ctx *ctx)
     ctx->ns.release(); ctx->nd.release(); ctx->nspa.release();
     ctx->G.release(); ctx->L.release(); ctx->aux.release(); ctx->out.release(); ctx->tmp.release();
     ctx->tmp2.release(); ctx->pk.release(); ctx->pk2.release(); ctx->ctr.release(); ctx->cond.release();
+    for (auto &e : ctx->ev_pack) if (e) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
