@@ -249,6 +249,19 @@ int staar_individual_analysis_chunk(staar_ctx *ctx, const double *G, int64_t n, 
                                     double *Est, double *Est_se);
 /* When the FP64 block lies in pinned (device-visible) host memory, this share of its variants is packed by the GPU,
  * which reads the host matrix over PCIe, while the host threads pack the rest (the two bandwidths add up). */
+/* Pipelined form of the three calls above.  staar_chunk_submit* packs the block (host threads, and the GPU for its
+ * share of a pinned FP64 block), enqueues the H2D copy and the kernels on the context's stream and returns;
+ * staar_chunk_wait blocks until that chunk is done and copies its seven result arrays out (any may be NULL).  Two
+ * chunks can be in flight (slot 0 and 1): submit(0); submit(1); wait(0); submit(0); wait(1); ... — while the GPU copies
+ * and scores one chunk the host already packs the next.  G must stay valid and unchanged until the slot's wait()
+ * returns.  Results are bit-identical to the synchronous calls; a block with real-valued genotypes is detected at
+ * wait() and re-run through the FP64 kernels there. */
+int staar_chunk_submit(staar_ctx *ctx, const double *G, int64_t n, int64_t p, int impute, int threads, int slot);
+int staar_chunk_submit_i32(staar_ctx *ctx, const int32_t *G, int64_t n, int64_t p, int impute, int threads, int slot);
+int staar_chunk_submit_u8(staar_ctx *ctx, const uint8_t *G, int64_t n, int64_t p, int impute, int threads, int slot);
+int staar_chunk_wait(staar_ctx *ctx, int slot, double *AF, double *MAF, double *Score, double *Score_se,
+                     double *pvalue_log, double *Est, double *Est_se);
+
 double staar_chunk_gpu_pack_share(void);
 /* the share the next FP64 chunk call on this context will use (re-balanced after every chunk unless fixed by the
  * environment variable) */

@@ -311,6 +311,25 @@ class Context:
         self._call(fn, gp, C.c_int64(n), C.c_int64(p), C.c_int(impute), C.c_int(threads), *[_p(a) for a in o])
         return dict(zip(("AF", "MAF", "Score", "Score_se", "pvalue_log", "Est", "Est_se"), o))
 
+    def chunk_submit(self, G, impute: int = IMPUTE_MEAN, threads: int = 0, slot: int = 0):
+        """Pipelined form of individual_analysis_chunk: pack + enqueue, returns at once.  G (F-order, float64 / int32 /
+        uint8) must stay alive and unchanged until chunk_wait(slot)."""
+        G = np.asarray(G)
+        if not G.flags.f_contiguous or G.dtype not in (np.float64, np.int32, np.uint8):
+            raise StaarError(1, "chunk_submit needs an F-ordered float64 / int32 / uint8 block (no hidden copy may be made)")
+        fn = {np.dtype(np.float64): "staar_chunk_submit", np.dtype(np.int32): "staar_chunk_submit_i32",
+              np.dtype(np.uint8): "staar_chunk_submit_u8"}[G.dtype]
+        n, p = G.shape
+        self._call(fn, G.ctypes.data_as(C.c_void_p), C.c_int64(n), C.c_int64(p), C.c_int(impute), C.c_int(threads), C.c_int(slot))
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[slot] = (G, p)
+
+    def chunk_wait(self, slot: int = 0, out=None):
+        G, p = self._inflight.pop(slot)
+        o = out if out is not None else [np.zeros(p) for _ in range(7)]
+        self._call("staar_chunk_wait", C.c_int(slot), *[_p(a) for a in o])
+        return dict(zip(("AF", "MAF", "Score", "Score_se", "pvalue_log", "Est", "Est_se"), o))
+
     def packed_debug_dump(self, p: int):
         """intermediates of the last packed score call (test hook)"""
         hi, lo = np.zeros((p, 16), dtype=np.int64), np.zeros((p, 16), dtype=np.int64)

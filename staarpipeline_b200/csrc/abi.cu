@@ -945,6 +945,112 @@ int chunk_impl(staar_ctx *ctx, const void *G, int elem, int64_t n, int64_t p, in
     STAAR_TRY(sync(ctx));
     return run_sparse_family(ctx, n, p, 0, nullptr, Score, Score_se, pl, Est, Est_se);
 }
+
+// ---- pipelined form: submit() packs and enqueues, wait() collects.  While the GPU copies and scores chunk i the host
+// threads already pack chunk i+1 (the synchronous call leaves the host idle for the H2D + kernels + D2H tail).
+int chunk_submit(staar_ctx *ctx, const void *G, int elem, int64_t n, int64_t p, int impute, int threads, int s)
+{
+    STAAR_TRY(check_dims(n, p));
+    if (s < 0 || s > 1) { set_error("chunk_submit: slot must be 0 or 1"); return STAAR_ERR_ARG; }
+    NullSparse &ns = ctx->ns;
+    if (!ns.set || ns.n != n) { set_error("chunk_submit: null model not set for n = %lld", (long long)n); return STAAR_ERR_STATE; }
+    if (ns.q + 2 > kColsPerSlice - 1) { set_error("chunk_submit: the packed path needs q <= %d covariates", kColsPerSlice - 3); return STAAR_ERR_ARG; }
+    if (!G || p == 0) { set_error("chunk_submit: empty block"); return STAAR_ERR_ARG; }
+    staar_ctx::ChunkSlot &sl = ctx->slot[s];
+    if (sl.busy) { set_error("chunk_submit: slot %d still holds a chunk (call staar_chunk_wait first)", s); return STAAR_ERR_STATE; }
+    if (!sl.done) {
+        STAAR_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        STAAR_CUDA(cudaEventCreate(&sl.ev0)); STAAR_CUDA(cudaEventCreate(&sl.ev1));
+    }
+    if (!ctx->stream2) STAAR_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    const size_t stride = staar_packed_stride(n);
+    if (stride * (size_t)p > sl.pinned_cap) {
+        if (sl.pinned) cudaFreeHost(sl.pinned);
+        sl.pinned = nullptr; sl.pinned_cap = 0;
+        STAAR_CUDA(cudaMallocHost(&sl.pinned, stride * (size_t)p));
+        sl.pinned_cap = stride * (size_t)p;
+    }
+    STAAR_TRY(ctx->pk.reserve(stride * (size_t)p + 16));
+    STAAR_TRY(sl.res.reserve(sizeof(double) * 7 * (size_t)p + 16));
+    double *o = sl.res.as<double>();
+    int *d_bad = reinterpret_cast<int *>(o + 7 * (size_t)p);
+    int64_t p_gpu = 0;
+    const double *G_dev = nullptr;
+    if (elem == 8) {
+        if (ctx->pack_share < 0.0) ctx->pack_share = staar_chunk_gpu_pack_share();
+        cudaPointerAttributes at;
+        if (ctx->pack_share > 0.0 && cudaPointerGetAttributes(&at, G) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            G_dev = static_cast<const double *>(at.devicePointer);
+            p_gpu = std::min<int64_t>(p, (int64_t)(ctx->pack_share * (double)p));
+        } else {
+            cudaGetLastError();
+        }
+    }
+    const int64_t p_cpu = p - p_gpu;
+    STAAR_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+    if (p_gpu > 0) {
+        STAAR_CUDA(cudaEventRecord(sl.ev0, ctx->stream));
+        STAAR_TRY(launch_pack_f64(ctx, G_dev + (size_t)p_cpu * n, n, p_gpu, ctx->pk.as<uint8_t>() + stride * (size_t)p_cpu, stride, d_bad));
+        STAAR_CUDA(cudaEventRecord(sl.ev1, ctx->stream));
+    }
+    uint8_t *dst = static_cast<uint8_t *>(sl.pinned);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = elem == 8   ? staar_pack_dosage_host(static_cast<const double *>(G), n, p_cpu, dst, stride, threads)
+                   : elem == 4 ? staar_pack_dosage_host_i32(static_cast<const int32_t *>(G), n, p, dst, stride, threads)
+                               : staar_pack_dosage_host_u8(static_cast<const uint8_t *>(G), n, p, dst, stride, threads);
+    sl.t_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (rc != STAAR_OK && elem != 8) { STAAR_TRY(sync(ctx)); return rc; }
+    sl.host_ok = rc == STAAR_OK;
+    sl.G = G; sl.elem = elem; sl.impute = impute; sl.threads = threads; sl.n = n; sl.p = p; sl.p_cpu = p_cpu; sl.p_gpu = p_gpu;
+    if (sl.host_ok) {
+        STAAR_TRY(h2d(ctx, ctx->pk.p, dst, stride * (size_t)p_cpu));
+        const uint8_t *d_cols = ctx->pk.as<uint8_t>();
+        if (ns.permuted) {
+            STAAR_TRY(ctx->pk2.reserve(stride * (size_t)p));
+            STAAR_TRY(launch_permute_packed(ctx, d_cols, ctx->pk2.as<uint8_t>(), stride, n, p, ns.perm));
+            d_cols = ctx->pk2.as<uint8_t>();
+        }
+        STAAR_TRY(staar_packed_score_device(ctx, d_cols, stride, n, p, impute, o, o + p, o + 2 * p, o + 3 * p, o + 4 * p,
+                                            o + 5 * p, o + 6 * p));
+    }
+    STAAR_CUDA(cudaEventRecord(sl.done, ctx->stream));
+    sl.busy = true;
+    return STAAR_OK;
+}
+
+int chunk_wait(staar_ctx *ctx, int s, double *AF, double *MAF, double *Score, double *Score_se, double *pl, double *Est,
+               double *Est_se)
+{
+    if (s < 0 || s > 1) { set_error("chunk_wait: slot must be 0 or 1"); return STAAR_ERR_ARG; }
+    staar_ctx::ChunkSlot &sl = ctx->slot[s];
+    if (!sl.busy) { set_error("chunk_wait: slot %d holds no chunk", s); return STAAR_ERR_STATE; }
+    sl.busy = false;
+    const int64_t p = sl.p;
+    double *o = sl.res.as<double>();
+    int bad = 0;
+    if (sl.host_ok) {
+        // read back on the second stream: the first may already hold the next chunk's work behind this one
+        STAAR_CUDA(cudaStreamWaitEvent(ctx->stream2, sl.done, 0));
+        double *dstv[7] = {AF, MAF, Score, Score_se, pl, Est, Est_se};
+        for (int a = 0; a < 7; a++)
+            if (dstv[a]) STAAR_CUDA(cudaMemcpyAsync(dstv[a], o + (size_t)a * p, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream2));
+        STAAR_CUDA(cudaMemcpyAsync(&bad, o + 7 * (size_t)p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream2));
+        STAAR_CUDA(cudaStreamSynchronize(ctx->stream2));
+        static const bool fixed = getenv("STAAR_B200_GPU_PACK_SHARE") != nullptr;
+        float t_gpu = 0.f;
+        if (!fixed && sl.p_gpu > 0 && sl.p_cpu > 0 && cudaEventElapsedTime(&t_gpu, sl.ev0, sl.ev1) == cudaSuccess && t_gpu > 0.f &&
+            sl.t_host > 0.0) {
+            const double r_cpu = (double)sl.p_cpu / sl.t_host, r_gpu = (double)sl.p_gpu / (double)t_gpu;
+            ctx->pack_share = std::min(0.6, std::max(0.05, 0.75 * ctx->pack_share + 0.25 * r_gpu / (r_cpu + r_gpu)));
+        }
+        if (bad == 0) return STAAR_OK;
+    } else {
+        STAAR_CUDA(cudaEventSynchronize(sl.done));
+    }
+    // real-valued genotypes somewhere in the block: the synchronous entry point takes the FP64 kernels
+    if (ctx->slot[s ^ 1].busy) STAAR_CUDA(cudaEventSynchronize(ctx->slot[s ^ 1].done));
+    return chunk_impl(ctx, sl.G, sl.elem, sl.n, sl.p, sl.impute, sl.threads, AF, MAF, Score, Score_se, pl, Est, Est_se);
+}
 }  // namespace
 }  // namespace staar
 
@@ -968,6 +1074,28 @@ int staar_individual_analysis_chunk_u8(staar_ctx *ctx, const uint8_t *G, int64_t
 {
     CHECK_CTX(ctx);
     return chunk_impl(ctx, G, 1, n, p, impute, threads, AF, MAF, Score, Score_se, pl, Est, Est_se);
+}
+
+int staar_chunk_submit(staar_ctx *ctx, const double *G, int64_t n, int64_t p, int impute, int threads, int slot)
+{
+    CHECK_CTX(ctx);
+    return chunk_submit(ctx, G, 8, n, p, impute, threads, slot);
+}
+int staar_chunk_submit_i32(staar_ctx *ctx, const int32_t *G, int64_t n, int64_t p, int impute, int threads, int slot)
+{
+    CHECK_CTX(ctx);
+    return chunk_submit(ctx, G, 4, n, p, impute, threads, slot);
+}
+int staar_chunk_submit_u8(staar_ctx *ctx, const uint8_t *G, int64_t n, int64_t p, int impute, int threads, int slot)
+{
+    CHECK_CTX(ctx);
+    return chunk_submit(ctx, G, 1, n, p, impute, threads, slot);
+}
+int staar_chunk_wait(staar_ctx *ctx, int slot, double *AF, double *MAF, double *Score, double *Score_se, double *pl,
+                     double *Est, double *Est_se)
+{
+    CHECK_CTX(ctx);
+    return chunk_wait(ctx, slot, AF, MAF, Score, Score_se, pl, Est, Est_se);
 }
 
 int staar_synth_packed_device(staar_ctx *ctx, uint8_t *d_packed, size_t stride, int64_t n, int64_t first_variant,

@@ -153,6 +153,17 @@ struct staar_ctx {
     // from the two measured packing rates (negative: not initialised; fixed when STAAR_B200_GPU_PACK_SHARE is set)
     double pack_share = -1.0;
     cudaEvent_t ev_pack[2] = {nullptr, nullptr};
+    // pipelined chunk driver (staar_chunk_submit / staar_chunk_wait): per-slot host staging and result buffers
+    struct ChunkSlot {
+        void *pinned = nullptr; size_t pinned_cap = 0;
+        staar::DevBuf res;                        // 7 p doubles + the GPU packer's bad-value flag
+        cudaEvent_t done = nullptr, ev0 = nullptr, ev1 = nullptr;
+        bool busy = false, host_ok = true;
+        const void *G = nullptr; int elem = 0, impute = 0, threads = 0;
+        int64_t n = 0, p = 0, p_cpu = 0, p_gpu = 0;
+        double t_host = 0.0;
+    } slot[2];
+    cudaStream_t stream2 = nullptr;               // result read-back of a finished chunk while the next one is queued
     // optional per-kernel timing of the packed path (bench.py roofline)
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -563,6 +563,12 @@ void staar_ctx_destroy(staar_ctx *ctx)
     ctx->G.release(); ctx->L.release(); ctx->aux.release(); ctx->out.release(); ctx->tmp.release();
     ctx->tmp2.release(); ctx->pk.release(); ctx->pk2.release(); ctx->ctr.release(); ctx->cond.release();
     for (auto &e : ctx->ev_pack) if (e) cudaEventDestroy(e);
+    for (auto &sl : ctx->slot) {
+        if (sl.pinned) cudaFreeHost(sl.pinned);
+        sl.res.release();
+        if (sl.done) { cudaEventDestroy(sl.done); cudaEventDestroy(sl.ev0); cudaEventDestroy(sl.ev1); }
+    }
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);

@@ -487,3 +487,55 @@ def test_cond_repeated_calls_reuse_and_invalidate(gpu_ctx, oracle):
     c3 = dict(c, residuals=c["residuals"] * 1.5)
     assert_stats_close(gpu_ctx.Individual_Score_Test_cond(**c3), oracle.Individual_Score_Test_cond(**c3), 1.5 * floor)
     assert_stats_close(gpu_ctx.Individual_Score_Test_cond(**c), want, floor)
+
+
+def test_pipelined_chunks_match_synchronous(gpu_ctx, oracle):
+    """staar_chunk_submit / staar_chunk_wait with two chunks in flight == staar_individual_analysis_chunk, for FP64
+    (pinned and pageable), int32 and uint8 blocks; a block with a real-valued genotype falls back at wait()."""
+    import torch
+    from staarpipeline_b200 import synth, api
+    n, p, q = 3000, 257, 6
+    nm = synth.nullmodel_sparse_grm(n, seed=8, q=q, shuffle=True)
+    gpu_ctx.set_nullmodel_sparse(nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+    blocks = [np.asfortranarray(cases.raw_dosage(n, p, seed)) for seed in (1, 2, 3, 4, 5)]
+    want = [gpu_ctx.individual_analysis_chunk(b, api.IMPUTE_MEAN) for b in blocks]
+    pinned = [torch.from_numpy(np.ascontiguousarray(b.T)).pin_memory() for b in blocks]       # (p, n) C-order == n x p F-order
+    views = [t.numpy().T for t in pinned]
+    got = [None] * len(blocks)
+    gpu_ctx.chunk_submit(views[0], api.IMPUTE_MEAN, 0, 0)
+    for i in range(len(blocks)):
+        if i + 1 < len(blocks):
+            gpu_ctx.chunk_submit(views[i + 1], api.IMPUTE_MEAN, 0, (i + 1) & 1)
+        got[i] = gpu_ctx.chunk_wait(i & 1)
+    for g, w in zip(got, want):
+        for k in w:
+            assert np.array_equal(g[k], w[k], equal_nan=True), k
+    # pageable FP64, int32, uint8
+    b = blocks[0]
+    bi = np.asfortranarray(np.where(np.isnan(b) | (b <= -1), np.iinfo(np.int32).min, b).astype(np.int32))
+    bu = np.asfortranarray(np.where(np.isnan(b) | (b <= -1), 255, b).astype(np.uint8))
+    for slot, blk in enumerate((b, bi)):
+        gpu_ctx.chunk_submit(blk, api.IMPUTE_MEAN, 0, slot)
+    for slot in (0, 1):
+        g = gpu_ctx.chunk_wait(slot)
+        for k in want[0]:
+            assert np.array_equal(g[k], want[0][k], equal_nan=True), (slot, k)
+    gpu_ctx.chunk_submit(bu, api.IMPUTE_MINOR, 0, 0)
+    g = gpu_ctx.chunk_wait(0)
+    w = gpu_ctx.individual_analysis_chunk(bu, api.IMPUTE_MINOR)
+    for k in w:
+        assert np.array_equal(g[k], w[k], equal_nan=True), k
+    # real-valued genotype (in the GPU-packed part of a pinned block, and in the host part): FP64 kernels at wait()
+    for col in (p - 2, 3):
+        t = pinned[1].clone().pin_memory(); v = t.numpy().T
+        v[7, col] = 0.37
+        w = gpu_ctx.individual_analysis_chunk(v, api.IMPUTE_MEAN)
+        gpu_ctx.chunk_submit(v, api.IMPUTE_MEAN, 0, 1)
+        g = gpu_ctx.chunk_wait(1)
+        for k in w:
+            assert np.array_equal(g[k], w[k], equal_nan=True), (col, k)
+    # a slot cannot be submitted twice
+    gpu_ctx.chunk_submit(views[0], api.IMPUTE_MEAN, 0, 0)
+    with pytest.raises(api.StaarError):
+        gpu_ctx.chunk_submit(views[1], api.IMPUTE_MEAN, 0, 0)
+    gpu_ctx.chunk_wait(0)
