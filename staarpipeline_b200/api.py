@@ -321,10 +321,11 @@ class Context:
               np.dtype(np.uint8): "staar_chunk_submit_u8"}[G.dtype]
         n, p = G.shape
         self._call(fn, G.ctypes.data_as(C.c_void_p), C.c_int64(n), C.c_int64(p), C.c_int(impute), C.c_int(threads), C.c_int(slot))
-        self._inflight = getattr(self, "_inflight", {})
-        self._inflight[slot] = (G, p)
+        self.__dict__.setdefault("_inflight", {})[slot] = (G, p)
 
     def chunk_wait(self, slot: int = 0, out=None):
+        if slot not in self.__dict__.get("_inflight", {}):
+            raise StaarError(3, f"chunk_wait: slot {slot} holds no chunk")
         G, p = self._inflight.pop(slot)
         o = out if out is not None else [np.zeros(p) for _ in range(7)]
         self._call("staar_chunk_wait", C.c_int(slot), *[_p(a) for a in o])

@@ -539,3 +539,37 @@ def test_pipelined_chunks_match_synchronous(gpu_ctx, oracle):
     with pytest.raises(api.StaarError):
         gpu_ctx.chunk_submit(views[1], api.IMPUTE_MEAN, 0, 0)
     gpu_ctx.chunk_wait(0)
+
+
+def test_resident_entry_points_argument_errors(gpu_ctx):
+    """error behaviour of the resident-path entry points: state and argument errors come back as StaarError, never
+    as a crash or a silent CPU path"""
+    import torch
+    from staarpipeline_b200 import api, synth
+    n = 512
+    nb = synth.nullmodel_binary(n, seed=2, q=3, intercept=-2.0)
+    dev = torch.device("cuda:0")
+    stride = api.packed_stride(n)
+    cols = torch.zeros((4, stride), dtype=torch.uint8, device=dev)
+    sel = torch.zeros(4, dtype=torch.int64, device=dev)
+    pv = torch.zeros(4, dtype=torch.float64, device=dev)
+    fresh = api.Context(0)
+    try:
+        with pytest.raises(api.StaarError):                                   # SPA operands not set
+            fresh.packed_spa_device(cols.data_ptr(), stride, n, sel.data_ptr(), 4, api.IMPUTE_MEAN, 1e-4, 10, pv.data_ptr())
+        fresh.set_nullmodel_spa(nb.XW, nb.XXWX_inv, nb.residuals, nb.muhat)
+        with pytest.raises(api.StaarError):                                   # n differs from the operands'
+            fresh.packed_spa_device(cols.data_ptr(), stride, n + 4, sel.data_ptr(), 4, api.IMPUTE_MEAN, 1e-4, 10, pv.data_ptr())
+        with pytest.raises(api.StaarError):                                   # stride not a multiple of 16
+            fresh.packed_spa_device(cols.data_ptr(), stride - 8, n, sel.data_ptr(), 4, api.IMPUTE_MEAN, 1e-4, 10, pv.data_ptr())
+        fresh.packed_spa_device(cols.data_ptr(), stride, n, sel.data_ptr(), 0, api.IMPUTE_MEAN, 1e-4, 10, pv.data_ptr())   # empty: no-op
+        fresh.packed_spa_device(cols.data_ptr(), stride, n, sel.data_ptr(), 4, api.IMPUTE_MEAN, 1e-4, 10, pv.data_ptr())
+        assert np.array_equal(pv.cpu().numpy(), np.ones(4))                   # monomorphic columns: p = 1
+        with pytest.raises(api.StaarError):                                   # XW / XXWX_inv shapes disagree
+            fresh.set_nullmodel_spa(nb.XW, nb.XXWX_inv[:-1], nb.residuals, nb.muhat)
+        with pytest.raises(api.StaarError):                                   # chunk driver without a null model
+            fresh.chunk_submit(np.zeros((n, 3), order="F"), api.IMPUTE_MEAN, 0, 0)
+        with pytest.raises(api.StaarError):
+            fresh.chunk_wait(0)
+    finally:
+        fresh.close()
