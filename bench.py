@@ -362,6 +362,16 @@ def run_ours(args):
                          f"driver (matrix_flip_mean, Individual_Score_Test, Individual_Score_Test_sp), {t:.1f} s; "
                          "reference sources with stand-in Armadillo/Rmath (oracle/ref_stub), dense GEMM on "
                          f"{'OpenBLAS all cores' if blas else 'in-order loops'}"}
+        # the same native call sequence, same chunk, through this library's frozen-signature entry points (what the Rcpp
+        # shim of INTEGRATION.md binds: FP64 G in and the flipped FP64 Geno back out over PCIe, dense + CSC marshalling)
+        if e2e is not None:
+            reference_chunk(ctx, Gc, nm_like)
+            tf, tested_f = reference_chunk(ctx, Gc, nm_like)
+            e2e["frozen_signatures"] = {"value": pc / tf, "unit": "variants/s", "ms_per_chunk": 1e3 * tf, "variants": pc,
+                                        "tested": tested_f,
+                                        "call": "staar_matrix_flip_mean -> staar_individual_score_test (common, dense FP64 G) -> "
+                                                "staar_individual_score_test_sp (rare, CSC G): the R driver's sequence "
+                                                "through the 13 unchanged signatures, host operands on every call"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "variants/s", "n_gpus": world, "steps": args.steps,

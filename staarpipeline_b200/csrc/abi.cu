@@ -29,16 +29,86 @@ struct Guard {   // every entry point runs on the context's device
     if (!(ctx)) { staar::set_error("null context"); return STAAR_ERR_ARG; } \
     staar::Guard guard__(ctx)
 
+// Large transfers from / to PAGEABLE host memory (the Rcpp boundary hands over ordinary R vectors: 4 GB of G per chunk,
+// and matrix_flip_* returns as much): a plain cudaMemcpy stages them through one driver thread at ~10 GB/s.  Here host
+// threads copy 32 MB slices into / out of a ring of pinned buffers while the DMA engine works on the previous slices,
+// which runs at the PCIe rate.  Pinned memory and small transfers go straight to cudaMemcpyAsync.
+constexpr size_t kStageBytes = 32u << 20;
+constexpr size_t kStageMin = 64u << 20;
+
+static bool is_pageable(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+static int stage_init(staar_ctx *ctx)
+{
+    if (ctx->stage[0]) return STAAR_OK;
+    for (int b = 0; b < staar_ctx::kStageBufs; b++) {
+        STAAR_CUDA(cudaMallocHost(&ctx->stage[b], kStageBytes));
+        STAAR_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[b], cudaEventDisableTiming));
+    }
+    return STAAR_OK;
+}
+
+static void parallel_memcpy(void *dst, const void *src, size_t bytes)
+{
+    static const unsigned nthreads = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    const size_t piece = (bytes / nthreads + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nthreads; t++) {
+        const size_t off = t * piece;
+        if (off >= bytes) break;
+        th.emplace_back([=] { memcpy(static_cast<char *>(dst) + off, static_cast<const char *>(src) + off, std::min(piece, bytes - off)); });
+    }
+    memcpy(dst, src, std::min(piece, bytes));
+    for (auto &x : th) x.join();
+}
+
 int h2d(staar_ctx *ctx, void *dst, const void *src, size_t bytes)
 {
     if (bytes == 0) return STAAR_OK;
-    STAAR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes < kStageMin || !is_pageable(src)) {
+        STAAR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return STAAR_OK;
+    }
+    STAAR_TRY(stage_init(ctx));
+    int b = 0;
+    for (size_t off = 0; off < bytes; off += kStageBytes, b = (b + 1) % staar_ctx::kStageBufs) {
+        const size_t len = std::min(kStageBytes, bytes - off);
+        STAAR_CUDA(cudaEventSynchronize(ctx->stage_ev[b]));                   // the DMA that last read this buffer is done
+        parallel_memcpy(ctx->stage[b], static_cast<const char *>(src) + off, len);
+        STAAR_CUDA(cudaMemcpyAsync(static_cast<char *>(dst) + off, ctx->stage[b], len, cudaMemcpyHostToDevice, ctx->stream));
+        STAAR_CUDA(cudaEventRecord(ctx->stage_ev[b], ctx->stream));
+    }
     return STAAR_OK;
 }
+
 int d2h(staar_ctx *ctx, void *dst, const void *src, size_t bytes)
 {
     if (bytes == 0 || !dst) return STAAR_OK;
-    STAAR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bytes < kStageMin || !is_pageable(dst)) {
+        STAAR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        return STAAR_OK;
+    }
+    STAAR_TRY(stage_init(ctx));
+    // slices are copied out one ring position behind the DMA; on return everything is in dst
+    const int nb = staar_ctx::kStageBufs;
+    const size_t nslice = (bytes + kStageBytes - 1) / kStageBytes;
+    for (size_t s = 0; s < nslice + (size_t)(nb - 1); s++) {
+        if (s >= (size_t)(nb - 1)) {                                           // drain slice s - (nb - 1)
+            const size_t k = s - (nb - 1), off = k * kStageBytes, len = std::min(kStageBytes, bytes - off);
+            STAAR_CUDA(cudaEventSynchronize(ctx->stage_ev[k % nb]));
+            parallel_memcpy(static_cast<char *>(dst) + off, ctx->stage[k % nb], len);
+        }
+        if (s < nslice) {
+            const size_t off = s * kStageBytes, len = std::min(kStageBytes, bytes - off);
+            STAAR_CUDA(cudaMemcpyAsync(ctx->stage[s % nb], static_cast<const char *>(src) + off, len, cudaMemcpyDeviceToHost, ctx->stream));
+            STAAR_CUDA(cudaEventRecord(ctx->stage_ev[s % nb], ctx->stream));
+        }
+    }
     return STAAR_OK;
 }
 int sync(staar_ctx *ctx)

@@ -164,6 +164,10 @@ struct staar_ctx {
         double t_host = 0.0;
     } slot[2];
     cudaStream_t stream2 = nullptr;               // result read-back of a finished chunk while the next one is queued
+    // staging ring for large transfers from / to pageable host memory (abi.cu:h2d / d2h)
+    static constexpr int kStageBufs = 4;
+    void *stage[kStageBufs] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t stage_ev[kStageBufs] = {nullptr, nullptr, nullptr, nullptr};
     // optional per-kernel timing of the packed path (bench.py roofline)
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

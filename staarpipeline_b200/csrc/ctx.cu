@@ -569,6 +569,10 @@ void staar_ctx_destroy(staar_ctx *ctx)
         if (sl.done) { cudaEventDestroy(sl.done); cudaEventDestroy(sl.ev0); cudaEventDestroy(sl.ev1); }
     }
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    for (int b = 0; b < staar_ctx::kStageBufs; b++) {
+        if (ctx->stage[b]) cudaFreeHost(ctx->stage[b]);
+        if (ctx->stage_ev[b]) cudaEventDestroy(ctx->stage_ev[b]);
+    }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
