@@ -8,6 +8,7 @@
 // g++ (not nvcc) so that the target attributes and intrinsics are available; chosen at run time by CPUID.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -146,7 +147,11 @@ int pack_block(const T *G, int64_t n, int64_t p, uint8_t *packed, size_t stride,
         staar::set_error("pack_dosage: bad arguments");
         return STAAR_ERR_ARG;
     }
-    if (threads < 1) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (threads < 1) {
+        // one process per GPU (torchrun sets LOCAL_WORLD_SIZE): the ranks of a box share its cores
+        static const int ranks = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;
+        threads = std::max(1, (int)std::thread::hardware_concurrency() / ranks);
+    }
     threads = (int)std::min<int64_t>(threads, std::max<int64_t>(p, 1));
     const bool simd = cpu_has_avx512() && !getenv("STAAR_B200_NO_AVX512");
     std::vector<int> bad(threads, 0);
