@@ -469,17 +469,66 @@ int check_dims(int64_t n, int64_t p)
     return STAAR_OK;
 }
 
+// matrix_flip_* of a large block in pageable host memory: the matrix goes to the device, through the flip kernel and
+// back in column blocks of one staging buffer each, the upload of block b+1 and the download of block b running at
+// the same time (PCIe is full duplex; two pinned rings, two streams), host threads filling and draining the rings.
+static int flip_entry_pipelined(staar_ctx *ctx, const double *G, int64_t n, int64_t p, bool minor, double *Geno_out,
+                                double *dAF, double *dMAF)
+{
+    STAAR_TRY(stage_init(ctx));
+    const int nbuf = staar_ctx::kStageBufs;
+    if (!ctx->stage_out[0])
+        for (int b = 0; b < nbuf; b++) {
+            STAAR_CUDA(cudaMallocHost(&ctx->stage_out[b], kStageBytes));
+            STAAR_CUDA(cudaEventCreateWithFlags(&ctx->stage_out_ev[b], cudaEventDisableTiming));
+            STAAR_CUDA(cudaEventCreateWithFlags(&ctx->stage_k_ev[b], cudaEventDisableTiming));
+        }
+    if (!ctx->stream2) STAAR_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    const int64_t cols = std::max<int64_t>(1, (int64_t)(kStageBytes / (sizeof(double) * (size_t)n)));
+    const int64_t nblk = (p + cols - 1) / cols;
+    const int lag = 2;
+    double *dG = ctx->G.as<double>();
+    for (int64_t b = 0; b < nblk + lag; b++) {
+        if (b < nblk) {
+            const int s = (int)(b % nbuf);
+            const int64_t c0 = b * cols, nc = std::min(cols, p - c0);
+            const size_t off = (size_t)c0 * n, len = sizeof(double) * (size_t)nc * n;
+            STAAR_CUDA(cudaEventSynchronize(ctx->stage_ev[s]));
+            parallel_memcpy(ctx->stage[s], G + off, len);
+            STAAR_CUDA(cudaMemcpyAsync(dG + off, ctx->stage[s], len, cudaMemcpyHostToDevice, ctx->stream));
+            STAAR_CUDA(cudaEventRecord(ctx->stage_ev[s], ctx->stream));
+            STAAR_TRY(launch_flip_dense(ctx, dG + off, n, nc, minor, true, dAF + c0, dMAF + c0));
+            STAAR_CUDA(cudaEventRecord(ctx->stage_k_ev[s], ctx->stream));
+            STAAR_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->stage_k_ev[s], 0));
+            STAAR_CUDA(cudaMemcpyAsync(ctx->stage_out[s], dG + off, len, cudaMemcpyDeviceToHost, ctx->stream2));
+            STAAR_CUDA(cudaEventRecord(ctx->stage_out_ev[s], ctx->stream2));
+        }
+        if (b >= lag) {
+            const int64_t k = b - lag, c0 = k * cols, nc = std::min(cols, p - c0);
+            STAAR_CUDA(cudaEventSynchronize(ctx->stage_out_ev[k % nbuf]));
+            parallel_memcpy(Geno_out + (size_t)c0 * n, ctx->stage_out[k % nbuf], sizeof(double) * (size_t)nc * n);
+        }
+    }
+    return STAAR_OK;
+}
+
 int flip_entry(staar_ctx *ctx, const double *G, int64_t n, int64_t p, bool minor, double *Geno_out, double *AF, double *MAF)
 {
     STAAR_TRY(check_dims(n, p));
     if (!G || !AF || !MAF) { set_error("matrix_flip: NULL pointer"); return STAAR_ERR_ARG; }
-    STAAR_TRY(upload_dense_G(ctx, G, n, p));
     STAAR_TRY(ctx->out.reserve(sizeof(double) * 2 * (size_t)std::max<int64_t>(p, 1)));
     double *o = ctx->out.as<double>();
-    STAAR_TRY(launch_flip_dense(ctx, ctx->G.as<double>(), n, p, minor, Geno_out != nullptr, o, o + p));
+    const size_t bytes = sizeof(double) * (size_t)n * p;
+    if (Geno_out && bytes >= kStageMin && sizeof(double) * (size_t)n <= kStageBytes && is_pageable(G) && is_pageable(Geno_out)) {
+        STAAR_TRY(ctx->G.reserve(bytes));
+        STAAR_TRY(flip_entry_pipelined(ctx, G, n, p, minor, Geno_out, o, o + p));
+    } else {
+        STAAR_TRY(upload_dense_G(ctx, G, n, p));
+        STAAR_TRY(launch_flip_dense(ctx, ctx->G.as<double>(), n, p, minor, Geno_out != nullptr, o, o + p));
+        STAAR_TRY(d2h(ctx, Geno_out, ctx->G.p, bytes));
+    }
     STAAR_TRY(d2h(ctx, AF, o, sizeof(double) * p));
     STAAR_TRY(d2h(ctx, MAF, o + p, sizeof(double) * p));
-    STAAR_TRY(d2h(ctx, Geno_out, ctx->G.p, sizeof(double) * (size_t)n * p));
     return sync(ctx);
 }
 

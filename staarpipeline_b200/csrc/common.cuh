@@ -168,6 +168,8 @@ struct staar_ctx {
     static constexpr int kStageBufs = 4;
     void *stage[kStageBufs] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t stage_ev[kStageBufs] = {nullptr, nullptr, nullptr, nullptr};
+    void *stage_out[kStageBufs] = {nullptr, nullptr, nullptr, nullptr};       // second ring: device -> host while the first feeds the device
+    cudaEvent_t stage_out_ev[kStageBufs] = {nullptr, nullptr, nullptr, nullptr}, stage_k_ev[kStageBufs] = {nullptr, nullptr, nullptr, nullptr};
     // optional per-kernel timing of the packed path (bench.py roofline)
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -572,6 +572,9 @@ void staar_ctx_destroy(staar_ctx *ctx)
     for (int b = 0; b < staar_ctx::kStageBufs; b++) {
         if (ctx->stage[b]) cudaFreeHost(ctx->stage[b]);
         if (ctx->stage_ev[b]) cudaEventDestroy(ctx->stage_ev[b]);
+        if (ctx->stage_out[b]) cudaFreeHost(ctx->stage_out[b]);
+        if (ctx->stage_out_ev[b]) cudaEventDestroy(ctx->stage_out_ev[b]);
+        if (ctx->stage_k_ev[b]) cudaEventDestroy(ctx->stage_k_ev[b]);
     }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

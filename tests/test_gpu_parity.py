@@ -573,3 +573,16 @@ def test_resident_entry_points_argument_errors(gpu_ctx):
             fresh.chunk_wait(0)
     finally:
         fresh.close()
+
+
+@pytest.mark.parametrize("fn", ["matrix_flip_mean", "matrix_flip_minor"])
+def test_flip_large_block_pipelined_transfers(gpu_ctx, oracle, fn):
+    """a block above 64 MB in pageable memory takes the column-block pipeline (upload, flip kernel and download of
+    different blocks in flight at once, staged through pinned rings): still bit-exact, also when the output aliases
+    the input as in the Rcpp shim"""
+    n, p = 20011, 530                                                       # 85 MB, odd n, several staging blocks
+    G0 = cases.raw_dosage(n, p, 123)
+    want = getattr(oracle, fn)(G0)
+    got = getattr(gpu_ctx, fn)(G0)
+    for k in ("Geno", "AF", "MAF"):
+        assert np.array_equal(got[k], want[k], equal_nan=True), k
