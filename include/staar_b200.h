@@ -221,6 +221,17 @@ int staar_packed_spa_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stri
                             const int64_t *d_variant, int64_t n_sel, int impute, double tol, int max_iter,
                             double *d_pvalue, int64_t *d_trace /* 4 per variant as staar_individual_score_test_SPA, or NULL */);
 
+/* Dense-GRM score test on resident packed columns (configuration 3).  staar_nullmodel_set_dense uploads P (n x n,
+ * column-major: Sigma^-1 - Sigma^-1 X cov X' Sigma^-1) and the residuals once.  staar_packed_score_dense_device then
+ * computes, for p resident 2-bit columns in the CALLER's sample order (P's order), AF / MAF as matrix_flip_mean|minor
+ * and the five statistics of Individual_Score_Test_denseGRM (src/Individual_Score_Test_denseGRM.cpp:9-61) into device
+ * arrays of length p.  Variants with at most n/8 non-zero genotypes after flip and imputation take the carrier form of
+ * g'Pg, the others are decoded in batches and go through P*G.  Synchronous. */
+int staar_nullmodel_set_dense(staar_ctx *ctx, int64_t n, const double *P, const double *residuals);
+int staar_packed_score_dense_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride_bytes, int64_t n, int64_t p,
+                                    int impute, double *d_AF, double *d_MAF, double *d_Score, double *d_Score_se,
+                                    double *d_pvalue_log, double *d_Est, double *d_Est_se);
+
 /* Per-kernel device times of the LAST staar_packed_score_device call, measured with CUDA events on the context
  * stream when profiling is on: ms[0] = scan (K1+K3), ms[1] = contraction (K2), ms[2] = finalize (K5).
  * Used by bench.py for the live roofline figure; off by default (no events recorded). */

@@ -359,6 +359,20 @@ class Context:
         self._lib.staar_ctx_gpu_pack_share.restype = C.c_double
         return float(self._lib.staar_ctx_gpu_pack_share(self._h))
 
+    def set_nullmodel_dense(self, P, residuals):
+        Pm = _f(P)
+        n = Pm.shape[0]
+        if Pm.shape != (n, n):
+            raise StaarError(1, "P must be square")
+        r = _f(residuals).ravel()
+        if r.size != n:
+            raise StaarError(1, "matrix multiplication: incompatible matrix dimensions (residuals)")
+        self._call("staar_nullmodel_set_dense", C.c_int64(n), _p(Pm), _p(r))
+
+    def packed_score_dense_device(self, d_packed: int, stride: int, n: int, p: int, impute: int, d_out7):
+        self._call("staar_packed_score_dense_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n), C.c_int64(p),
+                   C.c_int(impute), *[C.c_void_p(x) for x in d_out7])
+
     def set_nullmodel_spa(self, XW, XXWX_inv, residuals, muhat):
         XWm, XXi = _f(XW), _f(XXWX_inv)
         q, n = XWm.shape

@@ -938,6 +938,28 @@ int staar_packed_spa_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stri
     return sync(ctx);
 }
 
+int staar_nullmodel_set_dense(staar_ctx *ctx, int64_t n, const double *P, const double *residuals)
+{
+    CHECK_CTX(ctx);
+    if (n <= 0 || !P || !residuals) { set_error("nullmodel_set_dense: bad arguments"); return STAAR_ERR_ARG; }
+    STAAR_TRY(ensure_dense(ctx, n, P));
+    STAAR_TRY(h2d(ctx, ctx->nd.residuals, residuals, sizeof(double) * n));
+    return sync(ctx);
+}
+
+int staar_packed_score_dense_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
+                                    double *d_AF, double *d_MAF, double *d_Score, double *d_Score_se, double *d_pl,
+                                    double *d_Est, double *d_Est_se)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    if (!ctx->nd.set || ctx->nd.n != n) { set_error("packed dense-GRM score: call staar_nullmodel_set_dense for n = %lld first", (long long)n); return STAAR_ERR_STATE; }
+    if (stride % 16 != 0 || stride < (size_t)((n + 3) / 4)) { set_error("packed stride must be a multiple of 16 and >= ceil(n/4)"); return STAAR_ERR_ARG; }
+    if (p == 0) return STAAR_OK;
+    STAAR_TRY(packed_score_dense(ctx, d_packed, stride, n, p, impute, d_AF, d_MAF, d_Score, d_Score_se, d_pl, d_Est, d_Est_se));
+    return sync(ctx);
+}
+
 int staar_nullmodel_sample_order(staar_ctx *ctx, int64_t n, int32_t *order)
 {
     CHECK_CTX(ctx);

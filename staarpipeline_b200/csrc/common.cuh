@@ -233,6 +233,10 @@ int build_tc_operand(staar_ctx *ctx, const int8_t *digits, int ncol);
 int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, long long *d_hi,
                        long long *d_lo);
 int refresh_permuted_Y(staar_ctx *ctx, const double *hY);
+// packed_dense.cu — dense-GRM score test on resident packed columns
+int packed_score_dense(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
+                       double *d_AF, double *d_MAF, double *d_Score, double *d_Score_se, double *d_pl, double *d_Est,
+                       double *d_Est_se);
 // driver.cu — MAF/MAC filter + SPA pre-filter: stable compaction of the per-variant arrays
 int launch_compact_results(staar_ctx *ctx, int64_t p, const double *const d_in[7], double maf_cut, double p_cut,
                            long long *d_index, double *const d_out[7], long long *d_sel_index, long long *d_totals);

@@ -1,0 +1,178 @@
+// packed_dense.cu — dense-GRM score test (reference src/Individual_Score_Test_denseGRM.cpp:9-61 / _sp_denseGRM.cpp) on
+// RESIDENT 2-bit genotype columns: BASELINE config 3 without the FP64 matrix of the Rcpp boundary.
+//
+// Per variant: code counts -> AF / MAF / flip / imputation value exactly as matrix_flip_mean|minor (packed.cuh); the
+// column's non-zero entries after flip and imputation become a carrier list (row, value) in sample order; then
+//   Uscore = sum v_i r_i                      (quadform.cu:score_carriers)
+//   g'Pg   = sum_i sum_j v_i v_j P[i,j]       (quadform.cu:quad_pairs_carriers_P)   when the list has <= n/8 entries,
+//   g'Pg   = g . (P g) through the DMMA GEMM  (decode to FP64, quadform.cu)          for the common variants,
+// and the reference's per-variant statistics (epilogue.cu).  Columns are in the caller's sample order (P's order).
+#include <vector>
+#include "common.cuh"
+#include "packed.cuh"
+
+namespace staar {
+
+namespace {
+
+__device__ __forceinline__ double carrier_value(uint32_t code, const VariantFlip &vf)
+{
+    if (code == 3u) return vf.mu;
+    if (vf.flip && !(code & 1u)) code ^= 2u;
+    return (double)code;
+}
+
+// a warp per variant: AF, MAF, flip, mu and the number of non-zero entries of the flipped / imputed column
+__global__ void __launch_bounds__(256) carrier_count_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t n, int64_t p,
+                                                            int impute, double *__restrict__ AF, double *__restrict__ MAF,
+                                                            int32_t *__restrict__ flip, double *__restrict__ mu,
+                                                            long long *__restrict__ count)
+{
+    const int lane = threadIdx.x & 31;
+    for (int64_t i = blockIdx.x * 8ll + (threadIdx.x >> 5); i < p; i += gridDim.x * 8ll) {
+        const PackedCounts pc = count_packed_column(packed + (size_t)i * stride, stride, lane);
+        if (lane == 0) {
+            const VariantFlip vf = flip_from_counts(pc, n, impute);
+            const long long c0 = (long long)n - pc.c1 - pc.c2 - pc.cm;
+            AF[i] = vf.af; MAF[i] = vf.maf; flip[i] = vf.flip; mu[i] = vf.mu;
+            count[i] = pc.c1 + (vf.flip ? c0 : (long long)pc.c2) + (vf.mu != 0.0 ? pc.cm : 0);
+        }
+    }
+}
+
+// a warp per variant: the carrier list in increasing sample order (32 words = 512 samples per step, warp prefix sums)
+__global__ void __launch_bounds__(256) carrier_fill_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t n, int64_t p,
+                                                           const double *__restrict__ AF, const int32_t *__restrict__ flip,
+                                                           const double *__restrict__ mu, const long long *__restrict__ colptr,
+                                                           double *__restrict__ val, int64_t *__restrict__ row)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t nwords = (n + 15) / 16;
+    for (int64_t i = blockIdx.x * 8ll + (threadIdx.x >> 5); i < p; i += gridDim.x * 8ll) {
+        const uint32_t *col = reinterpret_cast<const uint32_t *>(packed + (size_t)i * stride);
+        const VariantFlip vf{AF[i], 0.0, mu[i], flip[i]};
+        long long base = colptr[i];
+        for (int64_t w0 = 0; w0 < nwords; w0 += 32) {
+            const int64_t w = w0 + lane;
+            uint32_t word = w < nwords ? __ldg(col + w) : 0u;
+            const int valid = w < nwords ? (int)min(16ll, (long long)(n - 16 * w)) : 0;
+            int cnt = 0;
+            for (int s = 0; s < valid; s++) cnt += carrier_value((word >> (2 * s)) & 3u, vf) != 0.0;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            long long at = base + incl - cnt;
+            for (int s = 0; s < valid; s++) {
+                const double v = carrier_value((word >> (2 * s)) & 3u, vf);
+                if (v != 0.0) { val[at] = v; row[at] = 16 * w + s; at++; }
+            }
+            base += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+}
+
+// selected packed columns -> flipped, imputed FP64 columns (the matrix the reference's dense entry point receives)
+__global__ void __launch_bounds__(256) decode_columns_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t n,
+                                                             const int32_t *__restrict__ list, int64_t first, int64_t count,
+                                                             const double *__restrict__ AF, const int32_t *__restrict__ flip,
+                                                             const double *__restrict__ mu, double *__restrict__ G)
+{
+    for (int64_t c = blockIdx.x; c < count; c += gridDim.x) {
+        const int64_t i = list[first + c];
+        const uint8_t *col = packed + (size_t)i * stride;
+        const VariantFlip vf{AF[i], 0.0, mu[i], flip[i]};
+        double *g = G + (size_t)c * n;
+        for (int64_t j = threadIdx.x; j < n; j += blockDim.x)
+            g[j] = carrier_value(((uint32_t)__ldg(col + (j >> 2)) >> (2 * (j & 3))) & 3u, vf);
+    }
+}
+
+__global__ void scatter_kernel(const double *__restrict__ src, const int32_t *__restrict__ list, int64_t first, int64_t count,
+                               double *__restrict__ dst)
+{
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < count; c += (int64_t)gridDim.x * blockDim.x)
+        dst[list[first + c]] = src[c];
+}
+
+}  // namespace
+
+int packed_score_dense(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
+                       double *d_AF, double *d_MAF, double *d_Score, double *d_Score_se, double *d_pl, double *d_Est,
+                       double *d_Est_se)
+{
+    const NullDense &nd = ctx->nd;
+    cudaStream_t st = ctx->stream;
+    // per-variant scratch: flip (i32) | mu | count / colptr (i64, p + 1) | quad | L (p x 8)
+    const size_t pi = (size_t)((p + 1) / 2 * 2);
+    STAAR_TRY(ctx->tmp2.reserve(sizeof(int32_t) * pi + sizeof(double) * ((size_t)p * 10 + 8) + sizeof(long long) * ((size_t)p + 2)));
+    int32_t *dflip = ctx->tmp2.as<int32_t>();
+    double *dmu = reinterpret_cast<double *>(dflip + pi);
+    long long *dcount = reinterpret_cast<long long *>(dmu + p);
+    double *dquad = reinterpret_cast<double *>(dcount + p + 2), *dL = dquad + p;
+    const int grid8 = (int)std::min<int64_t>((p + 7) / 8, (int64_t)ctx->sm_count * 8);
+    carrier_count_kernel<<<grid8, 256, 0, st>>>(d_packed, stride, n, p, impute, d_AF, d_MAF, dflip, dmu, dcount);
+    ctx->launches++;
+    // column pointers and the two routes are decided on the host from the p counts (8 B per variant over PCIe)
+    std::vector<long long> cnt((size_t)p + 1);
+    STAAR_CUDA(cudaMemcpyAsync(cnt.data(), dcount, sizeof(long long) * p, cudaMemcpyDeviceToHost, st));
+    STAAR_CUDA(cudaStreamSynchronize(st));
+    std::vector<int32_t> lists((size_t)p);                       // sparse-route variants first, dense-route after
+    int64_t ns_ = 0, nd_ = 0;
+    long long run = 0;
+    for (int64_t i = 0; i < p; i++) {
+        const long long c = cnt[i];
+        cnt[i] = run; run += c;
+        if (c <= n / 8) lists[ns_++] = (int32_t)i;
+    }
+    cnt[p] = run;
+    for (int64_t i = 0; i < p; i++)
+        if (cnt[i + 1] - cnt[i] > n / 8) lists[ns_ + nd_++] = (int32_t)i;
+    const long long nnz = run;
+    STAAR_TRY(ctx->pk2.reserve((size_t)nnz * 16 + sizeof(int32_t) * (size_t)p + 64));
+    double *dval = ctx->pk2.as<double>();
+    int64_t *drow = reinterpret_cast<int64_t *>(dval + nnz);
+    int32_t *dlist = reinterpret_cast<int32_t *>(drow + nnz);
+    STAAR_CUDA(cudaMemcpyAsync(dcount, cnt.data(), sizeof(long long) * (p + 1), cudaMemcpyHostToDevice, st));
+    STAAR_CUDA(cudaMemcpyAsync(dlist, lists.data(), sizeof(int32_t) * p, cudaMemcpyHostToDevice, st));
+    carrier_fill_kernel<<<grid8, 256, 0, st>>>(d_packed, stride, n, p, d_AF, dflip, dmu, dcount, dval, drow);
+    ctx->launches++;
+    const int ldL = 8;
+    STAAR_CUDA(cudaMemsetAsync(dL, 0, sizeof(double) * (size_t)p * ldL, st));
+    STAAR_TRY(launch_score_carriers(ctx, dval, drow, reinterpret_cast<const int64_t *>(dcount), p, nd.residuals, dL, ldL));
+    // sparse route: pairs (i, i) of the listed variants, results scattered to their variant
+    STAAR_TRY(ctx->aux.reserve(sizeof(double) * (size_t)std::max<int64_t>(p, 1)));
+    double *dtmp = ctx->aux.as<double>();
+    if (ns_ > 0) {
+        STAAR_TRY(launch_quad_pairs_carriers_P(ctx, dval, drow, reinterpret_cast<const int64_t *>(dcount), n, nd.P, dlist, dlist, ns_, dtmp));
+        scatter_kernel<<<(unsigned)std::min<int64_t>((ns_ + 255) / 256, 1024), 256, 0, st>>>(dtmp, dlist, 0, ns_, dquad);
+        ctx->launches++;
+    }
+    // dense route: batches of decoded FP64 columns through P*G
+    if (nd_ > 0) {
+        const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(nd_, (1ll << 30) / (8 * n)));
+        STAAR_TRY(ctx->G.reserve(sizeof(double) * (size_t)n * batch));
+        STAAR_TRY(ctx->tmp.reserve(sizeof(double) * (size_t)n * batch + sizeof(int32_t) * 2 * (size_t)batch + 64));
+        double *dW = ctx->tmp.as<double>();
+        int32_t *didx = reinterpret_cast<int32_t *>(dW + (size_t)n * batch);
+        std::vector<int32_t> idx((size_t)batch);
+        for (int64_t c = 0; c < batch; c++) idx[c] = (int32_t)c;
+        STAAR_CUDA(cudaMemcpyAsync(didx, idx.data(), sizeof(int32_t) * batch, cudaMemcpyHostToDevice, st));
+        for (int64_t first = 0; first < nd_; first += batch) {
+            const int64_t count = std::min(batch, nd_ - first);
+            decode_columns_kernel<<<(int)std::min<int64_t>(count, (int64_t)ctx->sm_count * 8), 256, 0, st>>>(
+                d_packed, stride, n, dlist, ns_ + first, count, d_AF, dflip, dmu, ctx->G.as<double>());
+            ctx->launches++;
+            STAAR_TRY(launch_dense_P_times_G(ctx, nd.P, ctx->G.as<double>(), n, count, dW));
+            STAAR_TRY(launch_dot_pairs(ctx, ctx->G.as<double>(), dW, n, didx, didx, count, dtmp));
+            scatter_kernel<<<(unsigned)std::min<int64_t>((count + 255) / 256, 1024), 256, 0, st>>>(dtmp, dlist, ns_ + first, count, dquad);
+            ctx->launches++;
+        }
+        STAAR_CUDA(cudaStreamSynchronize(st));                    // idx goes out of scope
+    }
+    STAAR_TRY(launch_epilogue_general(ctx, p, 0, dL, ldL, 0, nullptr, dquad, 0, nullptr, nullptr, 0, 0, d_Score, d_Score_se, d_pl,
+                                      d_Est, d_Est_se));
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+}  // namespace staar

@@ -586,3 +586,34 @@ def test_flip_large_block_pipelined_transfers(gpu_ctx, oracle, fn):
     got = getattr(gpu_ctx, fn)(G0)
     for k in ("Geno", "AF", "MAF"):
         assert np.array_equal(got[k], want[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("impute", ["mean", "minor"])
+def test_packed_dense_grm_vs_oracle(gpu_ctx, oracle, impute):
+    """config 3 on resident 2-bit columns: flip / impute from the code counts, carrier form of g'Pg for variants with
+    <= n/8 non-zero genotypes, decoded FP64 columns through P*G for the rest == matrix_flip_* followed by
+    Individual_Score_Test_denseGRM of the reference (adversarial columns included: all missing, monomorphic, AF = 0.5)"""
+    import torch
+    from staarpipeline_b200 import api, synth
+    n, p = 3000, 96
+    nd = synth.nullmodel_dense_grm(n, seed=12, q=5, markers=300)
+    G0 = cases.raw_dosage(n, p, 12)
+    G0[:, 5:40] = np.where(np.random.default_rng(1).random((n, 35)) < 0.97, 2.0, G0[:, 5:40])     # rare after the flip
+    codes = np.where(np.isnan(G0) | (G0 <= -1), 3, G0).astype(np.uint8)
+    packed = synth.pack_codes(np.asfortranarray(codes))
+    P_, stride = packed.shape
+    gpu_ctx.set_nullmodel_dense(nd.P, nd.residuals)
+    dev = torch.device("cuda:0")
+    d_cols = torch.from_numpy(packed).to(dev)
+    outs = torch.zeros((7, P_), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    flag = api.IMPUTE_MEAN if impute == "mean" else api.IMPUTE_MINOR
+    gpu_ctx.packed_score_dense_device(d_cols.data_ptr(), stride, n, P_, flag, [outs[i].data_ptr() for i in range(7)])
+    res = outs.cpu().numpy()
+    fl = getattr(oracle, f"matrix_flip_{impute}")(G0)
+    want = oracle.Individual_Score_Test_denseGRM(fl["Geno"], nd.P, nd.residuals)
+    assert np.array_equal(res[0], fl["AF"]) and np.array_equal(res[1], fl["MAF"])
+    nnz = (fl["Geno"] != 0).sum(axis=0)
+    assert (nnz <= n // 8).sum() >= 10 and (nnz > n // 8).sum() >= 10                # both routes are exercised
+    got = dict(zip(("Score", "Score_se", "pvalue_log", "Est", "Est_se"), res[2:]))
+    assert_stats_close(got, want, score_floor(fl["Geno"], nd.residuals))
