@@ -232,6 +232,15 @@ int staar_packed_score_dense_device(staar_ctx *ctx, const uint8_t *d_packed, siz
                                     int impute, double *d_AF, double *d_MAF, double *d_Score, double *d_Score_se,
                                     double *d_pvalue_log, double *d_Est, double *d_Est_se);
 
+/* Multi-trait score test on resident packed columns (configuration 4).  The null model is the (n k) x (n k) one of
+ * staar_nullmodel_set_sparse (trait-major stacking, as GMMAT / R/Individual_Analysis.R:57-68 deliver it).  For p
+ * resident 2-bit columns of G0 (n samples, caller's order) this computes AF / MAF as matrix_flip_mean|minor and what
+ * Individual_Score_Test_sp_multi (src/Individual_Score_Test_sp_multi.cpp:9-68) returns for Diagonal(k) (x) G0:
+ * d_Score (k p values: trait-major, index t p + i) and d_pvalue_log (p values).  Synchronous. */
+int staar_packed_score_multi_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride_bytes, int64_t n, int64_t p,
+                                    int n_pheno, int impute, double *d_AF, double *d_MAF, double *d_Score,
+                                    double *d_pvalue_log);
+
 /* Per-kernel device times of the LAST staar_packed_score_device call, measured with CUDA events on the context
  * stream when profiling is on: ms[0] = scan (K1+K3), ms[1] = contraction (K2), ms[2] = finalize (K5).
  * Used by bench.py for the live roofline figure; off by default (no events recorded). */

@@ -373,6 +373,11 @@ class Context:
         self._call("staar_packed_score_dense_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n), C.c_int64(p),
                    C.c_int(impute), *[C.c_void_p(x) for x in d_out7])
 
+    def packed_score_multi_device(self, d_packed: int, stride: int, n: int, p: int, n_pheno: int, impute: int, d_AF: int,
+                                  d_MAF: int, d_Score: int, d_pl: int):
+        self._call("staar_packed_score_multi_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n), C.c_int64(p),
+                   C.c_int(n_pheno), C.c_int(impute), C.c_void_p(d_AF), C.c_void_p(d_MAF), C.c_void_p(d_Score), C.c_void_p(d_pl))
+
     def set_nullmodel_spa(self, XW, XXWX_inv, residuals, muhat):
         XWm, XXi = _f(XW), _f(XXWX_inv)
         q, n = XWm.shape

@@ -960,6 +960,23 @@ int staar_packed_score_dense_device(staar_ctx *ctx, const uint8_t *d_packed, siz
     return sync(ctx);
 }
 
+int staar_packed_score_multi_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int n_pheno,
+                                    int impute, double *d_AF, double *d_MAF, double *d_Score, double *d_pl)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, p));
+    if (n_pheno < 1) { set_error("n_pheno must be >= 1"); return STAAR_ERR_ARG; }
+    if (!ctx->ns.set || ctx->ns.n != n * n_pheno) {
+        set_error("packed multi-trait score: call staar_nullmodel_set_sparse with the %lld x %lld null model first",
+                  (long long)(n * n_pheno), (long long)(n * n_pheno));
+        return STAAR_ERR_STATE;
+    }
+    if (stride % 16 != 0 || stride < (size_t)((n + 3) / 4)) { set_error("packed stride must be a multiple of 16 and >= ceil(n/4)"); return STAAR_ERR_ARG; }
+    if (p == 0) return STAAR_OK;
+    STAAR_TRY(packed_score_multi(ctx, d_packed, stride, n, p, n_pheno, impute, d_AF, d_MAF, d_Score, d_pl));
+    return sync(ctx);
+}
+
 int staar_nullmodel_sample_order(staar_ctx *ctx, int64_t n, int32_t *order)
 {
     CHECK_CTX(ctx);

@@ -237,6 +237,8 @@ int refresh_permuted_Y(staar_ctx *ctx, const double *hY);
 int packed_score_dense(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
                        double *d_AF, double *d_MAF, double *d_Score, double *d_Score_se, double *d_pl, double *d_Est,
                        double *d_Est_se);
+int packed_score_multi(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n0, int64_t pp, int k, int impute,
+                       double *d_AF, double *d_MAF, double *d_Score, double *d_pl);
 // driver.cu — MAF/MAC filter + SPA pre-filter: stable compaction of the per-variant arrays
 int launch_compact_results(staar_ctx *ctx, int64_t p, const double *const d_in[7], double maf_cut, double p_cut,
                            long long *d_index, double *const d_out[7], long long *d_sel_index, long long *d_totals);

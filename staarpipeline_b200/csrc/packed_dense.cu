@@ -94,7 +94,129 @@ __global__ void scatter_kernel(const double *__restrict__ src, const int32_t *__
         dst[list[first + c]] = src[c];
 }
 
+// Kronecker expansion Diagonal(k) (x) G0 of the carrier lists (R/Individual_Analysis.R:267): column t*pp + j holds the
+// entries of G0's column j at rows t*n0 + i
+__global__ void kron_expand_kernel(const double *__restrict__ val, const int64_t *__restrict__ row, const long long *__restrict__ colptr,
+                                   int64_t n0, int64_t pp, int k, long long nnz, double *__restrict__ val_k,
+                                   int64_t *__restrict__ row_k, long long *__restrict__ colptr_k)
+{
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = tid; e < nnz * k; e += nthreads) {
+        const int64_t t = e / nnz, e0 = e - t * nnz;
+        val_k[e] = val[e0];
+        row_k[e] = row[e0] + t * n0;
+    }
+    for (int64_t c = tid; c <= pp * k; c += nthreads) {
+        const int64_t t = c == pp * k ? k - 1 : c / pp, j = c - t * pp;
+        colptr_k[c] = t * nnz + colptr[j];
+    }
+}
+
+// All k x k quadratic forms g_(s,j)' Sigma_i g_(t,j) of one variant in one sweep over its carriers (a warp per variant):
+// for a carrier i and a trait block s, the row s*n0 + i of Sigma_i lists (trait t, relative i') entries, and g_(t,j)[i']
+// is read straight from the variant's 2-bit column — no search in a carrier list.  Output index j*k*k + s*k + t as
+// misc.cu:fill_pairs_kernel orders the pairs for the block test (src/Individual_Score_Test_sp_multi.cpp:47-62).
+template <int K>
+__global__ void __launch_bounds__(256) quad_multi_packed_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t n0, int64_t pp,
+                                                                const double *__restrict__ AF, const int32_t *__restrict__ flip,
+                                                                const double *__restrict__ mu, const double *__restrict__ val,
+                                                                const int64_t *__restrict__ row, const long long *__restrict__ colptr,
+                                                                const int64_t *__restrict__ S_row_ptr, const int32_t *__restrict__ S_col,
+                                                                const double *__restrict__ S_val, double *__restrict__ quad)
+{
+    const int lane = threadIdx.x & 31;
+    for (int64_t j = blockIdx.x * 8ll + (threadIdx.x >> 5); j < pp; j += gridDim.x * 8ll) {
+        const uint8_t *col = packed + (size_t)j * stride;
+        const VariantFlip vf{AF[j], 0.0, mu[j], flip[j]};
+        double acc[K * K];
+#pragma unroll
+        for (int a = 0; a < K * K; a++) acc[a] = 0.0;
+        for (long long e = colptr[j] + lane; e < colptr[j + 1]; e += 32) {
+            const int64_t i = row[e];
+            const double v = val[e];
+#pragma unroll
+            for (int s_ = 0; s_ < K; s_++) {
+                const int64_t r = s_ * n0 + i;
+                for (int64_t f = S_row_ptr[r]; f < S_row_ptr[r + 1]; f++) {
+                    const int64_t c = S_col[f];
+                    const int t = (int)(c / n0);
+                    const int64_t i2 = c - t * n0;
+                    const double gb = carrier_value(((uint32_t)__ldg(col + (i2 >> 2)) >> (2 * (i2 & 3))) & 3u, vf);
+                    const double term = v * S_val[f] * gb;
+#pragma unroll
+                    for (int t_ = 0; t_ < K; t_++) if (t == t_) acc[s_ * K + t_] += term;
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < K * K; a++) {
+            const double tot = warp_sum(acc[a]);
+            if (lane == 0) quad[j * (K * K) + a] = tot;
+        }
+    }
+}
+
 }  // namespace
+
+// Individual_Score_Test_multi / _sp_multi (src/Individual_Score_Test_sp_multi.cpp:9-68) on RESIDENT 2-bit columns of G0
+// (n0 samples, caller's order): the null model is the nk x nk one of staar_nullmodel_set_sparse (trait-major stacking).
+int packed_score_multi(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n0, int64_t pp, int k, int impute,
+                       double *d_AF, double *d_MAF, double *d_Score, double *d_pl)
+{
+    const NullSparse &ns = ctx->ns;
+    cudaStream_t st = ctx->stream;
+    const int64_t p = pp * k;
+    const size_t pi = (size_t)((pp + 1) / 2 * 2);
+    STAAR_TRY(ctx->tmp2.reserve(sizeof(int32_t) * pi + sizeof(double) * (size_t)pp + sizeof(long long) * ((size_t)pp + 2 + (size_t)p + 2)));
+    int32_t *dflip = ctx->tmp2.as<int32_t>();
+    double *dmu = reinterpret_cast<double *>(dflip + pi);
+    long long *dcount = reinterpret_cast<long long *>(dmu + pp), *dcolptr_k = dcount + pp + 2;
+    const int grid8 = (int)std::min<int64_t>((pp + 7) / 8, (int64_t)ctx->sm_count * 8);
+    carrier_count_kernel<<<grid8, 256, 0, st>>>(d_packed, stride, n0, pp, impute, d_AF, d_MAF, dflip, dmu, dcount);
+    ctx->launches++;
+    std::vector<long long> cnt((size_t)pp + 1);
+    STAAR_CUDA(cudaMemcpyAsync(cnt.data(), dcount, sizeof(long long) * pp, cudaMemcpyDeviceToHost, st));
+    STAAR_CUDA(cudaStreamSynchronize(st));
+    long long run = 0;
+    for (int64_t i = 0; i < pp; i++) { const long long c = cnt[i]; cnt[i] = run; run += c; }
+    cnt[pp] = run;
+    const long long nnz = run;
+    STAAR_TRY(ctx->pk2.reserve((size_t)nnz * 16 * (size_t)(k + 1) + 64));
+    double *dval = ctx->pk2.as<double>(), *dval_k = dval + nnz;
+    int64_t *drow = reinterpret_cast<int64_t *>(dval_k + nnz * k), *drow_k = drow + nnz;
+    STAAR_CUDA(cudaMemcpyAsync(dcount, cnt.data(), sizeof(long long) * (pp + 1), cudaMemcpyHostToDevice, st));
+    carrier_fill_kernel<<<grid8, 256, 0, st>>>(d_packed, stride, n0, pp, d_AF, dflip, dmu, dcount, dval, drow);
+    kron_expand_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(dval, drow, dcount, n0, pp, k, nnz, dval_k, drow_k, dcolptr_k);
+    ctx->launches += 2;
+    STAAR_CUDA(cudaStreamSynchronize(st));                        // cnt goes out of scope
+    const int ldY = ns.ldY, ncols = (int)(1 + ns.q);
+    STAAR_TRY(ctx->L.reserve(sizeof(double) * (size_t)p * ldY));
+    STAAR_CUDA(cudaMemsetAsync(ctx->L.p, 0, sizeof(double) * (size_t)p * ldY, st));
+    const int64_t *cp = reinterpret_cast<const int64_t *>(dcolptr_k);
+    STAAR_TRY(launch_contract_carriers(ctx, dval_k, drow_k, cp, p, ns.Y, ldY, ncols, ctx->L.as<double>(), ldY));
+    const int64_t npairs = pp * k * k;
+    STAAR_TRY(ctx->tmp.reserve(sizeof(int32_t) * 2 * (size_t)npairs + sizeof(double) * (size_t)npairs + 64));
+    double *dquad = ctx->tmp.as<double>();
+    int32_t *dcolA = reinterpret_cast<int32_t *>(dquad + npairs), *dcolB = dcolA + npairs;
+    if (k >= 1 && k <= 4) {
+        const long long *cp0 = dcount;
+#define STAAR_QUAD_MULTI(K) quad_multi_packed_kernel<K><<<grid8, 256, 0, st>>>(d_packed, stride, n0, pp, d_AF, dflip, dmu, dval, drow, cp0, \
+                                                                             ns.row_ptr, ns.col, ns.val, dquad)
+        if (k == 1) STAAR_QUAD_MULTI(1); else if (k == 2) STAAR_QUAD_MULTI(2); else if (k == 3) STAAR_QUAD_MULTI(3); else STAAR_QUAD_MULTI(4);
+#undef STAAR_QUAD_MULTI
+        ctx->launches++;
+    } else {
+        STAAR_TRY(launch_fill_pairs(ctx, pp, k, dcolA, dcolB));
+        STAAR_TRY(launch_quad_pairs_carriers_csr(ctx, dval_k, drow_k, cp, ns.row_ptr, ns.col, ns.val, dcolA, dcolB, npairs, dquad));
+    }
+    STAAR_TRY(ctx->out.reserve(sizeof(double) * 5 * (size_t)p));
+    double *o = ctx->out.as<double>();
+    STAAR_TRY(launch_epilogue_general(ctx, p, k, ctx->L.as<double>(), ldY, (int)ns.q, ns.cov, dquad, 0, nullptr, nullptr, 0, 0,
+                                      o, o + p, o + 2 * p, o + 3 * p, o + 4 * p));
+    STAAR_CUDA(cudaMemcpyAsync(d_Score, o, sizeof(double) * p, cudaMemcpyDeviceToDevice, st));
+    STAAR_CUDA(cudaMemcpyAsync(d_pl, o + 2 * p, sizeof(double) * pp, cudaMemcpyDeviceToDevice, st));
+    return STAAR_OK;
+}
 
 int packed_score_dense(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
                        double *d_AF, double *d_MAF, double *d_Score, double *d_Score_se, double *d_pl, double *d_Est,

@@ -617,3 +617,34 @@ def test_packed_dense_grm_vs_oracle(gpu_ctx, oracle, impute):
     assert (nnz <= n // 8).sum() >= 10 and (nnz > n // 8).sum() >= 10                # both routes are exercised
     got = dict(zip(("Score", "Score_se", "pvalue_log", "Est", "Est_se"), res[2:]))
     assert_stats_close(got, want, score_floor(fl["Geno"], nd.residuals))
+
+
+@pytest.mark.parametrize("impute", ["mean", "minor"])
+def test_packed_multi_trait_vs_oracle(gpu_ctx, oracle, impute):
+    """config 4 on resident 2-bit columns of G0: flip / impute from the code counts, Kronecker-expanded carrier lists on
+    the device == matrix_flip_* then Individual_Score_Test_sp_multi on Diagonal(k) (x) Geno (related samples, missing
+    genotypes, common and rare variants, adversarial columns)"""
+    import torch
+    from staarpipeline_b200 import api, synth
+    n, k, pp = 900, 3, 40
+    nm = synth.nullmodel_multi(n, k=k, seed=15, q=4)
+    G0 = cases.raw_dosage(n, pp, 15)
+    codes = np.where(np.isnan(G0) | (G0 <= -1), 3, G0).astype(np.uint8)
+    packed = synth.pack_codes(np.asfortranarray(codes))
+    P_, stride = packed.shape
+    gpu_ctx.set_nullmodel_sparse(nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+    dev = torch.device("cuda:0")
+    d_cols = torch.from_numpy(packed).to(dev)
+    af = torch.zeros(P_, dtype=torch.float64, device=dev); maf = torch.zeros_like(af)
+    score = torch.zeros(P_ * k, dtype=torch.float64, device=dev); pl = torch.zeros(P_, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    flag = api.IMPUTE_MEAN if impute == "mean" else api.IMPUTE_MINOR
+    gpu_ctx.packed_score_multi_device(d_cols.data_ptr(), stride, n, P_, k, flag, af.data_ptr(), maf.data_ptr(), score.data_ptr(),
+                                      pl.data_ptr())
+    fl = getattr(oracle, f"matrix_flip_{impute}")(G0)
+    GK = sp.kron(sp.identity(k, format="csc"), sp.csc_matrix(fl["Geno"]), format="csc")
+    want = oracle.Individual_Score_Test_sp_multi(GK, nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals, k)
+    assert np.array_equal(af.cpu().numpy(), fl["AF"]) and np.array_equal(maf.cpu().numpy(), fl["MAF"])
+    assert rel_err(score.cpu().numpy(), want["Score"], score_floor(GK, nm.residuals)) < 1e-10
+    got_pl = pl.cpu().numpy()
+    assert np.all(np.abs(got_pl - want["pvalue_log"]) <= 1e-8 * np.maximum(1.0, np.abs(want["pvalue_log"])))
