@@ -241,6 +241,16 @@ int staar_packed_score_multi_device(staar_ctx *ctx, const uint8_t *d_packed, siz
                                     int n_pheno, int impute, double *d_AF, double *d_MAF, double *d_Score,
                                     double *d_pvalue_log);
 
+/* Conditional test on resident columns (configuration 5, R/Individual_Analysis_cond.R:183-208).  The null model set by
+ * staar_nullmodel_set_sparse carries the REFIT residuals (residuals of lm(residuals ~ X_adj), :190-197); X_adj is the
+ * host n x m adjustment matrix (its derived operands stay on the device between calls with the same X_adj).  The n_sel
+ * columns listed in d_variant (device int64: column numbers of the resident block) are flipped / imputed as
+ * matrix_flip_mean|minor, decoded on the device and go through Individual_Score_Test_cond
+ * (src/Individual_Score_Test_cond.cpp:10-75).  Outputs: host arrays of length n_sel.  Synchronous. */
+int staar_packed_cond(staar_ctx *ctx, const uint8_t *d_packed, size_t stride_bytes, int64_t n, const int64_t *d_variant,
+                      int64_t n_sel, int impute, const double *X_adj, int64_t m, double *Score, double *Score_se,
+                      double *pvalue_log, double *Est, double *Est_se);
+
 /* Per-kernel device times of the LAST staar_packed_score_device call, measured with CUDA events on the context
  * stream when profiling is on: ms[0] = scan (K1+K3), ms[1] = contraction (K2), ms[2] = finalize (K5).
  * Used by bench.py for the live roofline figure; off by default (no events recorded). */

@@ -378,6 +378,15 @@ class Context:
         self._call("staar_packed_score_multi_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n), C.c_int64(p),
                    C.c_int(n_pheno), C.c_int(impute), C.c_void_p(d_AF), C.c_void_p(d_MAF), C.c_void_p(d_Score), C.c_void_p(d_pl))
 
+    def packed_cond(self, d_packed: int, stride: int, n: int, d_variant: int, n_sel: int, impute: int, X_adj):
+        A = _f(X_adj)
+        if A.ndim != 2 or A.shape[0] != n:
+            raise StaarError(1, "matrix multiplication: incompatible matrix dimensions (X_adj)")
+        o, po = self._out5(n_sel)
+        self._call("staar_packed_cond", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n), C.c_void_p(d_variant),
+                   C.c_int64(n_sel), C.c_int(impute), _p(A), C.c_int64(A.shape[1]), *po)
+        return self._pack5(o)
+
     def set_nullmodel_spa(self, XW, XXWX_inv, residuals, muhat):
         XWm, XXi = _f(XW), _f(XXWX_inv)
         q, n = XWm.shape

@@ -977,6 +977,28 @@ int staar_packed_score_multi_device(staar_ctx *ctx, const uint8_t *d_packed, siz
     return sync(ctx);
 }
 
+int staar_packed_cond(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, const int64_t *d_variant,
+                      int64_t n_sel, int impute, const double *X_adj, int64_t m, double *Score, double *Score_se, double *pl,
+                      double *Est, double *Est_se)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, n_sel));
+    NullSparse &ns = ctx->ns;
+    if (!ns.set || ns.n != n) { set_error("packed conditional test: call staar_nullmodel_set_sparse (with the refit residuals) for n = %lld first", (long long)n); return STAAR_ERR_STATE; }
+    if (!X_adj || m < 1) { set_error("packed conditional test: X_adj is empty"); return STAAR_ERR_ARG; }
+    if (stride % 16 != 0 || stride < (size_t)((n + 3) / 4)) { set_error("packed stride must be a multiple of 16 and >= ceil(n/4)"); return STAAR_ERR_ARG; }
+    if (n_sel == 0) return STAAR_OK;
+    std::vector<double> cov_host((size_t)ns.q * ns.q);
+    STAAR_TRY(d2h(ctx, cov_host.data(), ns.cov, sizeof(double) * cov_host.size()));
+    STAAR_TRY(sync(ctx));
+    CondOperands co;
+    STAAR_TRY(prepare_cond(ctx, X_adj, m, cov_host.data(), co));
+    STAAR_TRY(ctx->G.reserve(sizeof(double) * (size_t)n * n_sel));
+    STAAR_TRY(launch_decode_selected(ctx, d_packed, stride, n, reinterpret_cast<const long long *>(d_variant), n_sel, impute,
+                                     ns.permuted ? ns.perm : nullptr, ctx->G.as<double>(), nullptr, nullptr));
+    return run_sparse_family(ctx, n, n_sel, 0, &co, Score, Score_se, pl, Est, Est_se);
+}
+
 int staar_nullmodel_sample_order(staar_ctx *ctx, int64_t n, int32_t *order)
 {
     CHECK_CTX(ctx);

@@ -237,6 +237,8 @@ int refresh_permuted_Y(staar_ctx *ctx, const double *hY);
 int packed_score_dense(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
                        double *d_AF, double *d_MAF, double *d_Score, double *d_Score_se, double *d_pl, double *d_Est,
                        double *d_Est_se);
+int launch_decode_selected(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, const long long *d_variant,
+                           int64_t count, int impute, const int32_t *d_perm, double *dG, double *dAF, double *dMAF);
 int packed_score_multi(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n0, int64_t pp, int k, int impute,
                        double *d_AF, double *d_MAF, double *d_Score, double *d_pl);
 // driver.cu — MAF/MAC filter + SPA pre-filter: stable compaction of the per-variant arrays

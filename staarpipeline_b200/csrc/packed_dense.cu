@@ -87,6 +87,38 @@ __global__ void __launch_bounds__(256) decode_columns_kernel(const uint8_t *__re
     }
 }
 
+// Selected variants of a resident block (null-model sample order) -> the flipped, imputed FP64 columns the reference's
+// FP64 entry points receive, in the caller's sample order (perm: position -> original sample, nullptr = identity).  One
+// CTA per variant: popcounts -> flip / imputation value as matrix_flip_mean|minor, then every code as a double.
+__global__ void __launch_bounds__(256) decode_selected_kernel(const uint8_t *__restrict__ packed, size_t stride, int64_t n,
+                                                              const long long *__restrict__ variant, int64_t count, int impute,
+                                                              const int32_t *__restrict__ perm, double *__restrict__ G,
+                                                              double *__restrict__ AF, double *__restrict__ MAF)
+{
+    __shared__ int s_cnt[3][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int64_t c = blockIdx.x; c < count; c += gridDim.x) {
+        const uint8_t *col = packed + (size_t)variant[c] * stride;
+        int c1 = 0, c2 = 0, cm = 0;
+        const uint4 *v4 = reinterpret_cast<const uint4 *>(col);
+        for (int k = threadIdx.x; k < (int)(stride >> 4); k += blockDim.x) {
+            const uint4 q = __ldg(v4 + k);
+            count_word(q.x, c1, c2, cm); count_word(q.y, c1, c2, cm); count_word(q.z, c1, c2, cm); count_word(q.w, c1, c2, cm);
+        }
+        c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2); cm = __reduce_add_sync(0xffffffffu, cm);
+        __syncthreads();
+        if (lane == 0) { s_cnt[0][w] = c1; s_cnt[1][w] = c2; s_cnt[2][w] = cm; }
+        __syncthreads();
+        c1 = c2 = cm = 0;
+        for (int ww = 0; ww < 8; ww++) { c1 += s_cnt[0][ww]; c2 += s_cnt[1][ww]; cm += s_cnt[2][ww]; }
+        const VariantFlip vf = flip_from_counts(PackedCounts{c1, c2, cm}, n, impute);
+        if (threadIdx.x == 0) { if (AF) AF[c] = vf.af; if (MAF) MAF[c] = vf.maf; }
+        double *g = G + (size_t)c * n;
+        for (int64_t pos = threadIdx.x; pos < n; pos += blockDim.x)
+            g[perm ? perm[pos] : pos] = carrier_value(((uint32_t)__ldg(col + (pos >> 2)) >> (2 * (pos & 3))) & 3u, vf);
+    }
+}
+
 __global__ void scatter_kernel(const double *__restrict__ src, const int32_t *__restrict__ list, int64_t first, int64_t count,
                                double *__restrict__ dst)
 {
@@ -215,6 +247,17 @@ int packed_score_multi(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
                                       o, o + p, o + 2 * p, o + 3 * p, o + 4 * p));
     STAAR_CUDA(cudaMemcpyAsync(d_Score, o, sizeof(double) * p, cudaMemcpyDeviceToDevice, st));
     STAAR_CUDA(cudaMemcpyAsync(d_pl, o + 2 * p, sizeof(double) * pp, cudaMemcpyDeviceToDevice, st));
+    return STAAR_OK;
+}
+
+int launch_decode_selected(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, const long long *d_variant,
+                           int64_t count, int impute, const int32_t *d_perm, double *dG, double *dAF, double *dMAF)
+{
+    if (count == 0) return STAAR_OK;
+    decode_selected_kernel<<<(int)std::min<int64_t>(count, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
+        d_packed, stride, n, d_variant, count, impute, d_perm, dG, dAF, dMAF);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
     return STAAR_OK;
 }
 

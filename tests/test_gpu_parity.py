@@ -648,3 +648,32 @@ def test_packed_multi_trait_vs_oracle(gpu_ctx, oracle, impute):
     assert rel_err(score.cpu().numpy(), want["Score"], score_floor(GK, nm.residuals)) < 1e-10
     got_pl = pl.cpu().numpy()
     assert np.all(np.abs(got_pl - want["pvalue_log"]) <= 1e-8 * np.maximum(1.0, np.abs(want["pvalue_log"])))
+
+
+def test_packed_conditional_test_vs_oracle(gpu_ctx, oracle):
+    """conditional test on selected resident 2-bit columns (null-model sample order, missing genotypes) ==
+    matrix_flip_mean then Individual_Score_Test_cond on the same variants"""
+    import torch
+    from staarpipeline_b200 import api, synth
+    n, p, q = 2000, 60, 5
+    nm = synth.nullmodel_sparse_grm(n, seed=19, q=q, shuffle=True)
+    G0 = cases.raw_dosage(n, p, 19, adversarial=False)
+    fl = oracle.matrix_flip_mean(G0)
+    X_adj, res_c = synth.conditional_design(nm, fl["Geno"][:, :4], "optimal")       # four known variants + covariates
+    codes = np.where(np.isnan(G0) | (G0 <= -1), 3, G0).astype(np.uint8)
+    packed = synth.pack_codes(np.asfortranarray(codes))
+    P_, stride = packed.shape
+    gpu_ctx.set_nullmodel_sparse(nm.Sigma_i, nm.Sigma_iX, nm.cov, res_c)
+    dev = torch.device("cuda:0")
+    d_in = torch.from_numpy(packed).to(dev); d_cols = torch.zeros_like(d_in)
+    torch.cuda.synchronize()
+    gpu_ctx.packed_reorder_device(d_in.data_ptr(), d_cols.data_ptr(), stride, n, P_)
+    sel = np.array([10, 4, 33, 59, 21, 22, 47], dtype=np.int64)
+    d_sel = torch.from_numpy(sel).to(dev)
+    torch.cuda.synchronize()
+    got = gpu_ctx.packed_cond(d_cols.data_ptr(), stride, n, d_sel.data_ptr(), sel.size, api.IMPUTE_MEAN, X_adj)
+    want = oracle.Individual_Score_Test_cond(np.asfortranarray(fl["Geno"][:, sel]), nm.Sigma_i, nm.Sigma_iX, nm.cov, X_adj, res_c)
+    assert_stats_close(got, want, score_floor(fl["Geno"][:, sel], res_c))
+    again = gpu_ctx.packed_cond(d_cols.data_ptr(), stride, n, d_sel.data_ptr(), 1, api.IMPUTE_MEAN, X_adj)     # cached operands
+    for k_ in want:
+        assert np.array_equal(again[k_], got[k_][:1])
