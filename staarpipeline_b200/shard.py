@@ -52,3 +52,36 @@ def broadcast_nullmodel(parts, rank: int, world: int, device=None):
         dist.broadcast(t, 0)
         out.append(t.cpu().numpy())
     return out
+
+
+def broadcast_dense_operands(arrays, rank: int, world: int, device=None):
+    """Replicate rank 0's dense FP64 operands — the dense-GRM P and residuals, the SPA operands XW / XXWX_inv / muhat,
+    a conditional-analysis X_adj — on every rank (same collective as broadcast_nullmodel: one broadcast per operand at
+    run start).  `arrays`: list of ndarrays on rank 0 (ignored elsewhere).  Returns F-ordered 2-D arrays (a vector
+    comes back as n x 1)."""
+    if rank == 0:
+        arrays = [np.asarray(a, dtype=np.float64) for a in arrays]
+        arrays = [np.asfortranarray(a.reshape(-1, 1) if a.ndim < 2 else a) for a in arrays]
+        if len(arrays) > 16:
+            raise ValueError("at most 16 operands per call")
+    if world == 1:
+        return arrays
+    import torch
+    import torch.distributed as dist
+    dev = device if device is not None else torch.device("cpu")
+    flat = [0] * 33
+    if rank == 0:
+        flat[0] = len(arrays)
+        for i, a in enumerate(arrays):
+            flat[1 + 2 * i], flat[2 + 2 * i] = a.shape
+    meta = torch.tensor(flat, dtype=torch.int64, device=dev)
+    dist.broadcast(meta, 0)
+    m = meta.tolist()
+    out = []
+    for i in range(m[0]):
+        r, c = m[1 + 2 * i], m[2 + 2 * i]
+        t = (torch.from_numpy(arrays[i].ravel(order="F").copy()).to(dev) if rank == 0
+             else torch.empty(r * c, dtype=torch.float64, device=dev))
+        dist.broadcast(t, 0)
+        out.append(t.cpu().numpy().reshape((r, c), order="F"))
+    return out

@@ -68,3 +68,37 @@ def test_pack_roundtrip():
     Si, SX, cov, res = shard.unpack_nullmodel(shard.pack_nullmodel(nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals))
     assert (Si != nm.Sigma_i).nnz == 0 and np.array_equal(SX, nm.Sigma_iX)
     assert np.array_equal(cov, nm.cov) and np.array_equal(res, nm.residuals)
+
+
+def _worker_dense(rank, world, port, q):
+    import torch.distributed as dist
+    from staarpipeline_b200 import shard, synth
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ops = None
+    if rank == 0:
+        nb = synth.nullmodel_binary(257, seed=4, q=3, intercept=-2.0)
+        ops = [nb.XW, nb.XXWX_inv, nb.residuals, nb.muhat]
+    XW, XXi, res, mu = shard.broadcast_dense_operands(ops, rank, world)
+    q.put((rank, XW.shape, XXi.shape, res.shape, XW.flags.f_contiguous, float(XW[1, 5]), float(XXi[7, 2]), float(res.sum()), float(mu[11, 0])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dense_operand_broadcast_world2():
+    """SPA / dense-GRM / conditional operands replicate like the sparse null model: same values, shapes and layout"""
+    from staarpipeline_b200 import synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_dense, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    nb = synth.nullmodel_binary(257, seed=4, q=3, intercept=-2.0)
+    for rank, s1, s2, s3, fcont, a, b, c, d in got:
+        assert s1 == (3, 257) and s2 == (257, 3) and s3 == (257, 1) and fcont
+        assert a == float(nb.XW[1, 5]) and b == float(nb.XXWX_inv[7, 2]) and c == float(nb.residuals.sum()) and d == float(nb.muhat[11])
