@@ -677,3 +677,43 @@ def test_packed_conditional_test_vs_oracle(gpu_ctx, oracle):
     again = gpu_ctx.packed_cond(d_cols.data_ptr(), stride, n, d_sel.data_ptr(), 1, api.IMPUTE_MEAN, X_adj)     # cached operands
     for k_ in want:
         assert np.array_equal(again[k_], got[k_][:1])
+
+
+def test_resident_paths_odd_sizes(gpu_ctx, oracle):
+    """ragged shapes for the resident dense-GRM and multi-trait paths: n not a multiple of 4 / 16 / 64, one and three
+    columns (tail words of the 2-bit columns, carrier lists ending mid-word)"""
+    import torch
+    from staarpipeline_b200 import api, synth
+    dev = torch.device("cuda:0")
+    for n, p in ((1003, 3), (517, 1)):
+        G0 = cases.raw_dosage(n, max(p, 6), n)[:, :p]
+        codes = np.where(np.isnan(G0) | (G0 <= -1), 3, G0).astype(np.uint8)
+        packed = synth.pack_codes(np.asfortranarray(codes))
+        P_, stride = packed.shape
+        d_cols = torch.from_numpy(packed).to(dev)
+        fl = oracle.matrix_flip_mean(G0)
+        # dense GRM
+        nd = synth.nullmodel_dense_grm(n, seed=n, q=3, markers=100)
+        gpu_ctx.set_nullmodel_dense(nd.P, nd.residuals)
+        outs = torch.zeros((7, P_), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        gpu_ctx.packed_score_dense_device(d_cols.data_ptr(), stride, n, P_, api.IMPUTE_MEAN, [outs[i].data_ptr() for i in range(7)])
+        res = outs.cpu().numpy()
+        want = oracle.Individual_Score_Test_denseGRM(fl["Geno"], nd.P, nd.residuals)
+        assert np.array_equal(res[0], fl["AF"]) and np.array_equal(res[1], fl["MAF"])
+        assert_stats_close(dict(zip(("Score", "Score_se", "pvalue_log", "Est", "Est_se"), res[2:])), want,
+                           score_floor(fl["Geno"], nd.residuals))
+        # two traits
+        k = 2
+        nm = synth.nullmodel_multi(n, k=k, seed=n, q=3)
+        gpu_ctx.set_nullmodel_sparse(nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+        af = torch.zeros(P_, dtype=torch.float64, device=dev); maf = torch.zeros_like(af)
+        score = torch.zeros(P_ * k, dtype=torch.float64, device=dev); pl = torch.zeros(P_, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        gpu_ctx.packed_score_multi_device(d_cols.data_ptr(), stride, n, P_, k, api.IMPUTE_MEAN, af.data_ptr(), maf.data_ptr(),
+                                          score.data_ptr(), pl.data_ptr())
+        GK = sp.kron(sp.identity(k, format="csc"), sp.csc_matrix(fl["Geno"]), format="csc")
+        wantm = oracle.Individual_Score_Test_sp_multi(GK, nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals, k)
+        assert np.array_equal(af.cpu().numpy(), fl["AF"])
+        assert rel_err(score.cpu().numpy(), wantm["Score"], score_floor(GK, nm.residuals)) < 1e-10
+        assert np.all(np.abs(pl.cpu().numpy() - wantm["pvalue_log"]) <= 1e-8 * np.maximum(1.0, np.abs(wantm["pvalue_log"])))
