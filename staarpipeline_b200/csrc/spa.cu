@@ -482,7 +482,7 @@ int resident_clusters(staar_ctx *ctx, int width);
 // samples per variant decide the cluster width (a function of n and of the device only, so a variant's result does not
 // depend on which other variants share the call).  For long columns the width is the one among 8, 7, 6 that lets
 // resident clusters cover most SMs: a cluster lives inside one GPC, and on this B200 eight-wide clusters reach only 120
-// of the 148 SMs (15 clusters) while six-wide ones reach 144 (measured: 0.408 s vs 0.384 s for 940 variants at n = 4e5).
+// of the 148 SMs (15 clusters) while six-wide ones reach 132-144 (measured: 0.408 s vs 0.384 s for 940 variants at n = 4e5).
 int cluster_width(staar_ctx *ctx, int64_t n)
 {
     static const int cap = getenv("STAAR_B200_SPA_CLUSTER") ? atoi(getenv("STAAR_B200_SPA_CLUSTER")) : 0;
