@@ -717,3 +717,49 @@ def test_resident_paths_odd_sizes(gpu_ctx, oracle):
         assert np.array_equal(af.cpu().numpy(), fl["AF"])
         assert rel_err(score.cpu().numpy(), wantm["Score"], score_floor(GK, nm.residuals)) < 1e-10
         assert np.all(np.abs(pl.cpu().numpy() - wantm["pvalue_log"]) <= 1e-8 * np.maximum(1.0, np.abs(wantm["pvalue_log"])))
+
+
+def test_config5_resident_flow_vs_reference_flow(gpu_ctx, oracle):
+    """the whole config-5 chunk on the device (score test + MAC filter + SPA pre-filter, then the SPA stage on the
+    selected resident columns) against the R driver's flow on the host (R/Individual_Analysis.R:186-300):
+    matrix_flip_mean -> MAC filter -> Individual_Score_Test -> p < 0.05 -> Individual_Score_Test_SPA -> overwrite"""
+    import torch
+    from staarpipeline_b200 import api, synth
+    n, p, q = 6000, 400, 5
+    nb = synth.nullmodel_binary(n, seed=77, q=q, intercept=-3.0)
+    G0 = cases.raw_dosage(n, p, 77)
+    codes = np.where(np.isnan(G0) | (G0 <= -1), 3, G0).astype(np.uint8)
+    packed = synth.pack_codes(np.asfortranarray(codes))
+    P_, stride = packed.shape
+    gpu_ctx.set_nullmodel_sparse(nb.Sigma_i, nb.Sigma_iX, nb.cov, nb.residuals)
+    gpu_ctx.set_nullmodel_spa(nb.XW, nb.XXWX_inv, nb.residuals, nb.muhat)
+    dev = torch.device("cuda:0")
+    d_in = torch.from_numpy(packed).to(dev); d_cols = torch.zeros_like(d_in)
+    torch.cuda.synchronize()
+    gpu_ctx.packed_reorder_device(d_in.data_ptr(), d_cols.data_ptr(), stride, n, P_)
+    idx = torch.zeros(P_, dtype=torch.int64, device=dev); sel = torch.zeros(P_, dtype=torch.int64, device=dev)
+    outs = torch.zeros((7, P_), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    mac_cutoff = 20.0
+    nt, nsel = gpu_ctx.packed_analysis_device(d_cols.data_ptr(), stride, n, P_, api.IMPUTE_MEAN, mac_cutoff, 0.05, idx.data_ptr(),
+                                              [outs[i].data_ptr() for i in range(7)], sel.data_ptr())
+    cols = idx[sel[:nsel]].contiguous()
+    pv = torch.zeros(max(nsel, 1), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    gpu_ctx.packed_spa_device(d_cols.data_ptr(), stride, n, cols.data_ptr(), nsel, api.IMPUTE_MEAN, cases.TOL_SPA, cases.MAX_ITER,
+                              pv.data_ptr())
+    got_p = np.exp(-outs[4, :nt].cpu().numpy())
+    got_p[sel[:nsel].cpu().numpy()] = pv[:nsel].cpu().numpy()
+    # the host flow
+    fl = oracle.matrix_flip_mean(G0)
+    keep = fl["MAF"] > (mac_cutoff - 0.5) / n / 2
+    Gk = np.asfortranarray(fl["Geno"][:, keep])
+    st = oracle.Individual_Score_Test(Gk, nb.Sigma_i, nb.Sigma_iX, nb.cov, nb.residuals)
+    want_p = np.exp(-st["pvalue_log"])
+    hit = want_p < 0.05
+    want_p[hit] = oracle.Individual_Score_Test_SPA(np.asfortranarray(Gk[:, hit]), nb.XW, nb.XXWX_inv, nb.residuals, nb.muhat,
+                                                   cases.TOL_SPA, cases.MAX_ITER)
+    assert nt == keep.sum() and np.array_equal(idx[:nt].cpu().numpy(), np.flatnonzero(keep))
+    assert nsel == hit.sum() and nsel >= 5 and np.array_equal(sel[:nsel].cpu().numpy(), np.flatnonzero(hit))
+    assert_spa_pvalues_close(got_p[hit], want_p[hit])
+    assert rel_err(got_p[~hit], want_p[~hit], 1e-300) < 1e-8
