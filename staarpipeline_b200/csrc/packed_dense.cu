@@ -144,7 +144,60 @@ __global__ void kron_expand_kernel(const double *__restrict__ val, const int64_t
     }
 }
 
-// All k x k quadratic forms g_(s,j)' Sigma_i g_(t,j) of one variant in one sweep over its carriers (a warp per variant):
+// Multi-trait kernels: one CTA per variant of G0, variants drawn from an atomic counter (a common variant has 10^4-10^5
+// carriers, a rare one 10^1-10^3: with a warp per column the common ones set the makespan).  Both read the carrier list
+// of G0's column once for all k traits; the Kronecker expansion exists only as index arithmetic (row t*n0 + i).
+//
+// contraction: L[(t, j), c] = sum_e v_e Y[t*n0 + i_e, c], c < ncols = 1 + kq <= 64.  Warp w takes carriers w, w + 8, ...
+// (a carrier's Y row is one coalesced read per trait; lanes = columns c and c + 32), partial sums meet in shared memory
+// and are added in warp order.
+template <int K>
+__global__ void __launch_bounds__(256) contract_multi_packed_kernel(const double *__restrict__ val, const int64_t *__restrict__ row,
+                                                                    const long long *__restrict__ colptr, int64_t n0, int64_t pp,
+                                                                    const double *__restrict__ Y, int ldY, int ncols,
+                                                                    double *__restrict__ L, int ldL, unsigned long long *work)
+{
+    __shared__ double part[8][K][64];
+    __shared__ long long s_j;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool on0 = lane < ncols, on1 = lane + 32 < ncols;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_j = (long long)atomicAdd(work, 1ull);
+        __syncthreads();
+        const int64_t j = s_j;
+        if (j >= pp) break;
+        double a0[K], a1[K];
+#pragma unroll
+        for (int t = 0; t < K; t++) { a0[t] = 0.0; a1[t] = 0.0; }
+        const long long e1 = colptr[j + 1];
+        for (long long e = colptr[j] + warp; e < e1; e += 16) {               // two carriers per warp in flight
+            const bool two = e + 8 < e1;
+            const int64_t i0 = row[e], i1 = two ? row[e + 8] : 0;
+            const double v0 = val[e], v1 = two ? val[e + 8] : 0.0;
+#pragma unroll
+            for (int t = 0; t < K; t++) {
+                const double *y0 = Y + (size_t)(t * n0 + i0) * ldY, *y1 = Y + (size_t)(t * n0 + i1) * ldY;
+                const double p0 = on0 ? y0[lane] : 0.0, p1 = on1 ? y0[lane + 32] : 0.0;
+                const double q0 = (two && on0) ? y1[lane] : 0.0, q1 = (two && on1) ? y1[lane + 32] : 0.0;
+                a0[t] += v0 * p0; a1[t] += v0 * p1;
+                a0[t] += v1 * q0; a1[t] += v1 * q1;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < K; t++) { part[warp][t][lane] = a0[t]; part[warp][t][lane + 32] = a1[t]; }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < K * ncols; idx += 256) {
+            const int t = idx / ncols, c = idx - t * ncols;
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) tot += part[w][t][c];
+            L[((size_t)t * pp + j) * ldL + c] = tot;
+        }
+    }
+}
+
+// All k x k quadratic forms g_(s,j)' Sigma_i g_(t,j) of one variant in one sweep over its carriers (threads = carriers):
 // for a carrier i and a trait block s, the row s*n0 + i of Sigma_i lists (trait t, relative i') entries, and g_(t,j)[i']
 // is read straight from the variant's 2-bit column — no search in a carrier list.  Output index j*k*k + s*k + t as
 // misc.cu:fill_pairs_kernel orders the pairs for the block test (src/Individual_Score_Test_sp_multi.cpp:47-62).
@@ -154,16 +207,24 @@ __global__ void __launch_bounds__(256) quad_multi_packed_kernel(const uint8_t *_
                                                                 const double *__restrict__ mu, const double *__restrict__ val,
                                                                 const int64_t *__restrict__ row, const long long *__restrict__ colptr,
                                                                 const int64_t *__restrict__ S_row_ptr, const int32_t *__restrict__ S_col,
-                                                                const double *__restrict__ S_val, double *__restrict__ quad)
+                                                                const double *__restrict__ S_val, double *__restrict__ quad,
+                                                                unsigned long long *work)
 {
-    const int lane = threadIdx.x & 31;
-    for (int64_t j = blockIdx.x * 8ll + (threadIdx.x >> 5); j < pp; j += gridDim.x * 8ll) {
+    __shared__ double part[8][K * K];
+    __shared__ long long s_j;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_j = (long long)atomicAdd(work, 1ull);
+        __syncthreads();
+        const int64_t j = s_j;
+        if (j >= pp) break;
         const uint8_t *col = packed + (size_t)j * stride;
         const VariantFlip vf{AF[j], 0.0, mu[j], flip[j]};
         double acc[K * K];
 #pragma unroll
         for (int a = 0; a < K * K; a++) acc[a] = 0.0;
-        for (long long e = colptr[j] + lane; e < colptr[j + 1]; e += 32) {
+        for (long long e = colptr[j] + threadIdx.x; e < colptr[j + 1]; e += 256) {
             const int64_t i = row[e];
             const double v = val[e];
 #pragma unroll
@@ -183,7 +244,14 @@ __global__ void __launch_bounds__(256) quad_multi_packed_kernel(const uint8_t *_
 #pragma unroll
         for (int a = 0; a < K * K; a++) {
             const double tot = warp_sum(acc[a]);
-            if (lane == 0) quad[j * (K * K) + a] = tot;
+            if (lane == 0) part[warp][a] = tot;
+        }
+        __syncthreads();
+        if (threadIdx.x < K * K) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) tot += part[w][threadIdx.x];
+            quad[j * (K * K) + threadIdx.x] = tot;
         }
     }
 }
@@ -218,26 +286,35 @@ int packed_score_multi(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     int64_t *drow = reinterpret_cast<int64_t *>(dval_k + nnz * k), *drow_k = drow + nnz;
     STAAR_CUDA(cudaMemcpyAsync(dcount, cnt.data(), sizeof(long long) * (pp + 1), cudaMemcpyHostToDevice, st));
     carrier_fill_kernel<<<grid8, 256, 0, st>>>(d_packed, stride, n0, pp, d_AF, dflip, dmu, dcount, dval, drow);
-    kron_expand_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(dval, drow, dcount, n0, pp, k, nnz, dval_k, drow_k, dcolptr_k);
-    ctx->launches += 2;
+    ctx->launches++;
     STAAR_CUDA(cudaStreamSynchronize(st));                        // cnt goes out of scope
     const int ldY = ns.ldY, ncols = (int)(1 + ns.q);
     STAAR_TRY(ctx->L.reserve(sizeof(double) * (size_t)p * ldY));
     STAAR_CUDA(cudaMemsetAsync(ctx->L.p, 0, sizeof(double) * (size_t)p * ldY, st));
-    const int64_t *cp = reinterpret_cast<const int64_t *>(dcolptr_k);
-    STAAR_TRY(launch_contract_carriers(ctx, dval_k, drow_k, cp, p, ns.Y, ldY, ncols, ctx->L.as<double>(), ldY));
     const int64_t npairs = pp * k * k;
     STAAR_TRY(ctx->tmp.reserve(sizeof(int32_t) * 2 * (size_t)npairs + sizeof(double) * (size_t)npairs + 64));
     double *dquad = ctx->tmp.as<double>();
-    int32_t *dcolA = reinterpret_cast<int32_t *>(dquad + npairs), *dcolB = dcolA + npairs;
-    if (k >= 1 && k <= 4) {
-        const long long *cp0 = dcount;
-#define STAAR_QUAD_MULTI(K) quad_multi_packed_kernel<K><<<grid8, 256, 0, st>>>(d_packed, stride, n0, pp, d_AF, dflip, dmu, dval, drow, cp0, \
-                                                                             ns.row_ptr, ns.col, ns.val, dquad)
-        if (k == 1) STAAR_QUAD_MULTI(1); else if (k == 2) STAAR_QUAD_MULTI(2); else if (k == 3) STAAR_QUAD_MULTI(3); else STAAR_QUAD_MULTI(4);
-#undef STAAR_QUAD_MULTI
+    if (k <= 4 && ncols <= 64) {
+        STAAR_TRY(ctx->ctr.reserve(2 * sizeof(unsigned long long)));
+        unsigned long long *work = ctx->ctr.as<unsigned long long>();
+        STAAR_CUDA(cudaMemsetAsync(work, 0, 2 * sizeof(unsigned long long), st));
+        const int grid = (int)std::min<int64_t>(pp, (int64_t)ctx->sm_count * 8);
+#define STAAR_MULTI(K)                                                                                                          \
+    do {                                                                                                                        \
+        contract_multi_packed_kernel<K><<<grid, 256, 0, st>>>(dval, drow, dcount, n0, pp, ns.Y, ldY, ncols, ctx->L.as<double>(), \
+                                                              ldY, work);                                                       \
+        quad_multi_packed_kernel<K><<<grid, 256, 0, st>>>(d_packed, stride, n0, pp, d_AF, dflip, dmu, dval, drow, dcount,        \
+                                                          ns.row_ptr, ns.col, ns.val, dquad, work + 1);                         \
+    } while (0)
+        if (k == 1) STAAR_MULTI(1); else if (k == 2) STAAR_MULTI(2); else if (k == 3) STAAR_MULTI(3); else STAAR_MULTI(4);
+#undef STAAR_MULTI
+        ctx->launches += 2;
+    } else {                                  // generic: explicit Kronecker carrier lists and the pair kernels of quadform.cu
+        kron_expand_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(dval, drow, dcount, n0, pp, k, nnz, dval_k, drow_k, dcolptr_k);
         ctx->launches++;
-    } else {
+        const int64_t *cp = reinterpret_cast<const int64_t *>(dcolptr_k);
+        STAAR_TRY(launch_contract_carriers(ctx, dval_k, drow_k, cp, p, ns.Y, ldY, ncols, ctx->L.as<double>(), ldY));
+        int32_t *dcolA = reinterpret_cast<int32_t *>(dquad + npairs), *dcolB = dcolA + npairs;
         STAAR_TRY(launch_fill_pairs(ctx, pp, k, dcolA, dcolB));
         STAAR_TRY(launch_quad_pairs_carriers_csr(ctx, dval_k, drow_k, cp, ns.row_ptr, ns.col, ns.val, dcolA, dcolB, npairs, dquad));
     }
