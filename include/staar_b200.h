@@ -257,6 +257,26 @@ int staar_packed_cond(staar_ctx *ctx, const uint8_t *d_packed, size_t stride_byt
 int staar_ctx_set_profiling(staar_ctx *ctx, int on);
 int staar_ctx_last_stage_ms(staar_ctx *ctx, float ms[3]);
 
+/* Route of staar_packed_score_device (and everything built on it: the chunk driver, staar_packed_analysis_device):
+ *   STAAR_PACKED_PATH_FUSED (default) — one pass over the genotypes: tcgen05 contraction and the sparse terms from the
+ *     same shared-memory tiles (fused_tc.cu), warp-per-variant finaliser, block-per-variant redo of the few variants
+ *     whose streaming orientation guess was wrong or whose missing list overflowed.  Null models with a family of
+ *     more than 16 members fall back to the split route.  With profiling on, staar_ctx_last_stage_ms then reports
+ *     ms[0] = redo, ms[1] = fused kernel, ms[2] = finaliser.
+ *   STAAR_PACKED_PATH_SPLIT — contraction kernel, then block-per-variant scan, then finaliser (two passes over G).
+ * Both routes compute the same statistics (src/Individual_Score_Test.cpp:42-64); environment override:
+ * STAAR_B200_PACKED_PATH=fused|split at context creation. */
+#define STAAR_PACKED_PATH_FUSED 0
+#define STAAR_PACKED_PATH_SPLIT 1
+int staar_ctx_set_packed_path(staar_ctx *ctx, int path);
+/* 1 when the last staar_packed_score_device call took the fused route, 0 otherwise */
+int staar_ctx_last_packed_path_was_fused(staar_ctx *ctx);
+/* Test hook, fused route: per-variant scanner outputs of the LAST call (any pointer may be NULL): acc (2 x gathered
+ * hom-minor diagonal + kinship tables), cnt (hom-minor carriers in the uniform-diagonal region), cm (missing
+ * samples), guess (orientation assumed while streaming); redo_count = variants sent to the block-per-variant scan. */
+int staar_packed_debug_fused(staar_ctx *ctx, int64_t p, double *acc, int32_t *cnt, int32_t *cm, int32_t *guess,
+                             uint64_t *redo_count);
+
 /* Test hook: intermediates of the LAST staar_packed_score_device call, copied to host arrays (any may be NULL):
  * hi/lo (p x 16 int64: exact integer contraction of the raw codes, X = hi*2^24 + lo in units of col_scale[c]),
  * Sm (p x 16 sums over missing samples; slot 15 = sum of Sigma_i[j,j] over hom-minor carriers), quad (kinship off-diagonal part), mu, flip,

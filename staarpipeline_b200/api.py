@@ -341,6 +341,24 @@ class Context:
                    _p(quad), _p(mu), flip.ctypes.data_as(C.POINTER(C.c_int32)), _p(scale))
         return dict(hi=hi, lo=lo, Sm=Sm, quad=quad, mu=mu, flip=flip, col_scale=scale)
 
+    def set_packed_path(self, path: str):
+        """'fused' (default: one pass over G) or 'split' (contraction + block-per-variant scan); staar_b200.h"""
+        self._call("staar_ctx_set_packed_path", C.c_int({"fused": 0, "split": 1}[path]))
+
+    @property
+    def last_packed_path_was_fused(self) -> bool:
+        return bool(self._lib.staar_ctx_last_packed_path_was_fused(self._h))
+
+    def packed_debug_fused(self, p: int):
+        """scanner outputs of the last fused packed score call (test hook)"""
+        acc = np.zeros(p)
+        cnt, cm, guess = (np.zeros(p, dtype=np.int32) for _ in range(3))
+        redo = C.c_uint64(0)
+        i32 = C.POINTER(C.c_int32)
+        self._call("staar_packed_debug_fused", C.c_int64(p), _p(acc), cnt.ctypes.data_as(i32), cm.ctypes.data_as(i32),
+                   guess.ctypes.data_as(i32), C.byref(redo))
+        return dict(acc=acc, cnt=cnt, cm=cm, guess=guess, redo_count=int(redo.value))
+
     def packed_score_device(self, d_packed: int, stride: int, n: int, p: int, impute: int, d_out7):
         """device pointers (ints): packed columns and 7 output arrays; asynchronous on the context stream."""
         self._call("staar_packed_score_device", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n), C.c_int64(p),

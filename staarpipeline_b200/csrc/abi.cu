@@ -774,9 +774,48 @@ int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t st
     int32_t *dflip = ctx->tmp.as<int32_t>();
     double *dmu = reinterpret_cast<double *>(dflip + pi), *dquad = dmu + p, *dSm = dquad + p;
     long long *dhi = reinterpret_cast<long long *>(dSm + 16 * p), *dlo = dhi + 16 * p;
-    // order: contraction (raw codes; also yields the exact sum of codes per variant) -> scan (flip decision from
-    // that sum and its own missing count, sparse terms) -> finaliser.  ev[0..3] bracket the three kernels.
     const bool prof = ctx->profiling;
+    ctx->last_fused = false;
+    if (ctx->packed_path == 0 && !ctx->use_mma_sync && fused_path_available(ctx)) {
+        // single pass: fused contraction + scanners -> warp-per-variant finaliser -> (rare) redo of the variants whose
+        // orientation guess was wrong or whose missing list overflowed, through the block-per-variant scan.
+        // ev[0..3] bracket: fused kernel | finaliser | redo.
+        const int mcap = fused_missing_cap(n);
+        STAAR_TRY(ctx->fscan.reserve(sizeof(FusedScanOut) * (size_t)p));
+        STAAR_TRY(ctx->mlist.reserve(sizeof(uint2) * (size_t)mcap * (size_t)p));
+        STAAR_TRY(ctx->redo.reserve(sizeof(long long) * (size_t)p + 2 * sizeof(unsigned long long)));
+        FusedScanOut *dscan = ctx->fscan.as<FusedScanOut>();
+        uint2 *dml = ctx->mlist.as<uint2>();
+        unsigned long long *dcount = ctx->redo.as<unsigned long long>();
+        long long *dredo = reinterpret_cast<long long *>(dcount + 2);
+        STAAR_CUDA(cudaMemsetAsync(dcount, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+        STAAR_TRY(launch_fused_tc(ctx, d_packed, stride, n, p, dhi, dlo, dscan, dml, mcap));
+        if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+        STAAR_TRY(launch_fused_finalize(ctx, n, p, impute, dhi, dlo, dscan, dml, mcap, d_AF, d_MAF, d_Score, d_Score_se, d_pl,
+                                        d_Est, d_Est_se, dredo, dcount));
+        if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+        if (stride + 8192 <= 227 * 1024) {
+            STAAR_TRY(launch_scan_packed(ctx, d_packed, stride, n, p, impute, dlo, d_AF, d_MAF, dflip, dmu, dquad, dSm, dredo, dcount));
+            STAAR_TRY(launch_finalize_packed(ctx, p, dflip, dmu, dquad, dSm, dhi, dlo, d_Score, d_Score_se, d_pl, d_Est, d_Est_se,
+                                             dredo, dcount));
+        } else {
+            // columns too long for the block-per-variant kernel's shared memory: nothing may need it
+            unsigned long long pending = 0;
+            STAAR_CUDA(cudaMemcpyAsync(&pending, dcount, sizeof pending, cudaMemcpyDeviceToHost, ctx->stream));
+            STAAR_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (pending) {
+                set_error("packed score: %llu variants need the block-per-variant scan, but a column of %zu bytes does not fit "
+                          "in shared memory (n > ~9e5): use the FP64 entry points", pending, stride);
+                return STAAR_ERR_ARG;
+            }
+        }
+        if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+        ctx->last_fused = true;
+        return STAAR_OK;
+    }
+    // two passes: contraction (raw codes; also yields the exact sum of codes per variant) -> scan (flip decision from
+    // that sum and its own missing count, sparse terms) -> finaliser.  ev[0..3] bracket the three kernels.
     if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (ctx->use_mma_sync) STAAR_TRY(launch_contract_packed(ctx, d_packed, stride, n, p, dhi, dlo));
     else STAAR_TRY(launch_contract_tc(ctx, d_packed, stride, n, p, dhi, dlo));
@@ -810,6 +849,37 @@ int staar_packed_debug_dump(staar_ctx *ctx, int64_t p, long long *hi, long long 
     return sync(ctx);
 }
 
+int staar_ctx_set_packed_path(staar_ctx *ctx, int path)
+{
+    CHECK_CTX(ctx);
+    if (path != STAAR_PACKED_PATH_FUSED && path != STAAR_PACKED_PATH_SPLIT) { set_error("unknown packed path %d", path); return STAAR_ERR_ARG; }
+    ctx->packed_path = path;
+    return STAAR_OK;
+}
+
+int staar_ctx_last_packed_path_was_fused(staar_ctx *ctx) { return ctx && ctx->last_fused ? 1 : 0; }
+
+int staar_packed_debug_fused(staar_ctx *ctx, int64_t p, double *acc, int32_t *cnt, int32_t *cm, int32_t *guess,
+                             uint64_t *redo_count)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->last_fused) { set_error("the last packed score call did not take the fused route"); return STAAR_ERR_STATE; }
+    STAAR_TRY(sync(ctx));
+    std::vector<FusedScanOut> h((size_t)p);
+    STAAR_TRY(d2h(ctx, h.data(), ctx->fscan.p, sizeof(FusedScanOut) * (size_t)p));
+    unsigned long long rc = 0;
+    STAAR_TRY(d2h(ctx, &rc, ctx->redo.p, sizeof rc));
+    STAAR_TRY(sync(ctx));
+    for (int64_t i = 0; i < p; i++) {
+        if (acc) acc[i] = h[i].acc;
+        if (cnt) cnt[i] = h[i].cnt;
+        if (cm) cm[i] = h[i].cm;
+        if (guess) guess[i] = h[i].guess;
+    }
+    if (redo_count) *redo_count = rc;
+    return STAAR_OK;
+}
+
 int staar_ctx_set_profiling(staar_ctx *ctx, int on)
 {
     CHECK_CTX(ctx);
@@ -823,6 +893,13 @@ int staar_ctx_last_stage_ms(staar_ctx *ctx, float ms[3])
     CHECK_CTX(ctx);
     if (!ctx->ev[0]) { set_error("profiling was never enabled on this context"); return STAAR_ERR_STATE; }
     STAAR_CUDA(cudaEventSynchronize(ctx->ev[3]));
+    if (ctx->last_fused) {
+        // fused path: ms[] = redo (block-per-variant scan of the listed variants), fused kernel, finaliser
+        STAAR_CUDA(cudaEventElapsedTime(&ms[0], ctx->ev[2], ctx->ev[3]));
+        STAAR_CUDA(cudaEventElapsedTime(&ms[1], ctx->ev[0], ctx->ev[1]));
+        STAAR_CUDA(cudaEventElapsedTime(&ms[2], ctx->ev[1], ctx->ev[2]));
+        return STAAR_OK;
+    }
     // kernels run contraction, scan, finaliser; ms[] is reported as scan, contraction, finaliser
     STAAR_CUDA(cudaEventElapsedTime(&ms[0], ctx->ev[1], ctx->ev[2]));
     STAAR_CUDA(cudaEventElapsedTime(&ms[1], ctx->ev[0], ctx->ev[1]));

@@ -81,6 +81,7 @@ struct NullSparse {
     int64_t lut_entries = 0;
     SampleInfo *sinfo_p = nullptr;    // full kinship rows in null-model positions (missing related samples)
     double *diag_p = nullptr;         // Sigma_i[j,j] in null-model positions (n + 64 entries, zero padded)
+    double *diag2_p = nullptr;        // 2 * Sigma_i[j,j], same order and padding (fused path: g^2 - g = 2 [g == 2])
     int64_t diag_uniform_vec = -1;  // from this 64-sample vector on every sample has the same Sigma_i[j,j] (-1: none)
     double diag_uniform_val = 0.0;
     OffEntry *off_ent_p = nullptr;
@@ -121,12 +122,21 @@ struct NullSpa {
 };
 
 struct NullDense {
-    bool set = false;
+    bool set = false, res_set = false;   // res_set: residuals supplied by staar_nullmodel_set_dense (resident path)
     int64_t n = 0;
     double *P = nullptr;          // n x n column-major
     double *residuals = nullptr;
     uint64_t fingerprint = 0;
     void release();
+};
+
+// per-variant output of the fused kernel's scanners (fused_tc.cu)
+struct alignas(8) FusedScanOut {
+    double acc;      // 2 * sum of Sigma_i[j,j] over gathered hom-minor carriers + kinship table look-ups (guessed orientation)
+    int cnt;         // hom-minor carriers in the uniform-diagonal region
+    int cm;          // missing samples
+    int guess;       // orientation the scanners assumed (1 = flip)
+    int pad;
 };
 
 }  // namespace staar
@@ -147,6 +157,15 @@ struct staar_ctx {
     uint64_t cond_key = 0;
     int cond_m = 0, cond_ld = 0;
     bool use_mma_sync = false;       // STAAR_B200_CONTRACT=mma: legacy mma.sync contraction instead of tcgen05
+    // packed score path: 0 = fused single-pass kernel where the null model allows it (default), 1 = contraction +
+    // block-per-variant scan (two passes over G; cross-check and fallback).  STAAR_B200_PACKED_PATH=split|fused,
+    // staar_ctx_set_packed_path.  fused_tiles: accumulator tiles per CTA of the fused kernel (2; 1 for experiments).
+    int packed_path = 0, fused_tiles = 2;
+    staar::DevBuf fscan, mlist, redo;
+    bool last_fused = false;         // the last staar_packed_score_device call took the fused path
+    // per-device launch attributes already set (cudaFuncSetAttribute is per device, the context owns one device)
+    bool attr_contract_tc = false, attr_contract_packed = false, attr_permute = false;
+    int spa_best_width = 0, spa_resident[17] = {0};     // SPA cluster width / resident clusters per width (spa.cu)
     void *pinned = nullptr;
     size_t pinned_cap = 0;
     // hybrid host/GPU packing of pinned FP64 chunks: share of the variants the GPU packs, re-balanced after every chunk
@@ -222,12 +241,23 @@ int launch_spa_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, co
 // packed path — scan_packed.cu / contract_packed.cu / finalize
 int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
                        const long long *d_lo /* contraction output: slot 15 = sum of codes */, double *dAF, double *dMAF,
-                       int32_t *dflip, double *d_mu, double *d_quad, double *d_Sm);
+                       int32_t *dflip, double *d_mu, double *d_quad, double *d_Sm,
+                       const long long *d_vlist = nullptr, const unsigned long long *d_vcount = nullptr);
 int launch_contract_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p,
                            long long *d_hi, long long *d_lo);
 int launch_finalize_packed(staar_ctx *ctx, int64_t p, const int32_t *d_flip, const double *d_mu, const double *d_quad,
                            const double *d_Sm, const long long *d_hi, const long long *d_lo,
-                           double *dScore, double *dScore_se, double *dpl, double *dEst, double *dEst_se);
+                           double *dScore, double *dScore_se, double *dpl, double *dEst, double *dEst_se,
+                           const long long *d_vlist = nullptr, const unsigned long long *d_vcount = nullptr);
+// fused_tc.cu — single pass: contraction + scanners, then the warp-per-variant finaliser
+bool fused_path_available(const staar_ctx *ctx);
+int fused_missing_cap(int64_t n);
+int launch_fused_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, long long *d_hi,
+                    long long *d_lo, FusedScanOut *d_scan, uint2 *d_mlist, int mcap);
+int launch_fused_finalize(staar_ctx *ctx, int64_t n, int64_t p, int impute, const long long *d_hi, const long long *d_lo,
+                          const FusedScanOut *d_scan, const uint2 *d_mlist, int mcap, double *dAF, double *dMAF,
+                          double *dScore, double *dScore_se, double *dpl, double *dEst, double *dEst_se, long long *d_redo,
+                          unsigned long long *d_redo_count);
 int build_sliced_operand(staar_ctx *ctx, const double *hY /* n x ldY row-major host, natural sample order */);
 int build_tc_operand(staar_ctx *ctx, const int8_t *digits, int ncol);
 int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, long long *d_hi,

@@ -266,10 +266,9 @@ int launch_contract_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t strid
         STAAR_CUDA(cudaMemsetAsync(d_lo, 0, sizeof(long long) * (size_t)p * 16, ctx->stream));
     }
     const size_t smem = (size_t)kStages * kChunkBytesB + 2 * kStages * sizeof(uint64_t);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->attr_contract_packed) {           // per context: the attribute belongs to the context's device
         STAAR_CUDA(cudaFuncSetAttribute(contract_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        ctx->attr_contract_packed = true;
     }
     dim3 grid((unsigned)vt, (unsigned)ksplit);
     contract_packed_kernel<<<grid, kWarpsC * 32, smem, ctx->stream>>>(d_packed, stride, p, ns.Yfrag, n_chunks, cps, d_hi,

@@ -58,7 +58,7 @@ void NullSparse::release()
         cudaFree(row_ptr); cudaFree(col); cudaFree(val); cudaFree(SX); cudaFree(cov);
     }
     if (permuted) cudaFree(Yp);
-    cudaFree(diag); cudaFree(diag_p); cudaFree(sinfo_p); cudaFree(off_ent_p); cudaFree(relmask); cudaFree(rel); cudaFree(up_ent); cudaFree(Y);
+    cudaFree(diag); cudaFree(diag_p); cudaFree(diag2_p); cudaFree(sinfo_p); cudaFree(off_ent_p); cudaFree(relmask); cudaFree(rel); cudaFree(up_ent); cudaFree(Y);
     cudaFree(Yfrag); cudaFree(Ytc); cudaFree(col_scale); cudaFree(col_total); cudaFree(perm); cudaFree(inv_perm); cudaFree(kmask); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut);
     *this = NullSparse();
 }
@@ -448,6 +448,9 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
         std::vector<double> diag_p((size_t)n + 64, 0.0);
         for (int64_t pz = 0; pz < n; pz++) diag_p[pz] = sinfo[pz].diag;
         STAAR_TRY(upload_vec(ctx, &ns.diag_p, diag_p));
+        std::vector<double> diag2_p(diag_p.size());
+        for (size_t pz = 0; pz < diag_p.size(); pz++) diag2_p[pz] = 2.0 * diag_p[pz];
+        STAAR_TRY(upload_vec(ctx, &ns.diag2_p, diag2_p));
         // Unrelated samples of a linear mixed model all carry the same diagonal entry: find the longest suffix of
         // positions with one value (the scan multiplies a count by it instead of gathering, scan_packed.cu:hom_vec).
         int64_t first = n;
@@ -547,6 +550,10 @@ int staar_ctx_create(int device, staar_ctx **out)
     {
         const char *sel = getenv("STAAR_B200_CONTRACT");
         ctx->use_mma_sync = sel && strcmp(sel, "mma") == 0;
+        const char *path = getenv("STAAR_B200_PACKED_PATH");
+        ctx->packed_path = path && strcmp(path, "split") == 0 ? 1 : 0;
+        const char *tiles = getenv("STAAR_B200_FUSED_TILES");
+        ctx->fused_tiles = tiles && atoi(tiles) == 1 ? 1 : 2;
     }
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; staar::set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return STAAR_ERR_CUDA; }
@@ -562,6 +569,7 @@ void staar_ctx_destroy(staar_ctx *ctx)
     ctx->ns.release(); ctx->nd.release(); ctx->nspa.release();
     ctx->G.release(); ctx->L.release(); ctx->aux.release(); ctx->out.release(); ctx->tmp.release();
     ctx->tmp2.release(); ctx->pk.release(); ctx->pk2.release(); ctx->ctr.release(); ctx->cond.release();
+    ctx->fscan.release(); ctx->mlist.release(); ctx->redo.release();
     for (auto &e : ctx->ev_pack) if (e) cudaEventDestroy(e);
     for (auto &sl : ctx->slot) {
         if (sl.pinned) cudaFreeHost(sl.pinned);

@@ -196,10 +196,9 @@ int launch_permute_packed(staar_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, s
 {
     if (p == 0) return STAAR_OK;
     if (stride > 227 * 1024) { set_error("permute_packed: column of %zu bytes does not fit in shared memory", stride); return STAAR_ERR_ARG; }
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->attr_permute) {                   // per context: the attribute belongs to the context's device
         STAAR_CUDA(cudaFuncSetAttribute(permute_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+        ctx->attr_permute = true;
     }
     const int grid = (int)std::min<int64_t>(p, (int64_t)ctx->sm_count * 4);
     permute_packed_kernel<<<grid, 256, stride, ctx->stream>>>(d_in, d_out, stride, n, p, d_perm);

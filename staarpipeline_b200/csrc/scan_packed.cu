@@ -40,6 +40,8 @@ struct ScanParams {
     const NullSparse::OffEntry *off_ent;
     const double *Y; int ldY, ncol;        // Y rows in null-model order
     const long long *codesum;              // contraction output `lo` (p x 16): slot 15 = exact sum of the codes
+    // list mode (redo list of the fused path): work item k is variant vlist[k], k < *vcount (both device-resident)
+    const long long *vlist; const unsigned long long *vcount;
     double *AF, *MAF; int32_t *flip; double *mu, *quad, *Sm;
 };
 
@@ -112,11 +114,12 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             "}\n" ::"r"(smem_addr(&full[stage])), "r"(parity) : "memory");
     };
 
-    const unsigned long long pmax = (unsigned long long)P.p;
+    const unsigned long long pmax = P.vlist ? *P.vcount : (unsigned long long)P.p;
+    auto variant_of = [&](unsigned long long k) { return P.vlist ? (unsigned long long)P.vlist[k] : k; };
     if (tid == 0) {
         const unsigned long long v = atomicAdd(work, 1ull);
         s_work[0] = v;
-        if (v < pmax) issue(v, 0);
+        if (v < pmax) issue(variant_of(v), 0);
     }
     __syncthreads();
     unsigned long long cur = s_work[0];
@@ -136,12 +139,12 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         if (nstage == 2 && tid == 0) {                           // prefetch the next variant's column
             const unsigned long long v = atomicAdd(work, 1ull);
             s_work[it & 1] = v;
-            if (v < pmax) issue(v, stage ^ 1);
+            if (v < pmax) issue(variant_of(v), stage ^ 1);
         }
         wait_full(stage, (parity >> stage) & 1u);
         parity ^= 1u << stage;
         const uint8_t *col = cols + (size_t)stage * stride;
-        const int64_t i = (int64_t)cur;
+        const int64_t i = (int64_t)variant_of(cur);
 
         // ---- sweep 1 (whole column, 64 samples per lane and step).  The sum of the variant's codes S = c1 + 2 c2 + 3 cm
         //      comes EXACTLY from the tensor-core contraction (its constant-1 column), so no genotype popcounts are
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             if (tid == 0) {
                 const unsigned long long v = atomicAdd(work, 1ull);
                 s_work[it & 1] = v;
-                if (v < pmax) issue(v, 0);
+                if (v < pmax) issue(variant_of(v), 0);
             }
             __syncthreads();
             cur = s_work[it & 1];
@@ -431,6 +434,7 @@ struct FinParams {
     const long long *hi, *lo, *tot;
     const double *scale, *cov;
     double *Score, *Score_se, *pl, *Est, *Est_se;
+    const long long *vlist; const unsigned long long *vcount;     // list mode (see ScanParams)
 };
 
 // The contraction delivers, per variant and column c, the exact integers R_c = sum_j code_j X_jc over the RAW codes
@@ -443,7 +447,9 @@ struct FinParams {
 // imputation takes the reference's exact Cov == 0 branch from the integer counts (bit 1 of flip[]).
 __global__ void __launch_bounds__(128) finalize_packed_kernel(FinParams P)
 {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.p; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t count = P.vlist ? (int64_t)*P.vcount : P.p;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = P.vlist ? (int64_t)P.vlist[k] : k;
         const int fl = P.flip[i];
         const bool flip = (fl & 1) != 0, mono = (fl & 2) != 0;
         const double mu = P.mu[i];
@@ -485,7 +491,7 @@ __global__ void __launch_bounds__(128) finalize_packed_kernel(FinParams P)
 
 int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
                        const long long *d_lo, double *dAF, double *dMAF, int32_t *dflip, double *d_mu, double *d_quad,
-                       double *d_Sm)
+                       double *d_Sm, const long long *d_vlist, const unsigned long long *d_vcount)
 {
     if (p == 0) return STAAR_OK;
     const NullSparse &ns = ctx->ns;
@@ -497,7 +503,7 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     P.xterms = ns.xterms; P.lut = ns.lut; P.sinfo = ns.sinfo_p; P.off_ent = ns.off_ent_p; P.diag = ns.diag_p;
     P.uvec = ns.diag_uniform_vec >= 0 ? (int)ns.diag_uniform_vec : INT_MAX; P.dval = ns.diag_uniform_val;
     P.Y = ns.Yp; P.ldY = ns.ldY; P.ncol = (int)ns.q + 2;
-    P.codesum = d_lo;
+    P.codesum = d_lo; P.vlist = d_vlist; P.vcount = d_vcount;
     P.AF = dAF; P.MAF = dMAF; P.flip = dflip; P.mu = d_mu; P.quad = d_quad; P.Sm = d_Sm;
     // block-per-variant kernel, column in shared memory.  CTA width: 4 warps put more variants in flight per SM (7 vs 4 at
     // n = 1e5: 6.75 -> 6.63 ms per 250 k variants); when long columns leave room for few CTAs (n = 4e5: 2 per SM), 8 warps
@@ -544,7 +550,8 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
 
 int launch_finalize_packed(staar_ctx *ctx, int64_t p, const int32_t *d_flip, const double *d_mu, const double *d_quad,
                            const double *d_Sm, const long long *d_hi, const long long *d_lo, double *dScore,
-                           double *dScore_se, double *dpl, double *dEst, double *dEst_se)
+                           double *dScore_se, double *dpl, double *dEst, double *dEst_se, const long long *d_vlist,
+                           const unsigned long long *d_vcount)
 {
     if (p == 0) return STAAR_OK;
     const NullSparse &ns = ctx->ns;
@@ -552,6 +559,7 @@ int launch_finalize_packed(staar_ctx *ctx, int64_t p, const int32_t *d_flip, con
     P.p = p; P.q = (int)ns.q; P.flip = d_flip; P.mu = d_mu; P.quad = d_quad; P.Sm = d_Sm;
     P.hi = d_hi; P.lo = d_lo; P.tot = ns.col_total; P.scale = ns.col_scale; P.cov = ns.cov;
     P.Score = dScore; P.Score_se = dScore_se; P.pl = dpl; P.Est = dEst; P.Est_se = dEst_se;
+    P.vlist = d_vlist; P.vcount = d_vcount;
     int blocks = (int)std::min<int64_t>((p + 127) / 128, (int64_t)ctx->sm_count * 8);
     finalize_packed_kernel<<<blocks, 128, 0, ctx->stream>>>(P);
     ctx->launches++;

@@ -488,20 +488,19 @@ int cluster_width(staar_ctx *ctx, int64_t n)
     static const int cap = getenv("STAAR_B200_SPA_CLUSTER") ? atoi(getenv("STAAR_B200_SPA_CLUSTER")) : 0;
     if (cap > 0) return std::min(cap, kMaxCluster);
     if (n < (1 << 17)) return n >= (1 << 15) ? 4 : n >= (1 << 13) ? 2 : 1;
-    static int best = 0;
-    if (best == 0) {
+    if (ctx->spa_best_width == 0) {               // per context (= per device): occupancy depends on the GPC layout
         int cover = -1;
         for (int w = 8; w >= 6; w--) {
             const int c = resident_clusters(ctx, w) * w;
-            if (c > cover) { cover = c; best = w; }
+            if (c > cover) { cover = c; ctx->spa_best_width = w; }
         }
     }
-    return best;
+    return ctx->spa_best_width;
 }
 
 int resident_clusters(staar_ctx *ctx, int width)
 {
-    static int cached[kMaxCluster + 1] = {0};
+    int *cached = ctx->spa_resident;              // per context, see cluster_width
     if (cached[width] > 0) return cached[width];
     if (width > 8 && cudaFuncSetAttribute(spa_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
         cudaGetLastError();
