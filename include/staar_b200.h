@@ -258,12 +258,13 @@ int staar_ctx_set_profiling(staar_ctx *ctx, int on);
 int staar_ctx_last_stage_ms(staar_ctx *ctx, float ms[3]);
 
 /* Route of staar_packed_score_device (and everything built on it: the chunk driver, staar_packed_analysis_device):
- *   STAAR_PACKED_PATH_FUSED (default) — one pass over the genotypes: tcgen05 contraction and the sparse terms from the
+ *   STAAR_PACKED_PATH_FUSED — one pass over the genotypes: tcgen05 contraction and the sparse terms from the
  *     same shared-memory tiles (fused_tc.cu), warp-per-variant finaliser, block-per-variant redo of the few variants
  *     whose streaming orientation guess was wrong or whose missing list overflowed.  Null models with a family of
  *     more than 16 members fall back to the split route.  With profiling on, staar_ctx_last_stage_ms then reports
  *     ms[0] = redo, ms[1] = fused kernel, ms[2] = finaliser.
- *   STAAR_PACKED_PATH_SPLIT — contraction kernel, then block-per-variant scan, then finaliser (two passes over G).
+ *   STAAR_PACKED_PATH_SPLIT (default) — contraction kernel, then block-per-variant scan, then finaliser (two passes
+ *     over G; on B200 the faster of the two).
  * Both routes compute the same statistics (src/Individual_Score_Test.cpp:42-64); environment override:
  * STAAR_B200_PACKED_PATH=fused|split at context creation. */
 #define STAAR_PACKED_PATH_FUSED 0
@@ -276,6 +277,8 @@ int staar_ctx_last_packed_path_was_fused(staar_ctx *ctx);
  * samples), guess (orientation assumed while streaming); redo_count = variants sent to the block-per-variant scan. */
 int staar_packed_debug_fused(staar_ctx *ctx, int64_t p, double *acc, int32_t *cnt, int32_t *cm, int32_t *guess,
                              uint64_t *redo_count);
+/* Test hook, fused route with STAAR_B200_FUSED_DBG & 128: clocks per phase, 32 warps x 8 counters per CTA. */
+int staar_packed_debug_timers(staar_ctx *ctx, int64_t ctas, uint32_t *out);
 
 /* Test hook: intermediates of the LAST staar_packed_score_device call, copied to host arrays (any may be NULL):
  * hi/lo (p x 16 int64: exact integer contraction of the raw codes, X = hi*2^24 + lo in units of col_scale[c]),

@@ -780,9 +780,11 @@ int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t st
         // single pass: fused contraction + scanners -> warp-per-variant finaliser -> (rare) redo of the variants whose
         // orientation guess was wrong or whose missing list overflowed, through the block-per-variant scan.
         // ev[0..3] bracket: fused kernel | finaliser | redo.
-        const int mcap = fused_missing_cap(n);
+        const int msub = fused_missing_sub(n);
         STAAR_TRY(ctx->fscan.reserve(sizeof(FusedScanOut) * (size_t)p));
-        STAAR_TRY(ctx->mlist.reserve(sizeof(uint2) * (size_t)mcap * (size_t)p));
+        STAAR_TRY(ctx->mlist.reserve(sizeof(uint2) * 16 * (size_t)msub * (size_t)p));
+        STAAR_TRY(ctx->msubcnt.reserve(sizeof(uint16_t) * 16 * (size_t)p));
+        uint16_t *dmc = ctx->msubcnt.as<uint16_t>();
         STAAR_TRY(ctx->redo.reserve(sizeof(long long) * (size_t)p + 2 * sizeof(unsigned long long)));
         FusedScanOut *dscan = ctx->fscan.as<FusedScanOut>();
         uint2 *dml = ctx->mlist.as<uint2>();
@@ -790,9 +792,9 @@ int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t st
         long long *dredo = reinterpret_cast<long long *>(dcount + 2);
         STAAR_CUDA(cudaMemsetAsync(dcount, 0, 2 * sizeof(unsigned long long), ctx->stream));
         if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-        STAAR_TRY(launch_fused_tc(ctx, d_packed, stride, n, p, dhi, dlo, dscan, dml, mcap));
+        STAAR_TRY(launch_fused_tc(ctx, d_packed, stride, n, p, dhi, dlo, dscan, dml, msub, dmc));
         if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-        STAAR_TRY(launch_fused_finalize(ctx, n, p, impute, dhi, dlo, dscan, dml, mcap, d_AF, d_MAF, d_Score, d_Score_se, d_pl,
+        STAAR_TRY(launch_fused_finalize(ctx, n, p, impute, dhi, dlo, dscan, dml, msub, dmc, d_AF, d_MAF, d_Score, d_Score_se, d_pl,
                                         d_Est, d_Est_se, dredo, dcount));
         if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
         if (stride + 8192 <= 227 * 1024) {
@@ -878,6 +880,14 @@ int staar_packed_debug_fused(staar_ctx *ctx, int64_t p, double *acc, int32_t *cn
     }
     if (redo_count) *redo_count = rc;
     return STAAR_OK;
+}
+
+int staar_packed_debug_timers(staar_ctx *ctx, int64_t ctas, uint32_t *out)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(sync(ctx));
+    STAAR_TRY(d2h(ctx, out, ctx->tmp2.p, sizeof(uint32_t) * 256 * (size_t)ctas));
+    return sync(ctx);
 }
 
 int staar_ctx_set_profiling(staar_ctx *ctx, int on)

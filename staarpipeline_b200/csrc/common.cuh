@@ -81,7 +81,8 @@ struct NullSparse {
     int64_t lut_entries = 0;
     SampleInfo *sinfo_p = nullptr;    // full kinship rows in null-model positions (missing related samples)
     double *diag_p = nullptr;         // Sigma_i[j,j] in null-model positions (n + 64 entries, zero padded)
-    double *diag2_p = nullptr;        // 2 * Sigma_i[j,j], same order and padding (fused path: g^2 - g = 2 [g == 2])
+    double *lutf = nullptr;           // fused path: same offsets as lut; group tables indexed by all four codes, hom-minor diagonal folded in
+    int64_t diag2_off = 0;            // lutf[diag2_off + pos] = 2 * Sigma_i[j,j] (n + 64 entries): one array serves both gathers of the fused path
     int64_t diag_uniform_vec = -1;  // from this 64-sample vector on every sample has the same Sigma_i[j,j] (-1: none)
     double diag_uniform_val = 0.0;
     OffEntry *off_ent_p = nullptr;
@@ -157,11 +158,11 @@ struct staar_ctx {
     uint64_t cond_key = 0;
     int cond_m = 0, cond_ld = 0;
     bool use_mma_sync = false;       // STAAR_B200_CONTRACT=mma: legacy mma.sync contraction instead of tcgen05
-    // packed score path: 0 = fused single-pass kernel where the null model allows it (default), 1 = contraction +
-    // block-per-variant scan (two passes over G; cross-check and fallback).  STAAR_B200_PACKED_PATH=split|fused,
-    // staar_ctx_set_packed_path.  fused_tiles: accumulator tiles per CTA of the fused kernel (2; 1 for experiments).
-    int packed_path = 0, fused_tiles = 2;
-    staar::DevBuf fscan, mlist, redo;
+    // packed score path: 1 = contraction + block-per-variant scan (two passes over G; default), 0 = fused single-pass
+    // kernel where the null model allows it.  STAAR_B200_PACKED_PATH=split|fused, staar_ctx_set_packed_path.
+    // fused_tiles: accumulator tiles per CTA of the fused kernel (2; 1 for experiments).
+    int packed_path = 1, fused_tiles = 2;
+    staar::DevBuf fscan, mlist, msubcnt, redo;
     bool last_fused = false;         // the last staar_packed_score_device call took the fused path
     // per-device launch attributes already set (cudaFuncSetAttribute is per device, the context owns one device)
     bool attr_contract_tc = false, attr_contract_packed = false, attr_permute = false;
@@ -251,11 +252,12 @@ int launch_finalize_packed(staar_ctx *ctx, int64_t p, const int32_t *d_flip, con
                            const long long *d_vlist = nullptr, const unsigned long long *d_vcount = nullptr);
 // fused_tc.cu — single pass: contraction + scanners, then the warp-per-variant finaliser
 bool fused_path_available(const staar_ctx *ctx);
-int fused_missing_cap(int64_t n);
+int fused_missing_sub(int64_t n);
 int launch_fused_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, long long *d_hi,
-                    long long *d_lo, FusedScanOut *d_scan, uint2 *d_mlist, int mcap);
+                    long long *d_lo, FusedScanOut *d_scan, uint2 *d_mlist, int msub, uint16_t *d_msub_cnt);
 int launch_fused_finalize(staar_ctx *ctx, int64_t n, int64_t p, int impute, const long long *d_hi, const long long *d_lo,
-                          const FusedScanOut *d_scan, const uint2 *d_mlist, int mcap, double *dAF, double *dMAF,
+                          const FusedScanOut *d_scan, const uint2 *d_mlist, int msub, const uint16_t *d_msub_cnt,
+                          double *dAF, double *dMAF,
                           double *dScore, double *dScore_se, double *dpl, double *dEst, double *dEst_se, long long *d_redo,
                           unsigned long long *d_redo_count);
 int build_sliced_operand(staar_ctx *ctx, const double *hY /* n x ldY row-major host, natural sample order */);

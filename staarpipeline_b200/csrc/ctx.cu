@@ -58,8 +58,8 @@ void NullSparse::release()
         cudaFree(row_ptr); cudaFree(col); cudaFree(val); cudaFree(SX); cudaFree(cov);
     }
     if (permuted) cudaFree(Yp);
-    cudaFree(diag); cudaFree(diag_p); cudaFree(diag2_p); cudaFree(sinfo_p); cudaFree(off_ent_p); cudaFree(relmask); cudaFree(rel); cudaFree(up_ent); cudaFree(Y);
-    cudaFree(Yfrag); cudaFree(Ytc); cudaFree(col_scale); cudaFree(col_total); cudaFree(perm); cudaFree(inv_perm); cudaFree(kmask); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut);
+    cudaFree(diag); cudaFree(diag_p); cudaFree(sinfo_p); cudaFree(off_ent_p); cudaFree(relmask); cudaFree(rel); cudaFree(up_ent); cudaFree(Y);
+    cudaFree(Yfrag); cudaFree(Ytc); cudaFree(col_scale); cudaFree(col_total); cudaFree(perm); cudaFree(inv_perm); cudaFree(kmask); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut); cudaFree(lutf);
     *this = NullSparse();
 }
 void NullSpa::release()
@@ -335,7 +335,7 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
     std::vector<NullSparse::KinTerm> xterms;
     // group tables at a fixed stride: entry idx of group g (= 4 * word + group-in-word) lives at lut[(g << 8) + idx], so a
     // look-up needs no descriptor; the member x chunk tables of the cross words follow
-    std::vector<double> lut((size_t)std::max<int64_t>(ns.tab_words, 1) * 4 * 256, 0.0);
+    std::vector<double> lut((size_t)std::max<int64_t>(ns.tab_words, 1) * 4 * 256, 0.0), lutf;
     {
         auto codeval = [](int idx, int m) { const int c = (idx >> (2 * m)) & 3; return c == 3 ? 0.0 : (double)c; };
         // kinship entry between two positions (0 when unrelated)
@@ -448,14 +448,35 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
         std::vector<double> diag_p((size_t)n + 64, 0.0);
         for (int64_t pz = 0; pz < n; pz++) diag_p[pz] = sinfo[pz].diag;
         STAAR_TRY(upload_vec(ctx, &ns.diag_p, diag_p));
-        std::vector<double> diag2_p(diag_p.size());
-        for (size_t pz = 0; pz < diag_p.size(); pz++) diag2_p[pz] = 2.0 * diag_p[pz];
-        STAAR_TRY(upload_vec(ctx, &ns.diag2_p, diag2_p));
+        // Tables of the fused path (fused_tc.cu): same layout and offsets as `lut`, but a group's table is indexed by the
+        // codes of ALL four samples of the group (unrelated fillers included) and also carries the hom-minor part of
+        // g' diag(Sigma_i) g, 2 s_jj [g_j == 2]: one look-up per group serves both terms.  2 * Sigma_i[j,j] by position
+        // follows the tables (words outside the table region gather it per carrier).
+        lutf = lut;
+        for (int64_t g = 0; g < ns.tab_words * 4; g++) {
+            const int64_t p0 = g * 4;
+            const double *old = &lut[(size_t)g << 8];
+            uint32_t relmask4 = 0u;                                  // index bits of the related slots
+            for (int a = 0; a < 4; a++) if (sinfo[p0 + a].off_count > 0) relmask4 |= 3u << (2 * a);
+            for (int idx = 0; idx < 256; idx++) {
+                int ridx = 0;                                        // missing (3) never occurs in an index; map it to 0
+                double v = 0.0;
+                for (int a = 0; a < 4; a++) {
+                    const int c = (idx >> (2 * a)) & 3;
+                    if (c != 3) ridx |= c << (2 * a);
+                    if (c == 2) v += 2.0 * sinfo[p0 + a].diag;
+                }
+                lutf[((size_t)g << 8) + idx] = old[ridx & relmask4] + v;
+            }
+        }
+        ns.diag2_off = (int64_t)lutf.size();
+        for (size_t pz = 0; pz < diag_p.size(); pz++) lutf.push_back(2.0 * diag_p[pz]);
         // Unrelated samples of a linear mixed model all carry the same diagonal entry: find the longest suffix of
         // positions with one value (the scan multiplies a count by it instead of gathering, scan_packed.cu:hom_vec).
         int64_t first = n;
         while (first > 0 && memcmp(&diag_p[first - 1], &diag_p[n - 1], sizeof(double)) == 0) first--;
-        const int64_t vec = (first + 63) / 64;
+        // never inside the table words: their hom-minor carriers are served by the (folded) group tables of the fused path
+        const int64_t vec = std::max<int64_t>((first + 63) / 64, (ns.tab_words * 16 + 63) / 64);
         ns.diag_uniform_vec = (n > 0 && vec * 64 < n) ? vec : -1;
         ns.diag_uniform_val = n > 0 ? diag_p[n - 1] : 0.0;
     }
@@ -464,6 +485,7 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
     STAAR_TRY(upload_vec(ctx, &ns.wdesc, wdesc));
     STAAR_TRY(upload_vec(ctx, &ns.xterms, xterms));
     STAAR_TRY(upload_vec(ctx, &ns.lut, lut));
+    STAAR_TRY(upload_vec(ctx, &ns.lutf, lutf));
     STAAR_TRY(upload_vec(ctx, &ns.relmask, relmask));
     if (!rel.empty()) {
         STAAR_TRY(upload_vec(ctx, &ns.rel, rel));
@@ -551,7 +573,9 @@ int staar_ctx_create(int device, staar_ctx **out)
         const char *sel = getenv("STAAR_B200_CONTRACT");
         ctx->use_mma_sync = sel && strcmp(sel, "mma") == 0;
         const char *path = getenv("STAAR_B200_PACKED_PATH");
-        ctx->packed_path = path && strcmp(path, "split") == 0 ? 1 : 0;
+        // default: the two-kernel route — the single-pass kernel is parity-equal but, on B200, bound by the ALU pipe of
+        // its scanner warps and not faster; STAAR_B200_PACKED_PATH=fused selects it
+        ctx->packed_path = path && strcmp(path, "fused") == 0 ? 0 : 1;
         const char *tiles = getenv("STAAR_B200_FUSED_TILES");
         ctx->fused_tiles = tiles && atoi(tiles) == 1 ? 1 : 2;
     }
@@ -569,7 +593,7 @@ void staar_ctx_destroy(staar_ctx *ctx)
     ctx->ns.release(); ctx->nd.release(); ctx->nspa.release();
     ctx->G.release(); ctx->L.release(); ctx->aux.release(); ctx->out.release(); ctx->tmp.release();
     ctx->tmp2.release(); ctx->pk.release(); ctx->pk2.release(); ctx->ctr.release(); ctx->cond.release();
-    ctx->fscan.release(); ctx->mlist.release(); ctx->redo.release();
+    ctx->fscan.release(); ctx->mlist.release(); ctx->msubcnt.release(); ctx->redo.release();
     for (auto &e : ctx->ev_pack) if (e) cudaEventDestroy(e);
     for (auto &sl : ctx->slot) {
         if (sl.pinned) cudaFreeHost(sl.pinned);

@@ -32,6 +32,20 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity)
         "TC_DONE:\n"
         "}\n" ::"r"(s_addr(bar)), "r"(parity) : "memory");
 }
+// same, with a suspend-time hint: a waiting warp sleeps in the barrier unit instead of re-issuing the poll (issue slots
+// matter when other warps of the SM are issue-bound)
+__device__ __forceinline__ void bar_wait_hint(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TCH_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra TCH_DONE;\n"
+        "bra TCH_WAIT;\n"
+        "TCH_DONE:\n"
+        "}\n" ::"r"(s_addr(bar)), "r"(parity), "r"(20000u) : "memory");
+}
 // same, for roles that are far ahead of the critical path (keeps their polling out of the expanders' issue slots)
 __device__ __forceinline__ void bar_wait_relaxed(uint64_t *bar, uint32_t parity)
 {

@@ -116,8 +116,13 @@ def timing(ctx, n=100_000, p=250_000):
     outs = torch.zeros((7, p), dtype=torch.float64, device=dev)
     ctx.set_profiling(True)
     res = {}
-    for path, tiles in (("split", 2), ("fused", 2)):
+    runs = [("split", 2, 0), ("fused", 2, 0)]
+    if "--dbg" in sys.argv:
+        runs += [("fused", 2, d) for d in (2 + 32, 2 + 32 + 256, 2 + 32 + 512, 6)]
+    for path, tiles, dbg in runs:
         ctx.set_packed_path(path)
+        os.environ["STAAR_B200_FUSED_TILES"] = str(tiles)
+        os.environ["STAAR_B200_FUSED_DBG"] = str(dbg)
         for it in range(3):
             t0 = time.perf_counter()
             ctx.packed_score_device(cols.data_ptr(), stride, n, p, api.IMPUTE_MEAN, [outs[i].data_ptr() for i in range(7)])
@@ -127,8 +132,9 @@ def timing(ctx, n=100_000, p=250_000):
         extra = ""
         if path == "fused":
             extra = f" redo_count {ctx.packed_debug_fused(p)['redo_count']}"
-        print(f"time {path}: {dt * 1e3:.2f} ms per {p} variants = {dt / p * 1e9:.2f} ns/variant; stages {ms}{extra}", flush=True)
-        res[path] = outs.cpu().numpy().copy()
+        print(f"time {path} tiles={tiles} dbg={dbg}: {dt * 1e3:.2f} ms per {p} variants = {dt / p * 1e9:.2f} ns/variant; stages {ms}{extra}", flush=True)
+        if dbg == 0 and tiles == 2:
+            res[path] = outs.cpu().numpy().copy()
     for i, k in enumerate(KEYS):
         x, y = res["split"][i], res["fused"][i]
         with np.errstate(invalid="ignore", divide="ignore"):
