@@ -262,6 +262,12 @@ def run_ours(args):
     clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
     ms_total = float(ms.item())
     value = world * V * args.steps / (ms_total / 1e3)
+    # rank 0 owns variants [0, V) at every N: the hash of its seven output arrays must be the same in the N = 1, 2, 4, 8
+    # lines of the scaling run (no floating-point atomics, fixed reduction trees)
+    outputs_sha256 = None
+    if rank == 0:
+        import hashlib
+        outputs_sha256 = hashlib.sha256(outs.cpu().numpy().tobytes()).hexdigest()
 
     # ---- per-kernel device times (CUDA events on the launching stream) for the roofline figure
     ctx.set_profiling(True)
@@ -305,12 +311,23 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         p = CHUNK
-        host = torch.from_numpy(host_chunk_from_device(packed[:p], n, dev, d_order).T).pin_memory()   # (p, n) C-order, pinned
+        G_pageable = np.asfortranarray(host_chunk_from_device(packed[:p], n, dev, d_order))   # what R hands over: pageable FP64
+        host = torch.from_numpy(np.ascontiguousarray(G_pageable.T)).pin_memory()              # (p, n) C-order, pinned
         G = host.numpy().T                                                                    # n x p, F-order view
         out7 = [np.zeros(p) for _ in range(7)]
+        nchunk = max(args.steps, 16)            # chunks per e2e leg: a 30 ms chunk needs more than K = 5 repetitions for a stable rate
+        # headline leg: the block lies in PAGEABLE memory, as an R numeric matrix does (host threads pack everything)
+        out7g = [np.zeros(p) for _ in range(7)]
+        for _ in range(3):
+            ctx.individual_analysis_chunk(G_pageable, api.IMPUTE_MEAN, 0, out7g)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nchunk):
+            ctx.individual_analysis_chunk(G_pageable, api.IMPUTE_MEAN, 0, out7g)
+        barrier()
+        dt_page = time.perf_counter() - t0
         for _ in range(max(3, args.warmup)):             # also lets the host/GPU packing split settle
             ctx.individual_analysis_chunk(G, api.IMPUTE_MEAN, 0, out7)
-        nchunk = max(args.steps, 16)            # chunks per e2e leg: a 30 ms chunk needs more than K = 5 repetitions for a stable rate
         barrier()
         t0 = time.perf_counter()
         for _ in range(nchunk):
@@ -338,19 +355,30 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(dt_sync_t, op=dist.ReduceOp.MAX)
         dt_sync = float(dt_sync_t.item())
-        e2e = {"value": world * p * nchunk / dt_sync, "unit": "variants/s", "chunks_timed": nchunk,
-               "h2d_bytes_per_step": int((p - p_gpu) * stride + p_gpu * n * 8), "d2h_bytes_per_step": int(7 * p * 8),
-               "call": "staar_individual_analysis_chunk (host FP64 n x 5000 dosage block, pinned; 2-bit packing by host "
-                       f"threads ({p - p_gpu} variants, then H2D) and by the GPU reading the pinned block over PCIe ({p_gpu} "
-                       "variants); re-order, contraction, scan, finaliser; D2H of 7 result arrays — all inside the timed region)",
-               "ms_per_chunk": 1e3 * dt_sync / nchunk, "host_bytes_read_per_step": int(p * n * 8),
+        dt_page_t = torch.tensor([dt_page], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt_page_t, op=dist.ReduceOp.MAX)
+        dt_page = float(dt_page_t.item())
+        e2e = {"value": world * p * nchunk / dt_page, "unit": "variants/s", "chunks_timed": nchunk,
+               "h2d_bytes_per_step": int(p * stride), "d2h_bytes_per_step": int(7 * p * 8),
+               "call": "staar_individual_analysis_chunk (host FP64 n x 5000 dosage block in PAGEABLE memory, as R hands it "
+                       "over; 2-bit packing by host threads, H2D of the packed columns, re-order, contraction, scan, "
+                       "finaliser, D2H of 7 result arrays — all inside the timed region)",
+               "ms_per_chunk": 1e3 * dt_page / nchunk, "host_bytes_read_per_step": int(p * n * 8),
+               "host_read_gbs": world * p * n * 8 * nchunk / dt_page / 1e9,
+               "pinned_block": {"value": world * p * nchunk / dt_sync, "unit": "variants/s", "ms_per_chunk": 1e3 * dt_sync / nchunk,
+                                "h2d_bytes_per_step": int((p - p_gpu) * stride + p_gpu * n * 8),
+                                "host_read_gbs": world * p * n * 8 * nchunk / dt_sync / 1e9,
+                                "call": "same call, block in pinned memory: the GPU packs a share of the variants itself, "
+                                        f"reading the host matrix over PCIe ({p_gpu} of {p} variants after re-balancing)"},
                "gpu_pack_share": ctx.gpu_pack_share(),
                "pipelined_calls": {"value": world * p * nchunk / float(dt.item()), "unit": "variants/s",
                                    "ms_per_chunk": 1e3 * float(dt.item()) / nchunk,
                                    "call": "staar_chunk_submit / staar_chunk_wait, two chunks in flight"}}
         # parity of the device-resident step against the host-buffer path on the same variants (bit-identical)
         same = all(np.array_equal(outs[i, :p].cpu().numpy(), out7[i], equal_nan=True) and
-                   np.array_equal(out7[i], out7p[i], equal_nan=True) for i in range(7))
+                   np.array_equal(out7[i], out7p[i], equal_nan=True) and
+                   np.array_equal(out7[i], out7g[i], equal_nan=True) for i in range(7))
         e2e["matches_resident_path"] = bool(same)
         # the same chunk as SeqArray's raw dosage bytes (1 B/genotype on the host instead of the 8 B Rcpp widens it to)
         Gu8 = np.where(np.isnan(G), 255, G).astype(np.uint8, order="F")
@@ -365,41 +393,51 @@ def run_ours(args):
                 ctx.chunk_submit(Gu8, api.IMPUTE_MEAN, 0, (s_ + 1) & 1)
             ctx.chunk_wait(s_ & 1, out7b)
         barrier()
-        dtb = time.perf_counter() - t0
+        dtb_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dtb_t, op=dist.ReduceOp.MAX)
+        dtb = float(dtb_t.item())
         e2e["raw_u8_input"] = {"value": world * p * nchunk / dtb, "unit": "variants/s", "ms_per_chunk": 1e3 * dtb / nchunk,
                                "host_bytes_read_per_step": int(p * n),
                                "matches_fp64_input": bool(all(np.array_equal(out7[i], out7b[i], equal_nan=True) for i in range(7)))}
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
+    pc = args.cpu_chunk
+    nm_like = argparse.Namespace(Sigma_i=Sigma_i, Sigma_iX=Sigma_iX, cov=cov, residuals=residuals)
+    Gc = np.asfortranarray(host_chunk_from_device(packed[:pc], n, dev, d_order)) if (e2e is not None or (rank == 0 and world == 1)) else None
+    if e2e is not None:
+        # the R driver's native call sequence on one chunk through this library's frozen-signature entry points (what the
+        # Rcpp shim of INTEGRATION.md binds: FP64 G in, flipped FP64 Geno back out, dense + CSC marshalling, pageable
+        # memory, host operands on every call); every rank runs it, time = max over ranks
+        reference_chunk(ctx, Gc, nm_like)
+        barrier()
+        tf, tested_f = reference_chunk(ctx, Gc, nm_like)
+        tf_t = torch.tensor([tf], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tf_t, op=dist.ReduceOp.MAX)
+        tf = float(tf_t.item())
+        e2e["frozen_signatures"] = {"value": world * pc / tf, "unit": "variants/s", "ms_per_chunk": 1e3 * tf, "variants": pc,
+                                    "tested": tested_f,
+                                    "call": "staar_matrix_flip_mean -> staar_individual_score_test (common, dense FP64 G) -> "
+                                            "staar_individual_score_test_sp (rare, CSC G): the R driver's sequence "
+                                            "through the 13 unchanged signatures, host operands on every call"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ref, kind, blas = load_reference()
-        pc = args.cpu_chunk
-        Gc = np.asfortranarray(host_chunk_from_device(packed[:pc], n, dev, d_order))
-        nm_like = argparse.Namespace(Sigma_i=Sigma_i, Sigma_iX=Sigma_iX, cov=cov, residuals=residuals)
         t, tested = reference_chunk(ref, Gc, nm_like)
         cpu = {"value": pc / t, "unit": "variants/s", "cores": (os.cpu_count() or 1) if blas else 1, "kind": kind,
                "sample": f"one chunk of {pc} variants x {n} samples ({tested} pass the MAC filter): native calls of the R "
                          f"driver (matrix_flip_mean, Individual_Score_Test, Individual_Score_Test_sp), {t:.1f} s; "
                          "reference sources with stand-in Armadillo/Rmath (oracle/ref_stub), dense GEMM on "
                          f"{'OpenBLAS all cores' if blas else 'in-order loops'}"}
-        # the same native call sequence, same chunk, through this library's frozen-signature entry points (what the Rcpp
-        # shim of INTEGRATION.md binds: FP64 G in and the flipped FP64 Geno back out over PCIe, dense + CSC marshalling)
-        if e2e is not None:
-            reference_chunk(ctx, Gc, nm_like)
-            tf, tested_f = reference_chunk(ctx, Gc, nm_like)
-            e2e["frozen_signatures"] = {"value": pc / tf, "unit": "variants/s", "ms_per_chunk": 1e3 * tf, "variants": pc,
-                                        "tested": tested_f,
-                                        "call": "staar_matrix_flip_mean -> staar_individual_score_test (common, dense FP64 G) -> "
-                                                "staar_individual_score_test_sp (rare, CSC G): the R driver's sequence "
-                                                "through the 13 unchanged signatures, host operands on every call"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "variants/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int8 x int8 -> int32 exact contraction of 54-bit sliced f64 operands; f64 statistics",
                 "data": "synthetic", "config": workload_config(args, V), "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "outputs_sha256": outputs_sha256,
+                "packed_path": "fused" if ctx.last_packed_path_was_fused else "split"}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

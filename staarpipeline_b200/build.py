@@ -41,7 +41,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if src.endswith(".cpp"):
             cmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-pthread", "-c", src, "-o", obj]
         else:
-            cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
+            extra = os.environ.get("STAAR_B200_NVCC_EXTRA", "").split()      # e.g. -DFUSED_TIMERS (tools/fused_prof.py)
+            cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False

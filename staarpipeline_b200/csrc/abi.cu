@@ -13,7 +13,6 @@
 
 namespace staar {
 uint64_t hash_bytes(const void *data, size_t bytes, uint64_t seed);
-uint64_t hash_sampled(const double *data, size_t count, uint64_t seed);
 int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *Sv, const uint64_t *Sr,
                             const uint64_t *Sc, const double *SX, const double *cov, const double *res, uint64_t fp,
                             uint64_t res_fp, bool want_sliced);
@@ -144,9 +143,11 @@ int ensure_sparse(staar_ctx *ctx, int64_t n, int64_t q, const double *Sv, const 
 int ensure_dense(staar_ctx *ctx, int64_t n, const double *P)
 {
     if (!P) { set_error("P is NULL"); return STAAR_ERR_ARG; }
-    const uint64_t fp = hash_sampled(P, (size_t)n * n, 21) ^ (uint64_t)n;
+    // every byte of P is hashed (threaded, ~0.4 s for 3.2 GB — small next to the upload it saves): a P that differs in
+    // a few entries only must not be served from the resident copy
+    const uint64_t fp = hash_bytes(P, (size_t)n * n * sizeof(double), 21) ^ (uint64_t)n;
     if (ctx->nd.set && ctx->nd.fingerprint == fp && ctx->nd.n == n) return STAAR_OK;
-    return nullmodel_dense_upload(ctx, n, P, nullptr, fp);
+    return nullmodel_dense_upload(ctx, n, P, nullptr, fp);      // new allocation: resident residuals are gone (nd.res_set = false)
 }
 
 // ---- genotype block on the device ---------------------------------------------------------------------------
@@ -160,6 +161,11 @@ int upload_csc_G(staar_ctx *ctx, const double *Gv, const uint64_t *Gr, const uin
 {
     if (!Gv || !Gr || !Gc) { set_error("sparse G pointer is NULL"); return STAAR_ERR_ARG; }
     const uint64_t nnz = Gc[p];
+    // the scatter kernel writes G[c n + row]: a bad index would be an out-of-bounds device write
+    for (int64_t c = 0; c < p; c++)
+        if (Gc[c] > Gc[c + 1]) { set_error("sparse G: column pointers are not non-decreasing"); return STAAR_ERR_ARG; }
+    for (uint64_t e = 0; e < nnz; e++)
+        if (Gr[e] >= (uint64_t)n) { set_error("sparse G: row index out of range"); return STAAR_ERR_ARG; }
     STAAR_TRY(ctx->G.reserve(sizeof(double) * (size_t)n * std::max<int64_t>(p, 1)));
     const size_t bytes = nnz * 16 + (size_t)(p + 1) * 8;
     STAAR_TRY(ctx->pk.reserve(bytes + 64));
@@ -1031,7 +1037,9 @@ int staar_nullmodel_set_dense(staar_ctx *ctx, int64_t n, const double *P, const 
     if (n <= 0 || !P || !residuals) { set_error("nullmodel_set_dense: bad arguments"); return STAAR_ERR_ARG; }
     STAAR_TRY(ensure_dense(ctx, n, P));
     STAAR_TRY(h2d(ctx, ctx->nd.residuals, residuals, sizeof(double) * n));
-    return sync(ctx);
+    STAAR_TRY(sync(ctx));
+    ctx->nd.res_set = true;
+    return STAAR_OK;
 }
 
 int staar_packed_score_dense_device(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
@@ -1040,7 +1048,8 @@ int staar_packed_score_dense_device(staar_ctx *ctx, const uint8_t *d_packed, siz
 {
     CHECK_CTX(ctx);
     STAAR_TRY(check_dims(n, p));
-    if (!ctx->nd.set || ctx->nd.n != n) { set_error("packed dense-GRM score: call staar_nullmodel_set_dense for n = %lld first", (long long)n); return STAAR_ERR_STATE; }
+    // res_set: a frozen-signature denseGRM call with another P replaces the resident P and leaves no residuals behind
+    if (!ctx->nd.set || !ctx->nd.res_set || ctx->nd.n != n) { set_error("packed dense-GRM score: call staar_nullmodel_set_dense for n = %lld first", (long long)n); return STAAR_ERR_STATE; }
     if (stride % 16 != 0 || stride < (size_t)((n + 3) / 4)) { set_error("packed stride must be a multiple of 16 and >= ceil(n/4)"); return STAAR_ERR_ARG; }
     if (p == 0) return STAAR_OK;
     STAAR_TRY(packed_score_dense(ctx, d_packed, stride, n, p, impute, d_AF, d_MAF, d_Score, d_Score_se, d_pl, d_Est, d_Est_se));

@@ -115,19 +115,6 @@ uint64_t hash_bytes(const void *data, size_t bytes, uint64_t seed)
     return hash_bytes_serial(part.data(), pieces * 8, seed) ^ bytes;
 }
 
-// strided sample of a large dense matrix (P is 3.2 GB at n = 20k): every `step`-th word plus head and tail
-uint64_t hash_sampled(const double *data, size_t count, uint64_t seed)
-{
-    uint64_t h = seed ^ count;
-    const size_t step = std::max<size_t>(1, count / 65536);
-    for (size_t i = 0; i < count; i += step) {
-        uint64_t w; memcpy(&w, data + i, 8);
-        h = (h ^ w) * 0x100000001B3ull; h ^= h >> 29;
-    }
-    const size_t edge = std::min<size_t>(count, 4096);
-    return h ^ hash_bytes(data, edge * 8, 1) ^ hash_bytes(data + (count - edge), edge * 8, 2);
-}
-
 // ------------------------------------------------------------------------------------------------
 // sparse null model: CSC(uint64) host -> CSR(int64/int32) device, Y = [res | Sigma_iX | diag] row-major,
 // and the packed path's "null-model sample order" with its per-family kinship tables (common.cuh).
@@ -534,7 +521,7 @@ int nullmodel_dense_upload(staar_ctx *ctx, int64_t n, const double *P, const dou
     STAAR_CUDA(cudaMalloc(&nd.residuals, sizeof(double) * n));
     STAAR_CUDA(cudaMemcpyAsync(nd.P, P, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, ctx->stream));
     STAAR_CUDA(cudaStreamSynchronize(ctx->stream));
-    nd.n = n; nd.fingerprint = fp; nd.set = true;
+    nd.n = n; nd.fingerprint = fp; nd.set = true; nd.res_set = false;
     (void)res;
     return STAAR_OK;
 }

@@ -445,6 +445,7 @@ fused_tc_kernel(const __grid_constant__ CUtensorMap gmap, FusedParams P)
                 // per-word constants live in the lanes that own the word
                 const uint32_t km_c = __shfl_sync(0xffffffffu, km, w16), vm_c = __shfl_sync(0xffffffffu, vmask, w16);
                 const uint32_t cm_c = __shfl_sync(0xffffffffu, cmask, w16);
+                TM_MARK(2);
                 if (act && !(P.dbg & 512)) {
                     const double extra = serve(en.x, en.y, km_c, vm_c, cm_c, kb * 16 + w16);
                     pslot = (int)en.x;                                        // s_acc[row][word]

@@ -16,7 +16,10 @@ __global__ void csc_scatter_kernel(const double *__restrict__ val, const int64_t
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t c = warp; c < p; c += nwarps) {
         const int64_t e1 = colptr[c + 1];
-        for (int64_t e = colptr[c] + lane; e < e1; e += 32) G[c * n + row[e]] = val[e];
+        // duplicate (row, column) entries add up, as in Armadillo's sp_mat; a column is owned by one warp, and within the
+        // warp the atomic add makes entries of the same row in different lanes safe (entries are few: order effects
+        // only arise for duplicates, which sorted dgCMatrix input never has)
+        for (int64_t e = colptr[c] + lane; e < e1; e += 32) atomicAdd(&G[c * n + row[e]], val[e]);
     }
 }
 

@@ -309,6 +309,7 @@ int packed_score_multi(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
         if (k == 1) STAAR_MULTI(1); else if (k == 2) STAAR_MULTI(2); else if (k == 3) STAAR_MULTI(3); else STAAR_MULTI(4);
 #undef STAAR_MULTI
         ctx->launches += 2;
+        STAAR_CUDA(cudaGetLastError());
     } else {                                  // generic: explicit Kronecker carrier lists and the pair kernels of quadform.cu
         kron_expand_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(dval, drow, dcount, n0, pp, k, nnz, dval_k, drow_k, dcolptr_k);
         ctx->launches++;

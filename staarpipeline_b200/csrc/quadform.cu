@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(256) dot_pairs_kernel(const double *__restrict
 
 // One CTA per (a, b) pair of sparse columns; the b list sits in shared memory in tiles, the a list is walked serially
 // with the threads spread over b.  For a == b only j >= i is visited (P is symmetric: Sigma^-1 - Sigma^-1 X cov X' Sigma^-1).
+// ASSUMPTION: P is symmetric, as GMMAT's P always is; the reference's expression uses every entry of P, so for an
+// asymmetric P the a == b shortcut (off-diagonal terms counted twice from the upper triangle) would differ from it.
 constexpr int kCarrierTile = 1024;
 __global__ void __launch_bounds__(256) quad_pairs_carriers_P_kernel(const double *__restrict__ val, const int64_t *__restrict__ row,
                                                                     const int64_t *__restrict__ colptr, int64_t n,

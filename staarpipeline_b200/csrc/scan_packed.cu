@@ -73,7 +73,7 @@ __device__ __forceinline__ uint32_t code_smem(const uint8_t *col, int64_t k, boo
 }
 
 template <int kBlkWarps>
-__global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P, int nstage, unsigned long long *work)
+__global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P, int nstage, unsigned long long *work, int l2pf)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -140,6 +140,15 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             const unsigned long long v = atomicAdd(work, 1ull);
             s_work[it & 1] = v;
             if (v < pmax) issue(variant_of(v), stage ^ 1);
+        }
+        if (nstage == 1 && l2pf && tid == 0) {
+            // one stage: draw the next variant now and pull its column into L2 while this one is scanned — the bulk copy
+            // into shared memory issued at the end of the iteration then waits an L2 round trip, not an HBM one
+            const unsigned long long v = atomicAdd(work, 1ull);
+            s_work[it & 1] = v;
+            if (v < pmax)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.packed + (size_t)variant_of(v) * stride),
+                             "r"((uint32_t)stride) : "memory");
         }
         wait_full(stage, (parity >> stage) & 1u);
         parity ^= 1u << stage;
@@ -417,8 +426,9 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         } else {
             __syncthreads();
             if (tid == 0) {
-                const unsigned long long v = atomicAdd(work, 1ull);
-                s_work[it & 1] = v;
+                unsigned long long v;
+                if (l2pf) v = s_work[it & 1];
+                else { v = atomicAdd(work, 1ull); s_work[it & 1] = v; }
                 if (v < pmax) issue(variant_of(v), 0);
             }
             __syncthreads();
@@ -538,7 +548,9 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
         STAAR_TRY(ctx->ctr.reserve(sizeof(unsigned long long)));
         STAAR_CUDA(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(unsigned long long), ctx->stream));
         const int64_t blocks = std::min<int64_t>(p, (int64_t)ctx->sm_count * per_sm);
-        kern<<<(int)blocks, warps * 32, smem, ctx->stream>>>(P, nstage, ctx->ctr.as<unsigned long long>());
+        // STAAR_B200_SCAN_L2PF=0 switches the L2 prefetch of the next column off (experiments)
+        static const int l2pf = getenv("STAAR_B200_SCAN_L2PF") ? atoi(getenv("STAAR_B200_SCAN_L2PF")) : 1;
+        kern<<<(int)blocks, warps * 32, smem, ctx->stream>>>(P, nstage, ctx->ctr.as<unsigned long long>(), l2pf);
     } else {
         set_error("packed scan: a column of %zu bytes does not fit in shared memory (n > ~9e5): use the FP64 entry points", stride);
         return STAAR_ERR_ARG;

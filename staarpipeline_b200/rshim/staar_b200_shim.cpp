@@ -39,6 +39,9 @@ void check(int rc)
     if (rc != STAAR_OK) throw std::runtime_error(staar_last_error());
 }
 
+// the C ABI takes CSC indices as uint64 (ARMA_64BIT_WORD, reference src/Makevars:2): the reinterpret_casts below are only
+// valid for 8-byte arma::uword
+static_assert(sizeof(arma::uword) == 8, "build with -DARMA_64BIT_WORD=1 (reference src/Makevars)");
 template <typename SpMat> const uint64_t *rows(const SpMat &m) { return reinterpret_cast<const uint64_t *>(&m.row_indices[0]); }
 template <typename SpMat> const uint64_t *cols(const SpMat &m) { return reinterpret_cast<const uint64_t *>(&m.col_ptrs[0]); }
 template <typename SpMat> const double *vals(const SpMat &m) { return &m.values[0]; }

@@ -21,10 +21,11 @@ GOLD = np.load(os.path.join(HERE, "golden", "reference_outputs.npz"))
 
 
 def score_floor(G, residuals):
-    """|U| below this is cancellation noise for ANY summation order: 1e-3 of the typical |U| = ||r o g||_2."""
+    """Per variant: |U| below this is cancellation noise for ANY summation order — 1e-3 of that column's typical
+    |U| = ||r o g||_2 (a rare variant next to a common one keeps its own, smaller, floor)."""
     G = G.toarray() if sp.issparse(G) else np.asarray(G)
     r = np.asarray(residuals)[:, None] if G.shape[0] == np.size(residuals) else None
-    return 1e-3 * np.sqrt(((G * r) ** 2).sum(axis=0)).max() if r is not None else 0.0
+    return 1e-3 * np.sqrt(((G * r) ** 2).sum(axis=0)) if r is not None else 0.0
 
 
 # ------------------------------------------------------------------ K1

@@ -44,7 +44,7 @@ if int(os.environ.get("STAAR_B200_FUSED_DBG", "0")) & 128:
     np.set_printoptions(linewidth=200, suppress=True, precision=0)
     print("kclk per phase, mean over CTAs; expander warps 0-7: [wait a_empty, wait g_full, work]")
     print(m[:8, :3])
-    print("scanner warps 8-23: [wait g_full, phase1, consume+missing, compaction, barrier, batches, loop rest, tail]")
+    print("scanner warps 8-23: [wait g_full, phase1, -, consume+push, barrier, batches, loop head, tail]")
     print(m[8:24])
     print("mma issuer: [wait b_full, wait a_full, issue]", m[24, :3], " genotype producer [wait g_empty, issue]", m[26, :2])
     print("max over CTAs scanner total", buf[:, 8:24, :7].sum(axis=2).max() / 1e3, " mean", buf[:, 8:24, :7].sum(axis=2).mean() / 1e3)
