@@ -444,6 +444,167 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ other configurations
+def run_config(args):
+    """--config 0 / 2 / 3 / 4: the other BASELINE.json configurations on resident 2-bit columns, one JSON line of the same
+    shape (value = device-resident throughput of the configuration's flow; roofline against the roof that binds: HBM for
+    the packed score paths, the measured FP64 pipe for the dense-GRM GEMM and the SPA passes).  Weak scaling: every rank
+    runs the same shard size; time = max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from staarpipeline_b200 import api, synth
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    ctx = api.Context(local)
+    peaks, pipes = {}, {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        pipes = json.load(open(os.path.join(ROOT, "profiles", "r02_pipe_peaks.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0)); fp64_peak = float(pipes.get("fp64_fma_tflops", 37.0))
+    cfg = args.config
+    seed = synth.BASE_SEED
+
+    def resident(n, V, order=None):
+        stride = api.packed_stride(n)
+        packed = torch.empty((V, stride), dtype=torch.uint8, device=dev)
+        first = rank * V
+        for a in range(0, V, 125_000):
+            b = min(V, a + 125_000)
+            prm = synth.variant_params(n, first + a, b - a, seed)
+            t = lambda x: torch.from_numpy(x.view(np.int64) if x.dtype == np.uint64 else x).to(dev)
+            th, te, tm, sa = t(prm.thr_hom), t(prm.thr_het), t(prm.thr_miss), t(prm.store_alt)
+            torch.cuda.synchronize()
+            ctx.synth_packed_device(packed[a:b].data_ptr(), stride, n, first + a, b - a, seed, th.data_ptr(), te.data_ptr(),
+                                    tm.data_ptr(), sa.data_ptr(), order.data_ptr() if order is not None else 0)
+        return packed, stride
+
+    def timed(step, sync):
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        for _ in range(args.warmup):
+            step()
+        sync()
+        if world > 1:
+            dist.barrier()
+        ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_begin = time.perf_counter()
+        l0 = ctx.launch_count
+        e0.record(ext)
+        for _ in range(args.steps):
+            step()
+        e1.record(ext)
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
+        return float(ms.item()) / args.steps, clocks, (ctx.launch_count - l0) // max(args.steps, 1)
+
+    def sync_all():
+        ctx.synchronize(); torch.cuda.synchronize()
+
+    extra = {}
+    if cfg == 0:
+        n, V, q = 10_000, args.variants_per_gpu if args.variants_per_gpu != VARIANTS_PER_GPU else 2_000_000, Q_COVARIATES
+        nm = synth.nullmodel_unrelated(n, seed=seed, q=q)
+        ctx.set_nullmodel_sparse(nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+        packed, stride = resident(n, V)
+        outs = torch.zeros((7, V), dtype=torch.float64, device=dev); optrs = [outs[i].data_ptr() for i in range(7)]
+        ms, clocks, launches = timed(lambda: ctx.packed_score_device(packed.data_ptr(), stride, n, V, api.IMPUTE_MEAN, optrs), sync_all)
+        bytes_v = n * 2 / 8 + 56
+        roof = {"bound": "hbm", "achieved": V * bytes_v / (ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "traffic": None,
+                "kernel": "whole step (contract_tc_kernel + scan_block_kernel + finalize_packed_kernel)"}
+        work = "BASELINE configs[0]: Individual_Analysis continuous trait, unrelated samples, n=10,000 (resident 2-bit columns)"
+        dtype = "int8 x int8 -> int32 exact contraction of 54-bit sliced f64 operands; f64 statistics"
+    elif cfg == 2:
+        n, V = 20_000, args.variants_per_gpu if args.variants_per_gpu != VARIANTS_PER_GPU else 20_000
+        rng = np.random.default_rng(seed)
+        W = rng.normal(size=(n, 64))
+        P = -(W @ W.T) / 64.0
+        P[np.diag_indices(n)] += 3.0 + rng.random(n)
+        P = np.asfortranarray(0.5 * (P + P.T)); res = rng.normal(size=n)
+        ctx.set_nullmodel_dense(P, res)
+        packed, stride = resident(n, V)
+        outs = torch.zeros((7, V), dtype=torch.float64, device=dev); optrs = [outs[i].data_ptr() for i in range(7)]
+        ms, clocks, launches = timed(lambda: ctx.packed_score_dense_device(packed.data_ptr(), stride, n, V, api.IMPUTE_MEAN, optrs), sync_all)
+        af = outs[0].cpu().numpy(); maf = np.minimum(af, 1 - af)
+        # variants with more than n/8 non-zero genotypes take P*G (2 n^2 flop each); the rest the carrier form
+        dense_share = float((1 - (1 - maf) ** 2 > 1 / 8).mean())
+        flops = V * dense_share * 2.0 * n * n
+        roof = {"bound": "tensor", "achieved": flops / (ms / 1e3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "traffic": None,
+                "kernel": "dgemm_PG_kernel (FP64 DMMA) for the dense share of the variants", "dense_share": dense_share,
+                "peak_source": "measured FP64 FMA / DMMA rate (profiles/r02_pipe_peaks.json)"}
+        work = "BASELINE configs[2]: Individual_Analysis with dense GRM (_denseGRM), n=20,000 (resident 2-bit columns; P 3.2 GB resident)"
+        dtype = "f64"
+    elif cfg == 3:
+        n, k, V = 100_000, 3, args.variants_per_gpu if args.variants_per_gpu != VARIANTS_PER_GPU else 50_000
+        nm = synth.nullmodel_multi(n, k, seed=seed, q=Q_COVARIATES)
+        ctx.set_nullmodel_sparse(nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+        packed, stride = resident(n, V)
+        af = torch.zeros(V, dtype=torch.float64, device=dev); maf = torch.zeros_like(af)
+        score = torch.zeros(V * k, dtype=torch.float64, device=dev); pl = torch.zeros(V, dtype=torch.float64, device=dev)
+        ms, clocks, launches = timed(lambda: ctx.packed_score_multi_device(packed.data_ptr(), stride, n, V, k, api.IMPUTE_MEAN, af.data_ptr(),
+                                                                          maf.data_ptr(), score.data_ptr(), pl.data_ptr()), sync_all)
+        bytes_v = n * 2 / 8 + 8 * (k + 3)
+        roof = {"bound": "hbm", "achieved": V * bytes_v / (ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "traffic": None,
+                "kernel": "contract_multi_packed_kernel + quad_multi_packed_kernel (one CTA per variant, carrier lists)"}
+        work = "BASELINE configs[3]: 3 correlated traits jointly (_multi), sparse GRM, n=100,000 (resident 2-bit columns)"
+        dtype = "f64"
+    else:
+        n, V = 400_000, args.variants_per_gpu if args.variants_per_gpu != VARIANTS_PER_GPU else 20_000
+        nb = synth.nullmodel_binary(n, seed=seed, q=Q_COVARIATES)
+        ctx.set_nullmodel_sparse(nb.Sigma_i, nb.Sigma_iX, nb.cov, nb.residuals)
+        ctx.set_nullmodel_spa(nb.XW, nb.XXWX_inv, nb.residuals, nb.muhat)
+        order = torch.from_numpy(ctx.nullmodel_sample_order()).to(dev)
+        packed, stride = resident(n, V, order)
+        idx = torch.zeros(V, dtype=torch.int64, device=dev); sel = torch.zeros(V, dtype=torch.int64, device=dev)
+        outs = torch.zeros((7, V), dtype=torch.float64, device=dev); optrs = [outs[i].data_ptr() for i in range(7)]
+        pv = torch.zeros(V, dtype=torch.float64, device=dev); tr = torch.zeros((V, 4), dtype=torch.int64, device=dev)
+        tol = float(np.finfo(np.float64).eps ** 0.25)
+        stat = {}
+
+        def flow():
+            nt, nsel = ctx.packed_analysis_device(packed.data_ptr(), stride, n, V, api.IMPUTE_MEAN, 20.0, 0.05, idx.data_ptr(), optrs, sel.data_ptr())
+            cols = idx[sel[:nsel]].contiguous()
+            torch.cuda.synchronize()
+            ctx.packed_spa_device(packed.data_ptr(), stride, n, cols.data_ptr(), nsel, api.IMPUTE_MEAN, tol, 1000, pv.data_ptr(), tr.data_ptr())
+            stat.update(tested=int(nt), spa_variants=int(nsel))
+        ms, clocks, launches = timed(flow, sync_all)
+        passes = int(tr[:stat["spa_variants"], 0].sum().item())
+        flops = passes * float(n) * 66.0                       # SURVEY 8d: c_K ~ 2q (recompute) + ~40 per sample and pass
+        roof = {"bound": "tensor", "achieved": flops / (ms / 1e3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "traffic": None,
+                "kernel": "spa_kernel (FP64 ALU; one cluster per variant)", "cgf_passes": passes,
+                "peak_source": "measured FP64 FMA rate (profiles/r02_pipe_peaks.json); flop count = passes x n x 66 (SURVEY 8d)"}
+        extra = stat
+        work = ("BASELINE configs[4]: dichotomous trait 1:100 with SPA, n=400,000: score test + MAC filter + SPA pre-filter, "
+                "then SPA on the selected resident columns (resident 2-bit columns)")
+        dtype = "f64 (SPA), exact int8 contraction (stage 1)"
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof.setdefault("peak_source", "measured (MEASURED_PEAKS.json)" if peaks else "fallback")
+    if rank == 0:
+        line = {"metric": METRIC.replace("n=100k", f"n={n}"), "value": world * V / (ms / 1e3), "unit": "variants/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+                "config": {"workload": work, "n_samples": n, "variants_per_gpu_per_step": V, "genotype_bits": 2, "impute": "mean",
+                           "parallelism": f"variant-sharded x{world}", "l2": "inputs larger than L2" if V * stride > 2e8 else "inputs fit L2 partly", **extra},
+                "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def host_chunk_from_device(packed_rows, n, dev, d_order):
     """unpack device-resident 2-bit columns (null-model sample order) into the FP64 `$dosage` matrix in the caller's
     sample order (n x p, F-order, NaN = missing)"""
@@ -468,11 +629,15 @@ def main():
     ap.add_argument("--variants-per-gpu", type=int, default=VARIANTS_PER_GPU)
     ap.add_argument("--cpu-chunk", type=int, default=2000, help="variants in the bounded cpu_baseline sample")
     ap.add_argument("--ref-chunk", type=int, default=2000, help="variants per step of --impl reference")
+    ap.add_argument("--config", type=int, default=1, choices=[0, 1, 2, 3, 4],
+                    help="BASELINE.json configs[k]; 1 (default) is the headline workload, the others print the same line shape")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != 1:
+        run_config(args)
     else:
         run_ours(args)
 

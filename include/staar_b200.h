@@ -336,6 +336,38 @@ int staar_synth_packed_device(staar_ctx *ctx, uint8_t *d_packed, size_t stride_b
                               const uint64_t *d_thr_hom, const uint64_t *d_thr_het, const uint64_t *d_thr_miss,
                               const uint8_t *d_store_alt, const int32_t *d_sample_order);
 
+/* ======================================================================= */
+/* C. Several GPUs of one box behind one handle.    */
+/* ======================================================================= */
+/* One process, one staar_ctx per listed device, one host thread per device inside every call.  The variants (columns)
+ * of a call are sharded contiguously across the devices; there is no data-path collective, every variant is
+ * independent given the null model (R/Individual_Analysis.R:164-450 loops over variant chunks).  The sparse null
+ * model is built ONCE — the host pass (families, sample order, kinship tables, digit slicing) runs for the first
+ * device — and replicated to the others by device-to-device copies.  Results are bit-identical to the one-GPU calls:
+ * a variant's arithmetic does not depend on which device or which other variants share the call.
+ * The Rcpp shim opens such a handle when the environment variable STAAR_B200_DEVICES lists more than one device
+ * (e.g. "0,1,2,3"), and routes matrix_flip_* and the dense-G Individual_Score_Test through it. */
+typedef struct staar_multi staar_multi;
+int staar_multi_create(const int *devices, int n_devices, staar_multi **out);
+void staar_multi_destroy(staar_multi *m);
+int staar_multi_size(const staar_multi *m);
+staar_ctx *staar_multi_ctx(staar_multi *m, int i);            /* the per-device context (resident *_device entry points) */
+int staar_multi_nullmodel_set_sparse(staar_multi *m, int64_t n, int64_t q, const double *Si_values,
+                                     const uint64_t *Si_row_idx, const uint64_t *Si_col_ptr, const double *Sigma_iX,
+                                     const double *cov, const double *residuals);
+/* staar_individual_analysis_chunk over all devices (host FP64 n x p dosage block, seven arrays of length p out) */
+int staar_multi_individual_analysis_chunk(staar_multi *m, const double *G, int64_t n, int64_t p, int impute, int threads,
+                                          double *AF, double *MAF, double *Score, double *Score_se, double *pvalue_log,
+                                          double *Est, double *Est_se);
+/* frozen signatures, columns sharded: src/matrix_flip_mean.cpp:8-74, matrix_flip_minor.cpp:8-99,
+ * Individual_Score_Test.cpp:9-67 (each device moves its own columns over its own PCIe link) */
+int staar_multi_matrix_flip_mean(staar_multi *m, const double *G, int64_t n, int64_t p, double *Geno_out, double *AF, double *MAF);
+int staar_multi_matrix_flip_minor(staar_multi *m, const double *G, int64_t n, int64_t p, double *Geno_out, double *AF, double *MAF);
+int staar_multi_individual_score_test(staar_multi *m, const double *G, int64_t n, int64_t p,
+                                      const double *Si_values, const uint64_t *Si_row_idx, const uint64_t *Si_col_ptr,
+                                      const double *Sigma_iX, int64_t q, const double *cov, const double *residuals,
+                                      double *Score, double *Score_se, double *pvalue_log, double *Est, double *Est_se);
+
 #ifdef __cplusplus
 }
 #endif

@@ -443,6 +443,64 @@ class Context:
                    C.c_int64(n), C.c_int64(p))
 
 
+class MultiContext:
+    """several GPUs of one box behind one handle (include/staar_b200.h section C); mirrors the Context calls it covers"""
+
+    def __init__(self, devices):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        dev = (C.c_int * len(devices))(*devices)
+        rc = self._lib.staar_multi_create(dev, C.c_int(len(devices)), C.byref(self._h))
+        if rc != 0:
+            raise StaarError(rc, self._lib.staar_last_error().decode())
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.staar_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _call(self, name, *args):
+        rc = getattr(self._lib, name)(self._h, *args)
+        if rc != 0:
+            raise StaarError(rc, self._lib.staar_last_error().decode())
+
+    def set_nullmodel_sparse(self, Sigma_i, Sigma_iX, cov, residuals):
+        n = sp.csc_matrix(Sigma_i).shape[0]
+        keep, sargs = Context._sigma_args(n, Sigma_i, Sigma_iX, cov, residuals)
+        S, SX, cv, r = keep
+        self._call("staar_multi_nullmodel_set_sparse", C.c_int64(n), C.c_int64(SX.shape[1]), *S.args(), _p(SX), _p(cv), _p(r))
+
+    def individual_analysis_chunk(self, G, impute: int = IMPUTE_MEAN, threads: int = 0):
+        G = _f(G)
+        n, p = G.shape
+        o = [np.zeros(p) for _ in range(7)]
+        self._call("staar_multi_individual_analysis_chunk", _p(G), C.c_int64(n), C.c_int64(p), C.c_int(impute), C.c_int(threads),
+                   *[_p(a) for a in o])
+        return dict(zip(("AF", "MAF", "Score", "Score_se", "pvalue_log", "Est", "Est_se"), o))
+
+    def matrix_flip_mean(self, G):
+        G = _f(G)
+        n, p = G.shape
+        out, af, maf = np.empty((n, p), order="F"), np.zeros(p), np.zeros(p)
+        self._call("staar_multi_matrix_flip_mean", _p(G), C.c_int64(n), C.c_int64(p), _p(out), _p(af), _p(maf))
+        return {"Geno": out, "AF": af, "MAF": maf}
+
+    def Individual_Score_Test(self, G, Sigma_i, Sigma_iX, cov, residuals):
+        G = _f(G)
+        n, p = G.shape
+        keep, sargs = Context._sigma_args(n, Sigma_i, Sigma_iX, cov, residuals)
+        o, po = Context._out5(p)
+        self._call("staar_multi_individual_score_test", _p(G), C.c_int64(n), C.c_int64(p), *sargs, *po)
+        return Context._pack5(o)
+
+
 def packed_stride(n: int) -> int:
     return int(load_library().staar_packed_stride(C.c_int64(n)))
 

@@ -539,6 +539,14 @@ int flip_entry(staar_ctx *ctx, const double *G, int64_t n, int64_t p, bool minor
 }
 
 }  // namespace
+
+// content-hashed residency of the sparse null model, for multi.cu
+int ensure_sparse_shared(staar_ctx *ctx, int64_t n, int64_t q, const double *Sv, const uint64_t *Sr, const uint64_t *Sc,
+                         const double *SX, const double *cov, const double *res)
+{
+    Guard g(ctx);
+    return ensure_sparse(ctx, n, q, Sv, Sr, Sc, SX, cov, res);
+}
 }  // namespace staar
 
 using namespace staar;
@@ -1144,6 +1152,17 @@ double staar_ctx_gpu_pack_share(staar_ctx *ctx)
 // or any value <= -1 missing), 1 = uint8 (SeqArray raw dosage, 0xFF missing).
 namespace staar {
 namespace {
+// Upper bound of the share of a pinned FP64 block the GPU packs itself (reading the host matrix over its own PCIe
+// link).  With all cores behind one rank the host packers are the faster side and 0.6 keeps the split stable; when the
+// ranks of a box share the cores (fewer than 8 host threads per rank) nearly everything may go to the GPU — every GPU
+// has its own link, the host threads do not multiply.
+static double pack_share_cap()
+{
+    static const int ranks = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;
+    const int per_rank = std::max(1, (int)std::thread::hardware_concurrency() / ranks);
+    return per_rank < 8 ? 0.95 : 0.6;
+}
+
 int chunk_impl(staar_ctx *ctx, const void *G, int elem, int64_t n, int64_t p, int impute, int threads, double *AF,
                double *MAF, double *Score, double *Score_se, double *pl, double *Est, double *Est_se)
 {
@@ -1202,7 +1221,7 @@ int chunk_impl(staar_ctx *ctx, const void *G, int elem, int64_t n, int64_t p, in
                     t_gpu > 0.f && t_host > 0.0) {
                     const double r_cpu = (double)p_cpu / t_host, r_gpu = (double)p_gpu / (double)t_gpu;
                     const double target = r_gpu / (r_cpu + r_gpu);
-                    ctx->pack_share = std::min(0.6, std::max(0.05, 0.75 * ctx->pack_share + 0.25 * target));
+                    ctx->pack_share = std::min(pack_share_cap(), std::max(0.05, 0.75 * ctx->pack_share + 0.25 * target));
                 }
             }
         } else {
@@ -1317,7 +1336,7 @@ int chunk_wait(staar_ctx *ctx, int s, double *AF, double *MAF, double *Score, do
         if (!fixed && sl.p_gpu > 0 && sl.p_cpu > 0 && cudaEventElapsedTime(&t_gpu, sl.ev0, sl.ev1) == cudaSuccess && t_gpu > 0.f &&
             sl.t_host > 0.0) {
             const double r_cpu = (double)sl.p_cpu / sl.t_host, r_gpu = (double)sl.p_gpu / (double)t_gpu;
-            ctx->pack_share = std::min(0.6, std::max(0.05, 0.75 * ctx->pack_share + 0.25 * r_gpu / (r_cpu + r_gpu)));
+            ctx->pack_share = std::min(pack_share_cap(), std::max(0.05, 0.75 * ctx->pack_share + 0.25 * r_gpu / (r_cpu + r_gpu)));
         }
         if (bad == 0) return STAAR_OK;
     } else {

@@ -109,6 +109,15 @@ struct NullSparse {
     long long *col_total = nullptr;   // 2 x kColsPerSlice: exact column sums of the fixed-point operand, hi | lo (X = hi 2^24 + lo)
     uint64_t fingerprint = 0;     // content hash of (Sigma_i, Sigma_iX, cov): cache key of the frozen-signature entry points
     uint64_t res_fingerprint = 0; // content hash of the residual vector currently in column 0 of Y
+    // every device array above, as (offset of the pointer member in this struct, bytes): what a replica on another GPU
+    // of the same process has to copy (multi.cu: the host-side build of the sample order and tables runs once)
+    std::vector<std::pair<size_t, size_t>> arrays;
+    void reg(void *member, size_t bytes)
+    {
+        const size_t off = (size_t)(static_cast<char *>(member) - reinterpret_cast<char *>(this));
+        for (auto &a : arrays) if (a.first == off) { a.second = bytes; return; }
+        arrays.emplace_back(off, bytes);
+    }
     void release();
 };
 
@@ -265,6 +274,10 @@ int build_tc_operand(staar_ctx *ctx, const int8_t *digits, int ncol);
 int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, long long *d_hi,
                        long long *d_lo);
 int refresh_permuted_Y(staar_ctx *ctx, const double *hY);
+// ctx.cu / abi.cu — shared with multi.cu
+int nullmodel_sparse_clone(staar_ctx *dst, const staar_ctx *src);
+int ensure_sparse_shared(staar_ctx *ctx, int64_t n, int64_t q, const double *Sv, const uint64_t *Sr, const uint64_t *Sc,
+                         const double *SX, const double *cov, const double *res);
 // packed_dense.cu — dense-GRM score test on resident packed columns
 int packed_score_dense(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
                        double *d_AF, double *d_MAF, double *d_Score, double *d_Score_se, double *d_pl, double *d_Est,

@@ -362,6 +362,8 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
     STAAR_CUDA(cudaMalloc(&ns.Yfrag, frag.size()));
     STAAR_CUDA(cudaMalloc(&ns.col_scale, sizeof(double) * kColsPerSlice));
     STAAR_CUDA(cudaMalloc(&ns.col_total, sizeof(long long) * 2 * kColsPerSlice));
+    ns.reg(&ns.Yfrag, frag.size()); ns.reg(&ns.col_scale, sizeof(double) * kColsPerSlice);
+    ns.reg(&ns.col_total, sizeof(long long) * 2 * kColsPerSlice);
     STAAR_CUDA(cudaMemcpyAsync(ns.col_total, tot.data(), sizeof(long long) * tot.size(), cudaMemcpyHostToDevice, ctx->stream));
     STAAR_CUDA(cudaMemcpyAsync(ns.Yfrag, frag.data(), frag.size(), cudaMemcpyHostToDevice, ctx->stream));
     STAAR_CUDA(cudaMemcpyAsync(ns.col_scale, scale.data(), sizeof(double) * kColsPerSlice, cudaMemcpyHostToDevice, ctx->stream));

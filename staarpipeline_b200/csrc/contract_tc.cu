@@ -315,6 +315,7 @@ int build_tc_operand(staar_ctx *ctx, const int8_t *digits /* n x kColsPerSlice x
     cudaFree(ns.Ytc);
     ns.Ytc = nullptr;
     STAAR_CUDA(cudaMalloc(&ns.Ytc, img.size()));
+    ns.reg(&ns.Ytc, img.size());
     STAAR_CUDA(cudaMemcpyAsync(ns.Ytc, img.data(), img.size(), cudaMemcpyHostToDevice, ctx->stream));
     STAAR_CUDA(cudaStreamSynchronize(ctx->stream));
     return STAAR_OK;

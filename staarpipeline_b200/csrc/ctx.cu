@@ -125,6 +125,7 @@ template <typename T> int upload_vec(staar_ctx *ctx, T **dst, const std::vector<
 {
     const size_t count = std::max<size_t>(src.size(), 1);
     STAAR_CUDA(cudaMalloc(reinterpret_cast<void **>(dst), sizeof(T) * count));
+    ctx->ns.reg(dst, sizeof(T) * count);
     if (!src.empty())
         STAAR_CUDA(cudaMemcpyAsync(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice, ctx->stream));
     return STAAR_OK;
@@ -487,9 +488,11 @@ int nullmodel_sparse_upload(staar_ctx *ctx, int64_t n, int64_t q, const double *
     STAAR_TRY(upload_vec(ctx, &ns.Y, Y));
     STAAR_CUDA(cudaMalloc(&ns.SX, sizeof(double) * std::max<int64_t>(n * q, 1)));
     STAAR_CUDA(cudaMalloc(&ns.cov, sizeof(double) * std::max<int64_t>(q * q, 1)));
+    ns.reg(&ns.SX, sizeof(double) * std::max<int64_t>(n * q, 1));
+    ns.reg(&ns.cov, sizeof(double) * std::max<int64_t>(q * q, 1));
     STAAR_CUDA(cudaMemcpyAsync(ns.SX, SX, sizeof(double) * n * q, cudaMemcpyHostToDevice, st));
     STAAR_CUDA(cudaMemcpyAsync(ns.cov, cov, sizeof(double) * q * q, cudaMemcpyHostToDevice, st));
-    if (permute) STAAR_CUDA(cudaMalloc(&ns.Yp, sizeof(double) * (size_t)n * ldY));
+    if (permute) { STAAR_CUDA(cudaMalloc(&ns.Yp, sizeof(double) * (size_t)n * ldY)); ns.reg(&ns.Yp, sizeof(double) * (size_t)n * ldY); }
     else ns.Yp = ns.Y;
     STAAR_CUDA(cudaStreamSynchronize(st));
     ns.fingerprint = fp; ns.res_fingerprint = res_fp;
@@ -510,6 +513,35 @@ int refresh_permuted_Y(staar_ctx *ctx, const double *hY)
     for (int64_t pz = 0; pz < n; pz++) memcpy(&Yp[(size_t)pz * ldY], hY + (size_t)ns.h_perm[pz] * ldY, sizeof(double) * ldY);
     STAAR_CUDA(cudaMemcpyAsync(ns.Yp, Yp.data(), sizeof(double) * Yp.size(), cudaMemcpyHostToDevice, ctx->stream));
     STAAR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return STAAR_OK;
+}
+
+// Replica of src's resident sparse null model on dst's device (same process): every registered device array is copied
+// device to device; nothing of the host-side build (families, sample order, tables, digit slicing) is repeated.
+int nullmodel_sparse_clone(staar_ctx *dst, const staar_ctx *src)
+{
+    STAAR_CUDA(cudaSetDevice(dst->device));
+    dst->ns.release();
+    const NullSparse &s = src->ns;
+    if (!s.set) { set_error("nullmodel clone: the source context holds no sparse null model"); return STAAR_ERR_STATE; }
+    NullSparse &d = dst->ns;
+    d = s;                                               // scalars, host vectors; pointers are replaced below
+    d.row_ptr = nullptr; d.col = nullptr; d.val = nullptr; d.diag = nullptr; d.perm = nullptr; d.inv_perm = nullptr;
+    d.Yp = nullptr; d.kmask = nullptr; d.wdesc = nullptr; d.xterms = nullptr; d.lut = nullptr; d.lutf = nullptr;
+    d.sinfo_p = nullptr; d.diag_p = nullptr; d.off_ent_p = nullptr; d.relmask = nullptr; d.rel = nullptr; d.up_ent = nullptr;
+    d.SX = nullptr; d.Y = nullptr; d.cov = nullptr; d.Yfrag = nullptr; d.Ytc = nullptr; d.col_scale = nullptr; d.col_total = nullptr;
+    d.set = false;
+    for (const auto &a : s.arrays) {
+        void **slot = reinterpret_cast<void **>(reinterpret_cast<char *>(&d) + a.first);
+        void *const from = *reinterpret_cast<void *const *>(reinterpret_cast<const char *>(&s) + a.first);
+        if (!from) continue;
+        STAAR_CUDA(cudaMalloc(slot, a.second));
+        STAAR_CUDA(cudaMemcpyPeerAsync(*slot, dst->device, from, src->device, a.second, dst->stream));
+    }
+    if (!s.permuted) d.Yp = d.Y;
+    STAAR_CUDA(cudaStreamSynchronize(dst->stream));
+    d.owned = true;
+    d.set = true;
     return STAAR_OK;
 }
 

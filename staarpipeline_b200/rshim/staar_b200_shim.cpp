@@ -13,8 +13,10 @@
 // [[Rcpp::depends(RcppArmadillo)]]
 // [[Rcpp::interfaces(r, cpp)]]
 #include <RcppArmadillo.h>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
+#include <vector>
 #include "staar_b200.h"
 
 using namespace Rcpp;
@@ -31,6 +33,30 @@ staar_ctx *ctx()
             throw std::runtime_error(std::string("staar_b200: ") + staar_last_error());
     }
     return c;
+}
+
+// STAAR_B200_DEVICES="0,1,2,3": several GPUs of the box behind one handle (staar_b200.h section C); the columns of
+// matrix_flip_* and of the dense-G Individual_Score_Test are then sharded over the devices, each moving its share
+// over its own PCIe link.  NULL when the variable is unset or names a single device.
+staar_multi *multi()
+{
+    static staar_multi *m = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char *list = std::getenv("STAAR_B200_DEVICES");
+        std::vector<int> dev;
+        for (const char *c = list; c && *c;) {
+            char *end = nullptr;
+            const long v = std::strtol(c, &end, 10);
+            if (end == c) break;
+            dev.push_back((int)v);
+            c = (*end == ',') ? end + 1 : end;
+        }
+        if (dev.size() > 1 && staar_multi_create(dev.data(), (int)dev.size(), &m) != STAAR_OK)
+            throw std::runtime_error(std::string("staar_b200: ") + staar_last_error());
+    }
+    return m;
 }
 
 // non-zero status -> C++ exception -> R error through BEGIN_RCPP/END_RCPP (src/RcppExports.cpp:20,30)
@@ -64,7 +90,8 @@ List matrix_flip_mean(arma::mat G)
 {
     arma::vec AF, MAF;
     AF.zeros(G.n_cols); MAF.zeros(G.n_cols);
-    check(staar_matrix_flip_mean(ctx(), G.memptr(), G.n_rows, G.n_cols, G.memptr(), AF.memptr(), MAF.memptr()));
+    if (staar_multi *m = multi()) check(staar_multi_matrix_flip_mean(m, G.memptr(), G.n_rows, G.n_cols, G.memptr(), AF.memptr(), MAF.memptr()));
+    else check(staar_matrix_flip_mean(ctx(), G.memptr(), G.n_rows, G.n_cols, G.memptr(), AF.memptr(), MAF.memptr()));
     return List::create(Named("Geno") = G, Named("AF") = AF, Named("MAF") = MAF);
 }
 
@@ -73,7 +100,8 @@ List matrix_flip_minor(arma::mat G)
 {
     arma::vec AF, MAF;
     AF.zeros(G.n_cols); MAF.zeros(G.n_cols);
-    check(staar_matrix_flip_minor(ctx(), G.memptr(), G.n_rows, G.n_cols, G.memptr(), AF.memptr(), MAF.memptr()));
+    if (staar_multi *m = multi()) check(staar_multi_matrix_flip_minor(m, G.memptr(), G.n_rows, G.n_cols, G.memptr(), AF.memptr(), MAF.memptr()));
+    else check(staar_matrix_flip_minor(ctx(), G.memptr(), G.n_rows, G.n_cols, G.memptr(), AF.memptr(), MAF.memptr()));
     return List::create(Named("Geno") = G, Named("AF") = AF, Named("MAF") = MAF);
 }
 
@@ -81,6 +109,12 @@ List matrix_flip_minor(arma::mat G)
 List Individual_Score_Test(arma::mat G, arma::sp_mat Sigma_i, arma::mat Sigma_iX, arma::mat cov, arma::vec residuals)
 {
     Out5 o(G.n_cols);
+    if (staar_multi *m = multi())
+        check(staar_multi_individual_score_test(m, G.memptr(), G.n_rows, G.n_cols, vals(Sigma_i), rows(Sigma_i), cols(Sigma_i),
+                                                Sigma_iX.memptr(), Sigma_iX.n_cols, cov.memptr(), residuals.memptr(),
+                                                o.Score.memptr(), o.Score_se.memptr(), o.pvalue_log.memptr(), o.Est.memptr(),
+                                                o.Est_se.memptr()));
+    else
     check(staar_individual_score_test(ctx(), G.memptr(), G.n_rows, G.n_cols, vals(Sigma_i), rows(Sigma_i), cols(Sigma_i),
                                       Sigma_iX.memptr(), Sigma_iX.n_cols, cov.memptr(), residuals.memptr(),
                                       o.Score.memptr(), o.Score_se.memptr(), o.pvalue_log.memptr(), o.Est.memptr(),
