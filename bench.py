@@ -293,19 +293,28 @@ def run_ours(args):
         traffic = per_variant * V
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"bound": "hbm", "kernel": {"scan": "scan_block_kernel", "contract": "contract_tc_kernel",
-                                           "finalize": "finalize_packed_kernel"}[dominant],
+    fused = ctx.last_packed_path_was_fused
+    names = ({"scan": "scan_block_kernel (redo list)", "contract": "fused_tc_kernel", "finalize": "fused_finalize_kernel"} if fused
+             else {"scan": "scan_block_kernel", "contract": "contract_tc_kernel", "finalize": "finalize_packed_kernel"})
+    roofline = {"bound": "hbm", "kernel": names[dominant],
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "stage_ms": stage_ms, "step_frac": stage_ms[dominant] / sum(stage_ms.values()),
                 "whole_step": {"achieved": V * bytes_per_variant / (ms_total / args.steps / 1e3) / 1e9,
                                "frac": V * bytes_per_variant / (ms_total / args.steps / 1e3) / 1e9 / hbm_peak}}
-    # secondary roof: the INT8 tensor pipe the contraction runs on (tcgen05.mma.kind::i8).  No measured tcgen05 int8
-    # peak exists for this pool; the denominator is the NOMINAL dense figure (4.5 POP/s, same as fp8), stated as such.
+    # secondary roof: the INT8 tensor pipe the contraction runs on (tcgen05.mma.kind::i8).  Denominator = the rate
+    # measured on this pool's B200 for the contraction's instruction shape (M = 128, N = 112, K = 32, A in TMEM;
+    # tools/pipe_peaks.cu -> profiles/r02_pipe_peaks.json); nominal 4.5 POP/s only if that file is missing.
     ops = 2.0 * V * n * 112                             # 7 digit slices x 16 columns per genotype
+    int8_peak, int8_src = 4500.0, "nominal dense int8/fp8 (B200_PROFILING.md)"
+    try:
+        int8_peak = float(json.load(open(os.path.join(ROOT, "profiles", "r02_pipe_peaks.json")))["tcgen05_i8_ts_n112_tops"])
+        int8_src = "measured: tcgen05.mma kind::i8, M=128 N=112 K=32, A in TMEM (profiles/r02_pipe_peaks.json)"
+    except Exception:  # noqa: BLE001
+        pass
     roofline["int8_tensor"] = {"kernel": "contract_tc_kernel", "achieved_tops": ops / (stage_ms["contract"] / 1e3) / 1e12,
-                               "peak_tops": 4500.0, "peak_source": "nominal dense int8/fp8 (B200_PROFILING.md)",
-                               "frac": ops / (stage_ms["contract"] / 1e3) / 1e12 / 4500.0}
+                               "peak_tops": int8_peak, "peak_source": int8_src,
+                               "frac": ops / (stage_ms["contract"] / 1e3) / 1e12 / int8_peak}
 
     # ---- end to end: host FP64 dosage chunks (what the Rcpp boundary delivers) through the C-ABI chunk driver
     e2e = None

@@ -251,6 +251,21 @@ int staar_packed_cond(staar_ctx *ctx, const uint8_t *d_packed, size_t stride_byt
                       int64_t n_sel, int impute, const double *X_adj, int64_t m, double *Score, double *Score_se,
                       double *pvalue_log, double *Est, double *Est_se);
 
+/* Conditional analysis of ONE GROUP of tested variants that share their known loci, refit included (SURVEY §8f f3;
+ * R/Individual_Analysis_cond.R:183-212 does, per tested variant, lm(scaled.residuals ~ genotype_adj + X - 1)
+ * ["optimal", method = 0] or lm(scaled.residuals ~ genotype_adj) [intercept, method = 1], takes the fit's residuals and
+ * X_adj = model.matrix, and calls Individual_Score_Test_cond with p = 1).  Here the known variants (d_known, indices of
+ * resident columns) are decoded, flipped and imputed on the device into X_adj, the least-squares refit runs on the
+ * device (Gram contraction, m x m Cholesky of the column-scaled normal equations on the host, two rounds of iterative
+ * refinement), and all n_tested variants (d_tested) are tested in one call.  The null model set by
+ * staar_nullmodel_set_sparse* must hold the ORIGINAL scaled residuals.  X: host n x qx covariates (method 0; ignored
+ * for method 1).  coef_out (optional): the m = n_known + qx (or 1 + n_known) fitted coefficients.  The caller groups
+ * tested variants by identical known-loci sets (the +-1 Mb windows of R/Individual_Analysis_cond.R:185). */
+int staar_packed_cond_refit(staar_ctx *ctx, const uint8_t *d_packed, size_t stride_bytes, int64_t n, const int64_t *d_tested,
+                            int64_t n_tested, const int64_t *d_known, int64_t n_known, const double *X, int64_t qx, int method,
+                            int impute, double *Score, double *Score_se, double *pvalue_log, double *Est, double *Est_se,
+                            double *coef_out);
+
 /* Per-kernel device times of the LAST staar_packed_score_device call, measured with CUDA events on the context
  * stream when profiling is on: ms[0] = scan (K1+K3), ms[1] = contraction (K2), ms[2] = finalize (K5).
  * Used by bench.py for the live roofline figure; off by default (no events recorded). */

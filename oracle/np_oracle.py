@@ -71,3 +71,19 @@ def multi_from_cov(U, Cov, k, logtail):
             continue
         pl[i] = -logtail(float(U[idx] @ np.linalg.inv(C) @ U[idx]), float(k))
     return {"Score": U, "pvalue_log": pl}
+
+
+def conditional_refit(residuals, G_known, X, method: str = "optimal"):
+    """The refit R does per tested variant before Individual_Score_Test_cond (R/Individual_Analysis_cond.R:187-197):
+    lm(scaled.residuals ~ genotype_adj + X - 1) ("optimal") or lm(scaled.residuals ~ genotype_adj) (intercept);
+    returns (X_adj = model.matrix, residuals of the fit, coefficients).  lm() solves by Householder QR; numpy's
+    lstsq (SVD) is the same least-squares solution to rounding for a full-rank design."""
+    residuals = np.asarray(residuals, dtype=np.float64).ravel()
+    G_known = np.asarray(G_known, dtype=np.float64).reshape(residuals.size, -1)
+    if method == "optimal":
+        A = np.column_stack([G_known, np.asarray(X, dtype=np.float64)])
+    else:
+        A = np.column_stack([np.ones(residuals.size), G_known])
+    Q, R = np.linalg.qr(A)                                    # Householder QR, as lm()
+    coef = np.linalg.solve(R, Q.T @ residuals)
+    return np.asfortranarray(A), residuals - A @ coef, coef

@@ -405,6 +405,23 @@ class Context:
                    C.c_int64(n_sel), C.c_int(impute), _p(A), C.c_int64(A.shape[1]), *po)
         return self._pack5(o)
 
+    def packed_cond_refit(self, d_packed: int, stride: int, n: int, d_tested: int, n_tested: int, d_known: int, n_known: int,
+                          impute: int, X=None, method: str = "optimal"):
+        """conditional test of a group of resident variants sharing their known loci, least-squares refit on the device"""
+        qx = 0
+        Xp = None
+        if method == "optimal":
+            Xf = _f(X); qx = Xf.shape[1]; Xp = _p(Xf)
+        o, po = self._out5(n_tested)
+        m = n_known + qx if method == "optimal" else 1 + n_known
+        coef = np.zeros(m)
+        self._call("staar_packed_cond_refit", C.c_void_p(d_packed), C.c_size_t(stride), C.c_int64(n), C.c_void_p(d_tested),
+                   C.c_int64(n_tested), C.c_void_p(d_known), C.c_int64(n_known), Xp, C.c_int64(qx),
+                   C.c_int(0 if method == "optimal" else 1), C.c_int(impute), *po, _p(coef))
+        r = self._pack5(o)
+        r["coef"] = coef
+        return r
+
     def set_nullmodel_spa(self, XW, XXWX_inv, residuals, muhat):
         XWm, XXi = _f(XW), _f(XXWX_inv)
         q, n = XWm.shape

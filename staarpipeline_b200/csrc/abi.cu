@@ -54,7 +54,12 @@ static int stage_init(staar_ctx *ctx)
 
 static void parallel_memcpy(void *dst, const void *src, size_t bytes)
 {
-    static const unsigned nthreads = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    // copy threads: the ranks of a box share its cores (torchrun sets LOCAL_WORLD_SIZE); STAAR_B200_STAGE_THREADS overrides
+    static const unsigned nthreads = [] {
+        if (const char *e = getenv("STAAR_B200_STAGE_THREADS")) return (unsigned)std::max(1, atoi(e));
+        const unsigned ranks = getenv("LOCAL_WORLD_SIZE") ? (unsigned)std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1u;
+        return std::min(16u, std::max(1u, std::thread::hardware_concurrency() / ranks));
+    }();
     const size_t piece = (bytes / nthreads + 4095) & ~(size_t)4095;
     std::vector<std::thread> th;
     for (unsigned t = 1; t < nthreads; t++) {
@@ -211,7 +216,10 @@ int host_inv(std::vector<double> &A, int k, std::vector<double> &inv)
 struct CondOperands { int m = 0; double *dM = nullptr, *dMQM = nullptr; const double *dY = nullptr; int ldY = 0, colA0 = 0, colPA0 = 0; };
 
 // PX_adj, (X_adj'X_adj)^-1 and M (PX_adj'X_adj) M on the device / m x m host algebra; Ycond = [res|SX|A|PA]
-int prepare_cond(staar_ctx *ctx, const double *X_adj, int64_t m, const double *cov_host, CondOperands &co)
+// X_adj == nullptr: the adjustment matrix is already in place on the device (first n*m doubles of ctx->cond, see
+// staar_packed_cond_refit) and d_res holds the refit residual vector; nothing is cached across calls in that mode.
+int prepare_cond(staar_ctx *ctx, const double *X_adj, int64_t m, const double *cov_host, CondOperands &co,
+                 const double *d_res = nullptr)
 {
     NullSparse &ns = ctx->ns;
     const int64_t n = ns.n, q = ns.q;
@@ -219,10 +227,13 @@ int prepare_cond(staar_ctx *ctx, const double *X_adj, int64_t m, const double *c
     // aux layout: A (n*m) | PA (n*m) | Ycond (n*ldc) | Y2 (n*ld2) | T1 (q*m) | M (m*m) | MQM (m*m)
     const size_t need = sizeof(double) * ((size_t)2 * n * m + (size_t)n * ldc + (size_t)n * ld2 + q * m + 2 * m * m);
     // same X_adj, same null model, same residual vector as the previous call: everything below is still on the device
-    const uint64_t key = hash_bytes(X_adj, sizeof(double) * (size_t)n * m, 31) ^ ns.fingerprint ^ (ns.res_fingerprint * 3) ^ (uint64_t)m;
+    const uint64_t key = X_adj ? hash_bytes(X_adj, sizeof(double) * (size_t)n * m, 31) ^ ns.fingerprint ^ (ns.res_fingerprint * 3) ^ (uint64_t)m : 0;
     const void *before = ctx->cond.p;
     STAAR_TRY(ctx->cond.reserve(need));
-    if (ctx->cond.p != before) ctx->cond_key = 0;                     // buffer grew: contents are gone
+    if (ctx->cond.p != before) {
+        if (!X_adj) { set_error("internal: conditional scratch moved under a device-resident X_adj"); return STAAR_ERR_STATE; }
+        ctx->cond_key = 0;                                            // buffer grew: contents are gone
+    }
     double *dA = ctx->cond.as<double>(), *dPA = dA + n * m, *dYc = dPA + n * m, *dY2 = dYc + (size_t)n * ldc;
     double *dT1 = dY2 + (size_t)n * ld2, *dM = dT1 + q * m, *dMQM = dM + m * m;
     if (ctx->cond_key == key && ctx->cond_m == (int)m && ctx->cond_ld == ldc && key != 0) {
@@ -230,7 +241,7 @@ int prepare_cond(staar_ctx *ctx, const double *X_adj, int64_t m, const double *c
         return STAAR_OK;
     }
     ctx->cond_key = 0;
-    STAAR_TRY(h2d(ctx, dA, X_adj, sizeof(double) * n * m));
+    if (X_adj) STAAR_TRY(h2d(ctx, dA, X_adj, sizeof(double) * n * m));
     // trans(Sigma_iX) * X_adj  (q x m): contraction of the m columns of A against Y = [res | SX]
     STAAR_TRY(ctx->L.reserve(sizeof(double) * (size_t)m * std::max(ns.ldY, ld2)));
     STAAR_TRY(launch_contract_dense(ctx, dA, n, m, ns.Y, ns.ldY, (int)(1 + q), ctx->L.as<double>(), ns.ldY));
@@ -277,10 +288,13 @@ int prepare_cond(staar_ctx *ctx, const double *X_adj, int64_t m, const double *c
     STAAR_TRY(h2d(ctx, dM, M.data(), sizeof(double) * m * m));
     STAAR_TRY(h2d(ctx, dMQM, MQM.data(), sizeof(double) * m * m));
     // Ycond: column 0 is the refit residual vector of THIS call (already in ns.Y column 0 via ensure_sparse)
-    STAAR_TRY(ctx->tmp.reserve(sizeof(double) * n));
-    STAAR_CUDA(cudaMemcpy2DAsync(ctx->tmp.p, sizeof(double), ns.Y, sizeof(double) * ns.ldY, sizeof(double), n,
-                                 cudaMemcpyDeviceToDevice, ctx->stream));
-    STAAR_TRY(launch_build_Y(ctx, n, ldc, ctx->tmp.as<double>(), ns.SX, (int)q, dA, dPA, (int)m, dYc));
+    if (!d_res) {
+        STAAR_TRY(ctx->tmp.reserve(sizeof(double) * n));
+        STAAR_CUDA(cudaMemcpy2DAsync(ctx->tmp.p, sizeof(double), ns.Y, sizeof(double) * ns.ldY, sizeof(double), n,
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+        d_res = ctx->tmp.as<double>();
+    }
+    STAAR_TRY(launch_build_Y(ctx, n, ldc, d_res, ns.SX, (int)q, dA, dPA, (int)m, dYc));
     STAAR_TRY(sync(ctx));       // host vectors above go out of scope
     ctx->cond_key = key; ctx->cond_m = (int)m; ctx->cond_ld = ldc;
     co.m = (int)m; co.dM = dM; co.dMQM = dMQM; co.dY = dYc; co.ldY = ldc; co.colA0 = (int)(1 + q); co.colPA0 = (int)(1 + q + m);
@@ -1101,6 +1115,115 @@ int staar_packed_cond(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, in
     STAAR_TRY(launch_decode_selected(ctx, d_packed, stride, n, reinterpret_cast<const long long *>(d_variant), n_sel, impute,
                                      ns.permuted ? ns.perm : nullptr, ctx->G.as<double>(), nullptr, nullptr));
     return run_sparse_family(ctx, n, n_sel, 0, &co, Score, Score_se, pl, Est, Est_se);
+}
+
+// Conditional analysis of one group of tested variants that share their known loci, refit included
+// (R/Individual_Analysis_cond.R:183-212: per tested variant, lm(scaled.residuals ~ genotype_adj + X - 1) — or
+// ~ genotype_adj with an intercept — gives the refit residuals and X_adj = model.matrix, then a p = 1 call of
+// Individual_Score_Test_cond).  Everything runs on resident columns: the known variants are decoded (flipped / imputed
+// as matrix_flip_* does) into X_adj on the device, the least-squares refit is solved from the column-scaled Gram matrix
+// (device contraction, m x m Cholesky on the host) with two rounds of iterative refinement — the accuracy of a QR
+// solve — and the refit residuals never leave the device.
+int staar_packed_cond_refit(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, const int64_t *d_tested,
+                            int64_t n_tested, const int64_t *d_known, int64_t n_known, const double *X, int64_t qx, int method,
+                            int impute, double *Score, double *Score_se, double *pl, double *Est, double *Est_se,
+                            double *coef_out)
+{
+    CHECK_CTX(ctx);
+    STAAR_TRY(check_dims(n, n_tested));
+    NullSparse &ns = ctx->ns;
+    if (!ns.set || ns.n != n) { set_error("conditional refit: call staar_nullmodel_set_sparse (with the null model's scaled residuals) for n = %lld first", (long long)n); return STAAR_ERR_STATE; }
+    if (n_known < 1 || !d_known) { set_error("conditional refit: no known variants"); return STAAR_ERR_ARG; }
+    if (method != 0 && method != 1) { set_error("conditional refit: method must be 0 (optimal) or 1 (naive)"); return STAAR_ERR_ARG; }
+    if (method == 0 && (!X || qx < 1)) { set_error("conditional refit: method 'optimal' needs the covariate matrix X"); return STAAR_ERR_ARG; }
+    if (stride % 16 != 0 || stride < (size_t)((n + 3) / 4)) { set_error("packed stride must be a multiple of 16 and >= ceil(n/4)"); return STAAR_ERR_ARG; }
+    if (n_tested == 0) return STAAR_OK;
+    const int64_t q = ns.q;
+    const int64_t m = method == 0 ? n_known + qx : 1 + n_known;            // model.matrix: [G_known | X] or [1 | G_known]
+    // the scratch layout of prepare_cond: X_adj first
+    const int ldc = (int)((1 + q + 2 * m + 7) / 8 * 8), ld2 = (int)((1 + 2 * m + 7) / 8 * 8);
+    STAAR_TRY(ctx->cond.reserve(sizeof(double) * ((size_t)2 * n * m + (size_t)n * ldc + (size_t)n * ld2 + q * m + 2 * m * m)));
+    ctx->cond_key = 0;
+    double *dA = ctx->cond.as<double>();
+    double *dG_known = method == 0 ? dA : dA + n;
+    STAAR_TRY(launch_decode_selected(ctx, d_packed, stride, n, reinterpret_cast<const long long *>(d_known), n_known, impute,
+                                     ns.permuted ? ns.perm : nullptr, dG_known, nullptr, nullptr));
+    if (method == 0) {
+        STAAR_TRY(h2d(ctx, dA + (size_t)n * n_known, X, sizeof(double) * (size_t)n * qx));
+    } else {
+        std::vector<double> ones((size_t)n, 1.0);
+        STAAR_TRY(h2d(ctx, dA, ones.data(), sizeof(double) * (size_t)n));
+        STAAR_TRY(sync(ctx));
+    }
+    // ---- least squares: Gram matrix and X_adj' r by one contraction against [r | X_adj]
+    // (pk2, not tmp2: the dense contraction keeps its split-K partial sums in tmp2)
+    STAAR_TRY(ctx->pk2.reserve(sizeof(double) * ((size_t)3 * std::max<int64_t>(n, 64) + (size_t)n * ld2 + 64)));
+    double *d_r = ctx->pk2.as<double>(), *d_r1 = d_r + n, *d_coef = d_r1 + n, *dY2 = d_r + 3 * (size_t)std::max<int64_t>(n, 64);     // r | r1 | coef (<= 64) | [r | X_adj]
+    if (m > 64) { set_error("conditional refit: at most 64 adjustment columns"); return STAAR_ERR_ARG; }
+    STAAR_CUDA(cudaMemcpy2DAsync(d_r, sizeof(double), ns.Y, sizeof(double) * ns.ldY, sizeof(double), n, cudaMemcpyDeviceToDevice, ctx->stream));
+    STAAR_TRY(launch_build_Y(ctx, n, ld2, d_r, nullptr, 0, dA, nullptr, (int)m, dY2));
+    STAAR_TRY(ctx->L.reserve(sizeof(double) * (size_t)m * std::max<int>(ld2, 8)));
+    STAAR_TRY(launch_contract_dense(ctx, dA, n, m, dY2, ld2, (int)(1 + m), ctx->L.as<double>(), ld2));
+    std::vector<double> L2((size_t)m * ld2);
+    STAAR_TRY(d2h(ctx, L2.data(), ctx->L.p, sizeof(double) * L2.size()));
+    STAAR_TRY(sync(ctx));
+    std::vector<double> scale((size_t)m), R((size_t)m * m), b((size_t)m), coef((size_t)m, 0.0), delta((size_t)m);
+    for (int64_t a = 0; a < m; a++) {
+        const double d = L2[(size_t)a * ld2 + 1 + a];
+        if (!(d > 0.0)) { set_error("conditional refit: an adjustment column is identically zero (singular design)"); return STAAR_ERR_SINGULAR; }
+        scale[a] = 1.0 / sqrt(d);
+    }
+    for (int64_t a = 0; a < m; a++)                                       // Cholesky of the scaled Gram matrix (lower, in R)
+        for (int64_t c = 0; c <= a; c++) {
+            double sacc = L2[(size_t)a * ld2 + 1 + c] * scale[a] * scale[c];
+            for (int64_t k2 = 0; k2 < c; k2++) sacc -= R[a + k2 * m] * R[c + k2 * m];
+            if (a == c) {
+                if (!(sacc > 1e-13)) { set_error("conditional refit: the design [known variants | covariates] is rank deficient"); return STAAR_ERR_SINGULAR; }
+                R[a + a * m] = sqrt(sacc);
+            } else {
+                R[a + c * m] = sacc / R[c + c * m];
+            }
+        }
+    auto solve = [&](const std::vector<double> &rhs, std::vector<double> &x) {     // (D G D) y = D rhs, x = D y
+        std::vector<double> y((size_t)m);
+        for (int64_t a = 0; a < m; a++) {
+            double sacc = rhs[a] * scale[a];
+            for (int64_t k2 = 0; k2 < a; k2++) sacc -= R[a + k2 * m] * y[k2];
+            y[a] = sacc / R[a + a * m];
+        }
+        for (int64_t a = m - 1; a >= 0; a--) {
+            double sacc = y[a];
+            for (int64_t k2 = a + 1; k2 < m; k2++) sacc -= R[k2 + a * m] * y[k2];
+            y[a] = sacc / R[a + a * m];
+        }
+        for (int64_t a = 0; a < m; a++) x[a] = y[a] * scale[a];
+    };
+    for (int64_t a = 0; a < m; a++) b[a] = L2[(size_t)a * ld2];
+    for (int round = 0; round < 3; round++) {                             // solve, then refine twice on the true residual
+        solve(b, delta);
+        for (int64_t a = 0; a < m; a++) coef[a] += delta[a];
+        STAAR_TRY(h2d(ctx, d_coef, coef.data(), sizeof(double) * m));
+        STAAR_TRY(launch_residual_update(ctx, n, dA, (int)m, d_coef, d_r, d_r1));     // r1 = r - X_adj coef
+        if (round == 2) break;
+        STAAR_TRY(launch_build_Y(ctx, n, 8, d_r1, nullptr, 0, nullptr, nullptr, 0, dY2));
+        STAAR_TRY(launch_contract_dense(ctx, dA, n, m, dY2, 8, 1, ctx->L.as<double>(), 8));
+        std::vector<double> L1((size_t)m * 8);
+        STAAR_TRY(d2h(ctx, L1.data(), ctx->L.p, sizeof(double) * L1.size()));
+        STAAR_TRY(sync(ctx));
+        for (int64_t a = 0; a < m; a++) b[a] = L1[(size_t)a * 8];
+    }
+    STAAR_TRY(sync(ctx));
+    if (coef_out) memcpy(coef_out, coef.data(), sizeof(double) * m);
+    // ---- the conditional test with X_adj and the refit residuals in place
+    std::vector<double> cov_host((size_t)q * q);
+    STAAR_TRY(d2h(ctx, cov_host.data(), ns.cov, sizeof(double) * cov_host.size()));
+    STAAR_TRY(sync(ctx));
+    CondOperands co;
+    STAAR_TRY(prepare_cond(ctx, nullptr, m, cov_host.data(), co, d_r1));
+    STAAR_TRY(ctx->G.reserve(sizeof(double) * (size_t)n * n_tested));
+    STAAR_TRY(launch_decode_selected(ctx, d_packed, stride, n, reinterpret_cast<const long long *>(d_tested), n_tested, impute,
+                                     ns.permuted ? ns.perm : nullptr, ctx->G.as<double>(), nullptr, nullptr));
+    return run_sparse_family(ctx, n, n_tested, 0, &co, Score, Score_se, pl, Est, Est_se);
 }
 
 int staar_nullmodel_sample_order(staar_ctx *ctx, int64_t n, int32_t *order)

@@ -299,6 +299,7 @@ int launch_csc_to_dense(staar_ctx *ctx, const double *d_val, const int64_t *d_ro
 int launch_build_Y(staar_ctx *ctx, int64_t n, int ldY, const double *d_res, const double *d_SX, int q, const double *dA,
                    const double *dPA, int m, double *dY);
 int launch_set_Y_col0(staar_ctx *ctx, int64_t n, int ldY, const double *d_res, double *dY);
+int launch_residual_update(staar_ctx *ctx, int64_t n, const double *dA, int m, const double *d_coef, const double *d_r, double *d_out);
 int launch_px_adj(staar_ctx *ctx, int64_t n, const int64_t *row_ptr, const int32_t *col, const double *val,
                   const double *dA, int m, const double *dSX, int q, const double *dT1, double *dOut);
 int launch_fill_pairs(staar_ctx *ctx, int64_t pp, int k, int32_t *d_colA, int32_t *d_colB);

@@ -36,8 +36,22 @@ __global__ void build_Y_kernel(int64_t n, int ldY, const double *__restrict__ re
         if (c == 0) v = res ? res[j] : 0.0;
         else if (c <= q) v = SX[j + (int64_t)(c - 1) * n];
         else if (c <= q + m) v = A[j + (int64_t)(c - 1 - q) * n];
-        else if (c <= q + 2 * m) v = PA[j + (int64_t)(c - 1 - q - m) * n];
+        else if (c <= q + 2 * m) v = PA ? PA[j + (int64_t)(c - 1 - q - m) * n] : 0.0;
         Y[idx] = v;
+    }
+}
+
+// out = r - A coef  (A n x m column-major, m <= 64): the residuals of a least-squares fit (conditional refit)
+__global__ void residual_update_kernel(int64_t n, const double *__restrict__ A, int m, const double *__restrict__ coef,
+                                       const double *__restrict__ r, double *__restrict__ out)
+{
+    __shared__ double c[64];
+    if (threadIdx.x < m) c[threadIdx.x] = coef[threadIdx.x];
+    __syncthreads();
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int a = 0; a < m; a++) s += A[j + (int64_t)a * n] * c[a];
+        out[j] = r[j] - s;
     }
 }
 
@@ -172,6 +186,14 @@ int launch_build_Y(staar_ctx *ctx, int64_t n, int ldY, const double *d_res, cons
                    const double *dPA, int m, double *dY)
 {
     build_Y_kernel<<<grid_for(ctx, n * ldY, 256), 256, 0, ctx->stream>>>(n, ldY, d_res, d_SX, q, dA, dPA, m, dY);
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+int launch_residual_update(staar_ctx *ctx, int64_t n, const double *dA, int m, const double *d_coef, const double *d_r, double *d_out)
+{
+    residual_update_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(n, dA, m, d_coef, d_r, d_out);
     ctx->launches++;
     STAAR_CUDA(cudaGetLastError());
     return STAAR_OK;

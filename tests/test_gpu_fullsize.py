@@ -238,3 +238,35 @@ def test_cond_multi_more_shapes(gpu_ctx, oracle, n, p, k, q, n_known, seed):
     want = oracle.Individual_Score_Test_cond_multi(**c)
     assert rel_err(got["Score"], want["Score"], score_floor(c["G"], c["residuals"])) < 1e-10
     assert np.all(np.abs(got["pvalue_log"] - want["pvalue_log"]) <= 1e-8 * np.maximum(1.0, np.abs(want["pvalue_log"])))
+
+
+@pytest.mark.parametrize("n,n_known,method", [(3000, 4, "optimal"), (3000, 3, "naive"), (100_000, 10, "optimal")])
+def test_conditional_refit_on_device_vs_lm(gpu_ctx, oracle, n, n_known, method):
+    """f3: the refit of R/Individual_Analysis_cond.R:187-197 on the device (known variants decoded from resident columns,
+    least squares by scaled normal equations + refinement) followed by the conditional test of a whole group, against
+    lm()-equivalent QR least squares (oracle/np_oracle.py) + Individual_Score_Test_cond of the oracle"""
+    import torch
+    from oracle import np_oracle
+    from staarpipeline_b200 import api, synth
+    q, p = 13, 40
+    nm = synth.nullmodel_sparse_grm(n, seed=n % 91, q=q, shuffle=True)
+    codes, G0, packed = _codes(n, 3000, p)
+    stride = packed.shape[1]
+    fl = oracle.matrix_flip_mean(G0)
+    # known loci: the most common variants of the block (a rare known variant would make a near-singular design)
+    order = np.argsort(-fl["MAF"])
+    known = np.sort(order[:n_known]).astype(np.int64)
+    tested = np.setdiff1d(np.arange(p), known)[:20].astype(np.int64)
+    X_adj, res_c, coef = np_oracle.conditional_refit(nm.residuals, fl["Geno"][:, known], nm.X, method)
+    want = oracle.Individual_Score_Test_cond(np.asfortranarray(fl["Geno"][:, tested]), nm.Sigma_i, nm.Sigma_iX, nm.cov, X_adj, res_c)
+    gpu_ctx.set_nullmodel_sparse(nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)          # the ORIGINAL scaled residuals
+    dev = torch.device("cuda:0")
+    d_in = torch.from_numpy(packed).to(dev); d_cols = torch.zeros_like(d_in)
+    torch.cuda.synchronize()
+    gpu_ctx.packed_reorder_device(d_in.data_ptr(), d_cols.data_ptr(), stride, n, p)
+    d_t, d_k = torch.from_numpy(tested).to(dev), torch.from_numpy(known).to(dev)
+    torch.cuda.synchronize()
+    got = gpu_ctx.packed_cond_refit(d_cols.data_ptr(), stride, n, d_t.data_ptr(), tested.size, d_k.data_ptr(), known.size,
+                                    api.IMPUTE_MEAN, nm.X, method)
+    assert rel_err(got["coef"], coef, 1e-3 * np.abs(coef).max()) < 1e-9
+    assert_stats_close({k: got[k] for k in want}, want, score_floor(fl["Geno"][:, tested], res_c))
