@@ -264,10 +264,16 @@ def run_ours(args):
     value = world * V * args.steps / (ms_total / 1e3)
     # rank 0 owns variants [0, V) at every N: the hash of its seven output arrays must be the same in the N = 1, 2, 4, 8
     # lines of the scaling run (no floating-point atomics, fixed reduction trees)
-    outputs_sha256 = None
+    outputs_sha256 = outputs_sha256_arrays = None
     if rank == 0:
         import hashlib
-        outputs_sha256 = hashlib.sha256(outs.cpu().numpy().tobytes()).hexdigest()
+        outs_host = outs.cpu().numpy()
+        outputs_sha256 = hashlib.sha256(outs_host.tobytes()).hexdigest()
+        outputs_sha256_arrays = {k: hashlib.sha256(np.ascontiguousarray(outs_host[i]).tobytes()).hexdigest()[:16]
+                                 for i, k in enumerate(("AF", "MAF", "Score", "Score_se", "pvalue_log", "Est", "Est_se"))}
+        if os.environ.get("STAAR_B200_BENCH_DUMP"):
+            np.save(os.environ["STAAR_B200_BENCH_DUMP"], outs_host)
+        del outs_host
 
     # ---- per-kernel device times (CUDA events on the launching stream) for the roofline figure
     ctx.set_profiling(True)
@@ -445,7 +451,7 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int8 x int8 -> int32 exact contraction of 54-bit sliced f64 operands; f64 statistics",
                 "data": "synthetic", "config": workload_config(args, V), "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "outputs_sha256": outputs_sha256,
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "outputs_sha256": outputs_sha256, "outputs_sha256_arrays": outputs_sha256_arrays,
                 "packed_path": "fused" if ctx.last_packed_path_was_fused else "split"}
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -151,6 +151,24 @@ def adversarial_columns(n: int, rng: np.random.Generator) -> np.ndarray:
 # --------------------------------------------------------------------------
 # null models
 # --------------------------------------------------------------------------
+def _single_threaded_blas(fn):
+    """The generators' dense products (X'Sigma_iX, Sigma_i (y - X b), ...) go through BLAS, whose summation order depends
+    on the thread count — torchrun sets OMP_NUM_THREADS=1, a plain `python bench.py` does not — so the same seed gave
+    residuals that differed in the last bit between a 1-GPU and an N-GPU run.  One BLAS thread makes the generated
+    null model bit-identical everywhere (the operands are small: n x q)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        try:
+            from threadpoolctl import threadpool_limits
+        except ImportError:                                   # pragma: no cover
+            return fn(*args, **kwargs)
+        with threadpool_limits(limits=1):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 @dataclass
 class NullModel:
     n: int
@@ -215,6 +233,7 @@ def family_blocks(n: int, rng: np.random.Generator):
     return starts, blocks
 
 
+@_single_threaded_blas
 def nullmodel_unrelated(n: int, seed: int = BASE_SEED, q: int = 13) -> NullModel:
     """cfg1: continuous trait, unrelated samples: Sigma_i = I/sigma^2 as a diagonal sparse matrix."""
     rng = np.random.default_rng(seed)
@@ -230,6 +249,7 @@ def nullmodel_unrelated(n: int, seed: int = BASE_SEED, q: int = 13) -> NullModel
                      cov=np.asfortranarray(cov))
 
 
+@_single_threaded_blas
 def nullmodel_sparse_grm(n: int, seed: int = BASE_SEED, q: int = 13, tau_g: float = 0.6, tau_e: float = 0.9,
                          shuffle: bool = False) -> NullModel:
     """cfg2: Sigma = tau_g*2Phi + tau_e*I, block-diagonal kinship; Sigma_i is the exact block inverse."""
@@ -261,6 +281,7 @@ def nullmodel_sparse_grm(n: int, seed: int = BASE_SEED, q: int = 13, tau_g: floa
                      cov=np.asfortranarray(cov))
 
 
+@_single_threaded_blas
 def nullmodel_dense_grm(n: int, seed: int = BASE_SEED, q: int = 13, markers: int = 2000,
                         tau_g: float = 0.6, tau_e: float = 0.9) -> NullModel:
     """cfg3: Phi = ZZ'/M + 0.5 I; P = Sigma^-1 - Sigma^-1 X cov X' Sigma^-1 (dense n x n)."""
@@ -280,6 +301,7 @@ def nullmodel_dense_grm(n: int, seed: int = BASE_SEED, q: int = 13, markers: int
     return NullModel(n, "dense", X, P @ y, P=np.asfortranarray(P))
 
 
+@_single_threaded_blas
 def nullmodel_multi(n: int, k: int = 3, seed: int = BASE_SEED, q: int = 13) -> NullModel:
     """cfg4: k correlated traits; Sigma = Sg (x) 2Phi + Se (x) I, trait-major stacking (nk x nk sparse)."""
     rng = np.random.default_rng(seed)
@@ -312,6 +334,7 @@ def nullmodel_multi(n: int, k: int = 3, seed: int = BASE_SEED, q: int = 13) -> N
                      cov=np.asfortranarray(cov), n_pheno=k)
 
 
+@_single_threaded_blas
 def nullmodel_binary(n: int, seed: int = BASE_SEED, q: int = 13, intercept: float = -4.7) -> NullModel:
     """cfg5: imbalanced (~1:100) case-control, logistic null fitted by IRLS; SPA operands as in
     R/fit_nullmodel.R:153-162 (XW = t(X*w), XXWX_inv = X (X'WX)^-1)."""
@@ -343,6 +366,7 @@ def nullmodel_binary(n: int, seed: int = BASE_SEED, q: int = 13, intercept: floa
     return nm
 
 
+@_single_threaded_blas
 def conditional_design(nm: NullModel, G_known: np.ndarray, method: str = "optimal"):
     """X_adj and refit residuals as R/Individual_Analysis_cond.R:190-197 builds them with lm()."""
     n = nm.n
