@@ -295,7 +295,8 @@ def run_ours(args):
     achieved = V * bytes_per_variant / (stage_ms[dominant] / 1e3) / 1e9
     traffic = None                                      # DRAM bytes per launch of the dominant kernel (ncu --set full capture)
     try:
-        per_variant = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[dominant]["dram_bytes_per_variant"]
+        key = "fused" if (ctx.last_packed_path_was_fused and dominant == "contract") else dominant
+        per_variant = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[key]["dram_bytes_per_variant"]
         traffic = per_variant * V
     except Exception:  # noqa: BLE001
         pass
