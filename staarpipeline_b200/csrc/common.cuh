@@ -105,6 +105,7 @@ struct NullSparse {
     int64_t n_chunks = 0;
     int8_t *Yfrag = nullptr;      // n_chunks * kChunkBytesB (mma.sync fragment-major order)
     int8_t *Ytc = nullptr;        // n_chunks * kChunkBytesB (tcgen05 canonical K-major core-matrix order)
+    int8_t *Ypair = nullptr;      // the same digits split into two 56-row halves per k-block (CTA-pair contraction)
     double *col_scale = nullptr;  // kColsPerSlice: 2^(e_c - 54)
     long long *col_total = nullptr;   // 2 x kColsPerSlice: exact column sums of the fixed-point operand, hi | lo (X = hi 2^24 + lo)
     uint64_t fingerprint = 0;     // content hash of (Sigma_i, Sigma_iX, cov): cache key of the frozen-signature entry points
@@ -167,6 +168,8 @@ struct staar_ctx {
     uint64_t cond_key = 0;
     int cond_m = 0, cond_ld = 0;
     bool use_mma_sync = false;       // STAAR_B200_CONTRACT=mma: legacy mma.sync contraction instead of tcgen05
+    bool use_tc_pair = false;        // STAAR_B200_CONTRACT=pair: tcgen05 cta_group::2 contraction (CTA pairs share the digit stream)
+    bool attr_contract_pair = false;
     // packed score path: 1 = contraction + block-per-variant scan (two passes over G; default), 0 = fused single-pass
     // kernel where the null model allows it.  STAAR_B200_PACKED_PATH=split|fused, staar_ctx_set_packed_path.
     // fused_tiles: accumulator tiles per CTA of the fused kernel (2; 1 for experiments).

@@ -291,8 +291,8 @@ int build_sliced_operand(staar_ctx *ctx, const double *hY)
     const int64_t n = ns.n;
     const int ncol = (int)ns.q + 2, ldY = ns.ldY;      // [r | Sigma_iX | diag(Sigma_i)]
     ns.sliced = false;
-    cudaFree(ns.Yfrag); cudaFree(ns.col_scale); cudaFree(ns.col_total); cudaFree(ns.Ytc);
-    ns.Yfrag = nullptr; ns.col_scale = nullptr; ns.col_total = nullptr; ns.Ytc = nullptr;
+    cudaFree(ns.Yfrag); cudaFree(ns.col_scale); cudaFree(ns.col_total); cudaFree(ns.Ytc); cudaFree(ns.Ypair);
+    ns.Yfrag = nullptr; ns.col_scale = nullptr; ns.col_total = nullptr; ns.Ytc = nullptr; ns.Ypair = nullptr;
     if (ncol > kColsPerSlice - 1) return STAAR_OK;  // wider designs take the FP64 path (slot 15 is reserved)
     std::vector<double> pulled;
     if (!hY) {                                      // current operand (incl. an updated residual column) from HBM

@@ -59,7 +59,7 @@ void NullSparse::release()
     }
     if (permuted) cudaFree(Yp);
     cudaFree(diag); cudaFree(diag_p); cudaFree(sinfo_p); cudaFree(off_ent_p); cudaFree(relmask); cudaFree(rel); cudaFree(up_ent); cudaFree(Y);
-    cudaFree(Yfrag); cudaFree(Ytc); cudaFree(col_scale); cudaFree(col_total); cudaFree(perm); cudaFree(inv_perm); cudaFree(kmask); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut); cudaFree(lutf);
+    cudaFree(Yfrag); cudaFree(Ytc); cudaFree(Ypair); cudaFree(col_scale); cudaFree(col_total); cudaFree(perm); cudaFree(inv_perm); cudaFree(kmask); cudaFree(wdesc); cudaFree(xterms); cudaFree(lut); cudaFree(lutf);
     *this = NullSparse();
 }
 void NullSpa::release()
@@ -529,7 +529,7 @@ int nullmodel_sparse_clone(staar_ctx *dst, const staar_ctx *src)
     d.row_ptr = nullptr; d.col = nullptr; d.val = nullptr; d.diag = nullptr; d.perm = nullptr; d.inv_perm = nullptr;
     d.Yp = nullptr; d.kmask = nullptr; d.wdesc = nullptr; d.xterms = nullptr; d.lut = nullptr; d.lutf = nullptr;
     d.sinfo_p = nullptr; d.diag_p = nullptr; d.off_ent_p = nullptr; d.relmask = nullptr; d.rel = nullptr; d.up_ent = nullptr;
-    d.SX = nullptr; d.Y = nullptr; d.cov = nullptr; d.Yfrag = nullptr; d.Ytc = nullptr; d.col_scale = nullptr; d.col_total = nullptr;
+    d.SX = nullptr; d.Y = nullptr; d.cov = nullptr; d.Yfrag = nullptr; d.Ytc = nullptr; d.Ypair = nullptr; d.col_scale = nullptr; d.col_total = nullptr;
     d.set = false;
     for (const auto &a : s.arrays) {
         void **slot = reinterpret_cast<void **>(reinterpret_cast<char *>(&d) + a.first);
@@ -591,6 +591,7 @@ int staar_ctx_create(int device, staar_ctx **out)
     {
         const char *sel = getenv("STAAR_B200_CONTRACT");
         ctx->use_mma_sync = sel && strcmp(sel, "mma") == 0;
+        ctx->use_tc_pair = sel && strcmp(sel, "pair") == 0;
         const char *path = getenv("STAAR_B200_PACKED_PATH");
         // default: the two-kernel route — the single-pass kernel is parity-equal but, on B200, bound by the ALU pipe of
         // its scanner warps and not faster; STAAR_B200_PACKED_PATH=fused selects it

@@ -138,3 +138,59 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8])
 
 }  // namespace tc
 }  // namespace staar
+
+// ---- CTA pairs (tcgen05 cta_group::2): rank 0 of a 2-CTA cluster issues the MMAs for both SMs
+namespace staar {
+namespace tc {
+
+__device__ __forceinline__ uint32_t cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void bar_arrive_remote(uint64_t *bar, uint32_t rank)
+{
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(s_addr(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// wait on a local barrier whose arrivals come from the peer CTA (cluster-scope acquire)
+__device__ __forceinline__ void bar_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TCC_WAIT:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TCC_DONE;\n"
+        "bra TCC_WAIT;\n"
+        "TCC_DONE:\n"
+        "}\n" ::"r"(s_addr(bar)), "r"(parity) : "memory");
+}
+// completion of the pair's MMAs arrives on the barrier at this offset in both CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s_addr(bar)),
+                 "h"((uint16_t)3) : "memory");
+}
+// D[tmem, both CTAs] (+)= A[tmem, 128 rows per CTA] * B[smem, N/2 rows per CTA]; issued by the leader CTA only
+__device__ __forceinline__ void umma_i8_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+}  // namespace tc
+}  // namespace staar

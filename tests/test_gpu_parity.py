@@ -317,6 +317,21 @@ def test_resident_order_and_reorder(gpu_ctx, oracle):
         assert np.array_equal(res[i], host[k], equal_nan=True), k
 
 
+@pytest.fixture
+def gpu_ctx_pair(monkeypatch):
+    """a context whose packed contraction runs on CTA pairs (tcgen05 cta_group::2; selected when the context is created)"""
+    from staarpipeline_b200.api import Context
+    monkeypatch.setenv("STAAR_B200_CONTRACT", "pair")
+    ctx = Context(0)
+    yield ctx
+    ctx.close()
+
+
+def test_packed_contraction_cta_pair_is_exact_integer(gpu_ctx_pair, oracle):
+    """the cta_group::2 variant of K2 (two CTAs share one digit stream) gives the same exact integers"""
+    test_packed_contraction_is_exact_integer(gpu_ctx_pair, oracle)
+
+
 def test_packed_contraction_is_exact_integer(gpu_ctx, oracle):
     """K2 (packed): the INT8-sliced tensor-core contraction must equal, bit for bit, the integer sum
     sum_j code_j * round(Y[j,c] * 2^(54-e_c)) over the RAW 2-bit codes (missing = 3); flip and imputation are

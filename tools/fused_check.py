@@ -118,7 +118,9 @@ def timing(ctx, n=100_000, p=250_000):
     res = {}
     runs = [("split", 2, 0), ("fused", 2, 0)]
     if "--dbg" in sys.argv:
-        runs += [("fused", 2, d) for d in (2 + 32, 2 + 32 + 256, 2 + 32 + 512, 6)]
+        extra_dbg = sys.argv[sys.argv.index("--dbg") + 1:]
+        dbgs = [int(x) for x in extra_dbg if x.isdigit()] or [2 + 32, 2 + 32 + 256, 2 + 32 + 512, 6]
+        runs += [("fused", 2, d) for d in dbgs]
     for path, tiles, dbg in runs:
         ctx.set_packed_path(path)
         os.environ["STAAR_B200_FUSED_TILES"] = str(tiles)

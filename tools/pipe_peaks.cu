@@ -86,7 +86,7 @@ __device__ __forceinline__ uint64_t sdesc(uint32_t addr, uint32_t lbo, uint32_t 
 {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
-template <int N, bool A_TMEM>
+template <int N, bool A_TMEM, int COMMITS = 0, int DELAY = 0>
 __global__ void __launch_bounds__(128, 1) k_tcgen05_i8(int reps, int *out)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(128, 1) k_tcgen05_i8(int reps, int *out)
     for (int i = threadIdx.x; i < (128 + N) * 32 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(sA)[i] = 0x01010101u;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(saddr(bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(saddr(bar + 2)));   // intermediate commits (COMMITS > 0): nobody waits
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(saddr(bar + 3)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 32) {
@@ -122,6 +124,13 @@ __global__ void __launch_bounds__(128, 1) k_tcgen05_i8(int reps, int *out)
                                  "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n"
                                  ::"r"(tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(1u), "r"(0u) : "memory");
             }
+            // the contraction commits twice per 16 instructions (A stage and B stage released separately)
+            if (COMMITS >= 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(saddr(bar + 2)) : "memory");
+            if (COMMITS >= 2) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(saddr(bar + 3)) : "memory");
+            if (DELAY > 0) {           // the issuing thread is away for DELAY clocks (barrier waits between k-blocks): does the queue cover it?
+                const long long t0 = clock64();
+                while (clock64() - t0 < DELAY) { }
+            }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(saddr(bar)) : "memory");
         asm volatile("{\n.reg .pred p;\nW:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra D;\nbra W;\nD:\n}\n"
@@ -136,16 +145,16 @@ __global__ void __launch_bounds__(128, 1) k_tcgen05_i8(int reps, int *out)
     }
 }
 
-template <int N, bool A_TMEM> double tcgen05_tops(int sms, int *out)
+template <int N, bool A_TMEM, int COMMITS = 0, int DELAY = 0> double tcgen05_tops(int sms, int *out)
 {
     const int reps = 2048;
     const size_t smem = 1024 + (128 + N) * 32 + 1024;
-    cudaFuncSetAttribute(k_tcgen05_i8<N, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_tcgen05_i8<N, A_TMEM, COMMITS, DELAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    k_tcgen05_i8<N, A_TMEM><<<sms, 128, smem>>>(64, out); cudaDeviceSynchronize();
+    k_tcgen05_i8<N, A_TMEM, COMMITS, DELAY><<<sms, 128, smem>>>(64, out); cudaDeviceSynchronize();
     float best = 1e30f;
     for (int r = 0; r < 5; r++) {
-        cudaEventRecord(e0); k_tcgen05_i8<N, A_TMEM><<<sms, 128, smem>>>(reps, out); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventRecord(e0); k_tcgen05_i8<N, A_TMEM, COMMITS, DELAY><<<sms, 128, smem>>>(reps, out); cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
     return (double)sms * reps * 16 * (2.0 * 128 * N * 32) / best / 1e9;     // TOP/s
@@ -183,6 +192,12 @@ int main() {
     CK(cudaGetLastError());
     // tcgen05 kind::i8, M = 128, K = 32: A from TMEM (.ts) at N = 112 (the contraction's shape), 128, 256; A from smem at 112, 256
     printf(", \"tcgen05_i8_ts_n112_tops\": %.1f", tcgen05_tops<112, true>(sms, (int *)buf));
+    printf(", \"tcgen05_i8_ts_n112_commit1_tops\": %.1f", tcgen05_tops<112, true, 1>(sms, (int *)buf));
+    printf(", \"tcgen05_i8_ts_n112_commit2_tops\": %.1f", tcgen05_tops<112, true, 2>(sms, (int *)buf));
+    printf(", \"tcgen05_i8_ts_n112_commit2_delay100_tops\": %.1f", tcgen05_tops<112, true, 2, 100>(sms, (int *)buf));
+    printf(", \"tcgen05_i8_ts_n112_commit2_delay200_tops\": %.1f", tcgen05_tops<112, true, 2, 200>(sms, (int *)buf));
+    printf(", \"tcgen05_i8_ts_n112_commit2_delay400_tops\": %.1f", tcgen05_tops<112, true, 2, 400>(sms, (int *)buf));
+    printf(", \"tcgen05_i8_ts_n112_commit2_delay800_tops\": %.1f", tcgen05_tops<112, true, 2, 800>(sms, (int *)buf));
     printf(", \"tcgen05_i8_ts_n128_tops\": %.1f", tcgen05_tops<128, true>(sms, (int *)buf));
     printf(", \"tcgen05_i8_ts_n256_tops\": %.1f", tcgen05_tops<256, true>(sms, (int *)buf));
     printf(", \"tcgen05_i8_ts_n64_tops\": %.1f", tcgen05_tops<64, true>(sms, (int *)buf));
