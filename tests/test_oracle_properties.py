@@ -94,3 +94,22 @@ def test_spa_trace_probe(oracle):
     assert tested.sum() >= 10
     evals = tr[tested, :3].sum(axis=1)
     assert evals.min() >= 10 and np.median(evals) < 80
+
+
+def test_conditional_refit_is_the_least_squares_fit():
+    """np_oracle.conditional_refit (the lm() refit of R/Individual_Analysis_cond.R:187-197, checker of the device-side
+    refit): residuals orthogonal to the design, equal to the SVD least-squares solution, both model formulas."""
+    from staarpipeline_b200 import synth
+    n = 2500
+    nm = synth.nullmodel_unrelated(n, seed=77, q=6)
+    rng = np.random.default_rng(77)
+    G_known = rng.binomial(2, 0.2, size=(n, 4)).astype(np.float64)
+    for method in ("optimal", "naive"):
+        A, res, coef = np_oracle.conditional_refit(nm.residuals, G_known, nm.X, method)
+        assert A.shape == (n, 4 + (nm.X.shape[1] if method == "optimal" else 1))
+        assert np.abs(A.T @ res).max() < 1e-9 * np.abs(A).max() * np.abs(nm.residuals).max() * n
+        A2, res2 = synth.conditional_design(nm, G_known, method)
+        assert np.array_equal(A, A2)
+        assert rel_err(res, res2, 1e-300) < 1e-10
+        want, *_ = np.linalg.lstsq(A, nm.residuals, rcond=None)
+        assert rel_err(coef, want, 1e-300) < 1e-9
