@@ -166,7 +166,7 @@ def run_reference(args):
                                    "Armadillo/Rmath are stand-ins (oracle/ref_stub)"},
         "e2e": {"value": value, "unit": "variants/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def workload_config(args, variants_per_step):
@@ -454,7 +454,7 @@ def run_ours(args):
                 "data": "synthetic", "config": workload_config(args, V), "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "outputs_sha256": outputs_sha256, "outputs_sha256_arrays": outputs_sha256_arrays,
                 "packed_path": "fused" if ctx.last_packed_path_was_fused else "split"}
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -615,7 +615,7 @@ def run_config(args):
                 "config": {"workload": work, "n_samples": n, "variants_per_gpu_per_step": V, "genotype_bits": 2, "impute": "mean",
                            "parallelism": f"variant-sharded x{world}", "l2": "inputs larger than L2" if V * stride > 2e8 else "inputs fit L2 partly", **extra},
                 "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": None}
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -635,6 +635,16 @@ def host_chunk_from_device(packed_rows, n, dev, d_order):
     return G.cpu().numpy().T          # (n, p) view of a C-order (p, n) array == F-order n x p
 
 
+_json_out = None
+
+
+def emit(line: str):
+    """the bench line, on the process's original stdout"""
+    out = _json_out or sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -650,6 +660,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: anything a library writes to fd 1 (NCCL prints its version
+    # banner there when NCCL_DEBUG is set on the box) goes to stderr for the rest of the run
+    global _json_out
+    sys.stdout.flush()
+    _json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     elif args.config != 1:
