@@ -168,13 +168,14 @@ struct staar_ctx {
     uint64_t cond_key = 0;
     int cond_m = 0, cond_ld = 0;
     bool use_mma_sync = false;       // STAAR_B200_CONTRACT=mma: legacy mma.sync contraction instead of tcgen05
+    bool use_missing_lists = true;   // STAAR_B200_MISSING_LISTS=0: the scan detects missing samples itself (previous flow)
     bool use_tc_pair = false;        // STAAR_B200_CONTRACT=pair: tcgen05 cta_group::2 contraction (CTA pairs share the digit stream)
     bool attr_contract_pair = false;
     // packed score path: 1 = contraction + block-per-variant scan (two passes over G; default), 0 = fused single-pass
     // kernel where the null model allows it.  STAAR_B200_PACKED_PATH=split|fused, staar_ctx_set_packed_path.
     // fused_tiles: accumulator tiles per CTA of the fused kernel (2; 1 for experiments).
     int packed_path = 1, fused_tiles = 2;
-    staar::DevBuf fscan, mlist, msubcnt, redo;
+    staar::DevBuf fscan, mlist, msubcnt, redo, plist, pcnt;
     bool last_fused = false;         // the last staar_packed_score_device call took the fused path
     // per-device launch attributes already set (cudaFuncSetAttribute is per device, the context owns one device)
     bool attr_contract_tc = false, attr_contract_packed = false, attr_permute = false;
@@ -255,7 +256,12 @@ int launch_spa_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, co
 int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
                        const long long *d_lo /* contraction output: slot 15 = sum of codes */, double *dAF, double *dMAF,
                        int32_t *dflip, double *d_mu, double *d_quad, double *d_Sm,
-                       const long long *d_vlist = nullptr, const unsigned long long *d_vcount = nullptr);
+                       const long long *d_vlist = nullptr, const unsigned long long *d_vcount = nullptr,
+                       const uint32_t *d_plist = nullptr, const uint32_t *d_pcnt = nullptr, int pcap = 0);
+// segment records of the contraction (d_mlist / d_mcnt) -> positions d_plist[i * pcap ..] and counts d_pcnt[i] the scan's
+// list mode reads; variants whose lists did not fit -> d_vlist / *d_vcount (work list of the detection path)
+int launch_expand_lists(staar_ctx *ctx, const uint2 *d_mlist, const uint2 *d_mcnt, int mcap, int64_t p, uint32_t *d_plist,
+                        uint32_t *d_pcnt, int pcap, long long *d_vlist, unsigned long long *d_vcount);
 int launch_contract_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p,
                            long long *d_hi, long long *d_lo);
 int launch_finalize_packed(staar_ctx *ctx, int64_t p, const int32_t *d_flip, const double *d_mu, const double *d_quad,
@@ -274,8 +280,10 @@ int launch_fused_finalize(staar_ctx *ctx, int64_t n, int64_t p, int impute, cons
                           unsigned long long *d_redo_count);
 int build_sliced_operand(staar_ctx *ctx, const double *hY /* n x ldY row-major host, natural sample order */);
 int build_tc_operand(staar_ctx *ctx, const int8_t *digits, int ncol);
+// d_mlist / d_mcnt (optional): per variant two sub-lists of mcap records {32-sample segment, mask of its missing samples}
+// and per sub-list {records, missing samples} (records above mcap = list truncated); the scan's list mode consumes them
 int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, long long *d_hi,
-                       long long *d_lo);
+                       long long *d_lo, uint2 *d_mlist = nullptr, uint2 *d_mcnt = nullptr, int mcap = 0);
 int refresh_permuted_Y(staar_ctx *ctx, const double *hY);
 // ctx.cu / abi.cu — shared with multi.cu
 int nullmodel_sparse_clone(staar_ctx *dst, const staar_ctx *src);

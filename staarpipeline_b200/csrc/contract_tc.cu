@@ -74,7 +74,8 @@ __device__ int g_tc_dbg;
 // grid = ceil(p / 128); out_hi / out_lo: p x 16 int64, X = hi * 2^24 + lo
 __global__ void __launch_bounds__(kTcThreads, 1)
 contract_tc_kernel(const __grid_constant__ CUtensorMap gmap, int64_t p, const int8_t *__restrict__ Ytc,
-                   int64_t n_kblocks, long long *__restrict__ out_hi, long long *__restrict__ out_lo)
+                   int64_t n_kblocks, long long *__restrict__ out_hi, long long *__restrict__ out_lo,
+                   uint2 *__restrict__ mlist, uint2 *__restrict__ mcnt, int mcap)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sG = smem;                                                       // kRing x kTileBytes (1024-byte aligned: swizzle)
@@ -123,6 +124,14 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap gmap, int64_t p, const in
         uint32_t g_par = 0u;                                                 // parity to wait for on g_full[ring_slot]
         // this thread's row of the swizzled tile: logical 16-byte chunk c sits at physical chunk c ^ (row & 7)
         const uint8_t *my_row = sG + (size_t)row * kRowBytes;
+        // Missing samples (code 3) are listed here, where every word of the column passes through registers anyway and the
+        // expander threads have slack (they wait ~40 % of a k-block for the tensor pipe): thread (row, half) appends one
+        // record {32-sample segment, 32-bit mask} per segment that holds missing samples, in increasing order, to its own
+        // sub-list mlist[(2 v + half) * mcap ..] (mask bit 2 f + w = sample 16 w + f of the segment, the scan's own
+        // encoding); the scan kernel then needs no detection pass and knows the missing count up front.  A record count
+        // above mcap marks the variant for the scan's own detection path.
+        uint2 *my_list = mlist ? mlist + ((size_t)v * 2 + half) * (size_t)mcap : nullptr;
+        uint32_t mc = 0, mcm = 0;                                            // records, missing samples
 #ifdef TC_TIMERS
         long long tm_ae = 0, tm_st = 0, tm_gf = 0, tm_ex = 0, tm_ws = 0, tm_t0;
         const bool tm_on = threadIdx.x == 0 && blockIdx.x == 500;
@@ -130,7 +139,7 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap gmap, int64_t p, const in
 #else
 #define TCT(acc) do { } while (0)
 #endif
-        auto expand = [&](int64_t) {
+        auto expand = [&](int64_t kbx) {
             TC_WAIT_EXP(&g_full[ring_slot], g_par);                          // the tensor load of this k-block has landed
             TCT(tm_gf);
             const uint8_t *rowp = my_row + (size_t)ring_slot * kTileBytes;
@@ -148,6 +157,33 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap gmap, int64_t p, const in
             }
             bar_arrive(&g_empty[ring_slot]);                                 // words are in registers: the stage may be refilled
             if (++ring_slot == kRing) { ring_slot = 0; g_par ^= 1u; }
+            if (my_list) {
+                uint32_t anyc[kHalfBytes / 16];
+#pragma unroll
+                for (int c = 0; c < kHalfBytes / 16; c++)
+                    anyc[c] = ((w[4 * c] & (w[4 * c] >> 1)) | (w[4 * c + 1] & (w[4 * c + 1] >> 1)) |
+                               (w[4 * c + 2] & (w[4 * c + 2] >> 1)) | (w[4 * c + 3] & (w[4 * c + 3] >> 1))) & 0x55555555u;
+                uint32_t any = 0u;
+#pragma unroll
+                for (int c = 0; c < kHalfBytes / 16; c++) any |= anyc[c];
+                if (any) {                                                   // rare per thread: ~0.1 % of the samples
+                    const uint32_t seg0 = ((uint32_t)kbx * kTcSamples + (uint32_t)half * (kTcSamples / 2)) >> 5;
+#pragma unroll
+                    for (int c = 0; c < kHalfBytes / 16; c++)
+                        if (anyc[c]) {
+#pragma unroll
+                            for (int hh = 0; hh < 2; hh++) {
+                                const uint32_t wa = w[4 * c + 2 * hh], wb = w[4 * c + 2 * hh + 1];
+                                const uint32_t mask = (wa & (wa >> 1) & 0x55555555u) | ((wb & (wb >> 1) & 0x55555555u) << 1);
+                                if (mask) {
+                                    if (mc < (uint32_t)mcap) my_list[mc] = make_uint2(seg0 + 2u * c + hh, mask);
+                                    mc++;
+                                    mcm += __popc(mask);
+                                }
+                            }
+                        }
+                }
+            }
 #pragma unroll
             // right shifts as IMAD.HI (w * 2^(32-s) >> 32) run on the FMA pipe, leaving the ALU pipe the masks only
             for (int c = 0; c < kHalfCols; c++)
@@ -182,6 +218,7 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap gmap, int64_t p, const in
         if (tm_on) printf("expander: per k-block clk: wait a_empty %lld, st issue %lld, wait g_full %lld, lds+alu %lld, wait::st %lld\n",
                           tm_ae / n_kblocks, tm_st / n_kblocks, tm_gf / n_kblocks, tm_ex / n_kblocks, tm_ws / n_kblocks);
 #endif
+        if (my_list && rok) mcnt[v * 2 + half] = make_uint2(mc, mcm);
         // ===================================================================== epilogue: TMEM -> 64-bit recombination
         // half 0 reads the accumulators of digit slices 0-3 (the "hi" part), half 1 those of slices 4-6
         bar_wait(d_full, 0u);
@@ -558,13 +595,13 @@ static int encode_genotype_map(CUtensorMap *map, const uint8_t *d_packed, size_t
 }
 
 int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, long long *d_hi,
-                       long long *d_lo)
+                       long long *d_lo, uint2 *d_mlist, uint2 *d_mcnt, int mcap)
 {
     if (p == 0) return STAAR_OK;
     const NullSparse &ns = ctx->ns;
     if (!ns.sliced || !ns.Ytc) { set_error("packed contraction: sliced operand not built (q > 13?)"); return STAAR_ERR_STATE; }
     const int64_t n_kblocks = (n + kTcSamples - 1) / kTcSamples;
-    if (ctx->use_tc_pair && ns.Ypair) {
+    if (ctx->use_tc_pair && ns.Ypair && !d_mlist) {
         const size_t smem2 = (size_t)kRing * kTileBytes + (size_t)kStagesB2 * kPairBlockBytes + 40 * sizeof(uint64_t);
         if (!ctx->attr_contract_pair) {
             STAAR_CUDA(cudaFuncSetAttribute(contract_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
@@ -592,7 +629,7 @@ int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     CUtensorMap gmap;
     STAAR_TRY(encode_genotype_map(&gmap, d_packed, stride, p));
     const int64_t tiles = (p + kTcRows - 1) / kTcRows;
-    contract_tc_kernel<<<(unsigned)tiles, kTcThreads, smem, ctx->stream>>>(gmap, p, ns.Ytc, n_kblocks, d_hi, d_lo);
+    contract_tc_kernel<<<(unsigned)tiles, kTcThreads, smem, ctx->stream>>>(gmap, p, ns.Ytc, n_kblocks, d_hi, d_lo, d_mlist, d_mcnt, mcap);
     ctx->launches++;
     STAAR_CUDA(cudaGetLastError());
     return STAAR_OK;

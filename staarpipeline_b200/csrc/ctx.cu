@@ -592,6 +592,8 @@ int staar_ctx_create(int device, staar_ctx **out)
         const char *sel = getenv("STAAR_B200_CONTRACT");
         ctx->use_mma_sync = sel && strcmp(sel, "mma") == 0;
         ctx->use_tc_pair = sel && strcmp(sel, "pair") == 0;
+        const char *ml = getenv("STAAR_B200_MISSING_LISTS");
+        ctx->use_missing_lists = !(ml && atoi(ml) == 0);
         const char *path = getenv("STAAR_B200_PACKED_PATH");
         // default: the two-kernel route — the single-pass kernel is parity-equal but, on B200, bound by the ALU pipe of
         // its scanner warps and not faster; STAAR_B200_PACKED_PATH=fused selects it
@@ -614,6 +616,7 @@ void staar_ctx_destroy(staar_ctx *ctx)
     ctx->G.release(); ctx->L.release(); ctx->aux.release(); ctx->out.release(); ctx->tmp.release();
     ctx->tmp2.release(); ctx->pk.release(); ctx->pk2.release(); ctx->ctr.release(); ctx->cond.release();
     ctx->fscan.release(); ctx->mlist.release(); ctx->msubcnt.release(); ctx->redo.release();
+    ctx->plist.release(); ctx->pcnt.release();
     for (auto &e : ctx->ev_pack) if (e) cudaEventDestroy(e);
     for (auto &sl : ctx->slot) {
         if (sl.pinned) cudaFreeHost(sl.pinned);

@@ -42,6 +42,10 @@ struct ScanParams {
     const long long *codesum;              // contraction output `lo` (p x 16): slot 15 = exact sum of the codes
     // list mode (redo list of the fused path): work item k is variant vlist[k], k < *vcount (both device-resident)
     const long long *vlist; const unsigned long long *vcount;
+    // missing-sample lists (kLists instantiation): the contraction kernel writes segment records, expand_lists_kernel
+    // turns them into positions: variant i owns plist[i * pcap ..], pcnt[i] = number of missing samples, or kTruncated
+    // when the lists did not fit — such a variant is left to the detection path (list mode of the other instantiation)
+    const uint32_t *plist; const uint32_t *pcnt; int pcap;
     double *AF, *MAF; int32_t *flip; double *mu, *quad, *Sm;
 };
 
@@ -59,6 +63,7 @@ __device__ __forceinline__ double code_value(uint32_t code, double mu)
 // memory.  Variants are handed out by an atomic work counter (their cost varies >20x with allele frequency); each
 // variant's arithmetic is independent of which CTA runs it, so results stay bit-reproducible.
 // ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t kTruncated = 0xffffffffu;   // pcnt value of a variant whose missing-sample lists did not fit
 constexpr int kQueueCap = 96;            // per-warp queue of missing-sample positions; flushed when nearly full
 constexpr int kRelQueueCap = 64;         // per-warp queue of missing positions inside the table region (kept per variant)
 
@@ -72,16 +77,17 @@ __device__ __forceinline__ uint32_t code_smem(const uint8_t *col, int64_t k, boo
     return code;
 }
 
-template <int kBlkWarps>
+template <int kBlkWarps, bool kLists>
 __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P, int nstage, unsigned long long *work, int l2pf)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const size_t stride = P.stride;
     uint8_t *cols = smem;
-    uint32_t *wq = reinterpret_cast<uint32_t *>(smem + (size_t)nstage * stride) + wib * (kQueueCap + kRelQueueCap);   // this warp's queues
+    constexpr int kQueueWords = kLists ? 0 : kQueueCap + kRelQueueCap;            // the list instantiation keeps no queues
+    uint32_t *wq = reinterpret_cast<uint32_t *>(smem + (size_t)nstage * stride) + wib * kQueueWords;   // this warp's queues
     uint32_t *rq = wq + kQueueCap;
-    double *s_sm = reinterpret_cast<double *>(smem + (size_t)nstage * stride + sizeof(uint32_t) * kBlkWarps * (kQueueCap + kRelQueueCap));
+    double *s_sm = reinterpret_cast<double *>(smem + (size_t)nstage * stride + sizeof(uint32_t) * kBlkWarps * kQueueWords);
     double *s_quad = s_sm + kBlkWarps * kColsPerSlice;                           // [2][kBlkWarps]: kinship part, hom-minor diag part
     int *s_cnt = reinterpret_cast<int *>(s_quad + 2 * kBlkWarps);                // [4][kBlkWarps]
     unsigned long long *s_work = reinterpret_cast<unsigned long long *>(s_cnt + 4 * kBlkWarps);   // [2]
@@ -150,10 +156,28 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.packed + (size_t)variant_of(v) * stride),
                              "r"((uint32_t)stride) : "memory");
         }
+        const int64_t i = (int64_t)variant_of(cur);
+        // kLists: the missing samples were listed by the contraction, so their count — and with it the flip — is known
+        // before the column is touched: one orientation, no detection, no queues.
+        bool skip = false;
+        int cm = 0;
+        double sm = 0.0;
+        if constexpr (kLists) {
+            const uint32_t c = P.pcnt[i];
+            skip = c == kTruncated;
+            cm = skip ? 0 : (int)c;
+            // column sums of Y over the listed missing samples (two rows per warp instruction, four in flight): they do
+            // not need the column, so they are gathered while its bulk copy is still in flight
+            if (ycol < P.ncol) {
+                const uint32_t *L = P.plist + (size_t)i * (size_t)P.pcap;
+#pragma unroll 4
+                for (int e = 2 * wib + (lane >> 4); e < cm; e += 2 * kBlkWarps)
+                    sm += __ldg(P.Y + (int64_t)__ldg(L + e) * P.ldY + ycol);
+            }
+        }
         wait_full(stage, (parity >> stage) & 1u);
         parity ^= 1u << stage;
         const uint8_t *col = cols + (size_t)stage * stride;
-        const int64_t i = (int64_t)variant_of(cur);
 
         // ---- sweep 1 (whole column, 64 samples per lane and step).  The sum of the variant's codes S = c1 + 2 c2 + 3 cm
         //      comes EXACTLY from the tensor-core contraction (its constant-1 column), so no genotype popcounts are
@@ -164,8 +188,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         //      g' diag(Sigma_i) g that is not linear in the codes).  The latter needs the flip, which needs cm: it is
         //      computed under the guess cm = 0 and redone in the rare case that the missing count changes the decision.
         const long long S = P.codesum[i * 16 + 15];
-        int cm = 0;
-        double sm = 0.0, hom = 0.0;
+        double hom = 0.0;
         int qn = 0, rn = 0;
         bool rq_over = false;
         const uint4 *v4 = reinterpret_cast<const uint4 *>(col);
@@ -215,8 +238,17 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             }
         };
         // both imputation modes flip iff the mean dosage exceeds 1 when nothing is missing
-        const bool guess = S > (long long)P.n;
-        {
+        bool guess = S > (long long)P.n;
+        if constexpr (kLists) {
+            const long long gs = S - 3ll * cm, gn = (long long)P.n - cm;
+            if (P.impute == STAAR_IMPUTE_MEAN) guess = gs > gn;
+            else guess = gs + (gs > gn ? 2 : 0) * (long long)cm > (long long)P.n;
+            // hom-minor term beyond the table words; the table words get it inside the kinship sweep below (one read)
+            const int nv = skip ? 0 : nvec16;
+            for (int k = tab_vec + tid; k < nv; k += kBlkWarps * 32) hom_vec(v4[k], k, guess, hom);
+            sm += __shfl_xor_sync(0xffffffffu, sm, 16);
+            if (lane < kColsPerSlice) s_sm[wib * kColsPerSlice + lane] = sm;
+        } else {
             for (int k0 = wib * 32; k0 < nvec16; k0 += kBlkWarps * 32) {
                 const int k = k0 + lane;
                 uint4 q4 = make_uint4(0u, 0u, 0u, 0u);
@@ -300,10 +332,15 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         //     The kernel is latency-bound, so the look-ups of two words (8 groups) are issued together: the table of a
         //     group sits at a fixed stride (no descriptor fetch in front of it) and the related-slot masks of a lane's four
         //     words are one 128-bit load issued before anything else.
-        for (int k0 = wib * 32; k0 < tab_vec; k0 += kBlkWarps * 32) {
+        const int tab_vec_eff = skip ? 0 : tab_vec;
+        for (int k0 = wib * 32; k0 < tab_vec_eff; k0 += kBlkWarps * 32) {
             const int k = k0 + lane;
             uint4 q4 = make_uint4(0u, 0u, 0u, 0u), km4 = make_uint4(0u, 0u, 0u, 0u);
-            if (k < tab_vec) { km4 = __ldg(reinterpret_cast<const uint4 *>(P.kmask) + k); q4 = v4[k]; }
+            if (k < tab_vec) {
+                km4 = __ldg(reinterpret_cast<const uint4 *>(P.kmask) + k);
+                q4 = v4[k];
+                if constexpr (kLists) hom_vec(q4, k, flip, hom);
+            }
             const uint32_t wv[4] = {q4.x, q4.y, q4.z, q4.w}, kmv[4] = {km4.x, km4.y, km4.z, km4.w};
             uint32_t wzv[4], twov[4];
             bool crossv[4];
@@ -363,12 +400,21 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
                     }
                 }
         }
-        if (!rq_over && !mu_zero && rn > 0) {                        // missing samples queued in sweep 1 (this warp's)
+        if constexpr (kLists) {
+            if (!mu_zero && cm > 0) {                                // listed missing samples inside the table region
+                const double mu = mu_of();
+                const uint32_t *L = P.plist + (size_t)i * (size_t)P.pcap;
+                for (int e = tid; e < cm; e += kBlkWarps * 32) {
+                    const uint32_t pos = __ldg(L + e);
+                    if (pos < tab_samples) related_missing((int64_t)pos, mu);
+                }
+            }
+        } else if (!rq_over && !mu_zero && rn > 0) {                 // missing samples queued in sweep 1 (this warp's)
             const double mu = mu_of();
             for (int e = lane; e < rn; e += 32) related_missing((int64_t)rq[e], mu);
         }
         // (b) generic words [tab_words, kin_words): per-carrier records (families of more than 16 members)
-        for (int k = tab_words + tid; k < kin_words; k += kBlkWarps * 32) {
+        for (int k = tab_words + tid; k < (skip ? 0 : kin_words); k += kBlkWarps * 32) {
             const uint32_t w = col32[k];
             const uint32_t lo = w & 0x55555555u;
             const uint32_t mis = lo & (w >> 1);
@@ -397,7 +443,9 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         hom = warp_sum(hom);
         if (lane == 0) { s_quad[wib] = quad; s_quad[kBlkWarps + wib] = hom; }
         __syncthreads();                      // also: every read of this stage's column is complete
-        if (tid < kColsPerSlice) {
+        if (skip) {
+            // nothing to write: the detection path fills this variant's outputs
+        } else if (tid < kColsPerSlice) {
             double t = 0.0;
 #pragma unroll
             for (int w = 0; w < kBlkWarps; w++) t += s_sm[w * kColsPerSlice + tid];
@@ -501,10 +549,12 @@ __global__ void __launch_bounds__(128) finalize_packed_kernel(FinParams P)
 
 int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, int impute,
                        const long long *d_lo, double *dAF, double *dMAF, int32_t *dflip, double *d_mu, double *d_quad,
-                       double *d_Sm, const long long *d_vlist, const unsigned long long *d_vcount)
+                       double *d_Sm, const long long *d_vlist, const unsigned long long *d_vcount, const uint32_t *d_plist,
+                       const uint32_t *d_pcnt, int pcap)
 {
     if (p == 0) return STAAR_OK;
     const NullSparse &ns = ctx->ns;
+    const bool lists = d_plist != nullptr;
     if (n >= (1ll << 30)) { set_error("packed scan: n too large for 30-bit sample indices"); return STAAR_ERR_ARG; }
     ScanParams P;
     P.packed = d_packed; P.stride = stride; P.n = n; P.p = p; P.impute = impute;
@@ -514,12 +564,13 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     P.uvec = ns.diag_uniform_vec >= 0 ? (int)ns.diag_uniform_vec : INT_MAX; P.dval = ns.diag_uniform_val;
     P.Y = ns.Yp; P.ldY = ns.ldY; P.ncol = (int)ns.q + 2;
     P.codesum = d_lo; P.vlist = d_vlist; P.vcount = d_vcount;
+    P.plist = d_plist; P.pcnt = d_pcnt; P.pcap = pcap;
     P.AF = dAF; P.MAF = dMAF; P.flip = dflip; P.mu = d_mu; P.quad = d_quad; P.Sm = d_Sm;
     // block-per-variant kernel, column in shared memory.  CTA width: 4 warps put more variants in flight per SM (7 vs 4 at
     // n = 1e5: 6.75 -> 6.63 ms per 250 k variants); when long columns leave room for few CTAs (n = 4e5: 2 per SM), 8 warps
     // per CTA keep more warps resident (6.1 M -> 8.5 M variants/s).
-    auto extra_for = [](int warps) {
-        return sizeof(uint32_t) * warps * (kQueueCap + kRelQueueCap) + sizeof(double) * (warps * kColsPerSlice + 2 * warps) +
+    auto extra_for = [lists](int warps) {
+        return sizeof(uint32_t) * warps * (lists ? 0 : kQueueCap + kRelQueueCap) + sizeof(double) * (warps * kColsPerSlice + 2 * warps) +
                sizeof(int) * 4 * warps + 64;
     };
     const size_t smem_max = 227 * 1024;
@@ -540,7 +591,10 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     if (nstage == 1 && force == 2 && 2 * stride + extra <= smem_max) nstage = 2;
     if (nstage > 0) {
         const size_t smem = (size_t)nstage * stride + extra;
-        auto kern = warps == 1 ? scan_block_kernel<1> : warps == 2 ? scan_block_kernel<2> : warps == 4 ? scan_block_kernel<4> : scan_block_kernel<8>;
+        auto kern = lists ? (warps == 1 ? scan_block_kernel<1, true> : warps == 2 ? scan_block_kernel<2, true> :
+                             warps == 4 ? scan_block_kernel<4, true> : scan_block_kernel<8, true>)
+                          : (warps == 1 ? scan_block_kernel<1, false> : warps == 2 ? scan_block_kernel<2, false> :
+                             warps == 4 ? scan_block_kernel<4, false> : scan_block_kernel<8, false>);
         STAAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         STAAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
@@ -556,6 +610,61 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
         set_error("packed scan: a column of %zu bytes does not fit in shared memory (n > ~9e5): use the FP64 entry points", stride);
         return STAAR_ERR_ARG;
     }
+    ctx->launches++;
+    STAAR_CUDA(cudaGetLastError());
+    return STAAR_OK;
+}
+
+namespace {
+// Segment records of the contraction kernel -> positions.  One warp per variant: records are read 32 at a time, every
+// lane pops the bits of its record, positions are written in record order (exclusive prefix sum of the popcounts).
+// A variant whose lists were truncated, or whose positions do not fit, is marked kTruncated and appended to the work
+// list of the detection path.
+__global__ void __launch_bounds__(256) expand_lists_kernel(const uint2 *mlist, const uint2 *mcnt, int mcap, int64_t p, uint32_t *plist,
+                                                           uint32_t *pcnt, int pcap, long long *vlist, unsigned long long *vcount)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= p) return;
+    const uint2 a0 = mcnt[2 * i], a1 = mcnt[2 * i + 1];
+    if (a0.x > (uint32_t)mcap || a1.x > (uint32_t)mcap || a0.y + a1.y > (uint32_t)pcap) {
+        if (lane == 0) { pcnt[i] = kTruncated; vlist[atomicAdd(vcount, 1ull)] = i; }
+        return;
+    }
+    const uint2 *L0 = mlist + (size_t)(2 * i) * (size_t)mcap, *L1 = L0 + mcap;
+    uint32_t *out = plist + (size_t)i * (size_t)pcap;
+    const int nrec = (int)(a0.x + a1.x);
+    uint32_t done = 0u;
+    for (int base = 0; base < nrec; base += 32) {
+        const int e = base + lane;
+        uint2 rec = make_uint2(0u, 0u);
+        if (e < nrec) rec = (uint32_t)e < a0.x ? L0[e] : L1[e - (int)a0.x];
+        const uint32_t k = __popc(rec.y);
+        uint32_t incl = k;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        uint32_t at = done + incl - k;
+        while (rec.y) {
+            const int b = __ffs(rec.y) - 1;
+            rec.y &= rec.y - 1u;
+            out[at++] = rec.x * 32u + (uint32_t)((b & 1) * 16 + (b >> 1));
+        }
+        done += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) pcnt[i] = a0.y + a1.y;
+}
+}  // namespace
+
+int launch_expand_lists(staar_ctx *ctx, const uint2 *d_mlist, const uint2 *d_mcnt, int mcap, int64_t p, uint32_t *d_plist,
+                        uint32_t *d_pcnt, int pcap, long long *d_vlist, unsigned long long *d_vcount)
+{
+    if (p == 0) return STAAR_OK;
+    STAAR_CUDA(cudaMemsetAsync(d_vcount, 0, sizeof(unsigned long long), ctx->stream));
+    expand_lists_kernel<<<(unsigned)((p * 32 + 255) / 256), 256, 0, ctx->stream>>>(d_mlist, d_mcnt, mcap, p, d_plist, d_pcnt, pcap,
+                                                                                  d_vlist, d_vcount);
     ctx->launches++;
     STAAR_CUDA(cudaGetLastError());
     return STAAR_OK;

@@ -270,3 +270,42 @@ def test_conditional_refit_on_device_vs_lm(gpu_ctx, oracle, n, n_known, method):
                                     api.IMPUTE_MEAN, nm.X, method)
     assert rel_err(got["coef"], coef, 1e-3 * np.abs(coef).max()) < 1e-9
     assert_stats_close({k: got[k] for k in want}, want, score_floor(fl["Geno"][:, tested], res_c))
+
+
+@pytest.mark.parametrize("n,p,q,related,impute", [(20000, 160, 13, True, "mean"), (33000, 96, 5, False, "minor"),
+                                                 (5000, 120, 7, True, "mean")])
+def test_missing_lists_route_matches_detection_route(monkeypatch, oracle, n, p, q, related, impute):
+    """Two-kernel route, missing samples listed by the contraction kernel (default) against the scan's own detection pass
+    (STAAR_B200_MISSING_LISTS=0) and the oracle.  Missing rates per variant run from 0 to 60 %, so some lists fit and
+    some are truncated (those variants take the detection path inside the default flow); one variant is all missing.
+    AF / MAF bit-exact; statistics at the stated tolerance; twice through the default flow bit-identical."""
+    from staarpipeline_b200 import api, synth
+    nm = synth.nullmodel_sparse_grm(n, seed=n, q=q, shuffle=True) if related else synth.nullmodel_unrelated(n, seed=n, q=q)
+    G0 = cases.raw_dosage(n, p, n % 37)
+    p = G0.shape[1]                                                    # raw_dosage appends its edge-case columns
+    rng = np.random.default_rng(n + 1)
+    rates = np.concatenate([[0.0, 0.0005, 0.002, 0.01, 0.05, 0.3, 0.6], rng.choice([0.0, 0.001, 0.004, 0.02], size=p - 7)])
+    G0[rng.random(G0.shape) < rates[None, :]] = np.nan
+    G0[:, p - 1] = np.nan
+    codes = np.where(np.isnan(G0) | (G0 <= -1), 3, G0).astype(np.uint8)
+    packed = synth.pack_codes(np.asfortranarray(codes))
+    flag = api.IMPUTE_MEAN if impute == "mean" else api.IMPUTE_MINOR
+    fl = getattr(oracle, f"matrix_flip_{impute}")(G0)
+    want = oracle.Individual_Score_Test(fl["Geno"], nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+    res = {}
+    for lists in ("1", "0"):
+        monkeypatch.setenv("STAAR_B200_MISSING_LISTS", lists)
+        ctx = api.Context(0)
+        try:
+            ctx.set_nullmodel_sparse(nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+            res[lists] = ctx.packed_score_host(packed, n, flag)
+            if lists == "1":
+                again = ctx.packed_score_host(packed, n, flag)
+                for k in again:
+                    assert np.array_equal(again[k], res[lists][k], equal_nan=True), k
+        finally:
+            ctx.close()
+        assert np.array_equal(res[lists]["AF"], fl["AF"], equal_nan=True) and np.array_equal(res[lists]["MAF"], fl["MAF"], equal_nan=True)
+        assert_stats_close({k: res[lists][k] for k in want}, want, score_floor(fl["Geno"], nm.residuals))
+    for k in ("Score_se", "Est_se"):                                   # both flows hit the exact-zero branch on the same variants
+        assert np.array_equal(res["1"][k] == 0, res["0"][k] == 0) or np.array_equal(np.isfinite(res["1"][k]), np.isfinite(res["0"][k])), k
