@@ -302,7 +302,8 @@ def run_ours(args):
         pass
     fused = ctx.last_packed_path_was_fused
     names = ({"scan": "scan_block_kernel (redo list)", "contract": "fused_tc_kernel", "finalize": "fused_finalize_kernel"} if fused
-             else {"scan": "scan_block_kernel", "contract": "contract_tc_kernel", "finalize": "finalize_packed_kernel"})
+             else {"scan": "scan_block_kernel (+ expand_lists_kernel and the detection-path launch for truncated lists)",
+                   "contract": "contract_tc_kernel", "finalize": "finalize_packed_kernel"})
     roofline = {"bound": "hbm", "kernel": names[dominant],
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
@@ -540,7 +541,7 @@ def run_config(args):
         ms, clocks, launches = timed(lambda: ctx.packed_score_device(packed.data_ptr(), stride, n, V, api.IMPUTE_MEAN, optrs), sync_all)
         bytes_v = n * 2 / 8 + 56
         roof = {"bound": "hbm", "achieved": V * bytes_v / (ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "traffic": None,
-                "kernel": "whole step (contract_tc_kernel + scan_block_kernel + finalize_packed_kernel)"}
+                "kernel": "whole step (contract_tc_kernel + expand_lists_kernel + scan_block_kernel + finalize_packed_kernel)"}
         work = "BASELINE configs[0]: Individual_Analysis continuous trait, unrelated samples, n=10,000 (resident 2-bit columns)"
         dtype = "int8 x int8 -> int32 exact contraction of 54-bit sliced f64 operands; f64 statistics"
     elif cfg == 2:

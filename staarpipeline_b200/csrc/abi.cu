@@ -856,9 +856,10 @@ int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t st
     if (lists) {
         const int mcap = (int)std::min<int64_t>(2048, std::max<int64_t>(96, ((n / 1000 + 64) + 31) / 32 * 32));
         STAAR_TRY(ctx->mlist.reserve(sizeof(uint2) * 2 * (size_t)mcap * (size_t)p));
-        STAAR_TRY(ctx->msubcnt.reserve(sizeof(uint2) * 2 * (size_t)p));
+        STAAR_TRY(ctx->msubcnt.reserve(sizeof(uint32_t) * 2 * (size_t)p));
         STAAR_TRY(ctx->redo.reserve(sizeof(long long) * (size_t)p + 2 * sizeof(unsigned long long)));
-        uint2 *dml = ctx->mlist.as<uint2>(), *dmc = ctx->msubcnt.as<uint2>();
+        uint2 *dml = ctx->mlist.as<uint2>();
+        uint32_t *dmc = ctx->msubcnt.as<uint32_t>();
         unsigned long long *dcount = ctx->redo.as<unsigned long long>();
         long long *dredo = reinterpret_cast<long long *>(dcount + 2);
         STAAR_TRY(launch_contract_tc(ctx, d_packed, stride, n, p, dhi, dlo, dml, dmc, mcap));

@@ -260,7 +260,7 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
                        const uint32_t *d_plist = nullptr, const uint32_t *d_pcnt = nullptr, int pcap = 0);
 // segment records of the contraction (d_mlist / d_mcnt) -> positions d_plist[i * pcap ..] and counts d_pcnt[i] the scan's
 // list mode reads; variants whose lists did not fit -> d_vlist / *d_vcount (work list of the detection path)
-int launch_expand_lists(staar_ctx *ctx, const uint2 *d_mlist, const uint2 *d_mcnt, int mcap, int64_t p, uint32_t *d_plist,
+int launch_expand_lists(staar_ctx *ctx, const uint2 *d_mlist, const uint32_t *d_mcnt, int mcap, int64_t p, uint32_t *d_plist,
                         uint32_t *d_pcnt, int pcap, long long *d_vlist, unsigned long long *d_vcount);
 int launch_contract_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p,
                            long long *d_hi, long long *d_lo);
@@ -281,9 +281,9 @@ int launch_fused_finalize(staar_ctx *ctx, int64_t n, int64_t p, int impute, cons
 int build_sliced_operand(staar_ctx *ctx, const double *hY /* n x ldY row-major host, natural sample order */);
 int build_tc_operand(staar_ctx *ctx, const int8_t *digits, int ncol);
 // d_mlist / d_mcnt (optional): per variant two sub-lists of mcap records {32-sample segment, mask of its missing samples}
-// and per sub-list {records, missing samples} (records above mcap = list truncated); the scan's list mode consumes them
+// and per sub-list the number of records (above mcap = list truncated); expand_lists_kernel turns them into positions
 int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, long long *d_hi,
-                       long long *d_lo, uint2 *d_mlist = nullptr, uint2 *d_mcnt = nullptr, int mcap = 0);
+                       long long *d_lo, uint2 *d_mlist = nullptr, uint32_t *d_mcnt = nullptr, int mcap = 0);
 int refresh_permuted_Y(staar_ctx *ctx, const double *hY);
 // ctx.cu / abi.cu — shared with multi.cu
 int nullmodel_sparse_clone(staar_ctx *dst, const staar_ctx *src);

@@ -75,7 +75,7 @@ __device__ int g_tc_dbg;
 __global__ void __launch_bounds__(kTcThreads, 1)
 contract_tc_kernel(const __grid_constant__ CUtensorMap gmap, int64_t p, const int8_t *__restrict__ Ytc,
                    int64_t n_kblocks, long long *__restrict__ out_hi, long long *__restrict__ out_lo,
-                   uint2 *__restrict__ mlist, uint2 *__restrict__ mcnt, int mcap)
+                   uint2 *__restrict__ mlist, uint32_t *__restrict__ mcnt, int mcap)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sG = smem;                                                       // kRing x kTileBytes (1024-byte aligned: swizzle)
@@ -131,7 +131,7 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap gmap, int64_t p, const in
         // encoding); the scan kernel then needs no detection pass and knows the missing count up front.  A record count
         // above mcap marks the variant for the scan's own detection path.
         uint2 *my_list = mlist ? mlist + ((size_t)v * 2 + half) * (size_t)mcap : nullptr;
-        uint32_t mc = 0, mcm = 0;                                            // records, missing samples
+        uint32_t mc = 0;                                                     // records written (or counted, beyond mcap)
 #ifdef TC_TIMERS
         long long tm_ae = 0, tm_st = 0, tm_gf = 0, tm_ex = 0, tm_ws = 0, tm_t0;
         const bool tm_on = threadIdx.x == 0 && blockIdx.x == 500;
@@ -178,7 +178,6 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap gmap, int64_t p, const in
                                 if (mask) {
                                     if (mc < (uint32_t)mcap) my_list[mc] = make_uint2(seg0 + 2u * c + hh, mask);
                                     mc++;
-                                    mcm += __popc(mask);
                                 }
                             }
                         }
@@ -218,7 +217,7 @@ contract_tc_kernel(const __grid_constant__ CUtensorMap gmap, int64_t p, const in
         if (tm_on) printf("expander: per k-block clk: wait a_empty %lld, st issue %lld, wait g_full %lld, lds+alu %lld, wait::st %lld\n",
                           tm_ae / n_kblocks, tm_st / n_kblocks, tm_gf / n_kblocks, tm_ex / n_kblocks, tm_ws / n_kblocks);
 #endif
-        if (my_list && rok) mcnt[v * 2 + half] = make_uint2(mc, mcm);
+        if (my_list && rok) mcnt[v * 2 + half] = mc;
         // ===================================================================== epilogue: TMEM -> 64-bit recombination
         // half 0 reads the accumulators of digit slices 0-3 (the "hi" part), half 1 those of slices 4-6
         bar_wait(d_full, 0u);
@@ -595,7 +594,7 @@ static int encode_genotype_map(CUtensorMap *map, const uint8_t *d_packed, size_t
 }
 
 int launch_contract_tc(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, int64_t n, int64_t p, long long *d_hi,
-                       long long *d_lo, uint2 *d_mlist, uint2 *d_mcnt, int mcap)
+                       long long *d_lo, uint2 *d_mlist, uint32_t *d_mcnt, int mcap)
 {
     if (p == 0) return STAAR_OK;
     const NullSparse &ns = ctx->ns;

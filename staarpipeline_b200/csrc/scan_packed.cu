@@ -620,25 +620,22 @@ namespace {
 // lane pops the bits of its record, positions are written in record order (exclusive prefix sum of the popcounts).
 // A variant whose lists were truncated, or whose positions do not fit, is marked kTruncated and appended to the work
 // list of the detection path.
-__global__ void __launch_bounds__(256) expand_lists_kernel(const uint2 *mlist, const uint2 *mcnt, int mcap, int64_t p, uint32_t *plist,
+__global__ void __launch_bounds__(256) expand_lists_kernel(const uint2 *mlist, const uint32_t *mcnt, int mcap, int64_t p, uint32_t *plist,
                                                            uint32_t *pcnt, int pcap, long long *vlist, unsigned long long *vcount)
 {
     const int lane = threadIdx.x & 31;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= p) return;
-    const uint2 a0 = mcnt[2 * i], a1 = mcnt[2 * i + 1];
-    if (a0.x > (uint32_t)mcap || a1.x > (uint32_t)mcap || a0.y + a1.y > (uint32_t)pcap) {
-        if (lane == 0) { pcnt[i] = kTruncated; vlist[atomicAdd(vcount, 1ull)] = i; }
-        return;
-    }
+    const uint32_t c0 = mcnt[2 * i], c1 = mcnt[2 * i + 1];
+    bool fits = c0 <= (uint32_t)mcap && c1 <= (uint32_t)mcap;
     const uint2 *L0 = mlist + (size_t)(2 * i) * (size_t)mcap, *L1 = L0 + mcap;
     uint32_t *out = plist + (size_t)i * (size_t)pcap;
-    const int nrec = (int)(a0.x + a1.x);
+    const int nrec = fits ? (int)(c0 + c1) : 0;
     uint32_t done = 0u;
-    for (int base = 0; base < nrec; base += 32) {
+    for (int base = 0; base < nrec && fits; base += 32) {              // warp-uniform
         const int e = base + lane;
         uint2 rec = make_uint2(0u, 0u);
-        if (e < nrec) rec = (uint32_t)e < a0.x ? L0[e] : L1[e - (int)a0.x];
+        if (e < nrec) rec = (uint32_t)e < c0 ? L0[e] : L1[e - (int)c0];
         const uint32_t k = __popc(rec.y);
         uint32_t incl = k;
 #pragma unroll
@@ -646,19 +643,24 @@ __global__ void __launch_bounds__(256) expand_lists_kernel(const uint2 *mlist, c
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += t;
         }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (done + total > (uint32_t)pcap) { fits = false; break; }    // more missing samples than the position list holds
         uint32_t at = done + incl - k;
         while (rec.y) {
             const int b = __ffs(rec.y) - 1;
             rec.y &= rec.y - 1u;
             out[at++] = rec.x * 32u + (uint32_t)((b & 1) * 16 + (b >> 1));
         }
-        done += __shfl_sync(0xffffffffu, incl, 31);
+        done += total;
     }
-    if (lane == 0) pcnt[i] = a0.y + a1.y;
+    if (lane == 0) {
+        pcnt[i] = fits ? done : kTruncated;
+        if (!fits) vlist[atomicAdd(vcount, 1ull)] = i;
+    }
 }
 }  // namespace
 
-int launch_expand_lists(staar_ctx *ctx, const uint2 *d_mlist, const uint2 *d_mcnt, int mcap, int64_t p, uint32_t *d_plist,
+int launch_expand_lists(staar_ctx *ctx, const uint2 *d_mlist, const uint32_t *d_mcnt, int mcap, int64_t p, uint32_t *d_plist,
                         uint32_t *d_pcnt, int pcap, long long *d_vlist, unsigned long long *d_vcount)
 {
     if (p == 0) return STAAR_OK;
