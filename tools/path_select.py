@@ -1,5 +1,6 @@
 """Times the two resident packed-score routes (split: contraction + block-per-variant scan; fused: single pass) on
-several null-model shapes; the measurements behind the automatic route choice in abi.cu."""
+several null-model shapes (kind:n:variants ...; PATHS=split,fused; STAAR_B200_MISSING_LISTS / STAAR_B200_CONTRACT /
+STAAR_B200_SCAN_WARPS select variants of the split route).  The measurements quoted in DESIGN.md section 4."""
 import sys, os, time
 sys.path.insert(0, ".")
 import numpy as np, torch
