@@ -24,6 +24,7 @@ namespace {
 
 struct ScanParams {
     const uint8_t *packed; size_t stride; int64_t n, p; int impute;
+    size_t sbytes;                         // bytes of a column staged in shared memory (list mode: the kinship prefix only)
     // generic kinship path (positions in null-model order)
     const uint8_t *relmask;                // 2-bit mask, 11 = sample has kinship off-diagonals with a larger position
     const NullSparse::CarrierRec *rel;     // per-sample record: first two such entries inline (32 B)
@@ -82,12 +83,12 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    const size_t stride = P.stride;
+    const size_t stride = P.stride, sbytes = P.sbytes;
     uint8_t *cols = smem;
     constexpr int kQueueWords = kLists ? 0 : kQueueCap + kRelQueueCap;            // the list instantiation keeps no queues
-    uint32_t *wq = reinterpret_cast<uint32_t *>(smem + (size_t)nstage * stride) + wib * kQueueWords;   // this warp's queues
+    uint32_t *wq = reinterpret_cast<uint32_t *>(smem + (size_t)nstage * sbytes) + wib * kQueueWords;   // this warp's queues
     uint32_t *rq = wq + kQueueCap;
-    double *s_sm = reinterpret_cast<double *>(smem + (size_t)nstage * stride + sizeof(uint32_t) * kBlkWarps * kQueueWords);
+    double *s_sm = reinterpret_cast<double *>(smem + (size_t)nstage * sbytes + sizeof(uint32_t) * kBlkWarps * kQueueWords);
     double *s_quad = s_sm + kBlkWarps * kColsPerSlice;                           // [2][kBlkWarps]: kinship part, hom-minor diag part
     int *s_cnt = reinterpret_cast<int *>(s_quad + 2 * kBlkWarps);                // [4][kBlkWarps]
     unsigned long long *s_work = reinterpret_cast<unsigned long long *>(s_cnt + 4 * kBlkWarps);   // [2]
@@ -102,10 +103,10 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
 
     auto issue = [&](unsigned long long v, int stage) {          // thread 0 only
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&full[stage])),
-                     "r"((uint32_t)stride) : "memory");
+                     "r"((uint32_t)sbytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_addr(cols + (size_t)stage * stride)),
-                     "l"(P.packed + (size_t)v * stride), "r"((uint32_t)stride), "r"(smem_addr(&full[stage]))
+                         smem_addr(cols + (size_t)stage * sbytes)),
+                     "l"(P.packed + (size_t)v * stride), "r"((uint32_t)sbytes), "r"(smem_addr(&full[stage]))
                      : "memory");
     };
     auto wait_full = [&](int stage, uint32_t parity) {
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
         }
         wait_full(stage, (parity >> stage) & 1u);
         parity ^= 1u << stage;
-        const uint8_t *col = cols + (size_t)stage * stride;
+        const uint8_t *col = cols + (size_t)stage * sbytes;
 
         // ---- sweep 1 (whole column, 64 samples per lane and step).  The sum of the variant's codes S = c1 + 2 c2 + 3 cm
         //      comes EXACTLY from the tensor-core contraction (its constant-1 column), so no genotype popcounts are
@@ -243,9 +244,23 @@ __global__ void __launch_bounds__(kBlkWarps * 32) scan_block_kernel(ScanParams P
             const long long gs = S - 3ll * cm, gn = (long long)P.n - cm;
             if (P.impute == STAAR_IMPUTE_MEAN) guess = gs > gn;
             else guess = gs + (gs > gn ? 2 : 0) * (long long)cm > (long long)P.n;
-            // hom-minor term beyond the table words; the table words get it inside the kinship sweep below (one read)
+            // hom-minor term beyond the table words: read straight from global memory (only the kinship prefix of the
+            // column is staged in shared memory); the table words get it inside the kinship sweep below (one read)
             const int nv = skip ? 0 : nvec16;
-            for (int k = tab_vec + tid; k < nv; k += kBlkWarps * 32) hom_vec(v4[k], k, guess, hom);
+            const uint4 *g4 = reinterpret_cast<const uint4 *>(P.packed + (size_t)i * stride);
+            int k = tab_vec + tid;
+            if (sbytes == stride) {                                                  // short columns: everything is staged
+                for (; k < nv; k += kBlkWarps * 32) hom_vec(v4[k], k, guess, hom);
+            }
+            for (; k + 3 * kBlkWarps * 32 < nv; k += 4 * kBlkWarps * 32) {           // four 16-byte loads in flight
+                const uint4 qa = __ldg(g4 + k), qb = __ldg(g4 + k + kBlkWarps * 32), qc = __ldg(g4 + k + 2 * kBlkWarps * 32),
+                            qd = __ldg(g4 + k + 3 * kBlkWarps * 32);
+                hom_vec(qa, k, guess, hom);
+                hom_vec(qb, k + kBlkWarps * 32, guess, hom);
+                hom_vec(qc, k + 2 * kBlkWarps * 32, guess, hom);
+                hom_vec(qd, k + 3 * kBlkWarps * 32, guess, hom);
+            }
+            for (; k < nv; k += kBlkWarps * 32) hom_vec(__ldg(g4 + k), k, guess, hom);
             sm += __shfl_xor_sync(0xffffffffu, sm, 16);
             if (lane < kColsPerSlice) s_sm[wib * kColsPerSlice + lane] = sm;
         } else {
@@ -558,6 +573,14 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     if (n >= (1ll << 30)) { set_error("packed scan: n too large for 30-bit sample indices"); return STAAR_ERR_ARG; }
     ScanParams P;
     P.packed = d_packed; P.stride = stride; P.n = n; P.p = p; P.impute = impute;
+    // list mode stages only the kinship prefix of a column (table words, generic kinship words; at least one vector)
+    const size_t kin_bytes = (size_t)std::max<int64_t>(((ns.tab_words + 3) / 4) * 16, ((ns.kin_words * 4 + 15) / 16) * 16);
+    // Shorter columns are staged whole: the gain is occupancy (n = 1e5: 25 -> 14.5 KB per block), and below ~20 KB a whole
+    // column already leaves room for 10+ blocks per SM while the direct loads of a short tail are latency-bound
+    // (sparse GRM, prefix vs whole column: n = 2e4 5.15 vs 4.06 ms per 1 M variants, n = 6e4 4.95 vs 4.20 ms per 400 k,
+    // n = 1e5 4.52 vs 5.03 ms per 250 k, n = 4e5 6.18 vs 8.92 ms per 60 k).
+    const size_t sbytes = (lists && stride > 20000) ? std::min(stride, std::max<size_t>(kin_bytes, 16)) : stride;
+    P.sbytes = sbytes;
     P.relmask = ns.relmask; P.rel = ns.rel; P.up_ent = ns.up_ent;
     P.tab_words = ns.tab_words; P.kin_words = ns.kin_words; P.x_words = ns.x_words; P.kmask = ns.kmask; P.wdesc = ns.wdesc;
     P.xterms = ns.xterms; P.lut = ns.lut; P.sinfo = ns.sinfo_p; P.off_ent = ns.off_ent_p; P.diag = ns.diag_p;
@@ -578,7 +601,7 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     // or two warps and up to 32 blocks share an SM (measured per 400 k variants, sparse GRM: n = 2e4: 2.37 / 3.15 / 3.78 ms
     // with 1 / 2 / 4 warps; n = 4e4: 5.09 / 4.60 / 5.22 ms; n = 1e5: 27.9 / 13.8 / 10.5 ms).
     static const int force_warps = getenv("STAAR_B200_SCAN_WARPS") ? atoi(getenv("STAAR_B200_SCAN_WARPS")) : 0;
-    int warps = (6 * (stride + extra_for(4) + 1024) <= 228 * 1024) ? 4 : 8;
+    int warps = (6 * (sbytes + extra_for(4) + 1024) <= 228 * 1024) ? 4 : 8;
     if (stride <= 6144) warps = 1;
     else if (stride <= 14336) warps = 2;
     if (force_warps == 1 || force_warps == 2 || force_warps == 4 || force_warps == 8) warps = force_warps;
@@ -587,10 +610,10 @@ int launch_scan_packed(staar_ctx *ctx, const uint8_t *d_packed, size_t stride, i
     // overlapping the column copy: one column stage (measured at n = 1e5: 6.76 ms vs 7.13 ms with two stages per
     // 250 k variants); STAAR_B200_SCAN_STAGES=2 forces the double-buffered variant for experiments.
     static const int force = getenv("STAAR_B200_SCAN_STAGES") ? atoi(getenv("STAAR_B200_SCAN_STAGES")) : 0;
-    int nstage = (stride + extra <= smem_max) ? 1 : 0;
-    if (nstage == 1 && force == 2 && 2 * stride + extra <= smem_max) nstage = 2;
+    int nstage = (sbytes + extra <= smem_max) ? 1 : 0;
+    if (nstage == 1 && force == 2 && 2 * sbytes + extra <= smem_max) nstage = 2;
     if (nstage > 0) {
-        const size_t smem = (size_t)nstage * stride + extra;
+        const size_t smem = (size_t)nstage * sbytes + extra;
         auto kern = lists ? (warps == 1 ? scan_block_kernel<1, true> : warps == 2 ? scan_block_kernel<2, true> :
                              warps == 4 ? scan_block_kernel<4, true> : scan_block_kernel<8, true>)
                           : (warps == 1 ? scan_block_kernel<1, false> : warps == 2 ? scan_block_kernel<2, false> :
