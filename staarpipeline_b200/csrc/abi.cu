@@ -852,21 +852,27 @@ int staar_packed_score_device(staar_ctx *ctx, const uint8_t *d_packed, size_t st
     // truncated (missing rate far above the list capacity) go through the scan's own detection path afterwards.
     // (short columns of unrelated samples are the one case where the listing costs more than the detection it saves:
     // n = 1e4, no kinship: 5.79 vs 5.42 ms per 2 M variants)
-    const bool lists = ctx->use_missing_lists && !ctx->use_mma_sync && !ctx->use_tc_pair && (n >= 16384 || ctx->ns.kin_words > 0);
+    bool lists = ctx->use_missing_lists && !ctx->use_mma_sync && !ctx->use_tc_pair && (n >= 16384 || ctx->ns.kin_words > 0);
+    const int mcap = (int)std::min<int64_t>(2048, std::max<int64_t>(96, ((n / 1000 + 64) + 31) / 32 * 32)), pcap = 2 * mcap;
     if (lists) {
-        const int mcap = (int)std::min<int64_t>(2048, std::max<int64_t>(96, ((n / 1000 + 64) + 31) / 32 * 32));
-        STAAR_TRY(ctx->mlist.reserve(sizeof(uint2) * 2 * (size_t)mcap * (size_t)p));
-        STAAR_TRY(ctx->msubcnt.reserve(sizeof(uint32_t) * 2 * (size_t)p));
-        STAAR_TRY(ctx->redo.reserve(sizeof(long long) * (size_t)p + 2 * sizeof(unsigned long long)));
+        // list scratch: 16 mcap + 4 pcap + 16 bytes per variant (3.9 KB at n = 1e5).  If the device cannot hold it next to
+        // the caller's columns, the call still succeeds: the scan detects the missing samples itself.
+        if (ctx->mlist.reserve(sizeof(uint2) * 2 * (size_t)mcap * (size_t)p) != STAAR_OK ||
+            ctx->plist.reserve(sizeof(uint32_t) * (size_t)pcap * (size_t)p) != STAAR_OK ||
+            ctx->msubcnt.reserve(sizeof(uint32_t) * 2 * (size_t)p) != STAAR_OK || ctx->pcnt.reserve(sizeof(uint32_t) * (size_t)p) != STAAR_OK ||
+            ctx->redo.reserve(sizeof(long long) * (size_t)p + 2 * sizeof(unsigned long long)) != STAAR_OK) {
+            (void)cudaGetLastError();
+            ctx->mlist.release(); ctx->plist.release();
+            lists = false;
+        }
+    }
+    if (lists) {
         uint2 *dml = ctx->mlist.as<uint2>();
         uint32_t *dmc = ctx->msubcnt.as<uint32_t>();
         unsigned long long *dcount = ctx->redo.as<unsigned long long>();
         long long *dredo = reinterpret_cast<long long *>(dcount + 2);
         STAAR_TRY(launch_contract_tc(ctx, d_packed, stride, n, p, dhi, dlo, dml, dmc, mcap));
         if (prof) STAAR_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-        const int pcap = 2 * mcap;
-        STAAR_TRY(ctx->plist.reserve(sizeof(uint32_t) * (size_t)pcap * (size_t)p));
-        STAAR_TRY(ctx->pcnt.reserve(sizeof(uint32_t) * (size_t)p));
         STAAR_TRY(launch_expand_lists(ctx, dml, dmc, mcap, p, ctx->plist.as<uint32_t>(), ctx->pcnt.as<uint32_t>(), pcap, dredo, dcount));
         STAAR_TRY(launch_scan_packed(ctx, d_packed, stride, n, p, impute, dlo, d_AF, d_MAF, dflip, dmu, dquad, dSm, nullptr, nullptr,
                                      ctx->plist.as<uint32_t>(), ctx->pcnt.as<uint32_t>(), pcap));
