@@ -309,3 +309,26 @@ def test_missing_lists_route_matches_detection_route(monkeypatch, oracle, n, p, 
         assert_stats_close({k: res[lists][k] for k in want}, want, score_floor(fl["Geno"], nm.residuals))
     for k in ("Score_se", "Est_se"):                                   # both flows hit the exact-zero branch on the same variants
         assert np.array_equal(res["1"][k] == 0, res["0"][k] == 0) or np.array_equal(np.isfinite(res["1"][k]), np.isfinite(res["0"][k])), k
+
+
+def test_prefix_staged_scan_odd_long_column(gpu_ctx, oracle):
+    """n = 90 001 (not a multiple of 4 / 16 / 64, long enough for the list-mode scan to stage only the kinship prefix of a
+    column and read the rest from global memory): tail masks of the direct loads, padding, missing samples on both sides
+    of the table's end"""
+    from staarpipeline_b200 import api, synth
+    n, p, q = 90001, 40, 13
+    nm = synth.nullmodel_sparse_grm(n, seed=5, q=q, shuffle=True)
+    G0 = cases.raw_dosage(n, p, 5)
+    rng = np.random.default_rng(6)
+    G0[rng.random(G0.shape) < 0.002] = np.nan
+    G0[n - 70:, 3] = np.nan                                             # a run of missing samples in the last vectors
+    G0[n - 1, :8] = 2.0                                                 # carriers in the very last position
+    codes = np.where(np.isnan(G0) | (G0 <= -1), 3, G0).astype(np.uint8)
+    packed = synth.pack_codes(np.asfortranarray(codes))
+    for impute, flag in (("mean", api.IMPUTE_MEAN), ("minor", api.IMPUTE_MINOR)):
+        fl = getattr(oracle, f"matrix_flip_{impute}")(G0)
+        want = oracle.Individual_Score_Test(fl["Geno"], nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+        gpu_ctx.set_nullmodel_sparse(nm.Sigma_i, nm.Sigma_iX, nm.cov, nm.residuals)
+        got = gpu_ctx.packed_score_host(packed, n, flag)
+        assert np.array_equal(got["AF"], fl["AF"], equal_nan=True) and np.array_equal(got["MAF"], fl["MAF"], equal_nan=True)
+        assert_stats_close({k: got[k] for k in want}, want, score_floor(fl["Geno"], nm.residuals))
