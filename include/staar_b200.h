@@ -279,9 +279,14 @@ int staar_ctx_last_stage_ms(staar_ctx *ctx, float ms[3]);
  *     more than 16 members fall back to the split route.  With profiling on, staar_ctx_last_stage_ms then reports
  *     ms[0] = redo, ms[1] = fused kernel, ms[2] = finaliser.
  *   STAAR_PACKED_PATH_SPLIT (default) — contraction kernel, then block-per-variant scan, then finaliser (two passes
- *     over G; on B200 the faster of the two).
- * Both routes compute the same statistics (src/Individual_Score_Test.cpp:42-64); environment override:
- * STAAR_B200_PACKED_PATH=fused|split at context creation. */
+ *     over G; on B200 the faster of the two).  The contraction kernel also lists the missing samples of
+ *     every variant, so the scan knows the flip up front and runs without a detection pass (per-call scratch: 3.9 KB per
+ *     variant at n = 1e5; variants with more missing samples than the lists hold, and calls whose lists do not fit on
+ *     the device, go through the scan's own detection pass).  With profiling on: ms[0] = scan stage (list expansion +
+ *     both scan launches), ms[1] = contraction, ms[2] = finaliser.
+ * Both routes compute the same statistics (src/Individual_Score_Test.cpp:42-64); environment overrides at context
+ * creation: STAAR_B200_PACKED_PATH=fused|split; STAAR_B200_MISSING_LISTS=0 (split route without the lists);
+ * STAAR_B200_CONTRACT=pair|mma (CTA-pair tcgen05 kernel / legacy mma.sync kernel instead of the default tcgen05 one). */
 #define STAAR_PACKED_PATH_FUSED 0
 #define STAAR_PACKED_PATH_SPLIT 1
 int staar_ctx_set_packed_path(staar_ctx *ctx, int path);
